@@ -1,0 +1,275 @@
+/*
+ * usv_b200.h -- C ABI of the B200-native ASV (USV) hot path.
+ *
+ * One shared library (libusv_b200.so), plain pointers and sizes only.  Every
+ * entry point replaces a chain of eager torch ops behind one of the reference's
+ * Python method surfaces; the reference location each one stands in for is
+ * cited as  [ref: path:line]  relative to the reference repo root, with
+ *   OIGE = omniisaacgymenvs/,  SNAP = 811_3.5*(classic snapshot)/,  RLG = rl_games/rl_games/.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers owned by the caller (torch tensors); the
+ *     library never allocates, frees or synchronises; work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*), so calls are asynchronous and re-entrant.
+ *   - return value: 0 = ok, <0 = argument error (USV_E_*), >0 = cudaError_t of the
+ *     launch.  usv_b200_error_string() decodes both.
+ *   - float data is fp32; reset/done flags are int64 (torch.long) as in
+ *     [ref: OIGE/tasks/base/rl_task.py:129-130]; rollout dones are uint8 as in
+ *     [ref: RLG/common/a2c_common.py:454].
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point
+ *     returns a cudaError_t.
+ */
+#ifndef USV_B200_H_
+#define USV_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define USV_B200_ABI_VERSION 1
+
+enum {
+  USV_OK = 0,
+  USV_E_NULL = -1,      /* required pointer is NULL            */
+  USV_E_SIZE = -2,      /* negative / inconsistent size        */
+  USV_E_PARAM = -3,     /* parameter outside supported range   */
+  USV_E_ALIGN = -4,     /* pointer not aligned as documented   */
+  USV_E_UNSUPPORTED = -5
+};
+
+int usv_b200_abi_version(void);
+const char* usv_b200_error_string(int code);
+/* number of kernels this library has launched since load (bench.py "gpu_launches") */
+int64_t usv_b200_launch_count(void);
+
+/* ------------------------------------------------------------------------- */
+/* A1  HydrostaticsObject.compute_archimedes_metacentric_local                */
+/*     [ref: OIGE/envs/USV/Hydrostatics.py:63-133]                            */
+/* out6[n,6] = [R^T (0,0,-rho*g*V) , (-w*sin(roll)*F, -l*sin(pitch)*F, 0)*amp] */
+typedef struct {
+  float water_density;
+  float gravity;                          /* signed, e.g. -9.81 */
+  float metacentric_width;
+  float metacentric_length;
+  float average_hydrostatics_force_value; /* 275 */
+  float amplify_torque;
+} UsvHydrostaticsParams;
+
+int usv_hydrostatics_f32(const float* submerged_volume /*[n]*/, const float* rpy /*[n,3]*/,
+                         const float* quat /*[n,4] w,x,y,z*/, float* out6 /*[n,6]*/,
+                         float* force_global /*[n,3] or NULL*/, float* torque_global /*[n,3] or NULL*/,
+                         int64_t n, const UsvHydrostaticsParams* p, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* A2  HydrodynamicsObject.ComputeHydrodynamicsEffects + ComputeDampingMatrix */
+/*     [ref: OIGE/envs/USV/Hydrodynamics.py:176-245]                          */
+typedef struct {
+  float linear_damping_forward_speed[6];
+  float offset_linear_damping;
+  float offset_lin_forward_damping_speed;
+  float offset_nonlin_damping;
+  float scaling_damping;
+  int32_t use_drag_scale;    /* _use_drag_scale_randomization */
+  int32_t use_water_current;
+  float flow_vel[3];
+} UsvHydrodynamicsParams;
+
+int usv_hydrodynamics_f32(const float* quat /*[n,4]*/, const float* world_vel6 /*[n,6]*/,
+                          const float* linear_damping /*[n,6]*/, const float* quadratic_damping /*[n,6]*/,
+                          const float* drag_scale /*[n] (the (n,1) tensor)*/,
+                          float* drag6 /*[n,6]*/, float* local_vel6 /*[n,6] or NULL*/,
+                          int64_t n, const UsvHydrodynamicsParams* p, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* A4  DynamicsFirstOrder.get_cmd_interpolated / set_target_force             */
+/*     [ref: OIGE/envs/USV/ThrusterDynamics.py:179-219]                       */
+/* idx = clamp(round_half_even(((cmd+1)/2)*(n_lut-1)), 0, n_lut-1)            */
+int usv_thruster_target_f32(const float* cmd2 /*[n,2]*/, const float* lut_left /*[n_lut]*/,
+                            const float* lut_right /*[n_lut]*/, int32_t n_lut,
+                            const float* mult_left /*[n] or NULL (=1)*/,
+                            const float* mult_right /*[n] or NULL (=1)*/,
+                            float* before_dynamics2 /*[n,2]*/, float* after_randomization2 /*[n,2] or NULL*/,
+                            int64_t n, void* stream);
+
+/* A5  DynamicsFirstOrder.update / update_forces                              */
+/*     [ref: OIGE/envs/USV/ThrusterDynamics.py:129-141,221-234]               */
+/* cur = cur*alpha + (1-alpha)*target ; thrusters[:,0]=cur[:,0], [:,3]=cur[:,1] */
+int usv_thruster_lag_f32(float* current_forces2 /*[n,2] in/out*/, const float* target2 /*[n,2]*/,
+                         float alpha, float* thrusters6 /*[n,6]: only cols 0,3 written*/,
+                         int64_t n, void* stream);
+
+/* LUT builder: F.interpolate(points, size=n_out, mode="linear", align_corners=True) */
+/*     [ref: OIGE/envs/USV/ThrusterDynamics.py:152-177]                       */
+int usv_thruster_build_lut_f32(const float* points /*[n_pts]*/, int32_t n_pts,
+                               float* lut /*[n_out]*/, int32_t n_out, void* stream);
+
+/* A3/A6/A10  per-episode uniform re-draws of rows of an (N, ld) tensor:       */
+/*   dst[env_ids[j], c] = base[c] + (lo[c] + u*(hi[c]-lo[c]))                  */
+/* u from Philox4x32-10 keyed (seed; env_id, counter, stream_id+c/4).          */
+/*     [ref: OIGE/envs/USV/Hydrodynamics.py:136-174, ThrusterDynamics.py:112-127, */
+/*           OIGE/tasks/USV/USV_disturbances.py:127-151]                      */
+int usv_randomize_rows_f32(float* dst, int64_t ld, const int64_t* env_ids, int64_t n_ids,
+                           int32_t ncols, const float* base /*[ncols]*/, const float* lo /*[ncols]*/,
+                           const float* hi /*[ncols]*/, int32_t log_space,
+                           uint64_t seed, uint64_t counter, uint32_t stream_id, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* Fused env step (Variant A, classic CaptureXY) == VecEnvRLGames.step         */
+/*     [ref: OIGE/envs/vec_env_rlgames.py:120-217; SNAP/USV_Virtual.py:571-866; */
+/*           SNAP/USV_capture_xy.py:80-275; SNAP/USV_task_rewards.py:40-76,380-540; */
+/*           OIGE/tasks/USV/USV_disturbances.py; OIGE/tasks/base/rl_task.py:283-303] */
+/* State is structure-of-arrays: field f of env i lives at base[f*stride + i].  */
+
+/* dynamic fields (read+written every step) */
+enum {
+  USV_S_X = 0, USV_S_Y, USV_S_PSI, USV_S_VX, USV_S_VY, USV_S_R,
+  USV_S_THR_L, USV_S_THR_R,      /* DynamicsFirstOrder.current_forces            */
+  USV_S_PREV_D,                  /* prev_position_dist / prev_position_error     */
+  USV_S_PREV_W,                  /* Penalties.prev_state["angular_velocity"]     */
+  USV_S_PREV_ASUM,               /* sum(Penalties.prev_actions)                  */
+  USV_S_GOAL_CNT,                /* int32 bit pattern: CaptureXYTask._goal_reached */
+  USV_S_PROGRESS,                /* int32 bit pattern: RLTask.progress_buf       */
+  USV_S_COUNT
+};
+/* per-episode constants (read every step, rewritten on reset) */
+enum {
+  USV_C_TX = 0, USV_C_TY,        /* task._target_positions                       */
+  USV_C_MASS,                    /* MDD.platforms_mass                           */
+  USV_C_LIN_U, USV_C_LIN_V, USV_C_LIN_R,    /* hydrodynamics.linear_damping[:, (0,1,5)]    */
+  USV_C_QUAD_U, USV_C_QUAD_V, USV_C_QUAD_R, /* hydrodynamics.quadratic_damping[:, (0,1,5)] */
+  USV_C_KDRAG,                   /* hydrodynamics.drag_scale                     */
+  USV_C_THR_ML, USV_C_THR_MR,    /* effective left/right thruster multipliers    */
+  USV_C_KIZ,                     /* yaw-inertia scale                            */
+  USV_C_FCX, USV_C_FCY,          /* UF.disturbance_forces_const                  */
+  USV_C_FXF, USV_C_FYF, USV_C_FXS, USV_C_FYS, USV_C_FAMP,
+  USV_C_TC, USV_C_TF, USV_C_TS, USV_C_TAMP, /* TD.*                              */
+  USV_C_COUNT
+};
+/* optional per-episode statistics accumulators (episode_sums), SoA as well */
+enum {
+  USV_ST_DISTANCE_REWARD = 0, USV_ST_ALIGNMENT_REWARD, USV_ST_VELOCITY_REWARD,
+  USV_ST_POSITION_ERROR, USV_ST_VELOCITY_NORM, USV_ST_BOUNDARY_PENALTY, USV_ST_BOUNDARY_DIST,
+  USV_ST_LINEAR_VEL_PENALTY, USV_ST_ANGULAR_VEL_PENALTY, USV_ST_ANGULAR_VEL_VARIATION_PENALTY,
+  USV_ST_ENERGY_PENALTY, USV_ST_ACTION_VARIATION_PENALTY,
+  USV_ST_NORMED_LINEAR_VEL, USV_ST_NORMED_ANGULAR_VEL, USV_ST_ACTIONS_SUM,
+  USV_ST_COUNT
+};
+
+enum { USV_REWARD_LINEAR = 0, USV_REWARD_SQUARE = 1, USV_REWARD_EXPONENTIAL = 2 };
+
+/* closed set of penalty lambda forms that appear in cfg/task/USV  */
+enum {
+  USV_PEN_OFF = 0,
+  USV_PEN_NEG_SUM = 1,          /* -sum(x)*c1 + c2                               */
+  USV_PEN_EXP_NEG_SUMSQ = 2,    /* (exp(-sum(x^2)) - 1)*c1                       */
+  USV_PEN_NEG_ABS = 3,          /* -abs(x)*c1 + c2        (norm for vectors)     */
+  USV_PEN_NEG_DEADZONE = 4,     /* -clamp(abs(x)-d, min=0)*c1                    */
+  USV_PEN_EXP_NEG_ABS = 5       /* (exp(-k*abs(x)) - 1)*c1                       */
+};
+typedef struct { int32_t form; float c1; float c2; float k; } UsvPenaltyTerm;
+
+typedef struct {
+  uint64_t seed;               /* Philox key                                    */
+  uint64_t step_counter;       /* global control-step index (Philox counter)    */
+  int64_t  env_id_offset;      /* global id of local env 0 (rank sharding)      */
+  /* simulation */
+  float dt;                    /* sim.dt                                        */
+  int32_t n_substeps;          /* env.controlFrequencyInv                       */
+  int32_t max_episode_length;
+  float clip_actions;          /* env.clipActions                               */
+  float clip_obs;              /* env.clipObservations.state                    */
+  /* planar rigid body standing in for PhysX (DESIGN.md "integrator")          */
+  float izz;                   /* base yaw inertia [kg m^2] (config constant)   */
+  float thr_y_left, thr_y_right; /* thruster mount y  (heron.urdf:167,242)      */
+  float lag_alpha;             /* fp32 exp(-dt/timeConstant)                    */
+  /* env origins (world frame; only the sinusoidal disturbances read world positions):
+   * origin(i) = (grid_row_offset - (i / envs_per_row)*env_spacing, (i % envs_per_row)*env_spacing - grid_col_offset)
+   * envs_per_row == 0 -> all origins 0 */
+  float env_spacing, grid_row_offset, grid_col_offset;
+  int32_t envs_per_row;
+  /* hydrodynamics (planar components u,v,r of the 6-vectors) */
+  float lin_fwd[3];
+  float offset_linear_damping, offset_lin_forward_damping_speed, offset_nonlin_damping, scaling_damping;
+  int32_t use_drag_scale;
+  /* thruster LUT */
+  int32_t n_lut;
+  /* action path  [ref: SNAP/USV_Virtual.py:571-617 ; OIGE/tasks/USV_Virtual.py:1042-1101] */
+  int32_t action_affine;       /* 0 classic (raw +-1 to LUT) ; 1 live u=0.5(a+1) */
+  int32_t action_noise;  float action_noise_min, action_noise_max;
+  float action_bias;           /* live: initial_action_bias while the host-side call counter is below its limit */
+  int32_t penalties_use_u;     /* live: penalties see u in [0,1] instead of the raw action */
+  int32_t first_call;          /* 1 on the very first step: Penalties.prev_state is None -> deltas are 0 */
+  /* observation noise [ref: OIGE/tasks/USV/USV_disturbances.py:533-601] */
+  int32_t noise_pos;     float pos_noise_min, pos_noise_max;
+  int32_t noise_vel;     float vel_noise_min, vel_noise_max;
+  int32_t noise_heading; float heading_noise_min, heading_noise_max;
+  /* disturbances evaluated every sub-step */
+  int32_t use_const_force, use_sin_force, use_const_torque, use_sin_torque;
+  /* CaptureXY task [ref: SNAP/USV_capture_xy.py ; USV_task_parameters.py:17-57] */
+  float position_tolerance; int32_t kill_after_n_steps_in_tolerance;
+  float kill_dist, boundary_cost, goal_reward, time_reward;
+  float goal_speed_gate;       /* 0.05 in the classic task                      */
+  int32_t reward_mode; float position_scale, exponential_reward_coeff;
+  float align_la1, align_la2, align_la3;
+  /* penalties [ref: SNAP/USV_task_rewards.py:380-540] */
+  UsvPenaltyTerm pen_linear_vel, pen_angular_vel, pen_angular_vel_variation, pen_energy, pen_action_variation;
+  /* ---- reset-time randomisation (A3, A6, A10, A11, A14, A19) ---- */
+  float goal_random_position; int32_t retarget_on_reset;
+  float spawn_min_dist, spawn_max_dist;    /* after curriculum, set by host     */
+  float spawn_vel_range;                   /* 1.5: vx,vy ~ U(-1.5,1.5)          */
+  int32_t mass_rand; float mass_min, mass_max, mass_base;
+  int32_t drag_rand; float lin_base[3], quad_base[3], lin_rand[3], quad_rand[3];
+  int32_t kdrag_rand; float kdrag_min, kdrag_max; int32_t kdrag_log;
+  int32_t thr_rand, thr_separate; float thr_rand_frac, thr_left_frac, thr_right_frac;
+  int32_t mass_coupling; float couple_mass_max, couple_thr_a, couple_kiz_min, couple_kiz_max;
+  float force_const_min, force_const_max, force_sin_min, force_sin_max;
+  float force_min_freq, force_max_freq, force_min_shift, force_max_shift;
+  float torque_const_min, torque_const_max, torque_sin_min, torque_sin_max;
+  float torque_min_freq, torque_max_freq, torque_min_shift, torque_max_shift;
+  int32_t use_force_disturbance, use_torque_disturbance;
+} UsvStepParams;
+
+typedef struct {
+  float*   state;   int64_t state_stride;   /* [USV_S_COUNT][stride]  (16B aligned, stride%4==0) */
+  float*   consts;  int64_t consts_stride;  /* [USV_C_COUNT][stride]                           */
+  float*   stats;   int64_t stats_stride;   /* [USV_ST_COUNT][stride] or NULL (stats off)      */
+  int64_t* reset_buf;                        /* [n] RLTask.reset_buf (in: reset now; out: done) */
+  const float* lut_left;                     /* [n_lut]                                        */
+  const float* lut_right;                    /* [n_lut]                                        */
+  uint32_t* nonfinite_flag;                  /* device word, OR-ed with 1 on NaN/Inf obs/rew, or NULL */
+} UsvEnvBuffers;
+
+/* one control step for n envs: reset-if-flagged, action -> thrust target, n_substeps of
+ * {lag, forces, integrate}, obs (clamped), reward + penalties, kills, progress/done.      */
+int usv_step_fused_f32(const UsvEnvBuffers* b, const float* actions /*[n,2]*/,
+                       float* obs /*[n,13]*/, float* rew /*[n]*/,
+                       int64_t n, const UsvStepParams* p, void* stream);
+
+/* T control steps in ONE launch with the state held in registers between steps;
+ * actions[T,n,2] are given up-front (open loop), outputs are [T,n,...]; obs/rew/done may be NULL
+ * (then only the final state is written).  step_counter advances by 1 per step.           */
+int usv_rollout_fused_f32(const UsvEnvBuffers* b, const float* actions /*[T,n,2]*/,
+                          float* obs /*[T,n,13] or NULL*/, float* rew /*[T,n] or NULL*/,
+                          int64_t* done /*[T,n] or NULL*/, int32_t T,
+                          int64_t n, const UsvStepParams* p, void* stream);
+
+/* force/torque probe of the fused kernel's planar model (parity hook): for given planar states
+ * returns the body-frame drag (u,v,r), thrust wrench and world accelerations of ONE sub-step.  */
+int usv_planar_forces_f32(const UsvEnvBuffers* b, float* out /*[n,8]: du,dv,dr,Fx,Fy,Tz,ax,ay*/,
+                          int64_t n, const UsvStepParams* p, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* P1  A2CBase.discount_values (GAE) + returns                                */
+/*     [ref: RLG/common/a2c_common.py:525-540,761-763]                        */
+int ppo_gae_f32(const float* rewards /*[T,n]*/, const float* values /*[T,n]*/,
+                const uint8_t* dones /*[T,n] flag entering step t*/, const float* last_values /*[n]*/,
+                const uint8_t* last_dones /*[n]*/, float gamma, float tau,
+                float* advantages /*[T,n]*/, float* returns /*[T,n] or NULL*/,
+                int32_t T, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* USV_B200_H_ */

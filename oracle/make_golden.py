@@ -1,0 +1,276 @@
+"""TEST INFRASTRUCTURE ONLY.  Generates tests/golden/*.npz by executing the UNMODIFIED reference
+modules (/root/reference, CPU torch, fp32) under oracle/ref_shim.py on seeded synthetic inputs.
+
+Run in the build container (the reference does not exist on the GPU box):
+    python -m oracle.make_golden
+The fixtures are small (N=32) and committed; tests/test_oracle_cpu.py checks the oracle restatement
+against them and tests/test_gpu_parity.py checks the CUDA kernels against them.
+
+Synthetic inputs follow SURVEY 8(d): pos ~ U(-12,12)^2, yaw ~ U(-pi,pi), vx,vy ~ U(-1.5,1.5),
+r ~ U(-1,1), 6-DOF variant with random unit quaternions / N(0,0.3) heave-roll-pitch rates.
+"""
+from __future__ import annotations
+
+import math
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_shim  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+N = 32
+
+
+def gen():
+    return torch.Generator().manual_seed(1234)
+
+
+def t2n(d):
+    return {k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in d.items()}
+
+
+DRAG_CFG = dict(use_drag_randomization=False, u_linear_rand=0.1, v_linear_rand=0.1, w_linear_rand=0.0,
+                p_linear_rand=0.0, q_linear_rand=0.0, r_linear_rand=0.1, u_quad_rand=0.1, v_quad_rand=0.1,
+                w_quad_rand=0.0, p_quad_rand=0.0, q_quad_rand=0.0, r_quad_rand=0.1)
+LIN = [0.0, 99.99, 99.99, 13.0, 13.0, 0.82985084]
+QUAD = [17.257603, 99.99, 10.0, 5.0, 5.0, 17.33600724]
+LUT_CLASSIC_L = [-3.8, -3.8, -3.6, -3.6, -1.6, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 4.0, 10.0, 15.0, 21.0, 23.0, 22.0]
+LUT_CLASSIC_R = [-5.0, -5.0, -5.0, -4.6, -2.2, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 4.6, 10.0, 17.0, 24.0, 24.0, 23.0]
+LUT_LIVE = [0.0] * 11 + [8.0 * i for i in range(1, 11)]
+LUT_NOMINAL = [-19.88, -16.52, -12.6, -5.6, -1.4, 0.0, 2.24, 9.52, 21.28, 28.0, 33.6]
+THR_CFG = dict(use_thruster_randomization=False, thruster_rand=0.5, use_separate_randomization=False,
+               left_rand=0.5, right_rand=0.5)
+
+
+def force_modules():
+    hs, hd, td = ref_shim.load_force_modules()
+    g = gen()
+    out = {}
+    # ---- inputs: 6-DOF variant
+    q = torch.randn((N, 4), generator=g)
+    q = q / q.norm(dim=1, keepdim=True)
+    q[0] = torch.tensor([1.0, 0, 0, 0])
+    q[1] = torch.tensor([math.cos(math.pi / 6), 0, 0, math.sin(math.pi / 6)])
+    q[2] = q[2] * 1.7  # non-unit quaternion: two_s = 2/|q|^2 must absorb it
+    yaw = (torch.rand(N, generator=g) * 2 - 1) * math.pi
+    q_planar = torch.stack([torch.cos(yaw / 2), torch.zeros(N), torch.zeros(N), torch.sin(yaw / 2)], 1)
+    vel6 = torch.zeros((N, 6))
+    vel6[:, 0:2] = torch.rand((N, 2), generator=g) * 3 - 1.5
+    vel6[:, 2:5] = torch.randn((N, 3), generator=g) * 0.3
+    vel6[:, 5] = torch.rand(N, generator=g) * 2 - 1
+    vel6[0] = torch.tensor([1.0, 0.5, 0, 0, 0, 0.3])
+    vel6[1] = torch.tensor([-0.4, 1.2, 0, 0, 0, -0.7])
+    vel6_planar = vel6.clone()
+    vel6_planar[:, 2:5] = 0
+    vol = torch.rand(N, generator=g) * 0.05
+    rpy = torch.randn((N, 3), generator=g) * 0.1
+    out.update(quat=q, quat_planar=q_planar, yaw=yaw, vel6=vel6, vel6_planar=vel6_planar, vol=vol, rpy=rpy)
+
+    # ---- A1 hydrostatics  (ctor args as USV_Virtual.get_USV_dynamics passes them)
+    H = hs.HydrostaticsObject(N, "cpu", 1000, -9.81, 0.5, 0.65, 275, 1.0, 0.0, 1.0, 0.3, -10.0)
+    out["hs_out"] = H.compute_archimedes_metacentric_local(vol, rpy, q).clone()
+    out["hs_force_global"] = H.archimedes_force_global.clone()
+    out["hs_torque_global"] = H.archimedes_torque_global.clone()
+    out["hs_out_planar"] = H.compute_archimedes_metacentric_local(vol, rpy * 0, q_planar).clone()
+    H2 = hs.HydrostaticsObject(N, "cpu", 1025.0, -9.80665, 0.4, 0.7, 300.0, 2.5, 0.0, 1.0, 0.3, -10.0)
+    out["hs_out_alt"] = H2.compute_archimedes_metacentric_local(vol, rpy, q).clone()
+
+    # ---- A2 hydrodynamics
+    def mk(cfg_extra=None, **kw):
+        cfg = dict(DRAG_CFG)
+        cfg.update(cfg_extra or {})
+        args = dict(task_cfg=cfg, num_envs=N, device="cpu", water_density=1000, gravity=-9.81, linear_damping=LIN,
+                    quadratic_damping=QUAD, linear_damping_forward_speed=[0.0] * 6, offset_linear_damping=0.0,
+                    offset_lin_forward_damping_speed=0.0, offset_nonlin_damping=0.0, scaling_damping=1.0,
+                    offset_added_mass=0.0, scaling_added_mass=1.0, alpha=0.3, last_time=-10.0)
+        args.update(kw)
+        return hd.HydrodynamicsObject(**args)
+
+    D = mk()
+    out["hd_drag"] = D.ComputeHydrodynamicsEffects(0.01, q, vel6, False, [0.0, 0.0, 0.0]).clone()
+    out["hd_local_vel"] = D.local_velocities.clone()
+    out["hd_drag_planar"] = D.ComputeHydrodynamicsEffects(0.01, q_planar, vel6_planar, False, [0.0, 0.0, 0.0]).clone()
+    out["hd_drag_current"] = D.ComputeHydrodynamicsEffects(0.01, q, vel6, True, [0.3, -0.2, 0.05]).clone()
+    # per-env coefficients + drag scale + non-trivial offsets/scaling
+    D2 = mk(dict(use_drag_scale_randomization=True, k_drag_min=1.0, k_drag_max=1.5),
+            linear_damping_forward_speed=[0.1, 0.2, 0.0, 0.0, 0.0, 0.05], offset_linear_damping=0.5,
+            offset_lin_forward_damping_speed=0.25, offset_nonlin_damping=0.125, scaling_damping=1.25)
+    lin = torch.tensor([LIN] * N) * (1 + 0.1 * (torch.rand((N, 6), generator=g) * 2 - 1))
+    quad = torch.tensor([QUAD] * N) * (1 + 0.1 * (torch.rand((N, 6), generator=g) * 2 - 1))
+    kd = 1.0 + 0.5 * torch.rand((N, 1), generator=g)
+    D2.linear_damping[:] = lin
+    D2.quadratic_damping[:] = quad
+    D2.drag_scale[:] = kd
+    out.update(hd2_lin=lin, hd2_quad=quad, hd2_kdrag=kd)
+    out["hd2_drag"] = D2.ComputeHydrodynamicsEffects(0.01, q, vel6, False, [0.0, 0.0, 0.0]).clone()
+    out["hd2_drag_planar"] = D2.ComputeHydrodynamicsEffects(0.01, q_planar, vel6_planar, False, [0.0, 0.0, 0.0]).clone()
+
+    # ---- A4/A5 thrusters
+    def mkthr(L, R, cfg_extra=None, n_interp=1000):
+        cfg = dict(THR_CFG)
+        cfg.update(cfg_extra or {})
+        return td.DynamicsFirstOrder(cfg, N, "cpu", 0.05, 0.02, n_interp, L, R, [0.0] * 5, [0.0] * 5, -1.0, 1.0)
+
+    cmd = torch.rand((N, 2), generator=g) * 2 - 1
+    cmd[0] = torch.tensor([0.73, 0.5005])
+    cmd[1] = torch.tensor([0.0, 1.0])
+    cmd[2] = torch.tensor([-1.0, -0.999])
+    cmd[3] = torch.tensor([1.0 / 999.0, 3.0 / 999.0])    # half-integer indices after the affine map
+    cmd[4] = torch.tensor([-1.5, 1.5])                   # out of range -> clamp
+    out["thr_cmd"] = cmd
+    for name, (L, R) in {"classic": (LUT_CLASSIC_L, LUT_CLASSIC_R), "live": (LUT_LIVE, LUT_LIVE),
+                         "nominal": (LUT_NOMINAL, LUT_NOMINAL)}.items():
+        T = mkthr(L, R)
+        out[f"lut_{name}_left"] = T.y_linear_interp_left.clone()
+        out[f"lut_{name}_right"] = T.y_linear_interp_right.clone()
+        out[f"lut_{name}_points_left"] = torch.tensor(L)
+        out[f"lut_{name}_points_right"] = torch.tensor(R)
+        T.set_target_force(cmd)
+        out[f"thr_{name}_before"] = T.thruster_forces_before_dynamics.clone()
+        lag = []
+        for _ in range(6):
+            lag.append(T.update_forces().clone())
+        out[f"thr_{name}_lag6"] = torch.stack(lag)           # (6, N, 6)
+    # multipliers (separate + shared)
+    Ts = mkthr(LUT_CLASSIC_L, LUT_CLASSIC_R, dict(use_thruster_randomization=True, use_separate_randomization=True))
+    ml = 0.5 + torch.rand((N, 1), generator=g)
+    mr = 0.5 + torch.rand((N, 1), generator=g)
+    Ts.thruster_left_multiplier = ml
+    Ts.thruster_right_multiplier = mr
+    Ts.set_target_force(cmd)
+    out.update(thr_mult_left=ml, thr_mult_right=mr, thr_sep_after=Ts.thruster_forces_after_randomization.clone())
+    lag = [Ts.update_forces().clone() for _ in range(3)]
+    out["thr_sep_lag3"] = torch.stack(lag)
+    out["thr_alpha"] = torch.exp(torch.tensor(-0.02 / 0.05))
+    np.savez(os.path.join(OUT, "force_modules.npz"), **t2n(out))
+    print("force_modules.npz:", len(out), "arrays")
+
+
+def disturbances():
+    d = ref_shim.load_disturbances()
+    g = gen()
+    fcfg = dict(use_force_disturbance=True, use_constant_force=True, use_sinusoidal_force=True,
+                force_const_min=0.0, force_const_max=2.5, force_sin_min=0.0, force_sin_max=2.5,
+                force_min_freq=0.25, force_max_freq=3.0, force_min_shift=0.0, force_max_shift=100.0)
+    tcfg = dict(use_torque_disturbance=True, use_constant_torque=True, use_sinusoidal_torque=True,
+                torque_const_min=0.0, torque_const_max=1.0, torque_sin_min=0.0, torque_sin_max=1.0,
+                torque_min_freq=0.25, torque_max_freq=3.0, torque_min_shift=0.0, torque_max_shift=100.0)
+    UF = d.ForceDisturbance(fcfg, N, "cpu")
+    TD = d.TorqueDisturbance(tcfg, N, "cpu")
+    torch.manual_seed(7)
+    ids = torch.arange(N)
+    UF.generate_force(ids, N)
+    TD.generate_torque(ids, N)
+    root_pos = torch.zeros((N, 3))
+    root_pos[:, :2] = torch.rand((N, 2), generator=g) * 60 - 30
+    out = dict(root_pos=root_pos, f_const=UF.disturbance_forces_const.clone(), fxf=UF._force_x_freq.clone(),
+               fyf=UF._force_y_freq.clone(), fxs=UF._force_x_shift.clone(), fys=UF._force_y_shift.clone(),
+               famp=UF._force_amp.clone(), t_const=TD.disturbance_torques_const.clone(), tf=TD._torque_freq.clone(),
+               ts=TD._torque_shift.clone(), tamp=TD._torque_amp.clone())
+    out["forces"] = UF.get_disturbance_forces(root_pos).clone()
+    out["torques"] = TD.get_torque_disturbance(root_pos).clone()
+    out["ranges"] = torch.tensor([UF._const_min, UF._const_max, UF._sin_min, UF._sin_max])
+    np.savez(os.path.join(OUT, "disturbances.npz"), **t2n(out))
+    print("disturbances.npz")
+
+
+def classic_task():
+    """K steps of the classic CaptureXYTask + Penalties on a synthetic trajectory, with a reset batch
+    in the middle  [SNAP/USV_capture_xy.py, SNAP/USV_task_rewards.py]."""
+    core, rew, cap = ref_shim.load_classic()
+    cfg = ref_shim.classic_yaml()
+    g = gen()
+    K = 6
+    with ref_shim.quiet():
+        task = cap.CaptureXYTask(cfg["env"]["task_parameters"], cfg["env"]["reward_parameters"], N, "cpu")
+        pen = core.parse_data_dict(rew.Penalties(), cfg["env"]["penalties_parameters"])
+    task._target_positions[:] = torch.rand((N, 2), generator=g) * 2 - 1
+    pos = torch.rand((N, 2), generator=g) * 24 - 12
+    yaw = (torch.rand(N, generator=g) * 2 - 1) * math.pi
+    vel = torch.rand((N, 2), generator=g) * 3 - 1.5
+    w = torch.rand(N, generator=g) * 2 - 1
+    # crafted rows: inside tolerance & slow (goal), beyond kill distance, heading wrap cases
+    pos[0] = task._target_positions[0] + torch.tensor([0.03, 0.02]); vel[0] = torch.tensor([0.01, 0.02])
+    pos[1] = torch.tensor([-21.0, 0.0]); vel[1] = torch.tensor([0.0, 0.0])
+    pos[2] = task._target_positions[2] + torch.tensor([0.03, 0.02]); vel[2] = torch.tensor([0.2, 0.0])   # in tol, too fast
+    pos[3] = torch.tensor([5.0, 2.0]); yaw[3] = 3.1; task._target_positions[3] = torch.tensor([4.0, -2.0])
+    pos[4] = torch.tensor([5.0, 2.0]); yaw[4] = 3.0; task._target_positions[4] = torch.tensor([-4.0, 1.0])
+    pos[5] = torch.tensor([3.0, 0.0]); task._target_positions[5] = torch.tensor([0.0, 0.0])             # d = 3.0 zone
+    pos[6] = torch.tensor([2.0, 0.0]); task._target_positions[6] = torch.tensor([0.0, 0.0])             # d = 2.0 zone
+    pos[7] = torch.tensor([1.0, 0.0]); task._target_positions[7] = torch.tensor([0.0, 0.0])             # d = 1.0 zone
+    out = dict(target=task._target_positions.clone())
+    S = {k: [] for k in ("pos", "yaw", "vel", "w", "actions", "obs", "reward", "penalty", "die", "goal_reached",
+                         "distance_reward", "alignment_reward", "speed_reward")}
+    reset_ids = torch.tensor([1, 9, 17, 30])
+    for k in range(K):
+        actions = torch.rand((N, 2), generator=g) * 2.2 - 1.1
+        if k == 3:
+            task.reset(reset_ids)
+            pos[reset_ids] = torch.rand((4, 2), generator=g) * 10 - 5
+        heading = torch.stack([torch.cos(yaw), torch.sin(yaw)], 1)
+        state = {"position": pos.clone(), "orientation": heading, "linear_velocity": vel.clone(),
+                 "angular_velocity": w.clone()}
+        with ref_shim.quiet():
+            obs = task.get_state_observations(state, "local").clone()
+            r = task.compute_reward(state, actions).clone()
+            p = pen.compute_penalty(state, actions, 0.0).clone()
+            die = task.update_kills(0).clone()
+        for name, v in (("pos", pos), ("yaw", yaw), ("vel", vel), ("w", w), ("actions", actions), ("obs", obs),
+                        ("reward", r), ("penalty", p), ("die", die), ("goal_reached", task._goal_reached),
+                        ("distance_reward", task.distance_reward), ("alignment_reward", task.alignment_reward),
+                        ("speed_reward", task.a)):
+            S[name].append(v.clone())
+        # synthetic motion
+        pos = pos + 0.1 * vel
+        yaw = yaw + 0.1 * w
+        vel = vel * 0.9 + 0.1 * (torch.rand((N, 2), generator=g) * 3 - 1.5)
+        w = w * 0.9 + 0.1 * (torch.rand(N, generator=g) * 2 - 1)
+        vel[0] = torch.tensor([0.01, 0.02]); pos[0] = task._target_positions[0] + torch.tensor([0.03, 0.02])
+    out.update({k: torch.stack(v) for k, v in S.items()})
+    out["reset_step"] = np.int64(3)
+    out["reset_ids"] = reset_ids
+    np.savez(os.path.join(OUT, "capture_xy_classic.npz"), **t2n(out))
+    print("capture_xy_classic.npz")
+
+
+def gae():
+    rl = ref_shim.load_rl_games()
+    g = gen()
+    out = {}
+    for tag, (T, n) in {"a": (16, 32), "b": (16, 37), "c": (4, 2), "d": (1, 5)}.items():
+        ns = types.SimpleNamespace(horizon_length=T, gamma=0.99, tau=0.95)
+        rew = torch.randn((T, n, 1), generator=g) * 0.1
+        val = torch.randn((T, n, 1), generator=g)
+        dones = (torch.rand((T, n), generator=g) < 0.15).to(torch.uint8)
+        last_d = (torch.rand((n,), generator=g) < 0.15).to(torch.uint8)
+        last_v = torch.randn((n, 1), generator=g)
+        if tag == "c":
+            rew = torch.tensor([[0.1, 0], [0.2, -0.1], [0, 0.3], [0.5, 0.05]]).unsqueeze(-1)
+            val = torch.tensor([[1.0, 0.5], [0.9, 0.4], [1.1, 0.6], [0.8, 0.2]]).unsqueeze(-1)
+            dones = torch.tensor([[0, 0], [0, 1], [0, 0], [1, 0]], dtype=torch.uint8)
+            last_d = torch.tensor([0, 1], dtype=torch.uint8)
+            last_v = torch.tensor([[0.7], [0.3]])
+        adv = rl.a2c_common.A2CBase.discount_values(ns, last_d.float(), last_v, dones.float(), val, rew)
+        out.update({f"{tag}_rewards": rew, f"{tag}_values": val, f"{tag}_dones": dones, f"{tag}_last_dones": last_d,
+                    f"{tag}_last_values": last_v, f"{tag}_adv": adv, f"{tag}_returns": adv + val})
+    np.savez(os.path.join(OUT, "gae.npz"), **t2n(out))
+    print("gae.npz")
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(1)
+    force_modules()
+    disturbances()
+    classic_task()
+    gae()
+
+
+if __name__ == "__main__":
+    main()
