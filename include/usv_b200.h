@@ -43,6 +43,8 @@ int usv_b200_abi_version(void);
 const char* usv_b200_error_string(int code);
 /* number of kernels this library has launched since load (bench.py "gpu_launches") */
 int64_t usv_b200_launch_count(void);
+/* sizeof() of a struct of this header by name (-1 if unknown): lets FFI mirrors verify their layout */
+int64_t usv_b200_sizeof(const char* struct_name);
 
 /* ------------------------------------------------------------------------- */
 /* A1  HydrostaticsObject.compute_archimedes_metacentric_local                */
@@ -80,6 +82,7 @@ int usv_hydrodynamics_f32(const float* quat /*[n,4]*/, const float* world_vel6 /
                           const float* linear_damping /*[n,6]*/, const float* quadratic_damping /*[n,6]*/,
                           const float* drag_scale /*[n] (the (n,1) tensor)*/,
                           float* drag6 /*[n,6]*/, float* local_vel6 /*[n,6] or NULL*/,
+                          float* damping6 /*[n,6] or NULL: the diagonal of ComputeDampingMatrix*/,
                           int64_t n, const UsvHydrodynamicsParams* p, void* stream);
 
 /* ------------------------------------------------------------------------- */

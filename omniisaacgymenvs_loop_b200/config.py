@@ -1,0 +1,300 @@
+"""Host-side configuration of the fused USV env: the reference's task YAML -> UsvStepParams.
+
+`UsvEnvConfig.from_task_cfg` reads the same YAML tree the reference's USVVirtual.__init__ reads
+[ref: SNAP/USV_Virtual.py:62-215 ; OIGE/tasks/USV_Virtual.py:295-649] (PyYAML dict; hydra
+interpolations such as ${resolve_default:512,...} are resolved by `load_task_yaml`).
+"""
+from __future__ import annotations
+
+import dataclasses
+import math
+import re
+from dataclasses import dataclass, field
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+
+PEN_OFF, PEN_NEG_SUM, PEN_EXP_NEG_SUMSQ, PEN_NEG_ABS, PEN_NEG_DEADZONE, PEN_EXP_NEG_ABS = range(6)
+REWARD_MODES = {"linear": 0, "square": 1, "exponential": 2}
+
+
+@dataclass
+class PenaltyTerm:
+    form: int = PEN_OFF
+    c1: float = 0.0
+    c2: float = 0.0
+    k: float = 0.0
+
+
+_NUM = r"([-+]?\d*\.?\d+(?:[eE][-+]?\d+)?)"
+
+
+def parse_penalty_lambda(src: str, c1: float = 0.0, c2: float = 0.0) -> PenaltyTerm:
+    """Maps a YAML penalty lambda string onto the closed set the kernel implements.
+
+    The reference eval()s these strings [ref: OIGE/tasks/USV/USV_task_rewards.py:429-438]; a CUDA
+    kernel cannot, so only the forms that appear under cfg/task/USV/** are accepted and anything
+    else raises (no silent torch fallback).  `c1`/`c2` are the dataclass constants the default
+    lambdas refer to."""
+    s = re.sub(r"\s+", "", src)
+    s = re.sub(r"^lambdax,step:", "", s)
+    s = s.replace("c1", repr(float(c1))).replace("c2", repr(float(c2)))
+    pats = [
+        (rf"^-torch\.sum\(x,dim=-1\)\*{_NUM}(?:\+{_NUM})?$", lambda m: PenaltyTerm(PEN_NEG_SUM, float(m[1]), float(m[2] or 0))),
+        (rf"^\(torch\.exp\(-torch\.sum\(x\*\*2,dim=-1\)\)-1\.0\)\*{_NUM}$", lambda m: PenaltyTerm(PEN_EXP_NEG_SUMSQ, float(m[1]))),
+        (rf"^-torch\.norm\(x,dim=-1\)\*{_NUM}(?:\+{_NUM})?$", lambda m: PenaltyTerm(PEN_NEG_ABS, float(m[1]), float(m[2] or 0))),
+        (rf"^-torch\.abs\(x\)\*{_NUM}(?:\+{_NUM})?$", lambda m: PenaltyTerm(PEN_NEG_ABS, float(m[1]), float(m[2] or 0))),
+        (rf"^-torch\.clamp\(torch\.abs\(x\)-{_NUM},min=0(?:\.0)?\)\*{_NUM}$", lambda m: PenaltyTerm(PEN_NEG_DEADZONE, float(m[2]), 0.0, float(m[1]))),
+        (rf"^\(torch\.exp\(-{_NUM}\*torch\.abs\(x\)\)-1\.0\)\*{_NUM}$", lambda m: PenaltyTerm(PEN_EXP_NEG_ABS, float(m[2]), 0.0, float(m[1]))),
+        (rf"^torch\.exp\({_NUM}\*torch\.abs\(x\)\)-1\.0$", lambda m: PenaltyTerm(PEN_EXP_NEG_ABS, 1.0, 0.0, -float(m[1]))),
+    ]
+    for pat, mk in pats:
+        m = re.match(pat, s)
+        if m:
+            return mk(m)
+    raise NotImplementedError(f"penalty lambda not in the supported closed set: {src!r}")
+
+
+@dataclass
+class UsvEnvConfig:
+    """Mirror of UsvStepParams with the classic snapshot's defaults
+    [ref: SNAP/USV_Virtual_CaptureXY_SysID-TEST.yaml]."""
+    seed: int = 1234
+    num_envs: int = 512
+    dt: float = 0.02
+    n_substeps: int = 5
+    max_episode_length: int = 3000
+    horizon_length: int = 16
+    clip_actions: float = 1.0
+    clip_obs: float = 12.0
+    izz: float = 10.0                # yaw inertia: not recoverable from the tree (heron.urdf:69 placeholder)
+    thr_y_left: float = 0.377654     # heron.urdf:242
+    thr_y_right: float = -0.377654   # heron.urdf:167
+    time_constant: float = 0.05
+    env_spacing: float = 15.0
+    envs_per_row: int = 0
+    grid_row_offset: float = 0.0
+    grid_col_offset: float = 0.0
+    lin_fwd: Tuple[float, float, float] = (0.0, 0.0, 0.0)
+    offset_linear_damping: float = 0.0
+    offset_lin_forward_damping_speed: float = 0.0
+    offset_nonlin_damping: float = 0.0
+    scaling_damping: float = 1.0
+    use_drag_scale: bool = False
+    n_lut: int = 1000
+    lut_points_left: Tuple[float, ...] = (-3.8, -3.8, -3.6, -3.6, -1.6, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0,
+                                          0.0, 4.0, 10.0, 15.0, 21.0, 23.0, 22.0)
+    lut_points_right: Tuple[float, ...] = (-5.0, -5.0, -5.0, -4.6, -2.2, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0,
+                                           0.0, 4.6, 10.0, 17.0, 24.0, 24.0, 23.0)
+    action_affine: bool = False
+    action_noise: bool = True
+    action_noise_min: float = -0.05
+    action_noise_max: float = 0.05
+    action_bias: float = 0.0
+    penalties_use_u: bool = False
+    noise_pos: bool = False
+    pos_noise_min: float = -0.03
+    pos_noise_max: float = 0.03
+    noise_vel: bool = True
+    vel_noise_min: float = -0.03
+    vel_noise_max: float = 0.03
+    noise_heading: bool = True
+    heading_noise_min: float = -0.025
+    heading_noise_max: float = 0.025
+    use_force_disturbance: bool = False
+    use_const_force: bool = False
+    use_sin_force: bool = False
+    use_torque_disturbance: bool = False
+    use_const_torque: bool = False
+    use_sin_torque: bool = False
+    position_tolerance: float = 0.1
+    kill_after_n_steps_in_tolerance: int = 1
+    kill_dist: float = 20.0
+    boundary_cost: float = 25.0
+    goal_reward: float = 30.0
+    time_reward: float = -0.2
+    goal_speed_gate: float = 0.05
+    reward_mode: int = 0
+    position_scale: float = 1.0
+    exponential_reward_coeff: float = 0.25
+    align_la1: float = 0.02
+    align_la2: float = -10.0
+    align_la3: float = -0.1
+    pen_linear_vel: PenaltyTerm = field(default_factory=PenaltyTerm)
+    pen_angular_vel: PenaltyTerm = field(default_factory=PenaltyTerm)
+    pen_angular_vel_variation: PenaltyTerm = field(default_factory=lambda: PenaltyTerm(PEN_EXP_NEG_ABS, 1.0, 0.0, 0.033))
+    pen_energy: PenaltyTerm = field(default_factory=lambda: PenaltyTerm(PEN_EXP_NEG_SUMSQ, 0.01))
+    pen_action_variation: PenaltyTerm = field(default_factory=PenaltyTerm)
+    goal_random_position: float = 0.0
+    retarget_on_reset: bool = False
+    spawn_min_dist: float = 0.3
+    spawn_max_dist: float = 12.0
+    spawn_vel_range: float = 1.5
+    mass_rand: bool = False
+    mass_min: float = 34.96
+    mass_max: float = 36.96
+    mass_base: float = 35.96
+    drag_rand: bool = False
+    lin_base: Tuple[float, float, float] = (0.0, 99.99, 0.82985084)
+    quad_base: Tuple[float, float, float] = (17.257603, 99.99, 17.33600724)
+    lin_rand_frac: Tuple[float, float, float] = (0.1, 0.1, 0.1)
+    quad_rand_frac: Tuple[float, float, float] = (0.1, 0.1, 0.1)
+    kdrag_rand: bool = False
+    kdrag_min: float = 1.0
+    kdrag_max: float = 1.0
+    kdrag_log: bool = False
+    thr_rand: bool = False
+    thr_separate: bool = False
+    thr_rand_frac: float = 0.5
+    thr_left_frac: float = 0.5
+    thr_right_frac: float = 0.5
+    mass_coupling: bool = False
+    couple_mass_max: float = 54.96
+    couple_thr_a: float = 0.5
+    couple_kiz_min: float = 1.0
+    couple_kiz_max: float = 1.5
+    force_const_min: float = 0.0
+    force_const_max: float = 2.5
+    force_sin_min: float = 0.0
+    force_sin_max: float = 2.5
+    force_min_freq: float = 0.25
+    force_max_freq: float = 3.0
+    force_min_shift: float = 0.0
+    force_max_shift: float = 100.0
+    torque_const_min: float = 0.0
+    torque_const_max: float = 1.0
+    torque_sin_min: float = 0.0
+    torque_sin_max: float = 1.0
+    torque_min_freq: float = 0.25
+    torque_max_freq: float = 3.0
+    torque_min_shift: float = 0.0
+    torque_max_shift: float = 100.0
+
+    # ------------------------------------------------------------------------------------
+    def full_dr(self) -> "UsvEnvConfig":
+        """DR50 flag set: every per-env randomisation switched on ('A, full DR' of SURVEY 8(d))."""
+        return dataclasses.replace(
+            self, use_force_disturbance=True, use_const_force=True, use_sin_force=True, use_torque_disturbance=True,
+            use_const_torque=True, use_sin_torque=True, noise_pos=True, mass_rand=True, drag_rand=True, thr_rand=True)
+
+    @property
+    def lag_alpha(self) -> float:
+        # torch.exp(torch.tensor(-dt/tau)) evaluated in fp32 [ref: OIGE/envs/USV/ThrusterDynamics.py:132]
+        return float(np.exp(np.float32(-self.dt / self.time_constant), dtype=np.float32))
+
+    def to_params(self, step_counter: int = 0, env_id_offset: int = 0, first_call: bool = False):
+        p = _lib.UsvStepParams()
+        sq = lambda v: math.sqrt(v ** 2 / 2)   # ForceDisturbance.__init__ [ref: USV_disturbances.py:281-289]
+        special = {
+            "seed": self.seed, "step_counter": step_counter, "env_id_offset": env_id_offset,
+            "lag_alpha": self.lag_alpha, "first_call": int(first_call),
+            "lin_rand": tuple(f * b for f, b in zip(self.lin_rand_frac, self.lin_base)),
+            "quad_rand": tuple(f * b for f, b in zip(self.quad_rand_frac, self.quad_base)),
+            "force_const_min": sq(self.force_const_min), "force_const_max": sq(self.force_const_max),
+            "force_sin_min": sq(self.force_sin_min), "force_sin_max": sq(self.force_sin_max),
+        }
+        for name, ctype in p._fields_:
+            v = special[name] if name in special else getattr(self, name)
+            if isinstance(v, PenaltyTerm):
+                t = getattr(p, name)
+                t.form, t.c1, t.c2, t.k = int(v.form), float(v.c1), float(v.c2), float(v.k)
+            elif isinstance(v, (tuple, list)):
+                arr = getattr(p, name)
+                for i, x in enumerate(v):
+                    arr[i] = float(x)
+            elif isinstance(v, bool):
+                setattr(p, name, int(v))
+            else:
+                setattr(p, name, v)
+        return p
+
+    # ------------------------------------------------------------------------------------
+    @classmethod
+    def from_task_cfg(cls, task_cfg: dict, **overrides) -> "UsvEnvConfig":
+        """Builds the config from the reference's task YAML dict (env/sim/dynamics sections)."""
+        env, sim, dyn = task_cfg["env"], task_cfg["sim"], task_cfg["dynamics"]
+        dist = env["disturbances"]
+        f, t, o, a, m, dr, th = (dist["forces"], dist["torques"], dist["observations"], dist["actions"], dist["mass"],
+                                 dist["drag"], dist["thruster"])
+        tp, rp, pp = env["task_parameters"], env["reward_parameters"], env["penalties_parameters"]
+        hd, hs, thr = dyn["hydrodynamics"], dyn["hydrostatics"], dyn["thrusters"]
+        L, Q = hd["linear_damping"], hd["quadratic_damping"]
+        fw = hd["linear_damping_forward_speed"]
+
+        def pen(name, default_src, c1d, c2d=0.0):
+            if not pp.get(f"penalize_{name}", False):
+                return PenaltyTerm()
+            return parse_penalty_lambda(pp.get(f"penalize_{name}_fn", default_src), pp.get(f"penalize_{name}_c1", c1d),
+                                        pp.get(f"penalize_{name}_c2", c2d))
+
+        num_envs = env["numEnvs"] if isinstance(env["numEnvs"], int) else 512
+        clip_obs = env.get("clipObservations", {"state": 12.0})
+        cfg = cls(
+            num_envs=num_envs, dt=float(sim["dt"]), n_substeps=int(env["controlFrequencyInv"]),
+            max_episode_length=int(env["maxEpisodeLength"]), horizon_length=int(env.get("horizon_length", 16)),
+            clip_actions=float(env.get("clipActions", 1.0)),
+            clip_obs=float(clip_obs["state"] if isinstance(clip_obs, dict) else clip_obs),
+            time_constant=float(thr["timeConstant"]), env_spacing=float(env.get("envSpacing", 15)),
+            lin_fwd=(fw[0], fw[1], fw[5]), offset_linear_damping=hd["offset_linear_damping"],
+            offset_lin_forward_damping_speed=hd["offset_lin_forward_damping_speed"],
+            offset_nonlin_damping=hd["offset_nonlin_damping"], scaling_damping=hd["scaling_damping"],
+            use_drag_scale=bool(dr.get("use_drag_scale_randomization", False)),
+            n_lut=int(thr["interpolation"]["numberOfPointsForInterpolation"]),
+            lut_points_left=tuple(thr["interpolation"]["interpolationPointsFromRealDataLeft"]),
+            lut_points_right=tuple(thr["interpolation"]["interpolationPointsFromRealDataRight"]),
+            action_noise=bool(a["add_noise_on_act"]), action_noise_min=a["min_action_noise"], action_noise_max=a["max_action_noise"],
+            noise_pos=bool(o["add_noise_on_pos"]), pos_noise_min=o["position_noise_min"], pos_noise_max=o["position_noise_max"],
+            noise_vel=bool(o["add_noise_on_vel"]), vel_noise_min=o["velocity_noise_min"], vel_noise_max=o["velocity_noise_max"],
+            noise_heading=bool(o["add_noise_on_heading"]), heading_noise_min=o["heading_noise_min"], heading_noise_max=o["heading_noise_max"],
+            use_force_disturbance=bool(f["use_force_disturbance"]),
+            use_const_force=bool(f["use_constant_force"]), use_sin_force=bool(f["use_sinusoidal_force"]),
+            use_torque_disturbance=bool(t["use_torque_disturbance"]),
+            use_const_torque=bool(t["use_constant_torque"]), use_sin_torque=bool(t["use_sinusoidal_torque"]),
+            position_tolerance=tp.get("position_tolerance", 0.1),
+            kill_after_n_steps_in_tolerance=int(tp.get("kill_after_n_steps_in_tolerance", 1)),
+            kill_dist=tp.get("kill_dist", 20.0), boundary_cost=tp.get("boundary_cost", 25.0),
+            goal_reward=tp.get("goal_reward", 100.0), time_reward=tp.get("time_reward", -0.1),
+            goal_random_position=tp.get("goal_random_position", 0.0),
+            spawn_min_dist=tp.get("min_spawn_dist", 0.5), spawn_max_dist=tp.get("max_spawn_dist", 11.0),
+            reward_mode=REWARD_MODES[str(rp.get("reward_mode", "exponential")).lower()],
+            position_scale=rp.get("position_scale", 1.0), exponential_reward_coeff=rp.get("exponential_reward_coeff", 0.25),
+            align_la1=rp.get("align_la1", 0.02), align_la2=rp.get("align_la2", -10.0), align_la3=rp.get("align_la3", -0.1),
+            pen_linear_vel=pen("linear_velocities", "lambda x,step : -torch.norm(x, dim=-1)*c1 + c2", 0.01),
+            pen_angular_vel=pen("angular_velocities", "lambda x,step : -torch.abs(x)*c1 + c2", 0.01),
+            pen_angular_vel_variation=pen("angular_velocities_variation", "lambda x,step: torch.exp(c1 * torch.abs(x)) - 1.0", -0.033),
+            pen_energy=pen("energy", "lambda x,step : -torch.sum(x**2)*c1 + c2", 0.01),
+            pen_action_variation=pen("action_variation", "lambda x,step: torch.exp(c1 * torch.abs(x)) - 1.0", -0.033),
+            mass_rand=bool(m.get("add_mass_disturbances", False)), mass_min=float(m.get("min_mass", 0.0)),
+            mass_max=float(m.get("max_mass", 0.0)), mass_base=float(m.get("base_mass", hs["mass"])),
+            drag_rand=bool(dr["use_drag_randomization"]), lin_base=(L[0], L[1], L[5]), quad_base=(Q[0], Q[1], Q[5]),
+            lin_rand_frac=(dr["u_linear_rand"], dr["v_linear_rand"], dr["r_linear_rand"]),
+            quad_rand_frac=(dr["u_quad_rand"], dr["v_quad_rand"], dr["r_quad_rand"]),
+            kdrag_rand=bool(dr.get("use_drag_scale_randomization", False)), kdrag_min=float(dr.get("k_drag_min", 1.0)),
+            kdrag_max=float(dr.get("k_drag_max", 1.0)), kdrag_log=str(dr.get("k_drag_sample_space", "linear")) == "log",
+            thr_rand=bool(th["use_thruster_randomization"]), thr_separate=bool(th["use_separate_randomization"]),
+            thr_rand_frac=th["thruster_rand"], thr_left_frac=th["left_rand"], thr_right_frac=th["right_rand"],
+            force_const_min=f["force_const_min"], force_const_max=f["force_const_max"], force_sin_min=f["force_sin_min"],
+            force_sin_max=f["force_sin_max"], force_min_freq=f["force_min_freq"], force_max_freq=f["force_max_freq"],
+            force_min_shift=f["force_min_shift"], force_max_shift=f["force_max_shift"],
+            torque_const_min=t["torque_const_min"], torque_const_max=t["torque_const_max"], torque_sin_min=t["torque_sin_min"],
+            torque_sin_max=t["torque_sin_max"], torque_min_freq=t["torque_min_freq"], torque_max_freq=t["torque_max_freq"],
+            torque_min_shift=t["torque_min_shift"], torque_max_shift=t["torque_max_shift"],
+        )
+        return dataclasses.replace(cfg, **overrides)
+
+
+def load_task_yaml(path: str, num_envs: Optional[int] = None) -> dict:
+    """PyYAML loader for the reference's task files; resolves the hydra interpolations the env reads
+    (${resolve_default:D,${...x}} -> D or the override; everything else is left as a string)."""
+    import yaml
+
+    with open(path) as fh:
+        txt = fh.read()
+
+    def rd(m):
+        return str(num_envs) if (num_envs is not None and "num_envs" in m.group(2)) else m.group(1)
+
+    txt = re.sub(r"\$\{resolve_default:([^,]+),\$\{([^}]*)\}\}", rd, txt)
+    return yaml.safe_load(txt)

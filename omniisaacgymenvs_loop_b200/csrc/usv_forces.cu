@@ -4,6 +4,7 @@
 // planar specialisation of the same maths.  All are pure streaming kernels (HBM-bound):
 // one thread per env, row-major (n,k) tensors read/written with vector accesses where the
 // row size allows (quat = float4; (n,6) rows as 3 x float2; (n,2) rows as float2).
+#include <string.h>
 #include "usv_common.cuh"
 #include "philox.cuh"
 
@@ -49,7 +50,7 @@ struct HydroDevParams {
 __global__ void __launch_bounds__(256) hydrodynamics_kernel(
     const float4* __restrict__ quat, const float2* __restrict__ vel6, const float2* __restrict__ lin6,
     const float2* __restrict__ quad6, const float* __restrict__ kdrag, float2* __restrict__ drag6,
-    float2* __restrict__ local6, int64_t n, HydroDevParams p) {
+    float2* __restrict__ local6, float2* __restrict__ damp6, int64_t n, HydroDevParams p) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float4 q = quat[i];
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(256) hydrodynamics_kernel(
   }
   const float L[6] = {la.x, la.y, lb.x, lb.y, lc.x, lc.y};
   const float Q[6] = {qa.x, qa.y, qb.x, qb.y, qc.x, qc.y};
-  float d[6];
+  float d[6], Dm[6];
 #pragma unroll
   for (int c = 0; c < 6; ++c) {
     // [ref :186-203] D = ((L + off - (fwd+off_fwd)) + (Q+off_nl)*|v|)*scaling [*k_drag]; [ref :243] drag = -D*v
@@ -77,7 +78,13 @@ __global__ void __launch_bounds__(256) hydrodynamics_kernel(
     const float qd = (Q[c] + p.off_nl) * fabsf(v[c]);
     float D = (lin + qd) * p.scaling;
     if (p.use_scale) D = D * k;
+    Dm[c] = D;
     d[c] = -1.0f * D * v[c];
+  }
+  if (damp6) {
+    damp6[3 * i + 0] = make_float2(Dm[0], Dm[1]);
+    damp6[3 * i + 1] = make_float2(Dm[2], Dm[3]);
+    damp6[3 * i + 2] = make_float2(Dm[4], Dm[5]);
   }
   drag6[3 * i + 0] = make_float2(d[0], d[1]);
   drag6[3 * i + 1] = make_float2(d[2], d[3]);
@@ -184,6 +191,18 @@ int usv_b200_abi_version(void) { return USV_B200_ABI_VERSION; }
 
 int64_t usv_b200_launch_count(void) { return g_launch_count.load(); }
 
+int64_t usv_b200_sizeof(const char* name) {
+  if (!name) return -1;
+#define USV_SZ(T) if (!strcmp(name, #T)) return (int64_t)sizeof(T)
+  USV_SZ(UsvHydrostaticsParams);
+  USV_SZ(UsvHydrodynamicsParams);
+  USV_SZ(UsvPenaltyTerm);
+  USV_SZ(UsvStepParams);
+  USV_SZ(UsvEnvBuffers);
+#undef USV_SZ
+  return -1;
+}
+
 const char* usv_b200_error_string(int code) {
   switch (code) {
     case USV_OK: return "ok";
@@ -214,7 +233,7 @@ int usv_hydrostatics_f32(const float* vol, const float* rpy, const float* quat, 
 }
 
 int usv_hydrodynamics_f32(const float* quat, const float* vel6, const float* lin6, const float* quad6,
-                          const float* drag_scale, float* drag6, float* local6, int64_t n,
+                          const float* drag_scale, float* drag6, float* local6, float* damp6, int64_t n,
                           const UsvHydrodynamicsParams* p, void* stream) {
   if (!p) return USV_E_NULL;
   if (n < 0) return USV_E_SIZE;
@@ -222,7 +241,7 @@ int usv_hydrodynamics_f32(const float* quat, const float* vel6, const float* lin
   if (!quat || !vel6 || !lin6 || !quad6 || !drag6) return USV_E_NULL;
   if (p->use_drag_scale && !drag_scale) return USV_E_NULL;
   if (((uintptr_t)quat & 15) || ((uintptr_t)vel6 & 7) || ((uintptr_t)lin6 & 7) || ((uintptr_t)quad6 & 7) ||
-      ((uintptr_t)drag6 & 7) || ((uintptr_t)local6 & 7))
+      ((uintptr_t)drag6 & 7) || ((uintptr_t)local6 & 7) || ((uintptr_t)damp6 & 7))
     return USV_E_ALIGN;
   HydroDevParams d;
   for (int c = 0; c < 6; ++c)
@@ -235,7 +254,7 @@ int usv_hydrodynamics_f32(const float* quat, const float* vel6, const float* lin
   for (int c = 0; c < 3; ++c) d.flow[c] = p->flow_vel[c];
   hydrodynamics_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
       (const float4*)quat, (const float2*)vel6, (const float2*)lin6, (const float2*)quad6, drag_scale,
-      (float2*)drag6, (float2*)local6, n, d);
+      (float2*)drag6, (float2*)local6, (float2*)damp6, n, d);
   return finish_launch();
 }
 

@@ -546,6 +546,9 @@ __global__ void __launch_bounds__(kBlock) step_fused_kernel(UsvEnvBuffers b, con
 #pragma unroll
       for (int j = 0; j < kObs; ++j) bad |= !isfinite(o.obs[j]);
       if (bad) atomicOr(b.nonfinite_flag, 1u);
+      // torch.clamp propagates NaN actions and the reference fails fast on them [ref: vec_env_rlgames.py:143];
+      // fminf/fmaxf would silently scrub them, so flag them here
+      if (!isfinite(act.x) || !isfinite(act.y)) atomicOr(b.nonfinite_flag, 2u);
     }
   }
   write_obs_tile(s_obs, o, active, obs, block_start, n);
@@ -590,7 +593,7 @@ __global__ void __launch_bounds__(kBlock) rollout_fused_kernel(UsvEnvBuffers b, 
       if (kStats) accumulate_stats(b.stats, b.stats_stride, i, do_reset, o, p);
       if (rew) rew[(int64_t)t * n + i] = o.rew;
       if (done) done[(int64_t)t * n + i] = (int64_t)o.done;
-      bad |= !isfinite(o.rew);
+      bad |= !isfinite(o.rew) || !isfinite(act.x) || !isfinite(act.y);
       do_reset = o.done != 0;
     }
     first_call = false;

@@ -1,0 +1,153 @@
+"""FusedUsvEnv: owner of the structure-of-arrays env state in HBM and the thin caller of the fused
+step / rollout kernels.  This is what sits *below* the reference-shaped surfaces (USVVirtual,
+VecEnvRLGames) in this package: where the reference crosses into Isaac Sim / PhysX
+[ref: OIGE/envs/vec_env_rlgames.py:154-173], this class launches one sm_100a kernel.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import _lib
+from .config import UsvEnvConfig
+
+E = _lib.ENUMS
+OBS_DIM = 13
+
+
+def _round_up(n: int, m: int) -> int:
+    return (n + m - 1) // m * m
+
+
+class FusedUsvEnv:
+    def __init__(self, cfg: UsvEnvConfig, num_envs: Optional[int] = None, device="cuda:0", env_id_offset: int = 0,
+                 collect_stats: bool = False):
+        self.lib = _lib.lib()
+        self.cfg = cfg
+        self.num_envs = n = int(num_envs if num_envs is not None else cfg.num_envs)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.UsvLibraryError("FusedUsvEnv runs on CUDA only (no CPU fallback); got device=%s" % device)
+        self.env_id_offset = int(env_id_offset)
+        self.stride = stride = _round_up(max(n, 1), 32)       # every SoA row starts on a 128 B line
+        f32 = dict(dtype=torch.float32, device=self.device)
+        self.state = torch.zeros((E["USV_S_COUNT"], stride), **f32)
+        self.consts = torch.zeros((E["USV_C_COUNT"], stride), **f32)
+        self.stats = torch.zeros((E["USV_ST_COUNT"], stride), **f32) if collect_stats else None
+        self.reset_buf = torch.ones(n, dtype=torch.long, device=self.device)     # [ref: SNAP/USV_Virtual.py:342-344]
+        self.obs = torch.zeros((n, OBS_DIM), **f32)
+        self.rew = torch.zeros(n, **f32)
+        self.nonfinite = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.step_counter = 0
+        self.first_call = True
+        # per-episode constants start at their nominal values (reset_idx rewrites them)
+        c = self.consts
+        c[E["USV_C_MASS"]] = cfg.mass_base
+        for j, (lf, qf) in enumerate(zip(("USV_C_LIN_U", "USV_C_LIN_V", "USV_C_LIN_R"),
+                                         ("USV_C_QUAD_U", "USV_C_QUAD_V", "USV_C_QUAD_R"))):
+            c[E[lf]] = cfg.lin_base[j]
+            c[E[qf]] = cfg.quad_base[j]
+        for name in ("USV_C_KDRAG", "USV_C_THR_ML", "USV_C_THR_MR", "USV_C_KIZ"):
+            c[E[name]] = 1.0
+        # thruster LUTs  [ref: OIGE/envs/USV/ThrusterDynamics.py:152-177]
+        self.lut_left = self._build_lut(cfg.lut_points_left)
+        self.lut_right = self._build_lut(cfg.lut_points_right)
+        # post_reset -> set_targets -> task.get_goals on every env  [ref: SNAP/USV_Virtual.py:652-700]
+        if cfg.goal_random_position > 0:
+            self.randomize_targets(torch.arange(n, device=self.device))
+        self._buffers = self._make_buffers()
+
+    # ---- helpers -----------------------------------------------------------------------
+    def _build_lut(self, points) -> torch.Tensor:
+        pts = torch.tensor(points, dtype=torch.float32, device=self.device)
+        lut = torch.empty(self.cfg.n_lut, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.usv_thruster_build_lut_f32(_lib.ptr(pts), ctypes.c_int32(pts.numel()), _lib.ptr(lut),
+                                                       ctypes.c_int32(self.cfg.n_lut), _lib.stream()), "build_lut")
+        return lut
+
+    def _make_buffers(self):
+        b = _lib.UsvEnvBuffers()
+        b.state, b.state_stride = self.state.data_ptr(), self.stride
+        b.consts, b.consts_stride = self.consts.data_ptr(), self.stride
+        b.stats = self.stats.data_ptr() if self.stats is not None else None
+        b.stats_stride = self.stride
+        b.reset_buf = self.reset_buf.data_ptr()
+        b.lut_left, b.lut_right = self.lut_left.data_ptr(), self.lut_right.data_ptr()
+        b.nonfinite_flag = self.nonfinite.data_ptr()
+        return b
+
+    def field(self, name: str) -> torch.Tensor:
+        """(N,) view of one SoA field, e.g. field('USV_S_X') or field('USV_C_MASS')."""
+        src = self.state if name.startswith("USV_S_") else (self.consts if name.startswith("USV_C_") else self.stats)
+        return src[E[name], : self.num_envs]
+
+    def int_field(self, name: str) -> torch.Tensor:
+        return self.field(name).view(torch.int32)
+
+    @property
+    def progress_buf(self) -> torch.Tensor:
+        return self.int_field("USV_S_PROGRESS").long()
+
+    @property
+    def goal_reached(self) -> torch.Tensor:
+        return self.int_field("USV_S_GOAL_CNT")
+
+    def randomize_targets(self, env_ids: torch.Tensor) -> None:
+        g = float(self.cfg.goal_random_position)
+        tmp = torch.zeros((self.num_envs, 2), dtype=torch.float32, device=self.device)
+        base = torch.zeros(2, dtype=torch.float32, device=self.device)
+        lo, hi = base - g, base + g
+        ids = env_ids.to(torch.long).contiguous()
+        _lib.check(self.lib.usv_randomize_rows_f32(_lib.ptr(tmp), ctypes.c_int64(2), _lib.ptr(ids), ctypes.c_int64(ids.numel()),
+                                                   ctypes.c_int32(2), _lib.ptr(base), _lib.ptr(lo), _lib.ptr(hi), ctypes.c_int32(0),
+                                                   ctypes.c_uint64(self.cfg.seed), ctypes.c_uint64(self.step_counter),
+                                                   ctypes.c_uint32(0), _lib.stream()), "randomize_rows")
+        self.field("USV_C_TX")[ids] = tmp[ids, 0]
+        self.field("USV_C_TY")[ids] = tmp[ids, 1]
+
+    def params(self):
+        return self.cfg.to_params(self.step_counter, self.env_id_offset, self.first_call)
+
+    # ---- the hot path ------------------------------------------------------------------
+    def step(self, actions: torch.Tensor, obs: Optional[torch.Tensor] = None, rew: Optional[torch.Tensor] = None):
+        """One control step of every env (== VecEnvRLGames.step).  Returns (obs (N,13), rew (N,), reset_buf (N,) long);
+        the returned tensors are the env's own buffers (as in the reference, callers clone what they keep)."""
+        obs = self.obs if obs is None else obs
+        rew = self.rew if rew is None else rew
+        p = self.params()
+        rc = self.lib.usv_step_fused_f32(ctypes.byref(self._buffers), _lib.ptr(actions, torch.float32), _lib.ptr(obs),
+                                         _lib.ptr(rew), ctypes.c_int64(self.num_envs), ctypes.byref(p), _lib.stream())
+        _lib.check(rc, "usv_step_fused_f32")
+        self.step_counter += 1
+        self.first_call = False
+        return obs, rew, self.reset_buf
+
+    def rollout(self, actions: torch.Tensor, obs: Optional[torch.Tensor] = None, rew: Optional[torch.Tensor] = None,
+                done: Optional[torch.Tensor] = None):
+        """T control steps in one launch; actions (T,N,2), optional outputs (T,N,13)/(T,N)/(T,N) long."""
+        T = int(actions.shape[0])
+        p = self.params()
+        rc = self.lib.usv_rollout_fused_f32(ctypes.byref(self._buffers), _lib.ptr(actions, torch.float32), _lib.ptr(obs),
+                                            _lib.ptr(rew), _lib.ptr(done), ctypes.c_int32(T), ctypes.c_int64(self.num_envs),
+                                            ctypes.byref(p), _lib.stream())
+        _lib.check(rc, "usv_rollout_fused_f32")
+        self.step_counter += T
+        self.first_call = False
+
+    def planar_forces(self) -> torch.Tensor:
+        """(N,8): body drag (u,v,r), net body wrench (Fx,Fy,Tz), world accel (ax,ay) of one sub-step."""
+        out = torch.empty((self.num_envs, 8), dtype=torch.float32, device=self.device)
+        p = self.params()
+        _lib.check(self.lib.usv_planar_forces_f32(ctypes.byref(self._buffers), _lib.ptr(out), ctypes.c_int64(self.num_envs),
+                                                  ctypes.byref(p), _lib.stream()), "usv_planar_forces_f32")
+        return out
+
+    def check_finite(self) -> None:
+        """USV_NAN_PROBE semantics [ref: OIGE/envs/vec_env_rlgames.py:42-80] without a per-step host sync:
+        the kernels OR a device flag; this reads it (one sync) and raises like the reference does."""
+        flag = int(self.nonfinite.item())
+        if flag != 0:
+            what = "+".join(w for bit, w in ((1, "obs/reward"), (2, "actions(clamped)")) if flag & bit)
+            raise RuntimeError(f"[USV_NAN_PROBE] non-finite detected: {what} of the fused env step")
