@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the fused ASV env step (BASELINE.json metric: ASV env-steps/sec).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's algorithm on the host cores (oracle port)
+
+A "step" is one control step of every env of the batch (one launch of step_fused_kernel):
+reset-if-flagged + 5 physics sub-steps + CaptureXY obs + reward + penalties + done, full per-env
+domain randomisation ("A, full DR": 268 algorithmic bytes per env-step, SURVEY 8(d) / DESIGN.md).
+Workload: CaptureXY SysID (classic snapshot constants), --envs per GPU (default 2^20, the top point of
+BASELINE's env-count sweep: the SoA working set is ~2.2x the 126 MB L2, so every step streams from HBM);
+the 4096-env point of BASELINE config[1] is launch-latency bound and is reported beside it under "c2_4096".
+
+One JSON line on stdout (rank 0); everything else goes to stderr.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+BYTES_PER_ENV_STEP = 268          # "A, full DR, stats off" (SURVEY 8(d)): 156 B read + 112 B written
+METRIC, UNIT = "ASV env-steps/sec", "env-steps/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period: float = 0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._halt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            log("clock sampling unavailable:", e)
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self._halt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                r = get(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=1.0)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------
+def pick_threads(make_env, n_probe=4096):
+    """The CPU port may use every host thread; pick the thread count that is actually fastest on a short probe."""
+    ncpu = os.cpu_count() or 1
+    best = (None, 0.0)
+    for nt in sorted({1, max(1, ncpu // 2), ncpu}):
+        torch.set_num_threads(nt)
+        env = make_env(n_probe)
+        act = torch.zeros((n_probe, 2))
+        env.step(act)
+        t = time.perf_counter()
+        for _ in range(3):
+            env.step(act)
+        rate = 3 * n_probe / (time.perf_counter() - t)
+        log(f"  cpu probe: {nt} threads -> {rate:.3g} env-steps/s")
+        if rate > best[1]:
+            best = (nt, rate)
+    torch.set_num_threads(best[0])
+    return best[0]
+
+
+def cpu_port(budget_s: float, steps: int | None = None, warmup: int = 1, envs: int | None = None):
+    """Times the oracle port (the reference's torch algorithm, CPU) on a bounded sample of the workload."""
+    from oracle import usv_oracle as O
+
+    cfg = O.EnvConfig().full_dr()
+    mk = lambda n: O.ClassicEnvOracle(cfg, n)
+    threads = pick_threads(mk)
+    if envs is None or steps is None:
+        # size the sample: n envs per step so that `steps` steps fit the budget
+        probe = mk(16384)
+        act = torch.zeros((16384, 2))
+        probe.step(act)
+        t = time.perf_counter()
+        probe.step(act)
+        rate = 16384 / (time.perf_counter() - t)
+        steps = steps or 8
+        envs = envs or int(min(1 << 20, max(4096, rate * budget_s / (steps + warmup))))
+        envs = 1 << (envs.bit_length() - 1)
+    env = mk(envs)
+    g = torch.Generator().manual_seed(0)
+    acts = [torch.rand((envs, 2), generator=g) * 2 - 1 for _ in range(4)]
+    for w in range(warmup):
+        env.step(acts[w % 4])
+    t = time.perf_counter()
+    for k in range(steps):
+        env.step(acts[k % 4])
+    dt = time.perf_counter() - t
+    return {"value": envs * steps / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{envs} envs x {steps} control steps (oracle/usv_oracle.ClassicEnvOracle, torch CPU fp32, "
+                      f"{threads} of {os.cpu_count()} host threads), full DR, 5 sub-steps"}, dt / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    budget = 150.0
+    cb, s_per_step = cpu_port(budget, steps=args.steps if args.steps <= 64 else None, warmup=min(args.warmup, 3))
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.envs, note="reference arm: the oracle port of the reference's torch path on host cores "
+                                      "(the Python reference needs Isaac Sim and cannot travel to the GPU box); each step is a bounded sample"),
+            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(envs, note=None):
+    c = {"workload": f"CaptureXY SysID classic (13-dim obs), fused reset+dynamics+obs+reward+done step, {envs} envs/GPU, "
+                     f"full per-env DR, 5 sub-steps/control step",
+         "envs_per_gpu": envs, "substeps": 5, "obs_dim": 13, "bytes_per_env_step": BYTES_PER_ENV_STEP,
+         "l2": "inputs larger than L2 (SoA working set = envs*~280 B; 2^20 envs = 294 MB vs 126 MB L2), no flush needed"}
+    if note:
+        c["note"] = note
+    return c
+
+
+# ------------------------------------------------------------------------------------------------
+def time_steps(env, acts, steps, warmup, dist_on, device):
+    """Device-timed: W warm-up steps, then exactly K steps between CUDA events on the launching stream."""
+    import torch.distributed as dist
+
+    for w in range(warmup):
+        env.step(acts[w % len(acts)])
+    torch.cuda.synchronize(device)
+    if dist_on:
+        dist.barrier()
+        torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(steps):
+        env.step(acts[k % len(acts)])
+    e1.record()
+    torch.cuda.synchronize(device)
+    ms = e0.elapsed_time(e1)
+    if dist_on:
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.barrier()
+        ms = float(t.item())
+    return ms
+
+
+def time_e2e(env, steps, warmup, dist_on, device):
+    """The same metric through the public call with HOST buffers: per step pinned-host actions -> device,
+    fused step, obs + reward + done -> pinned host (copies inside the timed region)."""
+    import torch.distributed as dist
+
+    n = env.num_envs
+    g = torch.Generator().manual_seed(1)
+    h_act = [(torch.rand((n, 2), generator=g) * 2 - 1).pin_memory() for _ in range(2)]
+    d_act = torch.empty((n, 2), device=device)
+    h_obs = torch.empty((n, 13), dtype=torch.float32).pin_memory()
+    h_rew = torch.empty(n, dtype=torch.float32).pin_memory()
+    h_done = torch.empty(n, dtype=torch.long).pin_memory()
+
+    def one(k):
+        d_act.copy_(h_act[k & 1], non_blocking=True)
+        obs, rew, done = env.step(d_act)
+        h_obs.copy_(obs, non_blocking=True)
+        h_rew.copy_(rew, non_blocking=True)
+        h_done.copy_(done, non_blocking=True)
+
+    for w in range(warmup):
+        one(w)
+    torch.cuda.synchronize(device)
+    if dist_on:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(steps):
+        one(k)
+    e1.record()
+    torch.cuda.synchronize(device)
+    ms = e0.elapsed_time(e1)
+    if dist_on:
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    h2d = n * 2 * 4
+    d2h = n * 13 * 4 + n * 4 + n * 8
+    return ms, h2d, d2h, float(h_rew.mean())
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--envs", type=int, default=1 << 20, help="envs per GPU")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the 4096-env and e2e legs (profiling runs)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch.distributed as dist
+    from omniisaacgymenvs_loop_b200 import _lib
+    from omniisaacgymenvs_loop_b200.config import UsvEnvConfig
+    from omniisaacgymenvs_loop_b200.engine import FusedUsvEnv
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist_on = world > 1
+    device = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(device)
+    if dist_on:
+        dist.init_process_group("nccl", device_id=device)
+    n = args.envs
+    cfg = UsvEnvConfig().full_dr()
+    # envs are sharded across ranks: rank r owns global env ids [r*n, (r+1)*n) -- same Philox streams as one big env
+    env = FusedUsvEnv(cfg, n, device, env_id_offset=rank * n)
+    g = torch.Generator(device=device).manual_seed(1234 + rank)
+    acts = [torch.rand((n, 2), device=device, generator=g) * 2 - 1 for _ in range(8)]
+
+    sampler = ClockSampler(local)
+    launches0 = _lib.launch_count()
+    sampler.start()
+    ms = time_steps(env, acts, args.steps, args.warmup, dist_on, device)
+    clocks = sampler.stop()
+    launches = _lib.launch_count() - launches0 - args.warmup
+    env.check_finite()
+    value = world * n * args.steps / (ms * 1e-3)
+    ms_per_step = ms / args.steps
+    peak, peak_src = measured_peak()
+    achieved = BYTES_PER_ENV_STEP * n / (ms_per_step * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "kernel": "usv::step_fused_kernel<true,false>", "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": BYTES_PER_ENV_STEP * n}
+    tr = os.path.join(ROOT, "profiles", "traffic.json")      # dram bytes/launch from the committed ncu --set full capture
+    if os.path.exists(tr):
+        try:
+            with open(tr) as f:
+                t = json.load(f)
+            if int(t.get("envs", -1)) == n:
+                roofline["traffic"] = t["dram_bytes_per_launch"]
+        except Exception:
+            pass
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(n), "roofline": roofline, "clocks": clocks,
+            "gpu_launches": int(launches), "substeps_per_s": value * cfg.n_substeps}
+
+    if not args.no_extra:
+        e2e_steps = max(3, min(args.steps, 200))
+        ems, h2d, d2h, _ = time_e2e(env, e2e_steps, 3, dist_on, device)
+        line["e2e"] = {"value": world * n * e2e_steps / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                       "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                       "path": "FusedUsvEnv.step via C ABI; pinned host actions -> device, obs+reward+done -> pinned host every step"}
+        # BASELINE config[1]: 4096 envs/GPU -- launch-latency bound (working set ~1 MB, L2 resident): reported, not the headline
+        small = FusedUsvEnv(cfg, 4096, device, env_id_offset=rank * 4096)
+        sacts = [a[:4096].contiguous() for a in acts]
+        sms = time_steps(small, sacts, max(args.steps, 2000), 20, dist_on, device)
+        T = 512
+        roll_act = torch.rand((T, 4096, 2), device=device, generator=g) * 2 - 1
+        small.rollout(roll_act)
+        torch.cuda.synchronize(device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(4):
+            small.rollout(roll_act)
+        e1.record()
+        torch.cuda.synchronize(device)
+        rms = e0.elapsed_time(e1)
+        line["c2_4096"] = {"envs_per_gpu": 4096, "step_kernel_env_steps_per_s": world * 4096 * max(args.steps, 2000) / (sms * 1e-3),
+                           "us_per_step": sms * 1e3 / max(args.steps, 2000),
+                           "rollout_kernel_env_steps_per_s": world * 4096 * T * 4 / (rms * 1e-3),
+                           "note": "one launch per control step vs one launch per 512 control steps (state in registers); "
+                                   "latency-bound, working set L2-resident -> no HBM roofline claimed"}
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        cb, _ = cpu_port(20.0)
+        line["cpu_baseline"] = cb
+    if dist_on:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

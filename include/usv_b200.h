@@ -123,7 +123,10 @@ int usv_randomize_rows_f32(float* dst, int64_t ld, const int64_t* env_ids, int64
 /*     [ref: OIGE/envs/vec_env_rlgames.py:120-217; SNAP/USV_Virtual.py:571-866; */
 /*           SNAP/USV_capture_xy.py:80-275; SNAP/USV_task_rewards.py:40-76,380-540; */
 /*           OIGE/tasks/USV/USV_disturbances.py; OIGE/tasks/base/rl_task.py:283-303] */
-/* State is structure-of-arrays: field f of env i lives at base[f*stride + i].  */
+/* State is structure-of-arrays, tiled by warp (AoSoA): envs are grouped in tiles of 32 and inside a tile the
+ * fields are consecutive 128-byte lines:  field f of env i lives at
+ *     base[((i >> 5) * COUNT + f) * 32 + (i & 31)]          (COUNT = USV_S_COUNT / USV_C_COUNT / USV_ST_COUNT).
+ * `*_stride` is the capacity in envs (a multiple of 32, >= n); buffers hold stride*COUNT floats, 128 B aligned. */
 
 /* dynamic fields (read+written every step) */
 enum {
@@ -235,9 +238,9 @@ typedef struct {
 } UsvStepParams;
 
 typedef struct {
-  float*   state;   int64_t state_stride;   /* [USV_S_COUNT][stride]  (16B aligned, stride%4==0) */
-  float*   consts;  int64_t consts_stride;  /* [USV_C_COUNT][stride]                           */
-  float*   stats;   int64_t stats_stride;   /* [USV_ST_COUNT][stride] or NULL (stats off)      */
+  float*   state;   int64_t state_stride;   /* [stride/32][USV_S_COUNT][32]                    */
+  float*   consts;  int64_t consts_stride;  /* [stride/32][USV_C_COUNT][32]                    */
+  float*   stats;   int64_t stats_stride;   /* [stride/32][USV_ST_COUNT][32] or NULL (stats off) */
   int64_t* reset_buf;                        /* [n] RLTask.reset_buf (in: reset now; out: done) */
   const float* lut_left;                     /* [n_lut]                                        */
   const float* lut_right;                    /* [n_lut]                                        */

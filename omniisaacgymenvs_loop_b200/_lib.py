@@ -17,7 +17,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 HEADER = os.path.join(_ROOT, "include", "usv_b200.h")
-LIB_PATH = os.path.join(_HERE, "lib", "libusv_b200.so")
+LIB_PATH = os.environ.get("USV_B200_LIB", os.path.join(_HERE, "lib", "libusv_b200.so"))
 
 _CTYPES = {
     "float": ctypes.c_float, "int32_t": ctypes.c_int32, "uint32_t": ctypes.c_uint32,

@@ -48,10 +48,27 @@ __host__ __device__ __forceinline__ Uniform4 philox_uniform4(uint64_t seed, uint
   return Uniform4{u01(r.x), u01(r.y), u01(r.z), u01(r.w)};
 }
 
+// 8 x 16-bit uniforms in [0,1) from ONE Philox call (per-step observation / action noise: amplitudes are
+// <= 0.05, so 2^-16 resolution is ~1e-6 of the signal; halves the RNG cost of the step)
+struct Uniform8 { float v[8]; };
+__host__ __device__ __forceinline__ Uniform8 philox_uniform8x16(uint64_t seed, uint64_t env_id, uint64_t step,
+                                                                uint32_t stream) {
+  Philox4 r = philox4x32_10((uint32_t)env_id, (uint32_t)step, (uint32_t)(step >> 32),
+                            stream ^ ((uint32_t)(env_id >> 32) << 8), (uint32_t)seed, (uint32_t)(seed >> 32));
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  Uniform8 u;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    u.v[2 * i] = (float)(w[i] & 0xFFFFu) * (1.0f / 65536.0f);
+    u.v[2 * i + 1] = (float)(w[i] >> 16) * (1.0f / 65536.0f);
+  }
+  return u;
+}
+
 // Philox stream ids used by the fused env step (DESIGN.md "RNG streams")
 enum : uint32_t {
-  RS_STEP_A = 0,   // act0, act1, vel_x, vel_y
-  RS_STEP_B = 1,   // vel_r, heading, pos_x, pos_y
+  RS_STEP_A = 0,   // 8x16-bit: act0, act1, vel_x, vel_y, vel_r, heading, pos_x, pos_y
+  RS_STEP_B = 1,   // (reserved)
   RS_RESET_0 = 2,  // goal_x, goal_y, spawn_r, spawn_theta
   RS_RESET_1 = 3,  // spawn_yaw, vel_x, vel_y, mass
   RS_RESET_2 = 4,  // (com_x, com_y, com_z reserved), k_drag

@@ -16,7 +16,13 @@
 
 namespace usv {
 
-constexpr int kBlock = 256;
+#ifndef USV_BLOCK
+#define USV_BLOCK 256
+#endif
+#ifndef USV_MINB
+#define USV_MINB 3
+#endif
+constexpr int kBlock = USV_BLOCK;
 constexpr int kObs = 13;
 // python: math.pi / 2*math.pi are doubles that meet fp32 tensors -> rounded to fp32
 #define USV_PI_F 3.14159274101257324f
@@ -34,12 +40,24 @@ struct StepOut {
   float obs[kObs];
   float rew;
   int done;
+  bool finite;
   // diagnostics for stats
   float dist_rew, align_rew, speed_rew, d, speed, bpen, bdist;
   float pen_lin, pen_ang, pen_angvar, pen_energy, pen_actvar, absw, asum;
 };
 
-__device__ __forceinline__ void load_state(const float* __restrict__ s, int64_t stride, int64_t i, EnvState& e) {
+// AoSoA: envs are grouped in tiles of 32 (one warp); inside a tile the fields are consecutive 128 B lines:
+//   field f of env i lives at base[((i >> 5) * COUNT + f) * 32 + (i & 31)].
+// A warp reads/writes one full line per field, and every field of an env is an IMMEDIATE offset from one
+// per-thread base pointer (plain field-major SoA with a runtime stride cost two 64-bit adds per access,
+// ~100 of the 1678 instructions per env-step in the r01 profile).
+constexpr int kTile = 32;
+__device__ __forceinline__ int64_t tile_base(int64_t i, int count) { return (i >> 5) * (int64_t)(count * kTile) + (i & 31); }
+#define stride kTile
+
+__device__ __forceinline__ void load_state(const float* __restrict__ s0, int64_t /*cap*/, int64_t i0, EnvState& e) {
+  const float* __restrict__ s = s0 + tile_base(i0, USV_S_COUNT);
+  constexpr int i = 0;
   e.x = s[USV_S_X * stride + i];
   e.y = s[USV_S_Y * stride + i];
   e.psi = s[USV_S_PSI * stride + i];
@@ -55,7 +73,9 @@ __device__ __forceinline__ void load_state(const float* __restrict__ s, int64_t 
   e.progress = __float_as_int(s[USV_S_PROGRESS * stride + i]);
 }
 
-__device__ __forceinline__ void store_state(float* __restrict__ s, int64_t stride, int64_t i, const EnvState& e) {
+__device__ __forceinline__ void store_state(float* __restrict__ s0, int64_t /*cap*/, int64_t i0, const EnvState& e) {
+  float* __restrict__ s = s0 + tile_base(i0, USV_S_COUNT);
+  constexpr int i = 0;
   s[USV_S_X * stride + i] = e.x;
   s[USV_S_Y * stride + i] = e.y;
   s[USV_S_PSI * stride + i] = e.psi;
@@ -72,7 +92,9 @@ __device__ __forceinline__ void store_state(float* __restrict__ s, int64_t strid
 }
 
 template <bool kDisturb>
-__device__ __forceinline__ void load_consts(const float* __restrict__ c, int64_t stride, int64_t i, EnvConst& k) {
+__device__ __forceinline__ void load_consts(const float* __restrict__ c0, int64_t /*cap*/, int64_t i0, EnvConst& k) {
+  const float* __restrict__ c = c0 + tile_base(i0, USV_C_COUNT);
+  constexpr int i = 0;
   k.tx = c[USV_C_TX * stride + i];
   k.ty = c[USV_C_TY * stride + i];
   k.mass = c[USV_C_MASS * stride + i];
@@ -104,7 +126,9 @@ __device__ __forceinline__ void load_consts(const float* __restrict__ c, int64_t
 }
 
 template <bool kDisturb>
-__device__ __forceinline__ void store_consts(float* __restrict__ c, int64_t stride, int64_t i, const EnvConst& k) {
+__device__ __forceinline__ void store_consts(float* __restrict__ c0, int64_t /*cap*/, int64_t i0, const EnvConst& k) {
+  float* __restrict__ c = c0 + tile_base(i0, USV_C_COUNT);
+  constexpr int i = 0;
   c[USV_C_TX * stride + i] = k.tx;
   c[USV_C_TY * stride + i] = k.ty;
   c[USV_C_MASS * stride + i] = k.mass;
@@ -135,13 +159,63 @@ __device__ __forceinline__ void store_consts(float* __restrict__ c, int64_t stri
 
 __device__ __forceinline__ float urange(float u, float lo, float hi) { return u * (hi - lo) + lo; }
 
+// Branch-free sin/cos for |x| < ~1e5 (every angle in this kernel is bounded: headings, phases x*f+shift):
+// 3-term Cody-Waite reduction by pi/2 + the classic single-precision minimax polynomials on [-pi/4, pi/4]
+// (~1 ulp).  libdevice's sinf/cosf carry a Payne-Hanek slow path behind a branch + convergence barrier per
+// call; 22 calls per env-step made that ~10% of the issued instructions (profiles/r01_step_kernel.md).
+__device__ __forceinline__ void trig_reduce(float x, float& r, int& q) {
+  const float j = rintf(x * 0.636619772f);
+  q = (int)j;
+  r = fmaf(j, -1.57079601e+00f, x);
+  r = fmaf(j, -3.13916473e-07f, r);
+  r = fmaf(j, -5.39030253e-15f, r);
+}
+__device__ __forceinline__ float poly_sin(float r, float r2) {
+  float p = fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f);
+  p = fmaf(p, r2, -1.6666654611e-1f);
+  return fmaf(p * r2, r, r);
+}
+__device__ __forceinline__ float poly_cos(float r2) {
+  float p = fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f);
+  p = fmaf(p, r2, 4.166664568298827e-2f);
+  p = fmaf(p, r2, -0.5f);
+  return fmaf(p, r2, 1.0f);
+}
+__device__ __forceinline__ void fsincos(float x, float* sp, float* cp) {
+  float r; int q;
+  trig_reduce(x, r, q);
+  const float r2 = r * r;
+  const float s = poly_sin(r, r2), c = poly_cos(r2);
+  const float ss = (q & 1) ? c : s;
+  const float cc = (q & 1) ? s : c;
+  // sign flips as sign-bit XORs: sin negated in quadrants 2,3; cos in quadrants 1,2
+  *sp = __int_as_float(__float_as_int(ss) ^ ((q & 2) << 30));
+  *cp = __int_as_float(__float_as_int(cc) ^ (((q + 1) & 2) << 30));
+}
+// sin() for the sinusoidal force/torque disturbances, evaluated 3x per physics sub-step: explicit 2-term
+// Cody-Waite reduction to [-pi, pi], then the SFU (MUFU.SIN, abs error <= 2^-21.4 on that interval).  With
+// amplitudes <= 1.77 N / 1 Nm the force error is < 1e-6 N against drag/thrust forces of 1..100 N, i.e. far inside
+// the 1e-5 parity bar, and it replaces ~17 issue slots by 6 (the loop was 48% of the kernel, r01 profile).
+__device__ __forceinline__ float fsin_sfu(float x) {
+  const float k = rintf(x * 0.159154943f);
+  float r = fmaf(k, -6.28318548e+00f, x);
+  r = fmaf(k, 1.74845553e-07f, r);
+  return __sinf(r);
+}
+__device__ __forceinline__ float fsin(float x) {
+  float r; int q;
+  trig_reduce(x, r, q);
+  const float r2 = r * r;
+  const float v = (q & 1) ? poly_cos(r2) : poly_sin(r, r2);
+  return __int_as_float(__float_as_int(v) ^ ((q & 2) << 30));
+}
+
 // wrap an angle into (-pi, pi]  (the branch torch.atan2 returns for the yaw read-back)
 __device__ __forceinline__ float wrap_pi(float a) {
-  if (a > USV_PI_F || a <= -USV_PI_F) {
-    a = a - USV_2PI_F * rintf(a * (1.0f / USV_2PI_F));
-    if (a > USV_PI_F) a -= USV_2PI_F;
-    if (a <= -USV_PI_F) a += USV_2PI_F;
-  }
+  // in-range values pass through bit-exactly (rintf gives 0): same as the oracle's masked wrap
+  a = a - USV_2PI_F * rintf(a * (1.0f / USV_2PI_F));
+  a = (a > USV_PI_F) ? a - USV_2PI_F : a;
+  a = (a <= -USV_PI_F) ? a + USV_2PI_F : a;
   return a;
 }
 
@@ -149,7 +223,7 @@ __device__ __forceinline__ float penalty_scalar(const UsvPenaltyTerm& t, float x
   switch (t.form) {
     case USV_PEN_NEG_ABS: return -fabsf(x) * t.c1 + t.c2;
     case USV_PEN_NEG_DEADZONE: return -fmaxf(fabsf(x) - t.k, 0.0f) * t.c1;
-    case USV_PEN_EXP_NEG_ABS: return (expf(-t.k * fabsf(x)) - 1.0f) * t.c1;
+    case USV_PEN_EXP_NEG_ABS: return (__expf(-t.k * fabsf(x)) - 1.0f) * t.c1;
     default: return 0.0f;
   }
 }
@@ -177,8 +251,10 @@ __device__ __forceinline__ void reset_env(EnvState& e, EnvConst& k, const UsvSte
       if (p.use_const_force) {
         const float rr = urange(r6.d, p.force_const_min, p.force_const_max);
         const float th = r7.a * USV_PI_F * 2.0f;
-        k.fcx = cosf(th) * rr;
-        k.fcy = sinf(th) * rr;
+        float sth_, cth_;
+        fsincos(th, &sth_, &cth_);
+        k.fcx = cth_ * rr;
+        k.fcy = sth_ * rr;
       }
     }
     if (p.use_torque_disturbance) {
@@ -247,8 +323,10 @@ __device__ __forceinline__ void reset_env(EnvState& e, EnvConst& k, const UsvSte
   // get_spawns  [ref SNAP/USV_capture_xy.py:330-394]: annulus around the target, yaw on a half circle
   const float sr = r0.c * (p.spawn_max_dist - p.spawn_min_dist) + p.spawn_min_dist;
   const float sth = r0.d * 2.0f * USV_PI_F;
-  e.x = sr * cosf(sth) + k.tx;
-  e.y = sr * sinf(sth) + k.ty;
+  float ssp, csp;
+  fsincos(sth, &ssp, &csp);
+  e.x = sr * csp + k.tx;
+  e.y = sr * ssp + k.ty;
   // quaternion (cos(a/2),0,0,sin(a/2)) with a ~ U[0,pi)  ->  yaw = a
   e.psi = r1.a * USV_PI_F;
   // root velocities: zero, then vx,vy ~ U(-1.5,1.5) in the world frame  [ref SNAP/USV_Virtual.py:786-794]
@@ -263,10 +341,9 @@ __device__ __forceinline__ void reset_env(EnvState& e, EnvConst& k, const UsvSte
 // planar force model for one physics sub-step; returns body wrench and world acceleration
 template <bool kDisturb>
 __device__ __forceinline__ void planar_wrench(const EnvState& e, const EnvConst& k, const UsvStepParams& p, float ox,
-                                              float oy, float& du, float& dv, float& dr, float& Fx, float& Fy,
-                                              float& Tz, float& ax, float& ay, float& rdot) {
-  float s, c;
-  sincosf(e.psi, &s, &c);
+                                              float oy, float inv_m, float inv_iz, float s, float c, float& du, float& dv,
+                                              float& dr, float& Fx, float& Fy, float& Tz, float& ax, float& ay,
+                                              float& rdot) {
   // R^T v (world -> body)  [ref Hydrodynamics.py:213-222, planar quaternion]
   const float u = c * e.vx + s * e.vy;
   const float v = -s * e.vx + c * e.vy;
@@ -288,32 +365,32 @@ __device__ __forceinline__ void planar_wrench(const EnvState& e, const EnvConst&
   if (kDisturb) {
     if (p.use_const_force) { fdx = k.fcx; fdy = k.fcy; }
     if (p.use_sin_force) {
-      fdx = k.fcx + sinf((e.x + ox) * k.fxf + k.fxs) * k.famp;
-      fdy = k.fcy + sinf((e.y + oy) * k.fyf + k.fys) * k.famp;
+      fdx = k.fcx + fsin_sfu((e.x + ox) * k.fxf + k.fxs) * k.famp;
+      fdy = k.fcy + fsin_sfu((e.y + oy) * k.fyf + k.fys) * k.famp;
     }
     if (p.use_const_torque) td = k.tc;
-    if (p.use_sin_torque) td = k.tc + sinf(((e.x + ox) + (e.y + oy)) * k.tf + k.ts) * k.tamp;
+    if (p.use_sin_torque) td = k.tc + fsin_sfu(((e.x + ox) + (e.y + oy)) * k.tf + k.ts) * k.tamp;
   }
   // net wrench at the base link; thrusters push along body x at (thr_x, thr_y_*)  (heron.urdf:167,242)
   Fx = fdx + du + e.thrL + e.thrR;
   Fy = fdy + dv;
   Tz = td + dr - p.thr_y_left * e.thrL - p.thr_y_right * e.thrR;
-  const float inv_m = 1.0f / k.mass;
   ax = (c * Fx - s * Fy) * inv_m;
   ay = (s * Fx + c * Fy) * inv_m;
-  rdot = Tz / (p.izz * k.kiz);
+  rdot = Tz * inv_iz;
 }
 
 // one full control step for one env, state in registers
-template <bool kDisturb>
+template <bool kDisturb, bool kLutGlobal>
 __device__ __forceinline__ void control_step(EnvState& e, EnvConst& k, const UsvStepParams& p, bool do_reset,
                                              float2 act, uint64_t gid, int64_t lid, uint64_t step, bool first_call,
                                              const float* __restrict__ s_lutL, const float* __restrict__ s_lutR,
                                              StepOut& o) {
   // ---- pre_physics_step ------------------------------------------------------------------
   if (do_reset) reset_env<kDisturb>(e, k, p, gid, step);
-  const Uniform4 na = philox_uniform4(p.seed, gid, step, RS_STEP_A);
-  const Uniform4 nb = philox_uniform4(p.seed, gid, step, RS_STEP_B);
+  const Uniform8 nz = philox_uniform8x16(p.seed, gid, step, RS_STEP_A);
+  const float u_a0 = nz.v[0], u_a1 = nz.v[1], u_vx = nz.v[2], u_vy = nz.v[3], u_w = nz.v[4], u_h = nz.v[5],
+              u_px = nz.v[6], u_py = nz.v[7];
   // VecEnvRLGames.step clamps to +-clipActions  [ref vec_env_rlgames.py:136-140]
   float a0 = fminf(fmaxf(act.x, -p.clip_actions), p.clip_actions);
   float a1 = fminf(fmaxf(act.y, -p.clip_actions), p.clip_actions);
@@ -323,8 +400,8 @@ __device__ __forceinline__ void control_step(EnvState& e, EnvConst& k, const Usv
     // classic [ref SNAP/USV_Virtual.py:589-615]: AN.add_noise_on_act works IN PLACE on the tensor that
     // self.actions aliases -> penalties see the noisy, unclamped action; resets zero only the thrust.
     if (p.action_noise) {
-      a0 += urange(na.a, p.action_noise_min, p.action_noise_max);
-      a1 += urange(na.b, p.action_noise_min, p.action_noise_max);
+      a0 += urange(u_a0, p.action_noise_min, p.action_noise_max);
+      a1 += urange(u_a1, p.action_noise_min, p.action_noise_max);
     }
     pa0 = a0; pa1 = a1;
     c0 = fminf(fmaxf(a0, -1.0f), 1.0f);
@@ -333,8 +410,8 @@ __device__ __forceinline__ void control_step(EnvState& e, EnvConst& k, const Usv
     // live [ref OIGE/tasks/USV_Virtual.py:1064-1097]
     float t0 = a0 + p.action_bias, t1 = a1 + p.action_bias;
     if (p.action_noise) {
-      t0 += urange(na.a, p.action_noise_min, p.action_noise_max);
-      t1 += urange(na.b, p.action_noise_min, p.action_noise_max);
+      t0 += urange(u_a0, p.action_noise_min, p.action_noise_max);
+      t1 += urange(u_a1, p.action_noise_min, p.action_noise_max);
     }
     t0 = fminf(fmaxf(t0, -1.0f), 1.0f);
     t1 = fminf(fmaxf(t1, -1.0f), 1.0f);
@@ -345,8 +422,9 @@ __device__ __forceinline__ void control_step(EnvState& e, EnvConst& k, const Usv
   }
   if (do_reset) { c0 = 0.0f; c1 = 0.0f; }
   // set_target_force -> get_cmd_interpolated  [ref ThrusterDynamics.py:179-219]
-  const float tgtL = s_lutL[lut_index(c0, p.n_lut)] * k.mL;
-  const float tgtR = s_lutR[lut_index(c1, p.n_lut)] * k.mR;
+  const int iL = lut_index(c0, p.n_lut), iR = lut_index(c1, p.n_lut);
+  const float tgtL = (kLutGlobal ? __ldg(s_lutL + iL) : s_lutL[iL]) * k.mL;
+  const float tgtR = (kLutGlobal ? __ldg(s_lutR + iR) : s_lutR[iR]) * k.mR;
 
   // ---- physics sub-steps -----------------------------------------------------------------
   float ox = 0.0f, oy = 0.0f;
@@ -356,20 +434,36 @@ __device__ __forceinline__ void control_step(EnvState& e, EnvConst& k, const Usv
     oy = (float)col * p.env_spacing - p.grid_col_offset;
   }
   const float oma = 1.0f - p.lag_alpha;
+  const float inv_m = 1.0f / k.mass, inv_iz = 1.0f / (p.izz * k.kiz);
+  // heading (cos psi, sin psi): one full evaluation per control step, then advanced by the small per-sub-step yaw
+  // increment with a rotation by (cos d, sin d) from short Taylor polynomials (|d| = dt*|r| <= 0.5: error < 5e-9)
+  float hsn, hcs;
+  fsincos(e.psi, &hsn, &hcs);
   for (int ss = 0; ss < p.n_substeps; ++ss) {
     // apply_forces(): update_forces() advances the lag BEFORE the wrench is applied
     // [ref ThrusterDynamics.py:129-141; SNAP/USV_Virtual.py:640]
     e.thrL = __fadd_rn(__fmul_rn(e.thrL, p.lag_alpha), __fmul_rn(oma, tgtL));
     e.thrR = __fadd_rn(__fmul_rn(e.thrR, p.lag_alpha), __fmul_rn(oma, tgtR));
     float du, dv, dr, Fx, Fy, Tz, ax, ay, rdot;
-    planar_wrench<kDisturb>(e, k, p, ox, oy, du, dv, dr, Fx, Fy, Tz, ax, ay, rdot);
+    planar_wrench<kDisturb>(e, k, p, ox, oy, inv_m, inv_iz, hsn, hcs, du, dv, dr, Fx, Fy, Tz, ax, ay, rdot);
     // world.step(): semi-implicit Euler (velocities first, then positions)
     e.vx += p.dt * ax;
     e.vy += p.dt * ay;
     e.r += p.dt * rdot;
     e.x += p.dt * e.vx;
     e.y += p.dt * e.vy;
-    e.psi += p.dt * e.r;
+    const float dpsi = p.dt * e.r;
+    e.psi += dpsi;
+    if (fabsf(dpsi) <= 0.5f) {
+      const float d2 = dpsi * dpsi;
+      const float sd = dpsi * fmaf(d2, fmaf(d2, fmaf(d2, -1.0f / 5040.0f, 1.0f / 120.0f), -1.0f / 6.0f), 1.0f);
+      const float cd = fmaf(d2, fmaf(d2, fmaf(d2, fmaf(d2, 1.0f / 40320.0f, -1.0f / 720.0f), 1.0f / 24.0f), -0.5f), 1.0f);
+      const float nc = hcs * cd - hsn * sd;
+      hsn = hsn * cd + hcs * sd;
+      hcs = nc;
+    } else {
+      fsincos(e.psi, &hsn, &hcs);
+    }
   }
   e.psi = wrap_pi(e.psi);
 
@@ -377,23 +471,26 @@ __device__ __forceinline__ void control_step(EnvState& e, EnvConst& k, const Usv
   e.progress += 1;  // [ref rl_task.py:294]
   // update_state: observation noise  [ref SNAP/USV_Virtual.py:476-530 ; USV_disturbances.py:552-601]
   float pxn = e.x, pyn = e.y, vxn = e.vx, vyn = e.vy, wn = e.r, yawn = e.psi;
-  if (p.noise_pos) { pxn += urange(nb.c, p.pos_noise_min, p.pos_noise_max); pyn += urange(nb.d, p.pos_noise_min, p.pos_noise_max); }
+  if (p.noise_pos) { pxn += urange(u_px, p.pos_noise_min, p.pos_noise_max); pyn += urange(u_py, p.pos_noise_min, p.pos_noise_max); }
   if (p.noise_vel) {
-    vxn += urange(na.c, p.vel_noise_min, p.vel_noise_max);
-    vyn += urange(na.d, p.vel_noise_min, p.vel_noise_max);
-    wn += urange(nb.a, p.vel_noise_min, p.vel_noise_max);
+    vxn += urange(u_vx, p.vel_noise_min, p.vel_noise_max);
+    vyn += urange(u_vy, p.vel_noise_min, p.vel_noise_max);
+    wn += urange(u_w, p.vel_noise_min, p.vel_noise_max);
   }
-  if (p.noise_heading) yawn += urange(nb.b, p.heading_noise_min, p.heading_noise_max);
+  if (p.noise_heading) yawn += urange(u_h, p.heading_noise_min, p.heading_noise_max);
   float hs, hc;
-  sincosf(yawn, &hs, &hc);
+  fsincos(yawn, &hs, &hc);
   // get_state_observations  [ref SNAP/USV_capture_xy.py:80-97]
   const float ex = k.tx - pxn, ey = k.ty - pyn;
   const float theta = wrap_pi(yawn);  // == atan2(sin, cos) up to rounding, same (-pi,pi] branch
   const float beta = atan2f(ey, ex);
-  const float alpha = fmodf(beta - theta + USV_PI_F, USV_2PI_F) - USV_PI_F;  // C fmod: sign of the dividend
+  // torch.fmod(x, 2pi) has C semantics (sign of the dividend).  beta, theta in [-pi, pi] -> x in [-pi, 3pi]:
+  // fmod only acts for x >= 2pi, where x - 2pi is exact; negative x stays unwrapped (reference quirk).
+  const float xa = beta - theta + USV_PI_F;
+  const float alpha = ((xa >= USV_2PI_F) ? xa - USV_2PI_F : xa) - USV_PI_F;
   const float herr = fabsf(alpha);
   float sa, ca;
-  sincosf(alpha, &sa, &ca);
+  fsincos(alpha, &sa, &ca);
   const float d = sqrtf(ex * ex + ey * ey);
   // Core.update_observation_tensor, "local" frame  [ref SNAP/USV_core.py:41-54]
   o.obs[0] = hc * vxn + hs * vyn;
@@ -422,14 +519,14 @@ __device__ __forceinline__ void control_step(EnvState& e, EnvConst& k, const Usv
     dist_rew = p.position_scale * (expf(-d / p.exponential_reward_coeff) - expf(-e.prev_d / p.exponential_reward_coeff));
   }
   const float h2 = herr * herr;
-  const float align = p.align_la1 * (expf(p.align_la2 * (h2 * h2)) + expf(p.align_la3 * h2));
+  const float align = p.align_la1 * (__expf(p.align_la2 * (h2 * h2)) + __expf(p.align_la3 * h2));
   if (do_reset) dist_rew = 0.0f;  // distance_reward[just_had_been_reset] = 0
   float speed_rew;
   const float sclamp = 1.0f - fminf(fmaxf(speed / 1.0f, 0.0f), 1.0f);
   if (d > 3.5f) {
     const bool in_range = (speed >= 0.8f) && (speed <= 1.5f);
     const float ds = speed - 1.15f;
-    speed_rew = in_range ? 0.1f : expf(-(ds * ds) / 0.2f) * 0.1f;
+    speed_rew = in_range ? 0.1f : __expf(-(ds * ds) * 5.0f) * 0.1f;
   } else if (d > 2.5f) {
     speed_rew = sclamp * 0.15f;
   } else if (d > 1.5f) {
@@ -450,7 +547,7 @@ __device__ __forceinline__ void control_step(EnvState& e, EnvConst& k, const Usv
   if (p.pen_angular_vel.form != USV_PEN_OFF) pen_ang = penalty_scalar(p.pen_angular_vel, wn);
   if (p.pen_angular_vel_variation.form != USV_PEN_OFF) pen_angvar = penalty_scalar(p.pen_angular_vel_variation, dw);
   if (p.pen_energy.form == USV_PEN_NEG_SUM) pen_energy = -(pa0 + pa1) * p.pen_energy.c1 + p.pen_energy.c2;
-  else if (p.pen_energy.form == USV_PEN_EXP_NEG_SUMSQ) pen_energy = (expf(-(pa0 * pa0 + pa1 * pa1)) - 1.0f) * p.pen_energy.c1;
+  else if (p.pen_energy.form == USV_PEN_EXP_NEG_SUMSQ) pen_energy = (__expf(-(pa0 * pa0 + pa1 * pa1)) - 1.0f) * p.pen_energy.c1;
   if (p.pen_action_variation.form != USV_PEN_OFF) pen_actvar = penalty_scalar(p.pen_action_variation, dasum);
   const float penalties = pen_lin + pen_ang + pen_angvar + pen_energy + pen_actvar;
   e.prev_w = wn;
@@ -466,13 +563,20 @@ __device__ __forceinline__ void control_step(EnvState& e, EnvConst& k, const Usv
   o.bpen = -expf(-o.bdist / 0.25f) * p.boundary_cost;
   o.pen_lin = pen_lin; o.pen_ang = pen_ang; o.pen_angvar = pen_angvar; o.pen_energy = pen_energy; o.pen_actvar = pen_actvar;
   o.absw = fabsf(wn); o.asum = asum;
+  // NaN probe on the un-clamped obs and the reward [ref vec_env_rlgames.py:187-192]: x*0 is 0 for finite x, NaN otherwise
+  float chk = o.rew * 0.0f;
+#pragma unroll
+  for (int j = 0; j < kObs; ++j) chk = fmaf(o.obs[j], 0.0f, chk);
+  o.finite = (chk == 0.0f);
   // _process_data: clamp obs to +-clipObservations  [ref vec_env_rlgames.py:82-95]
 #pragma unroll
   for (int j = 0; j < kObs; ++j) o.obs[j] = fminf(fmaxf(o.obs[j], -p.clip_obs), p.clip_obs);
 }
 
-__device__ __forceinline__ void accumulate_stats(float* __restrict__ st, int64_t stride, int64_t i, bool was_reset,
+__device__ __forceinline__ void accumulate_stats(float* __restrict__ st0, int64_t /*cap*/, int64_t i0, bool was_reset,
                                                  const StepOut& o, const UsvStepParams& p) {
+  float* __restrict__ st = st0 + tile_base(i0, USV_ST_COUNT);
+  constexpr int i = 0;
   // episode_sums[k][i] += term  [ref SNAP/USV_capture_xy.py:278-306 ; SNAP/USV_task_rewards.py:526-540 ;
   // SNAP/USV_Virtual.py:819-830]; sums are cleared by the reset that precedes this step.
   const float v[USV_ST_COUNT] = {o.dist_rew, o.align_rew, o.speed_rew, o.d, o.speed, o.bpen, o.bdist,
@@ -485,39 +589,46 @@ __device__ __forceinline__ void accumulate_stats(float* __restrict__ st, int64_t
   }
 }
 
-// stage the CTA's observation tile in smem and write it as contiguous float4 lines
+#undef stride
+
+// Each WARP stages its own 32 x 13 observation tile in smem (stride 13 is odd -> conflict-free) and writes it
+// out as one contiguous 1664 B run of float4 lines: only a __syncwarp, no CTA barrier on the store path.
 __device__ __forceinline__ void write_obs_tile(float* s_obs, const StepOut& o, bool active, float* __restrict__ obs,
                                                int64_t block_start, int64_t n) {
-  const int t = threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* sw = s_obs + warp * (32 * kObs);
   if (active) {
 #pragma unroll
-    for (int j = 0; j < kObs; ++j) s_obs[t * kObs + j] = o.obs[j];
+    for (int j = 0; j < kObs; ++j) sw[lane * kObs + j] = o.obs[j];
   }
-  __syncthreads();
-  const int64_t rows = min((int64_t)kBlock, n - block_start);
-  const int total = (int)rows * kObs;
-  float* g = obs + block_start * kObs;
-  if ((total & 3) == 0 && (((uintptr_t)g & 15) == 0)) {
-    const float4* s4 = reinterpret_cast<const float4*>(s_obs);
+  __syncwarp();
+  const int64_t warp_start = block_start + (int64_t)warp * 32;
+  if (warp_start >= n) return;
+  const int rows = (int)min((int64_t)32, n - warp_start);
+  const int total = rows * kObs;
+  float* g = obs + warp_start * kObs;
+  if (rows == 32 && (((uintptr_t)g & 15) == 0)) {
+    const float4* s4 = reinterpret_cast<const float4*>(sw);
     float4* g4 = reinterpret_cast<float4*>(g);
-    for (int q = t; q < (total >> 2); q += kBlock) g4[q] = s4[q];
+#pragma unroll
+    for (int q = lane; q < (32 * kObs) / 4; q += 32) g4[q] = s4[q];
   } else {
-    for (int q = t; q < total; q += kBlock) g[q] = s_obs[q];
+    for (int q = lane; q < total; q += 32) g[q] = sw[q];
   }
+  __syncwarp();
 }
 
 template <bool kDisturb, bool kStats>
-__global__ void __launch_bounds__(kBlock) step_fused_kernel(UsvEnvBuffers b, const float2* __restrict__ actions,
+__global__ void __launch_bounds__(kBlock, USV_MINB) step_fused_kernel(UsvEnvBuffers b, const float2* __restrict__ actions,
                                                             float* __restrict__ obs, float* __restrict__ rew,
                                                             int64_t n, const __grid_constant__ UsvStepParams p) {
   extern __shared__ __align__(16) float smem[];
   float* s_obs = smem;                       // [kBlock*13]
-  float* s_lutL = smem + kBlock * kObs;      // [n_lut]
-  float* s_lutR = s_lutL + p.n_lut;          // [n_lut]
-  for (int t = threadIdx.x; t < p.n_lut; t += kBlock) {
-    s_lutL[t] = b.lut_left[t];
-    s_lutR[t] = b.lut_right[t];
-  }
+  // The two 4 KB thruster LUTs are gathered at 2 random indices per env-step.  Staging them per CTA cost 16 LDG+STS
+  // per thread plus a CTA barrier in this one-tile-per-CTA kernel (r01 profile); the read-only path keeps the 8 KB
+  // resident in L1 instead.  (The multi-step rollout kernel, whose CTAs live for T steps, does stage them in smem.)
+  const float* __restrict__ s_lutL = b.lut_left;
+  const float* __restrict__ s_lutR = b.lut_right;
   const int64_t block_start = (int64_t)blockIdx.x * kBlock;
   const int64_t i = block_start + threadIdx.x;
   const bool active = i < n;
@@ -531,21 +642,17 @@ __global__ void __launch_bounds__(kBlock) step_fused_kernel(UsvEnvBuffers b, con
     do_reset = b.reset_buf[i] != 0;
     act = actions[i];
   }
-  __syncthreads();  // LUT staged
   StepOut o;
   if (active) {
-    control_step<kDisturb>(e, k, p, do_reset, act, (uint64_t)(p.env_id_offset + i), i, p.step_counter,
-                           p.first_call != 0, s_lutL, s_lutR, o);
+    control_step<kDisturb, true>(e, k, p, do_reset, act, (uint64_t)(p.env_id_offset + i), i, p.step_counter,
+                                 p.first_call != 0, s_lutL, s_lutR, o);
     store_state(b.state, b.state_stride, i, e);
     if (do_reset) store_consts<kDisturb>(b.consts, b.consts_stride, i, k);
     if (kStats) accumulate_stats(b.stats, b.stats_stride, i, do_reset, o, p);
     rew[i] = o.rew;
     b.reset_buf[i] = (int64_t)o.done;
     if (b.nonfinite_flag) {
-      bool bad = !isfinite(o.rew);
-#pragma unroll
-      for (int j = 0; j < kObs; ++j) bad |= !isfinite(o.obs[j]);
-      if (bad) atomicOr(b.nonfinite_flag, 1u);
+      if (!o.finite) atomicOr(b.nonfinite_flag, 1u);
       // torch.clamp propagates NaN actions and the reference fails fast on them [ref: vec_env_rlgames.py:143];
       // fminf/fmaxf would silently scrub them, so flag them here
       if (!isfinite(act.x) || !isfinite(act.y)) atomicOr(b.nonfinite_flag, 2u);
@@ -587,19 +694,18 @@ __global__ void __launch_bounds__(kBlock) rollout_fused_kernel(UsvEnvBuffers b, 
     StepOut o;
     if (active) {
       const float2 act = actions[(int64_t)t * n + i];
-      control_step<kDisturb>(e, k, p, do_reset, act, (uint64_t)(p.env_id_offset + i), i, p.step_counter + (uint64_t)t,
+      control_step<kDisturb, false>(e, k, p, do_reset, act, (uint64_t)(p.env_id_offset + i), i, p.step_counter + (uint64_t)t,
                              first_call, s_lutL, s_lutR, o);
       consts_dirty |= do_reset;
       if (kStats) accumulate_stats(b.stats, b.stats_stride, i, do_reset, o, p);
       if (rew) rew[(int64_t)t * n + i] = o.rew;
       if (done) done[(int64_t)t * n + i] = (int64_t)o.done;
-      bad |= !isfinite(o.rew) || !isfinite(act.x) || !isfinite(act.y);
+      bad |= !o.finite || !isfinite(act.x) || !isfinite(act.y);
       do_reset = o.done != 0;
     }
     first_call = false;
     if (obs) {
       write_obs_tile(s_obs, o, active, obs + (int64_t)t * n * kObs, block_start, n);
-      __syncthreads();  // s_obs is reused by the next step
     }
   }
   if (active) {
@@ -624,8 +730,9 @@ __global__ void __launch_bounds__(kBlock) planar_forces_kernel(UsvEnvBuffers b, 
     ox = p.grid_row_offset - (float)(int)(i / p.envs_per_row) * p.env_spacing;
     oy = (float)(int)(i % p.envs_per_row) * p.env_spacing - p.grid_col_offset;
   }
-  float du, dv, dr, Fx, Fy, Tz, ax, ay, rdot;
-  planar_wrench<kDisturb>(e, k, p, ox, oy, du, dv, dr, Fx, Fy, Tz, ax, ay, rdot);
+  float du, dv, dr, Fx, Fy, Tz, ax, ay, rdot, hsn, hcs;
+  fsincos(e.psi, &hsn, &hcs);
+  planar_wrench<kDisturb>(e, k, p, ox, oy, 1.0f / k.mass, 1.0f / (p.izz * k.kiz), hsn, hcs, du, dv, dr, Fx, Fy, Tz, ax, ay, rdot);
   float* o = out + i * 8;
   o[0] = du; o[1] = dv; o[2] = dr; o[3] = Fx; o[4] = Fy; o[5] = Tz; o[6] = ax; o[7] = ay;
 }
@@ -634,8 +741,8 @@ static int check_common(const UsvEnvBuffers* b, int64_t n, const UsvStepParams* 
   if (!b || !p) return USV_E_NULL;
   if (n < 0) return USV_E_SIZE;
   if (!b->state || !b->consts || !b->reset_buf || !b->lut_left || !b->lut_right) return USV_E_NULL;
-  if (b->state_stride < n || b->consts_stride < n) return USV_E_SIZE;
-  if (b->stats && b->stats_stride < n) return USV_E_SIZE;
+  if (b->state_stride < n || b->consts_stride < n || (b->state_stride & 31) || (b->consts_stride & 31)) return USV_E_SIZE;
+  if (b->stats && (b->stats_stride < n || (b->stats_stride & 31))) return USV_E_SIZE;
   if (p->n_lut < 2 || p->n_lut > 8192) return USV_E_PARAM;
   if (p->n_substeps < 0 || p->n_substeps > 1024) return USV_E_PARAM;
   if (!(p->izz > 0.0f)) return USV_E_PARAM;
@@ -649,6 +756,7 @@ static bool wants_disturb(const UsvStepParams* p) {
 }
 
 static size_t step_smem(const UsvStepParams* p) { return (size_t)(kBlock * kObs + 2 * p->n_lut) * sizeof(float); }
+static size_t step_smem_nolut() { return (size_t)(kBlock * kObs) * sizeof(float); }
 
 template <typename K>
 static void ensure_smem(K kernel, size_t smem) {
@@ -668,7 +776,7 @@ int usv_step_fused_f32(const UsvEnvBuffers* b, const float* actions, float* obs,
   if (n == 0) return USV_OK;
   if (!actions || !obs || !rew) return USV_E_NULL;
   if ((uintptr_t)actions & 7) return USV_E_ALIGN;
-  const size_t smem = step_smem(p);
+  const size_t smem = step_smem_nolut();
   const int grid = grid_for(n, kBlock);
   const bool dis = wants_disturb(p), st = b->stats != nullptr;
   cudaStream_t s = (cudaStream_t)stream;

@@ -33,9 +33,11 @@ class FusedUsvEnv:
         self.env_id_offset = int(env_id_offset)
         self.stride = stride = _round_up(max(n, 1), 32)       # every SoA row starts on a 128 B line
         f32 = dict(dtype=torch.float32, device=self.device)
-        self.state = torch.zeros((E["USV_S_COUNT"], stride), **f32)
-        self.consts = torch.zeros((E["USV_C_COUNT"], stride), **f32)
-        self.stats = torch.zeros((E["USV_ST_COUNT"], stride), **f32) if collect_stats else None
+        # AoSoA: [tile][field][32 lanes] -- a warp owns one tile; every field of an env is an immediate offset
+        nt = stride // 32
+        self.state = torch.zeros((nt, E["USV_S_COUNT"], 32), **f32)
+        self.consts = torch.zeros((nt, E["USV_C_COUNT"], 32), **f32)
+        self.stats = torch.zeros((nt, E["USV_ST_COUNT"], 32), **f32) if collect_stats else None
         self.reset_buf = torch.ones(n, dtype=torch.long, device=self.device)     # [ref: SNAP/USV_Virtual.py:342-344]
         self.obs = torch.zeros((n, OBS_DIM), **f32)
         self.rew = torch.zeros(n, **f32)
@@ -44,13 +46,13 @@ class FusedUsvEnv:
         self.first_call = True
         # per-episode constants start at their nominal values (reset_idx rewrites them)
         c = self.consts
-        c[E["USV_C_MASS"]] = cfg.mass_base
+        c[:, E["USV_C_MASS"]] = cfg.mass_base
         for j, (lf, qf) in enumerate(zip(("USV_C_LIN_U", "USV_C_LIN_V", "USV_C_LIN_R"),
                                          ("USV_C_QUAD_U", "USV_C_QUAD_V", "USV_C_QUAD_R"))):
-            c[E[lf]] = cfg.lin_base[j]
-            c[E[qf]] = cfg.quad_base[j]
+            c[:, E[lf]] = cfg.lin_base[j]
+            c[:, E[qf]] = cfg.quad_base[j]
         for name in ("USV_C_KDRAG", "USV_C_THR_ML", "USV_C_THR_MR", "USV_C_KIZ"):
-            c[E[name]] = 1.0
+            c[:, E[name]] = 1.0
         # thruster LUTs  [ref: OIGE/envs/USV/ThrusterDynamics.py:152-177]
         self.lut_left = self._build_lut(cfg.lut_points_left)
         self.lut_right = self._build_lut(cfg.lut_points_right)
@@ -78,13 +80,36 @@ class FusedUsvEnv:
         b.nonfinite_flag = self.nonfinite.data_ptr()
         return b
 
+    def _src(self, name: str) -> torch.Tensor:
+        return self.state if name.startswith("USV_S_") else (self.consts if name.startswith("USV_C_") else self.stats)
+
+    def field_view(self, name: str) -> torch.Tensor:
+        """(tiles, 32) strided VIEW of one field (in-place ops write through to the kernel's buffers)."""
+        return self._src(name)[:, E[name], :]
+
     def field(self, name: str) -> torch.Tensor:
-        """(N,) view of one SoA field, e.g. field('USV_S_X') or field('USV_C_MASS')."""
-        src = self.state if name.startswith("USV_S_") else (self.consts if name.startswith("USV_C_") else self.stats)
-        return src[E[name], : self.num_envs]
+        """(N,) COPY of one field in env order, e.g. field('USV_S_X') or field('USV_C_MASS')."""
+        return self.field_view(name).reshape(-1)[: self.num_envs]
+
+    def set_field(self, name: str, values, env_ids: Optional[torch.Tensor] = None) -> None:
+        """Writes (N,) values (or values for `env_ids`) into a field; int tensors are stored as int32 bit patterns."""
+        v = torch.as_tensor(values, device=self.device)
+        v = v.to(torch.int32).view(torch.float32) if not v.is_floating_point() else v.to(torch.float32)
+        view = self.field_view(name)
+        if env_ids is None:
+            flat = torch.zeros(self.stride, dtype=torch.float32, device=self.device)
+            flat[: self.num_envs] = v
+            view.copy_(flat.view(-1, 32))
+        else:
+            ids = env_ids.to(self.device, torch.long)
+            view[ids >> 5, ids & 31] = v
 
     def int_field(self, name: str) -> torch.Tensor:
         return self.field(name).view(torch.int32)
+
+    def stats_matrix(self) -> torch.Tensor:
+        """(USV_ST_COUNT, N) copy of the episode-sum accumulators."""
+        return self.stats.permute(1, 0, 2).reshape(E["USV_ST_COUNT"], -1)[:, : self.num_envs]
 
     @property
     def progress_buf(self) -> torch.Tensor:
@@ -104,11 +129,17 @@ class FusedUsvEnv:
                                                    ctypes.c_int32(2), _lib.ptr(base), _lib.ptr(lo), _lib.ptr(hi), ctypes.c_int32(0),
                                                    ctypes.c_uint64(self.cfg.seed), ctypes.c_uint64(self.step_counter),
                                                    ctypes.c_uint32(0), _lib.stream()), "randomize_rows")
-        self.field("USV_C_TX")[ids] = tmp[ids, 0]
-        self.field("USV_C_TY")[ids] = tmp[ids, 1]
+        self.set_field("USV_C_TX", tmp[ids, 0], ids)
+        self.set_field("USV_C_TY", tmp[ids, 1], ids)
 
     def params(self):
-        return self.cfg.to_params(self.step_counter, self.env_id_offset, self.first_call)
+        # the struct is built once (130 fields); per call only the counters change
+        p = getattr(self, "_params", None)
+        if p is None:
+            p = self._params = self.cfg.to_params(0, self.env_id_offset, False)
+        p.step_counter = self.step_counter
+        p.first_call = int(self.first_call)
+        return p
 
     # ---- the hot path ------------------------------------------------------------------
     def step(self, actions: torch.Tensor, obs: Optional[torch.Tensor] = None, rew: Optional[torch.Tensor] = None):

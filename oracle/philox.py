@@ -52,3 +52,18 @@ def uniform4(seed: int, env_ids, step: int, stream: int) -> np.ndarray:
     r = philox4x32_10(lo, np.uint64(step & 0xFFFFFFFF), np.uint64((step >> 32) & 0xFFFFFFFF), c3,
                       seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
     return np.stack([u01(x) for x in r], axis=-1)
+
+
+def uniform8x16(seed: int, env_ids, step: int, stream: int) -> np.ndarray:
+    """(len(env_ids), 8) float32: the 16-bit halves (lo, hi) of the four Philox words, each * 2**-16."""
+    env_ids = np.asarray(env_ids, dtype=np.uint64)
+    lo = env_ids & MASK
+    hi = (env_ids >> np.uint64(32)) & MASK
+    c3 = (np.uint64(stream) ^ (hi << np.uint64(8))) & MASK
+    r = philox4x32_10(lo, np.uint64(step & 0xFFFFFFFF), np.uint64((step >> 32) & 0xFFFFFFFF), c3,
+                      seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    cols = []
+    for w in r:
+        cols.append((w & np.uint32(0xFFFF)).astype(np.float32) * np.float32(1.0 / 65536.0))
+        cols.append((w >> np.uint32(16)).astype(np.float32) * np.float32(1.0 / 65536.0))
+    return np.stack(cols, axis=-1).astype(np.float32)

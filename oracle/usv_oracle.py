@@ -488,21 +488,21 @@ class ClassicEnvOracle:
         c = self.cfg
         n = self.n
         step = self.step_counter
-        na = torch.from_numpy(philox.uniform4(c.seed, self.env_ids, step, philox.RS_STEP_A))
-        nb = torch.from_numpy(philox.uniform4(c.seed, self.env_ids, step, philox.RS_STEP_B))
+        # one Philox call per env-step: 8 x 16-bit uniforms (act0, act1, vel_x, vel_y, vel_r, heading, pos_x, pos_y)
+        nz = torch.from_numpy(philox.uniform8x16(c.seed, self.env_ids, step, philox.RS_STEP_A))
         actions = torch.clamp(actions, -c.clip_actions, c.clip_actions).clone()
         # pre_physics_step  [SNAP/USV_Virtual.py:571-617]
         reset_ids = self.reset_buf.nonzero(as_tuple=False).squeeze(-1)
         self.reset_idx(reset_ids, step)
         if not c.action_affine:
             if c.action_noise:
-                actions = actions + _u(na[:, 0:2], c.action_noise_min, c.action_noise_max)
+                actions = actions + _u(nz[:, 0:2], c.action_noise_min, c.action_noise_max)
             pen_actions = actions
             cmd = torch.clamp(actions, -1.0, 1.0)
         else:                                                               # [OIGE/tasks/USV_Virtual.py:1064-1097]
             t = actions + c.action_bias
             if c.action_noise:
-                t = t + _u(na[:, 0:2], c.action_noise_min, c.action_noise_max)
+                t = t + _u(nz[:, 0:2], c.action_noise_min, c.action_noise_max)
             t = torch.clamp(t, -1.0, 1.0)
             cmd = torch.clamp(0.5 * (t + 1.0), 0.0, 1.0)
             pen_actions = cmd.clone() if c.penalties_use_u else actions
@@ -517,12 +517,12 @@ class ClassicEnvOracle:
         # update_state  [SNAP/USV_Virtual.py:476-530]
         pos = self.pos.clone(); vel = self.vel.clone(); w = self.r.clone(); yaw = self.psi.clone()
         if c.noise_pos:
-            pos = pos + _u(nb[:, 2:4], c.pos_noise_min, c.pos_noise_max)
+            pos = pos + _u(nz[:, 6:8], c.pos_noise_min, c.pos_noise_max)
         if c.noise_vel:
-            vel = vel + _u(na[:, 2:4], c.vel_noise_min, c.vel_noise_max)
-            w = w + _u(nb[:, 0], c.vel_noise_min, c.vel_noise_max)
+            vel = vel + _u(nz[:, 2:4], c.vel_noise_min, c.vel_noise_max)
+            w = w + _u(nz[:, 4], c.vel_noise_min, c.vel_noise_max)
         if c.noise_heading:
-            yaw = yaw + _u(nb[:, 1], c.heading_noise_min, c.heading_noise_max)
+            yaw = yaw + _u(nz[:, 5], c.heading_noise_min, c.heading_noise_max)
         heading = torch.stack([torch.cos(yaw), torch.sin(yaw)], 1)
         state = {"position": pos, "orientation": heading, "linear_velocity": vel, "angular_velocity": w}
         obs, aux = capture_xy_observation(state, self.target)

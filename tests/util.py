@@ -44,9 +44,9 @@ def push_oracle_state(orc, env):
     """Overwrites the engine's SoA state with the oracle's AoS state (so a step starts from identical inputs)."""
     dev = env.device
     for name, get in STATE_MAP + CONST_MAP:
-        env.field(name).copy_(get(orc).to(dev))
-    env.int_field("USV_S_GOAL_CNT").copy_(orc.goal_reached.to(dev))
-    env.int_field("USV_S_PROGRESS").copy_(orc.progress_buf.to(torch.int32).to(dev))
+        env.set_field(name, get(orc).to(dev))
+    env.set_field("USV_S_GOAL_CNT", orc.goal_reached.to(dev))
+    env.set_field("USV_S_PROGRESS", orc.progress_buf.to(torch.int32).to(dev))
     env.reset_buf.copy_(orc.reset_buf.to(dev))
     env.step_counter = orc.step_counter
     env.first_call = orc.first_call
