@@ -275,6 +275,69 @@ int ppo_gae_f32(const float* rewards /*[T,n]*/, const float* values /*[T,n]*/,
                 float* advantages /*[T,n]*/, float* returns /*[T,n] or NULL*/,
                 int32_t T, int64_t n, void* stream);
 
+/* ------------------------------------------------------------------------- */
+/* P4/P5  USV_PPOcontinuous_MLP: shared-trunk actor-critic                     */
+/*   obs(D) -> RunningMeanStd norm (clamp +-5) -> Linear(D,128)+tanh -> Linear(128,128)+tanh -> {mu: Linear(128,2),  */
+/*   value: Linear(128,1)}, state-independent logstd parameter (2,)                                                */
+/*     [ref: RLG/algos_torch/models.py:366-401 ; RLG/algos_torch/network_builder.py:1480-1678 ;                    */
+/*           RLG/algos_torch/running_mean_std.py:81-117 ; OIGE/cfg/train/USV/USV_PPOcontinuous_MLP.yaml]           */
+/* All parameters live in ONE flat fp32 buffer in rl_games' model.parameters() order (Adam state and the gradient  */
+/* all-reduce work on the same span):                                                                              */
+/*   sigma[2] | actor_mlp.0.weight[128,D] | .bias[128] | actor_mlp.2.weight[128,128] | .bias[128] |                 */
+/*   value.weight[1,128] | value.bias[1] | mu.weight[2,128] | mu.bias[2]            (18 693 floats for D = 13)      */
+#define PPO_HIDDEN 128
+#define PPO_ACTIONS 2
+#define PPO_MAX_OBS 64
+int64_t ppo_param_count(int32_t obs_dim);
+
+/* rollout inference (is_train=False): a = mu + sigma*N(0,1) (Philox, Box-Muller), neglogp, de-normalised value   */
+/* any output pointer may be NULL; with actions==NULL no sampling happens (get_values)                            */
+int ppo_policy_forward_f32(const float* params, const float* obs /*[M,D]*/, int32_t obs_dim,
+                           const float* obs_mean /*[D] fp32 copy of the fp64 running mean*/, const float* obs_var /*[D]*/,
+                           const float* value_mean /*[1]*/, const float* value_var /*[1]*/,
+                           uint64_t seed, uint64_t counter, int64_t row_offset,
+                           float* actions /*[M,2]*/, float* neglogp /*[M]*/, float* values /*[M] de-normalised*/,
+                           float* mus /*[M,2]*/, float* sigmas /*[M,2]*/, int64_t M, void* stream);
+
+typedef struct {
+  float e_clip;            /* 0.2  */
+  float critic_coef;       /* 0.5 (the loss uses 0.5*c_loss*critic_coef) */
+  float entropy_coef;      /* 0.0  */
+  float bounds_loss_coef;  /* 1e-4 */
+  float bound_soft;        /* 1.1  */
+  int32_t clip_value;      /* 1    */
+} PpoLossParams;
+
+/* layout of the small statistics vector the train kernels fill (means over the minibatch) */
+enum { PPO_STAT_A_LOSS = 0, PPO_STAT_C_LOSS, PPO_STAT_ENTROPY, PPO_STAT_B_LOSS, PPO_STAT_KL, PPO_STAT_LOSS,
+       PPO_STAT_GRAD_NORM, PPO_STAT_LR, PPO_STAT_COUNT };
+
+/* one PPO minibatch: forward (train mode), clipped surrogate / clipped value / bound losses, backward.           */
+/*   [ref: RLG/algos_torch/a2c_continuous.py:78-196 ; RLG/common/common_losses.py:10-48 ; torch_ext.py:27-36]     */
+/* grads[P+PPO_STAT_COUNT]: d(loss)/d(params) followed by the statistics (so one all-reduce carries both);        */
+/* new_mu/new_sigma are what PPODataset.update_mu_sigma stores back.  scratch: ppo_train_scratch_floats(D) floats */
+int64_t ppo_train_scratch_floats(int32_t obs_dim);
+int ppo_minibatch_grad_f32(const float* params, const float* obs /*[M,D]*/, int32_t obs_dim,
+                           const float* obs_mean, const float* obs_var,
+                           const float* actions /*[M,2]*/, const float* old_neglogp /*[M]*/, const float* advantages /*[M]*/,
+                           const float* old_values /*[M] normalised*/, const float* returns /*[M] normalised*/,
+                           float* old_mu /*[M,2] in: KL reference, out: new mu*/, float* old_sigma /*[M,2] in/out*/,
+                           const PpoLossParams* lp, float* grads /*[P+PPO_STAT_COUNT]*/, float* scratch,
+                           int64_t M, void* stream);
+
+/* gradient-norm clip + Adam + adaptive-KL learning rate, all on device (no kl.item() host sync)                  */
+/*   [ref: RLG/common/a2c_common.py:308-330 ; torch.optim.Adam ; RLG/common/schedulers.py:19-32]                  */
+typedef struct {
+  float beta1, beta2, eps;        /* 0.9, 0.999, 1e-8 */
+  float grad_norm;                /* 1.0; <=0 disables truncation */
+  float inv_world;                /* 1/world_size applied to the (summed) gradient and statistics */
+  int32_t adaptive_lr;            /* 1: lr/=1.5 if kl > 2*thr ; lr*=1.5 if kl < 0.5*thr ; clamp [min_lr,max_lr] */
+  float kl_threshold, min_lr, max_lr;
+} PpoAdamParams;
+int ppo_adam_step_f32(float* params, float* grads /*[P+PPO_STAT_COUNT], scaled in place*/, float* exp_avg, float* exp_avg_sq,
+                      float* lr /*device scalar, updated*/, int32_t* step /*device scalar, incremented*/,
+                      int64_t P, const PpoAdamParams* ap, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

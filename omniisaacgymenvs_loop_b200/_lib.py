@@ -23,7 +23,7 @@ _CTYPES = {
     "float": ctypes.c_float, "int32_t": ctypes.c_int32, "uint32_t": ctypes.c_uint32,
     "int64_t": ctypes.c_int64, "uint64_t": ctypes.c_uint64,
     "float*": ctypes.c_void_p, "const float*": ctypes.c_void_p, "int64_t*": ctypes.c_void_p,
-    "uint32_t*": ctypes.c_void_p,
+    "uint32_t*": ctypes.c_void_p, "int32_t*": ctypes.c_void_p,
 }
 
 
@@ -78,7 +78,7 @@ def _parse_enums(src: str) -> Dict[str, int]:
             else:
                 k, cur = item, cur + 1
             vals[k] = cur
-    for m in re.finditer(r"#define\s+(USV_\w+)\s+(\d+)", src):
+    for m in re.finditer(r"#define\s+((?:USV|PPO)_\w+)\s+(\d+)", src):
         vals[m.group(1)] = int(m.group(2))
     return vals
 
@@ -92,6 +92,8 @@ UsvHydrodynamicsParams = STRUCTS["UsvHydrodynamicsParams"]
 UsvPenaltyTerm = STRUCTS["UsvPenaltyTerm"]
 UsvStepParams = STRUCTS["UsvStepParams"]
 UsvEnvBuffers = STRUCTS["UsvEnvBuffers"]
+PpoLossParams = STRUCTS["PpoLossParams"]
+PpoAdamParams = STRUCTS["PpoAdamParams"]
 
 _lib = None
 
@@ -114,6 +116,8 @@ def lib() -> ctypes.CDLL:
     L.usv_b200_launch_count.restype = ctypes.c_int64
     L.usv_b200_sizeof.restype = ctypes.c_int64
     L.usv_b200_sizeof.argtypes = [ctypes.c_char_p]
+    L.ppo_param_count.restype = ctypes.c_int64
+    L.ppo_train_scratch_floats.restype = ctypes.c_int64
     for name, st in STRUCTS.items():
         want = L.usv_b200_sizeof(name.encode())
         if want != ctypes.sizeof(st):

@@ -263,6 +263,88 @@ def gae():
     print("gae.npz")
 
 
+def ppo():
+    """rl_games model / losses / optimizer on a seeded minibatch  [RLG/algos_torch/*, RLG/common/common_losses.py]"""
+    rl = ref_shim.load_rl_games()
+    torch.manual_seed(7)
+    D, M = 13, 200
+    with ref_shim.quiet():
+        net = rl.model_builder.ModelBuilder().load({
+            "model": {"name": "continuous_a2c_logstd"},
+            "network": {"name": "actor_critic_mlp_dict", "separate": False,
+                        "space": {"continuous": {"mu_activation": "None", "sigma_activation": "None", "mu_init": {"name": "default"},
+                                                 "sigma_init": {"name": "const_initializer", "val": 0}, "fixed_sigma": True}},
+                        "mlp": {"units": [128, 128], "activation": "tanh", "d2rl": False, "initializer": {"name": "default"},
+                                "regularizer": {"name": "None"}}}})
+        model = net.build({"actions_num": 2, "input_shape": {"state": (D,)}, "num_seqs": 1, "value_size": 1,
+                           "normalize_value": True, "normalize_input": True, "normalize_input_keys": ["state"]})
+    g = gen()
+    with torch.no_grad():
+        # biases are zero-initialised in the reference; perturb everything so every gradient path is exercised
+        for prm in model.parameters():
+            prm.add_(0.05 * torch.randn(prm.shape, generator=g))
+        model.a2c_network.sigma.copy_(torch.tensor([-0.3, 0.2]))
+    rms = model.running_mean_std.running_mean_std["state"]
+    out = {"param_names": np.array([n for n, _ in model.named_parameters()])}
+    obs0 = torch.randn((64, D), generator=g) * torch.linspace(0.5, 6.0, D) + torch.linspace(-2, 2, D)
+    model.train()
+    rms(obs0)                                  # one training-mode update of the obs normaliser
+    vms = model.value_mean_std
+    vms(torch.randn((64, 1), generator=g) * 2.0 + 0.5)
+    model.eval()
+    out.update(rms_update_obs=obs0, obs_mean=rms.running_mean.clone(), obs_var=rms.running_var.clone(), obs_count=rms.count.clone(),
+               val_mean=vms.running_mean.clone(), val_var=vms.running_var.clone(), val_count=vms.count.clone())
+    params0 = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    out["params0"] = params0.clone()
+    obs = torch.randn((M, D), generator=g) * torch.linspace(0.5, 6.0, D) * 1.5 + torch.linspace(-2, 2, D)
+    obs[0] = 100.0                              # exercises the +-5 clamp of the normaliser
+    with torch.no_grad():
+        r = model({"is_train": False, "prev_actions": None, "obs": {"state": obs.clone()}, "rnn_states": None})
+    out.update(obs=obs, inf_mus=r["mus"], inf_sigmas=r["sigmas"], inf_values=r["values"], inf_actions=r["actions"],
+               inf_neglogpacs=r["neglogpacs"])
+    # a minibatch as prepare_dataset would hand it over
+    actions = r["actions"] + 0.3 * torch.randn((M, 2), generator=g)
+    actions[1] = torch.tensor([3.0, -3.0])
+    old_nlp = r["neglogpacs"] + 0.2 * torch.randn(M, generator=g)
+    adv = torch.randn(M, generator=g)
+    old_v = torch.randn((M, 1), generator=g) * 0.5
+    ret = old_v + torch.randn((M, 1), generator=g) * 0.5
+    old_mu = r["mus"] + 0.05 * torch.randn((M, 2), generator=g)
+    old_sigma = r["sigmas"] * (1 + 0.05 * torch.randn((M, 2), generator=g))
+    out.update(mb_actions=actions, mb_old_neglogp=old_nlp, mb_adv=adv, mb_old_values=old_v, mb_returns=ret, mb_old_mu=old_mu,
+               mb_old_sigma=old_sigma)
+    opt = torch.optim.Adam(model.parameters(), 3e-4, eps=1e-08, weight_decay=0.0)
+    ns = types.SimpleNamespace(bounds_loss_coef=1e-4)
+    lr = 3e-4
+    sched = rl.schedulers.AdaptiveScheduler(0.016)
+    for it in range(3):
+        res = model({"is_train": True, "prev_actions": actions, "obs": {"state": obs.clone()}})
+        a_loss = rl.common_losses.actor_loss(old_nlp, res["prev_neglogp"], adv, True, 0.2)
+        c_loss = rl.common_losses.critic_loss(model, old_v, res["values"], 0.2, ret, True)
+        b_loss = rl.a2c_continuous.A2CAgent.bound_loss(ns, res["mus"])
+        a_m, c_m, e_m, b_m = a_loss.mean(), c_loss.mean(), res["entropy"].mean(), b_loss.mean()
+        loss = a_m + 0.5 * c_m * 0.5 - e_m * 0.0 + b_m * 1e-4
+        for prm in model.parameters():
+            prm.grad = None
+        loss.backward()
+        grads = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+        kl = rl.torch_ext.policy_kl(res["mus"].detach(), res["sigmas"].detach(), old_mu, old_sigma, True)
+        norm = torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        for gp in opt.param_groups:
+            gp["lr"] = lr
+        opt.step()
+        new_lr, _ = sched.update(lr, 0.0, 0, 0, kl.item())
+        out.update({f"it{it}_loss": loss.detach(), f"it{it}_a_loss": a_m.detach(), f"it{it}_c_loss": c_m.detach(),
+                    f"it{it}_entropy": e_m.detach(), f"it{it}_b_loss": b_m.detach(), f"it{it}_kl": kl, f"it{it}_grads": grads.clone(),
+                    f"it{it}_grad_norm": norm, f"it{it}_train_values": res["values"].detach(), f"it{it}_train_neglogp": res["prev_neglogp"].detach(),
+                    f"it{it}_mus": res["mus"].detach(), f"it{it}_lr": torch.tensor(lr), f"it{it}_new_lr": torch.tensor(new_lr),
+                    f"it{it}_params_after": torch.cat([p.detach().reshape(-1) for p in model.parameters()])})
+        old_mu, old_sigma = res["mus"].detach(), res["sigmas"].detach()     # dataset.update_mu_sigma
+        lr = new_lr
+    np.savez(os.path.join(OUT, "ppo.npz"), **t2n(out))
+    print("ppo.npz")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)
@@ -270,6 +352,7 @@ def main():
     disturbances()
     classic_task()
     gae()
+    ppo()
 
 
 if __name__ == "__main__":

@@ -1,0 +1,118 @@
+"""GPU parity of the PPO kernels (through the C ABI) against goldens produced by the reference's rl_games classes
+and against the CPU oracle.  Bar: 1e-5 relative in fp32 (atol scaled to the quantity), written at each assert."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from omniisaacgymenvs_loop_b200.rl.policy import PolicyMLP  # noqa: E402
+from oracle import ppo_oracle as P  # noqa: E402
+from tests.util import assert_close  # noqa: E402
+
+DEV = "cuda:0"
+D = 13
+cu = lambda a: torch.as_tensor(a).to(DEV).contiguous()
+
+
+def _policy(G, **kw):
+    pol = PolicyMLP(D, DEV, lr=3e-4, **kw)
+    pol.params.copy_(cu(G["params0"]))
+    pol.obs_rms.load(G["obs_mean"], G["obs_var"], G["obs_count"])
+    pol.val_rms.load(G["val_mean"], G["val_var"], G["val_count"])
+    return pol
+
+
+def test_param_contract(golden):
+    G = golden("ppo")
+    pol = PolicyMLP(D, DEV)
+    assert pol.P == 18693 and PolicyMLP(33, DEV).P == 21253
+    sd = pol.state_dict()
+    assert [k for k in sd if k.startswith("a2c_network")] == [str(n) for n in G["param_names"]]
+    assert sd["running_mean_std.running_mean_std.state.running_mean"].dtype == torch.float64
+    v = pol.views()
+    assert float(v["a2c_network.actor_mlp.0.bias"].abs().max()) == 0.0 and float(v["a2c_network.sigma"].abs().max()) == 0.0
+    assert float(v["a2c_network.actor_mlp.2.weight"].abs().max()) <= 1 / np.sqrt(128) + 1e-7
+
+
+def test_running_mean_std_update_vs_reference(golden):
+    G = golden("ppo")
+    pol = PolicyMLP(D, DEV)
+    pol.obs_rms.update(cu(G["rms_update_obs"]))
+    assert_close(pol.obs_rms.mean, G["obs_mean"], 1e-6, 1e-7); assert_close(pol.obs_rms.var, G["obs_var"], 1e-6, 1e-7)
+    assert float(pol.obs_rms.count) == float(G["obs_count"])
+
+
+def test_policy_inference_vs_reference(golden):
+    G = golden("ppo")
+    pol = _policy(G)
+    M = G["obs"].shape[0]
+    out = pol.act(cu(G["obs"]))
+    assert_close(out["mus"], G["inf_mus"], 1e-5, 2e-6, "mus")
+    assert_close(out["sigmas"], G["inf_sigmas"], 1e-6, 1e-7, "sigmas")
+    assert_close(out["values"], G["inf_values"], 1e-5, 1e-5, "values (de-normalised)")
+    # sampled actions follow a = mu + sigma * eps with the Philox/Box-Muller eps of the mirror; neglogp matches the
+    # reference formula evaluated on the kernel's own actions
+    eps = P.normal_eps(pol.seed, np.arange(M), 0)
+    assert_close(out["actions"], T(G["inf_mus"]) + T(G["inf_sigmas"]) * eps, 1e-5, 1e-5, "actions")
+    sg = out["sigmas"].cpu()
+    nlp = P.neglogp(out["actions"].cpu(), out["mus"].cpu(), sg, torch.log(sg))
+    assert_close(out["neglogpacs"], nlp, 1e-5, 1e-5, "neglogp")
+    assert_close(pol.values(cu(G["obs"])), G["inf_values"], 1e-5, 1e-5, "get_values")
+    # a second call draws fresh noise
+    out2 = pol.act(cu(G["obs"]))
+    assert not torch.equal(out2["actions"], out["actions"]) and torch.equal(out2["mus"], out["mus"])
+
+
+T = torch.from_numpy
+
+
+def test_minibatch_grad_adam_lr_vs_reference(golden):
+    """3 consecutive PPO minibatch steps: loss terms, KL, full gradient, grad-norm, Adam update, adaptive lr."""
+    G = golden("ppo")
+    pol = _policy(G)
+    obs, act = cu(G["obs"]), cu(G["mb_actions"])
+    old_nlp, adv = cu(G["mb_old_neglogp"]), cu(G["mb_adv"])
+    old_v, ret = cu(G["mb_old_values"]).reshape(-1).contiguous(), cu(G["mb_returns"]).reshape(-1).contiguous()
+    mu, sigma = cu(G["mb_old_mu"]).clone(), cu(G["mb_old_sigma"]).clone()
+    for it in range(3):
+        g = pol.minibatch_grad(obs, act, old_nlp, adv, old_v, ret, mu, sigma)
+        st = pol.stats()
+        for k in ("a_loss", "c_loss", "entropy", "b_loss", "kl", "loss"):
+            assert_close(torch.tensor(st[k]), G[f"it{it}_{k}"], 2e-5, 2e-6, f"it{it} {k}")
+        # gradient entries span 1e-7..1e-1: 1e-5 relative + 2e-7 absolute (fp32 sums over 200 samples)
+        assert_close(g[: pol.P], G[f"it{it}_grads"], 1e-4, 2e-7, f"it{it} grads")
+        assert_close(mu, G[f"it{it}_mus"], 1e-5, 2e-6, "update_mu_sigma")
+        pol.optimizer_step()
+        st = pol.stats()
+        assert_close(torch.tensor(st["grad_norm"]), G[f"it{it}_grad_norm"], 1e-5, 1e-7, "grad norm")
+        assert abs(st["lr"] - float(G[f"it{it}_lr"])) < 1e-9
+        assert_close(pol.params, G[f"it{it}_params_after"], 1e-5, 2e-7, f"it{it} params after Adam")
+        assert abs(float(pol.lr) - float(G[f"it{it}_new_lr"])) < 1e-9
+    assert int(pol.step) == 3
+
+
+def test_minibatch_grad_vs_oracle_autograd_large():
+    """8192-sample minibatch (the reference's minibatch_size) against torch autograd on the oracle."""
+    torch.manual_seed(3)
+    M = 8192 + 50
+    pol = PolicyMLP(D, DEV, seed=5)
+    pol.params.add_(0.02 * torch.randn(pol.P, device=DEV))
+    obs = torch.randn((M, D)) * 2
+    pol.obs_rms.update(cu(obs[:500]))
+    orc_rms = P.RunningMeanStd((D,)); orc_rms.mean, orc_rms.var = pol.obs_rms.mean.cpu(), pol.obs_rms.var.cpu()
+    params = pol.params.cpu().clone().requires_grad_(True)
+    inf = P.policy_inference(params.detach(), obs, D, orc_rms, P.RunningMeanStd((1,)), eps=torch.randn((M, 2)))
+    batch = dict(obs=obs, actions=inf["actions"] + 0.2 * torch.randn((M, 2)), old_logp_actions=inf["neglogpacs"] + 0.1 * torch.randn(M),
+                 advantages=torch.randn(M), old_values=torch.randn((M, 1)) * 0.3, returns=torch.randn((M, 1)) * 0.5,
+                 mu=inf["mus"] + 0.02 * torch.randn((M, 2)), sigma=inf["sigmas"].clone())
+    loss, st = P.minibatch_loss(params, batch, D, orc_rms)
+    loss.backward()
+    mu, sg = cu(batch["mu"]).clone(), cu(batch["sigma"]).clone()
+    g = pol.minibatch_grad(cu(obs), cu(batch["actions"]), cu(batch["old_logp_actions"]), cu(batch["advantages"]),
+                           cu(batch["old_values"]).reshape(-1).contiguous(), cu(batch["returns"]).reshape(-1).contiguous(), mu, sg)
+    s = pol.stats()
+    assert_close(torch.tensor(s["loss"]), loss.detach(), 2e-5, 2e-6, "loss")
+    assert_close(torch.tensor(s["kl"]), st["kl"], 1e-4, 1e-6, "kl")
+    assert_close(g[: pol.P], params.grad, 2e-4, 3e-7, "grads (fp32 sums over 8k samples)")
+    assert_close(mu, st["mu"], 1e-5, 2e-6, "new mu")

@@ -1,0 +1,83 @@
+"""CPU suite: the PPO oracle restatement vs goldens produced by the reference's own rl_games classes."""
+import numpy as np
+import torch
+
+from oracle import ppo_oracle as P
+
+T = torch.from_numpy
+D = 13
+
+
+def _rms(G):
+    o = P.RunningMeanStd((D,)); o.mean, o.var, o.count = T(G["obs_mean"]), T(G["obs_var"]), T(G["obs_count"])
+    v = P.RunningMeanStd((1,)); v.mean, v.var, v.count = T(G["val_mean"]), T(G["val_var"]), T(G["val_count"])
+    return o, v
+
+
+def test_param_layout_matches_reference_names(golden):
+    G = golden("ppo")
+    names = [str(n) for n in G["param_names"]]
+    assert names == ["a2c_network.sigma", "a2c_network.actor_mlp.0.weight", "a2c_network.actor_mlp.0.bias",
+                     "a2c_network.actor_mlp.2.weight", "a2c_network.actor_mlp.2.bias", "a2c_network.value.weight",
+                     "a2c_network.value.bias", "a2c_network.mu.weight", "a2c_network.mu.bias"]
+    assert P.param_layout(D)["P"] == 18693 == G["params0"].shape[0] and P.param_layout(33)["P"] == 21253
+
+
+def test_running_mean_std_update(golden):
+    G = golden("ppo")
+    r = P.RunningMeanStd((D,))
+    r.update(T(G["rms_update_obs"]))
+    assert torch.equal(r.mean, T(G["obs_mean"])) and torch.equal(r.var, T(G["obs_var"])) and float(r.count) == float(G["obs_count"])
+    assert r.mean.dtype == torch.float64
+
+
+def test_inference_vs_reference(golden):
+    G = golden("ppo")
+    o, v = _rms(G)
+    params = T(G["params0"])
+    out = P.policy_inference(params, T(G["obs"]), D, o, v)
+    assert torch.allclose(out["mus"], T(G["inf_mus"]), rtol=1e-6, atol=1e-6)
+    assert torch.equal(out["sigmas"], T(G["inf_sigmas"]))
+    assert torch.allclose(out["values"], T(G["inf_values"]), rtol=1e-6, atol=1e-6)
+    mu, sg = T(G["inf_mus"]), T(G["inf_sigmas"])
+    nlp = P.neglogp(T(G["inf_actions"]), mu, sg, torch.log(sg))
+    assert torch.allclose(nlp, T(G["inf_neglogpacs"]), rtol=1e-5, atol=1e-5)
+
+
+def test_minibatch_loss_grads_adam_vs_reference(golden):
+    G = golden("ppo")
+    o, _ = _rms(G)
+    params = T(G["params0"]).clone()
+    m, v = torch.zeros_like(params), torch.zeros_like(params)
+    batch = dict(obs=T(G["obs"]), actions=T(G["mb_actions"]), old_logp_actions=T(G["mb_old_neglogp"]), advantages=T(G["mb_adv"]),
+                 old_values=T(G["mb_old_values"]), returns=T(G["mb_returns"]), mu=T(G["mb_old_mu"]), sigma=T(G["mb_old_sigma"]))
+    lr = 3e-4
+    for it in range(3):
+        prm = params.clone().requires_grad_(True)
+        loss, st = P.minibatch_loss(prm, batch, D, o)
+        loss.backward()
+        assert torch.allclose(loss.detach(), T(G[f"it{it}_loss"]), rtol=1e-5, atol=1e-6), it
+        for k in ("a_loss", "c_loss", "entropy", "b_loss", "kl"):
+            assert torch.allclose(st[k].detach(), T(G[f"it{it}_{k}"]), rtol=2e-5, atol=1e-6), (it, k)
+        assert torch.allclose(prm.grad, T(G[f"it{it}_grads"]), rtol=1e-4, atol=1e-7), it
+        assert abs(lr - float(G[f"it{it}_lr"])) < 1e-9
+        params, m, v, norm = P.adam_step(params, prm.grad, m, v, it + 1, lr)
+        assert torch.allclose(norm, T(G[f"it{it}_grad_norm"]), rtol=1e-5)
+        assert torch.allclose(params, T(G[f"it{it}_params_after"]), rtol=1e-5, atol=1e-7), it
+        lr = P.adaptive_lr(lr, float(st["kl"]))
+        assert abs(lr - float(G[f"it{it}_new_lr"])) < 1e-9
+        batch["mu"], batch["sigma"] = st["mu"], st["sigma"]
+
+
+def test_gae_oracle_vs_reference(golden):
+    G = golden("gae")
+    for tag in "abcd":
+        f = lambda k: T(G[f"{tag}_{k}"])
+        adv = P.discount_values(f("last_dones").float(), f("last_values").squeeze(-1), f("dones").float(),
+                                f("values").squeeze(-1), f("rewards").squeeze(-1))
+        assert torch.equal(adv, f("adv").squeeze(-1)), tag
+
+
+def test_normal_eps_statistics():
+    e = P.normal_eps(1234, np.arange(200000), 7)
+    assert abs(float(e.mean())) < 5e-3 and abs(float(e.std()) - 1.0) < 5e-3 and torch.isfinite(e).all()
