@@ -211,6 +211,91 @@ class UsvEnvConfig:
         return p
 
     # ------------------------------------------------------------------------------------
+    def to_task_cfg(self) -> dict:
+        """The reference's task-YAML tree (env / sim / dynamics) for this config: what USVVirtual.__init__ reads."""
+        inv_mode = {v: k for k, v in REWARD_MODES.items()}
+        lam = {PEN_NEG_SUM: lambda t: f"lambda x,step : -torch.sum(x, dim=-1)*{t.c1!r} + {t.c2!r}",
+               PEN_EXP_NEG_SUMSQ: lambda t: f"lambda x,step : (torch.exp(-torch.sum(x**2, dim=-1)) - 1.0) * {t.c1!r}",
+               PEN_NEG_ABS: lambda t: f"lambda x,step : -torch.abs(x)*{t.c1!r} + {t.c2!r}",
+               PEN_NEG_DEADZONE: lambda t: f"lambda x,step: -torch.clamp(torch.abs(x)-{t.k!r}, min=0)*{t.c1!r}",
+               PEN_EXP_NEG_ABS: lambda t: f"lambda x,step: (torch.exp(-{t.k!r} * torch.abs(x)) - 1.0) * {t.c1!r}"}
+        pen = {}
+        for name, t in (("linear_velocities", self.pen_linear_vel), ("angular_velocities", self.pen_angular_vel),
+                        ("angular_velocities_variation", self.pen_angular_vel_variation), ("energy", self.pen_energy),
+                        ("action_variation", self.pen_action_variation)):
+            pen[f"penalize_{name}"] = t.form != PEN_OFF
+            if t.form != PEN_OFF:
+                src = lam[t.form](t)
+                if name == "linear_velocities":
+                    src = src.replace("torch.abs(x)", "torch.norm(x, dim=-1)")
+                pen[f"penalize_{name}_fn"] = src
+        L = [self.lin_base[0], self.lin_base[1], 99.99, 13.0, 13.0, self.lin_base[2]]
+        Q = [self.quad_base[0], self.quad_base[1], 10.0, 5.0, 5.0, self.quad_base[2]]
+        return {
+            "name": "USVVirtual",
+            "env": {"numEnvs": self.num_envs, "envSpacing": self.env_spacing, "maxEpisodeLength": self.max_episode_length,
+                    "action_mode": "Continuous", "horizon_length": self.horizon_length, "observation_frame": "local",
+                    "controlFrequencyInv": self.n_substeps, "clipObservations": {"state": self.clip_obs}, "clipActions": self.clip_actions,
+                    "water_current": {"use_water_current": False, "flow_velocity": [0.0, 0.0, 0.0]},
+                    "disturbances": {
+                        "forces": dict(use_force_disturbance=self.use_force_disturbance, use_constant_force=self.use_const_force,
+                                       use_sinusoidal_force=self.use_sin_force, force_const_min=self.force_const_min,
+                                       force_const_max=self.force_const_max, force_sin_min=self.force_sin_min, force_sin_max=self.force_sin_max,
+                                       force_min_freq=self.force_min_freq, force_max_freq=self.force_max_freq,
+                                       force_min_shift=self.force_min_shift, force_max_shift=self.force_max_shift),
+                        "torques": dict(use_torque_disturbance=self.use_torque_disturbance, use_constant_torque=self.use_const_torque,
+                                        use_sinusoidal_torque=self.use_sin_torque, torque_const_min=self.torque_const_min,
+                                        torque_const_max=self.torque_const_max, torque_sin_min=self.torque_sin_min,
+                                        torque_sin_max=self.torque_sin_max, torque_min_freq=self.torque_min_freq,
+                                        torque_max_freq=self.torque_max_freq, torque_min_shift=self.torque_min_shift,
+                                        torque_max_shift=self.torque_max_shift),
+                        "observations": dict(add_noise_on_pos=self.noise_pos, position_noise_min=self.pos_noise_min,
+                                             position_noise_max=self.pos_noise_max, add_noise_on_vel=self.noise_vel,
+                                             velocity_noise_min=self.vel_noise_min, velocity_noise_max=self.vel_noise_max,
+                                             add_noise_on_heading=self.noise_heading, heading_noise_min=self.heading_noise_min,
+                                             heading_noise_max=self.heading_noise_max),
+                        "actions": dict(add_noise_on_act=self.action_noise, min_action_noise=self.action_noise_min,
+                                        max_action_noise=self.action_noise_max),
+                        "mass": dict(add_mass_disturbances=self.mass_rand, min_mass=self.mass_min, max_mass=self.mass_max,
+                                     CoM_max_displacement=0.0, base_mass=self.mass_base),
+                        "drag": dict(use_drag_randomization=self.drag_rand, u_linear_rand=self.lin_rand_frac[0],
+                                     v_linear_rand=self.lin_rand_frac[1], w_linear_rand=0.0, p_linear_rand=0.0, q_linear_rand=0.0,
+                                     r_linear_rand=self.lin_rand_frac[2], u_quad_rand=self.quad_rand_frac[0],
+                                     v_quad_rand=self.quad_rand_frac[1], w_quad_rand=0.0, p_quad_rand=0.0, q_quad_rand=0.0,
+                                     r_quad_rand=self.quad_rand_frac[2], use_drag_scale_randomization=self.kdrag_rand,
+                                     k_drag_min=self.kdrag_min, k_drag_max=self.kdrag_max,
+                                     k_drag_sample_space="log" if self.kdrag_log else "linear"),
+                        "thruster": dict(use_thruster_randomization=self.thr_rand, thruster_rand=self.thr_rand_frac,
+                                         use_separate_randomization=self.thr_separate, left_rand=self.thr_left_frac,
+                                         right_rand=self.thr_right_frac)},
+                    "task_parameters": dict(name="CaptureXY", position_tolerance=self.position_tolerance,
+                                            kill_after_n_steps_in_tolerance=self.kill_after_n_steps_in_tolerance,
+                                            goal_random_position=self.goal_random_position, max_spawn_dist=self.spawn_max_dist,
+                                            min_spawn_dist=self.spawn_min_dist, kill_dist=self.kill_dist, boundary_cost=self.boundary_cost,
+                                            goal_reward=self.goal_reward, time_reward=self.time_reward),
+                    "reward_parameters": dict(name="CaptureXY", reward_mode=inv_mode[self.reward_mode], position_scale=self.position_scale,
+                                              exponential_reward_coeff=self.exponential_reward_coeff, align_la1=self.align_la1,
+                                              align_la2=self.align_la2, align_la3=self.align_la3),
+                    "penalties_parameters": pen},
+            "sim": {"dt": self.dt, "gravity": [0.0, 0.0, -9.81]},
+            "dynamics": {
+                "thrusters": {"cmd_lower_range": -1.0, "cmd_upper_range": 1.0, "timeConstant": self.time_constant,
+                              "interpolation": {"numberOfPointsForInterpolation": self.n_lut,
+                                                "interpolationPointsFromRealDataLeft": list(self.lut_points_left),
+                                                "interpolationPointsFromRealDataRight": list(self.lut_points_right)},
+                              "leastSquareMethod": {"neg_cmd_coeff": [0.0] * 5, "pos_cmd_coeff": [0.0] * 5}},
+                "hydrodynamics": {"linear_damping": L, "quadratic_damping": Q,
+                                  "linear_damping_forward_speed": [self.lin_fwd[0], self.lin_fwd[1], 0.0, 0.0, 0.0, self.lin_fwd[2]],
+                                  "offset_linear_damping": self.offset_linear_damping,
+                                  "offset_lin_forward_damping_speed": self.offset_lin_forward_damping_speed,
+                                  "offset_nonlin_damping": self.offset_nonlin_damping, "scaling_damping": self.scaling_damping,
+                                  "offset_added_mass": 0.0, "scaling_added_mass": 1.0},
+                "hydrostatics": {"average_hydrostatics_force_value": 275, "amplify_torque": 1.0, "material_density": 133,
+                                 "water_density": 1000, "mass": self.mass_base, "box_width": 1.0, "box_length": 1.3,
+                                 "waterplane_area": 0.233333, "heron_zero_height": 0.24},
+                "acceleration": {"alpha": 0.3, "last_time": -10.0}},
+        }
+
     @classmethod
     def from_task_cfg(cls, task_cfg: dict, **overrides) -> "UsvEnvConfig":
         """Builds the config from the reference's task YAML dict (env/sim/dynamics sections)."""

@@ -1,0 +1,234 @@
+"""A2CAgent: the rl_games continuous PPO loop [ref: RLG/common/a2c_common.py:65-1486, RLG/algos_torch/a2c_continuous.py]
+re-hosted on the C-ABI kernels.  One process per GPU; envs are sharded across ranks; NCCL carries one all-reduce per
+minibatch (gradient + KL + loss statistics in ONE span) and the episode statistics once per epoch.
+
+Reference behaviours kept on purpose: env-major contiguous minibatches with no shuffling,
+mu/sigma written back into the dataset after every minibatch, obs normaliser updated during mini-epoch 0 only, value
+normaliser fed values then returns, rewards scaled by reward_shaper.scale_value at rollout time, critic weight
+0.5*critic_coef, per-minibatch adaptive-KL learning rate ('legacy' schedule) -- here evaluated on device, so there is no
+kl.item() host sync anywhere in the epoch.
+"""
+from __future__ import annotations
+
+import ctypes
+import time
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from .. import _lib
+from .policy import PolicyMLP
+
+A = 2
+
+
+@dataclass
+class PPOConfig:
+    """OIGE/cfg/train/USV/USV_PPOcontinuous_MLP.yaml `config:` section."""
+    gamma: float = 0.99
+    tau: float = 0.95
+    learning_rate: float = 1e-4
+    lr_schedule: str = "adaptive"
+    kl_threshold: float = 0.016
+    grad_norm: float = 1.0
+    entropy_coef: float = 0.0
+    truncate_grads: bool = True
+    e_clip: float = 0.2
+    horizon_length: int = 16
+    minibatch_size: int = 8192
+    mini_epochs: int = 8
+    critic_coef: float = 0.5
+    clip_value: bool = True
+    bounds_loss_coef: float = 1e-4
+    normalize_input: bool = True
+    normalize_value: bool = True
+    normalize_advantage: bool = True
+    reward_scale: float = 0.01
+    max_epochs: int = 3000
+    seed: int = 42
+
+    @classmethod
+    def from_train_cfg(cls, cfg: dict) -> "PPOConfig":
+        c = cfg["params"]["config"] if "params" in cfg else cfg
+        kw = {k: c[k] for k in cls.__dataclass_fields__ if k in c and not isinstance(c[k], str) or k == "lr_schedule" and k in c}
+        if "reward_shaper" in c:
+            kw["reward_scale"] = c["reward_shaper"].get("scale_value", 1.0)
+        return cls(**kw)
+
+
+def gae(rewards, values, dones, last_values, last_dones, gamma, tau, adv, ret):
+    """A2CBase.discount_values + returns  [ref: RLG/common/a2c_common.py:525-540,763] -- one kernel."""
+    T, n = rewards.shape
+    rc = _lib.lib().ppo_gae_f32(_lib.ptr(rewards), _lib.ptr(values), _lib.ptr(dones, torch.uint8), _lib.ptr(last_values),
+                                _lib.ptr(last_dones, torch.uint8), ctypes.c_float(gamma), ctypes.c_float(tau), _lib.ptr(adv), _lib.ptr(ret),
+                                ctypes.c_int32(T), ctypes.c_int64(n), _lib.stream())
+    _lib.check(rc, "ppo_gae_f32")
+
+
+class A2CAgent:
+    def __init__(self, vec_env, cfg: PPOConfig, device="cuda:0", rank: int = 0, world_size: int = 1):
+        """`vec_env` follows the rl_games IVecEnv contract (step/reset/get_env_info), e.g. RLGPUEnv(VecEnvRLGames)."""
+        self.vec_env, self.cfg = vec_env, cfg
+        self.device = torch.device(device)
+        self.rank, self.world = rank, world_size
+        self.multi_gpu = world_size > 1
+        info = vec_env.get_env_info()
+        self.obs_dim = int(info["observation_space"]["state"].shape[0])
+        self.num_actors = int(vec_env.env.num_envs)
+        self.T = cfg.horizon_length
+        self.batch_size = self.T * self.num_actors
+        self.minibatch_size = min(cfg.minibatch_size, self.batch_size)
+        assert self.batch_size % self.minibatch_size == 0, "batch_size must be a multiple of minibatch_size (as in rl_games)"
+        self.num_minibatches = self.batch_size // self.minibatch_size
+        self.policy = PolicyMLP(self.obs_dim, self.device, seed=cfg.seed, lr=cfg.learning_rate, e_clip=cfg.e_clip,
+                                critic_coef=cfg.critic_coef, entropy_coef=cfg.entropy_coef, bounds_loss_coef=cfg.bounds_loss_coef,
+                                clip_value=cfg.clip_value, grad_norm=cfg.grad_norm if cfg.truncate_grads else 0.0,
+                                kl_threshold=cfg.kl_threshold, adaptive_lr=cfg.lr_schedule == "adaptive", world_size=world_size)
+        self.policy.seed = cfg.seed + rank                                  # [ref: RLG/torch_runner.py:74-75]
+        if self.multi_gpu:                                                  # [ref: a2c_common.py:1350-1355]
+            dist.broadcast(self.policy.params, 0)
+        N, T, D = self.num_actors, self.T, self.obs_dim
+        f32 = dict(dtype=torch.float32, device=self.device)
+        self.buf = dict(obses=torch.zeros((T, N, D), **f32), rewards=torch.zeros((T, N), **f32), values=torch.zeros((T, N, 1), **f32),
+                        neglogpacs=torch.zeros((T, N), **f32), dones=torch.zeros((T, N), dtype=torch.uint8, device=self.device),
+                        actions=torch.zeros((T, N, A), **f32), mus=torch.zeros((T, N, A), **f32), sigmas=torch.zeros((T, N, A), **f32))
+        self.advs = torch.zeros((T, N), **f32)
+        self.returns = torch.zeros((T, N), **f32)
+        self.last_values = torch.zeros((N, 1), **f32)
+        self.dones = torch.ones(N, dtype=torch.uint8, device=self.device)   # [ref: a2c_common.py:454]
+        self.current_rewards = torch.zeros(N, **f32)
+        self.current_lengths = torch.zeros(N, **f32)
+        # finished-episode accumulators: [sum of returns, sum of lengths, count] (all-reduced once per epoch)
+        self.episode_acc = torch.zeros(3, dtype=torch.float64, device=self.device)
+        self.obs = None
+        self.epoch_num = 0
+        self.frame = 0
+        self.mean_reward = float("nan")
+
+    # ---- rollout  [ref: a2c_common.py:670-774] -------------------------------------------------------
+    def play_steps(self):
+        b, pol, T = self.buf, self.policy, self.T
+        if self.obs is None:
+            self.obs = self.vec_env.reset()["obs"]["state"]
+        for n in range(T):
+            b["obses"][n].copy_(self.obs)
+            b["dones"][n].copy_(self.dones)
+            out = dict(actions=b["actions"][n], neglogpacs=b["neglogpacs"][n], values=b["values"][n], mus=b["mus"][n], sigmas=b["sigmas"][n])
+            pol.act(b["obses"][n], out, row_offset=self.rank * self.num_actors)
+            # preprocess_actions: clamp to [-1, 1]  [ref: a2c_common.py:1134-1144] (the stored action stays unclamped)
+            obs_dict, rew, dones, infos = self.vec_env.step(torch.clamp(b["actions"][n], -1.0, 1.0))
+            self.obs = obs_dict["obs"]["state"]
+            b["rewards"][n] = rew * self.cfg.reward_scale                    # DefaultRewardsShaper [ref: tr_helpers.py:33-42]
+            self.dones = dones.to(torch.uint8)
+            # episode bookkeeping without host syncs  [ref: a2c_common.py:720-747]
+            self.current_rewards += rew
+            self.current_lengths += 1
+            d = dones.to(torch.float32)
+            self.episode_acc += torch.stack([(self.current_rewards * d).sum(), (self.current_lengths * d).sum(), d.sum()]).double()
+            self.current_rewards *= 1.0 - d
+            self.current_lengths *= 1.0 - d
+        pol.values(self.obs, self.last_values)
+        gae(b["rewards"], b["values"].view(T, -1), b["dones"], self.last_values.view(-1), self.dones, self.cfg.gamma, self.cfg.tau,
+            self.advs, self.returns)
+
+    # ---- dataset  [ref: a2c_common.py:1257-1320 ; swap_and_flatten01 :30-37] ---------------------------
+    def prepare_dataset(self):
+        b, pol = self.buf, self.policy
+        flat = lambda x: x.transpose(0, 1).reshape(self.batch_size, *x.shape[2:]).contiguous()      # (T,N,..) -> env-major (N*T,..)
+        values, returns = flat(b["values"]).view(-1), flat(self.returns)
+        advantages = returns - values
+        if self.cfg.normalize_value:                       # train(): update with values, normalise; then with returns
+            pol.val_rms.update(values.view(-1, 1))
+            values = pol.val_rms.normalize(values.view(-1, 1)).view(-1)
+            pol.val_rms.update(returns.view(-1, 1))
+            returns = pol.val_rms.normalize(returns.view(-1, 1)).view(-1)
+        if self.cfg.normalize_advantage:
+            advantages = (advantages - advantages.mean()) / (advantages.std() + 1e-8)
+        self.ds = dict(obs=flat(b["obses"]), actions=flat(b["actions"]), old_logp_actions=flat(b["neglogpacs"]),
+                       advantages=advantages.contiguous(), old_values=values.contiguous(), returns=returns.contiguous(),
+                       mu=flat(b["mus"]), sigma=flat(b["sigmas"]))
+
+    # ---- update  [ref: a2c_common.py:1197-1245 ; a2c_continuous.py:78-196] -----------------------------
+    def train_epoch(self):
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            self.play_steps()
+            t1 = time.perf_counter()
+            self.prepare_dataset()
+            ds, pol, mb = self.ds, self.policy, self.minibatch_size
+            for mini_ep in range(self.cfg.mini_epochs):
+                for i in range(self.num_minibatches):
+                    s = slice(i * mb, (i + 1) * mb)
+                    if self.cfg.normalize_input and mini_ep == 0:
+                        pol.obs_rms.update(ds["obs"][s])                    # train-mode forward updates the normaliser first
+                    pol.minibatch_grad(ds["obs"][s], ds["actions"][s], ds["old_logp_actions"][s], ds["advantages"][s],
+                                       ds["old_values"][s], ds["returns"][s], ds["mu"][s], ds["sigma"][s])
+                    if self.multi_gpu:
+                        dist.all_reduce(pol.grads, op=dist.ReduceOp.SUM)     # gradient + KL + loss stats in one span
+                    pol.optimizer_step()
+        self.epoch_num += 1
+        self.frame += self.batch_size * self.world
+        return t1 - t0, time.perf_counter() - t1
+
+    def episode_stats(self):
+        """Mean return / length of the episodes finished since the last call, reduced over ranks (one small all-reduce)."""
+        acc = self.episode_acc.clone()
+        if self.multi_gpu:
+            dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+        self.episode_acc.zero_()
+        s, l, c = acc.tolist()
+        return (s / c, l / c, int(c)) if c > 0 else (float("nan"), float("nan"), 0)
+
+    def train(self, max_epochs: Optional[int] = None, log_every: int = 10, log=print):
+        max_epochs = max_epochs or self.cfg.max_epochs
+        while self.epoch_num < max_epochs:
+            play, update = self.train_epoch()
+            if self.epoch_num % log_every == 0:
+                torch.cuda.synchronize(self.device)
+                rew, length, cnt = self.episode_stats()
+                if cnt:
+                    self.mean_reward = rew
+                st = self.policy.stats()
+                if self.rank == 0 and log:
+                    log(f"epoch {self.epoch_num} frames {self.frame} reward {rew:.3f} len {length:.1f} ({cnt} eps) "
+                        f"kl {st['kl']:.5f} lr {st['lr']:.2e} a_loss {st['a_loss']:.4f} c_loss {st['c_loss']:.4f}")
+        return self.mean_reward
+
+    # ---- checkpoints: the reference's .pth schema  [ref: a2c_common.py:590-654] --------------------------
+    def get_full_state_weights(self):
+        P = self.policy
+        off, state = 0, {}
+        from .policy import param_shapes
+        import math
+        for idx, shp in enumerate(param_shapes(P.D)):
+            n = math.prod(shp)
+            state[idx] = {"step": P.step.float().cpu().reshape(()), "exp_avg": P.exp_avg[off:off + n].view(shp).clone(),
+                          "exp_avg_sq": P.exp_avg_sq[off:off + n].view(shp).clone()}
+            off += n
+        opt = {"state": state, "param_groups": [{"lr": float(P.lr), "betas": (0.9, 0.999), "eps": 1e-08, "weight_decay": 0,
+                                                 "amsgrad": False, "params": list(range(9))}]}
+        return {"model": P.state_dict(), "epoch": self.epoch_num, "optimizer": opt, "frame": self.frame,
+                "last_mean_rewards": self.mean_reward, "env_state": None}
+
+    def save(self, path: str):
+        torch.save(self.get_full_state_weights(), path)
+
+    def restore(self, path: str):
+        ck = torch.load(path, map_location="cpu", weights_only=False)
+        self.policy.load_state_dict(ck["model"])
+        self.epoch_num, self.frame = int(ck.get("epoch", 0)), int(ck.get("frame", 0))
+        opt = ck.get("optimizer")
+        if opt and opt.get("state"):
+            from .policy import param_shapes
+            import math
+            off = 0
+            for idx, shp in enumerate(param_shapes(self.policy.D)):
+                n = math.prod(shp)
+                st = opt["state"][idx]
+                self.policy.exp_avg[off:off + n].copy_(st["exp_avg"].reshape(-1))
+                self.policy.exp_avg_sq[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+                off += n
+            self.policy.step.fill_(int(opt["state"][0]["step"]))
+            self.policy.lr.fill_(float(opt["param_groups"][0]["lr"]))

@@ -1,0 +1,89 @@
+"""GPU tests of the reference-shaped surfaces: VecEnvRLGames / USVVirtual / RLGPUEnv over the fused step, and the PPO loop."""
+import dataclasses
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from omniisaacgymenvs_loop_b200.config import UsvEnvConfig  # noqa: E402
+from omniisaacgymenvs_loop_b200.rl.a2c import A2CAgent, PPOConfig  # noqa: E402
+from oracle import usv_oracle as O  # noqa: E402
+from scripts.train_usv import make_env  # noqa: E402
+from tests.util import assert_close, oracle_cfg  # noqa: E402
+
+DEV = "cuda:0"
+
+
+def test_vecenv_step_matches_oracle_and_contract():
+    cfg = UsvEnvConfig(num_envs=600, max_episode_length=9, seed=77).full_dr()
+    env = make_env(cfg.to_task_cfg(), DEV, seed=77)
+    info = env.get_env_info()
+    assert info["observation_space"]["state"].shape == (13,) and info["action_space"].shape == (2,)
+    assert env.get_number_of_agents() == 1
+    orc = O.ClassicEnvOracle(oracle_cfg(cfg), 600)
+    obs = env.reset()
+    o_obs, _, _ = orc.step(torch.zeros((600, 2)))                    # VecEnvRLGames.reset == one zero-action step
+    assert set(obs.keys()) == {"obs", "states"} and obs["obs"]["state"].shape == (600, 13) and obs["states"].shape == (600, 0)
+    assert_close(obs["obs"]["state"], o_obs, 1e-5, 2e-5, "reset obs")
+    g = torch.Generator().manual_seed(0)
+    for k in range(20):
+        act = torch.rand((600, 2), generator=g) * 3 - 1.5              # beyond clipActions: the vec-env clamps
+        od, rew, done, extras = env.step(act.to(DEV))
+        o_obs, o_rew, o_done = orc.step(act)
+        assert rew.shape == (600,) and done.dtype == torch.int64 and rew.dtype == torch.float32
+        assert_close(od["obs"]["state"], o_obs, 1e-4, 2e-3, f"obs {k}"); assert_close(rew, o_rew, 1e-4, 2e-3, f"rew {k}")
+        assert torch.equal(done.cpu(), o_done), k
+    ep = extras["episode"]
+    assert {"distance_reward", "alignment_reward", "position_error", "energy_penalty", "angular_vel_variation_penalty", "actions_sum"} <= set(ep)
+    assert "linear_vel_penalty" not in ep                             # disabled penalties have no stat [ref: USV_task_rewards.py:508-523]
+    assert all(torch.isfinite(v) for v in ep.values()) and float(ep["position_error"]) > 0
+    task = env.env._task
+    task.update_state()
+    assert task.current_state["position"].shape == (600, 2) and task.progress_buf.dtype == torch.int64
+    assert task.hydrodynamics.drag_scale.shape == (600, 1) and task.thrusters_dynamics.thruster_multiplier.shape == (600, 1)
+
+
+def test_nan_probe_raises_like_reference(monkeypatch):
+    monkeypatch.setenv("USV_NAN_PROBE", "1")
+    cfg = UsvEnvConfig(num_envs=64)
+    tc = cfg.to_task_cfg()
+    env = make_env(tc, DEV, seed=1)
+    env.env._task._nan_probe_interval = 1
+    env.reset()
+    bad = torch.zeros((64, 2), device=DEV); bad[3, 1] = float("nan")
+    with pytest.raises(RuntimeError, match="USV_NAN_PROBE"):
+        env.step(bad)
+
+
+def test_ppo_loop_runs_and_learns(tmp_path):
+    """A short CaptureXY training run: finite losses, KL-adaptive lr moves, reward improves, checkpoint round-trips in the
+    reference's .pth schema."""
+    cfg = UsvEnvConfig(num_envs=2048, max_episode_length=400)
+    env = make_env(cfg.to_task_cfg(), DEV, seed=3, collect_stats=False)
+    agent = A2CAgent(env, PPOConfig(seed=3, minibatch_size=8192), DEV)
+    assert agent.batch_size == 32768 and agent.num_minibatches == 4
+    p0 = agent.policy.params.clone()
+    rewards = []
+    for chunk in range(4):
+        for _ in range(15):
+            agent.train_epoch()
+        r, l, c = agent.episode_stats()
+        rewards.append(r)
+        st = agent.policy.stats()
+        assert all(map(lambda v: v == v, st.values())), st                 # no NaN
+    assert not torch.equal(p0, agent.policy.params) and int(agent.policy.step) == 60 * 8 * 4
+    assert torch.isfinite(agent.policy.params).all()
+    assert float(agent.policy.obs_rms.count) == 1 + 60 * 32768              # obs normaliser sees each frame once per epoch
+    assert float(agent.policy.val_rms.count) == 1 + 2 * 60 * 32768           # values + returns (SURVEY 4.3 accounting)
+    assert rewards[-1] > rewards[0], rewards                                # learning signal
+    path = os.path.join(tmp_path, "last.pth")
+    agent.save(path)
+    ck = torch.load(path, weights_only=False)
+    assert set(ck) == {"model", "epoch", "optimizer", "frame", "last_mean_rewards", "env_state"} and ck["frame"] == 60 * 32768
+    assert ck["model"]["a2c_network.actor_mlp.0.weight"].shape == (128, 13) and ck["optimizer"]["state"][0]["exp_avg"].shape == (2,)
+    other = A2CAgent(make_env(cfg.to_task_cfg(), DEV, seed=4, collect_stats=False), PPOConfig(seed=9), DEV)
+    other.restore(path)
+    assert torch.equal(other.policy.params, agent.policy.params) and torch.equal(other.policy.exp_avg_sq, agent.policy.exp_avg_sq)
+    assert float(other.policy.lr) == pytest.approx(float(agent.policy.lr)) and other.epoch_num == 60
