@@ -236,6 +236,49 @@ def time_e2e(env, steps, warmup, dist_on, device):
     return ms, h2d, d2h, float(h_rew.mean())
 
 
+def bench_ppo(args, rank, world, device, dist_on):
+    """BASELINE config[2]: CaptureXY + USV_PPOcontinuous_MLP, 16384 envs/GPU, env-sharded, NCCL grad all-reduce.
+    PPO frames/s = horizon * envs * world / epoch time (rollout + GAE + dataset + 8 mini-epochs x 32 minibatches)."""
+    import torch.distributed as dist
+    from omniisaacgymenvs_loop_b200 import _lib
+    from omniisaacgymenvs_loop_b200.config import UsvEnvConfig
+    from omniisaacgymenvs_loop_b200.rl.a2c import A2CAgent, PPOConfig
+    from scripts.train_usv import make_env
+
+    n = args.ppo_envs
+    cfg = UsvEnvConfig(num_envs=n)
+    env = make_env(cfg.to_task_cfg(), str(device), seed=1234, env_id_offset=rank * n, collect_stats=False)
+    env.env._task._nan_probe = False
+    agent = A2CAgent(env, PPOConfig(seed=1234), device, rank, world)
+    for _ in range(3):
+        agent.train_epoch()
+    torch.cuda.synchronize(device)
+    if dist_on:
+        dist.barrier()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    play = upd = 0.0
+    e0.record()
+    for _ in range(args.ppo_epochs):
+        p, u = agent.train_epoch()
+        play += p
+        upd += u
+    e1.record()
+    torch.cuda.synchronize(device)
+    ms = e0.elapsed_time(e1)
+    if dist_on:
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    frames = agent.batch_size * world * args.ppo_epochs
+    st = agent.policy.stats()
+    return {"metric": "PPO frames/sec", "value": frames / (ms * 1e-3), "unit": "frames/s", "envs_per_gpu": n, "horizon": agent.T,
+            "minibatch": agent.minibatch_size, "mini_epochs": agent.cfg.mini_epochs, "epochs_timed": args.ppo_epochs,
+            "ms_per_epoch": ms / args.ppo_epochs, "host_play_s": play, "host_update_s": upd,
+            "our_kernel_launches_per_epoch": (_lib.launch_count() - l0) / args.ppo_epochs,
+            "mlp": "fp32 SIMT fused kernels (csrc/ppo_mlp.cu)", "kl": st["kl"], "lr": st["lr"]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -245,6 +288,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the 4096-env and e2e legs (profiling runs)")
+    ap.add_argument("--no-ppo", action="store_true", help="skip the PPO frames/s leg")
+    ap.add_argument("--ppo-envs", type=int, default=16384, help="envs per GPU of the PPO leg (BASELINE config[2])")
+    ap.add_argument("--ppo-epochs", type=int, default=10)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -327,6 +373,8 @@ def main():
                            "rollout_kernel_env_steps_per_s": world * 4096 * T * 4 / (rms * 1e-3),
                            "note": "one launch per control step vs one launch per 512 control steps (state in registers); "
                                    "latency-bound, working set L2-resident -> no HBM roofline claimed"}
+    if not args.no_extra and not args.no_ppo:
+        line["ppo"] = bench_ppo(args, rank, world, device, dist_on)
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         cb, _ = cpu_port(20.0)
         line["cpu_baseline"] = cb

@@ -299,6 +299,12 @@ int ppo_policy_forward_f32(const float* params, const float* obs /*[M,D]*/, int3
                            float* actions /*[M,2]*/, float* neglogp /*[M]*/, float* values /*[M] de-normalised*/,
                            float* mus /*[M,2]*/, float* sigmas /*[M,2]*/, int64_t M, void* stream);
 
+/* the same contract on the tcgen05 tensor cores (TF32 operands, fp32 accumulation in TMEM, tanh.approx): ~1e-3 relative
+ * of the fp32 entry point above; requires obs_dim <= 15 (one padded K column carries the first-layer bias) */
+int ppo_policy_forward_tc(const float* params, const float* obs, int32_t obs_dim, const float* obs_mean, const float* obs_var,
+                          const float* value_mean, const float* value_var, uint64_t seed, uint64_t counter, int64_t row_offset,
+                          float* actions, float* neglogp, float* values, float* mus, float* sigmas, int64_t M, void* stream);
+
 typedef struct {
   float e_clip;            /* 0.2  */
   float critic_coef;       /* 0.5 (the loss uses 0.5*c_loss*critic_coef) */
@@ -335,7 +341,8 @@ typedef struct {
   float kl_threshold, min_lr, max_lr;
 } PpoAdamParams;
 int ppo_adam_step_f32(float* params, float* grads /*[P+PPO_STAT_COUNT], scaled in place*/, float* exp_avg, float* exp_avg_sq,
-                      float* lr /*device scalar, updated*/, int32_t* step /*device scalar, incremented*/,
+                      float* lr /*device float[2]: [0] current lr (updated), [1] scratch*/,
+                      int32_t* step /*device int32[2]: [0] Adam step count (incremented), [1] scratch*/,
                       int64_t P, const PpoAdamParams* ap, void* stream);
 
 #ifdef __cplusplus

@@ -454,64 +454,73 @@ __global__ void __launch_bounds__(NT, 1) train_kernel(const float* __restrict__ 
   }
 }
 
-// second stage: grads[e] = sum over CTAs of partial[c][e]  (fixed order -> deterministic)
+// second stage: grads[e] = sum over CTAs of partial[c][e]  (fixed order -> deterministic).
+// 64 columns x 4 row-groups per block: four 32-long dependent load chains instead of one 128-long one.
 __global__ void __launch_bounds__(256) reduce_kernel(const float* __restrict__ partial, int nparts, int n,
                                                      float* __restrict__ grads, PpoLossParams lp, int P) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n) return;
+  __shared__ float sm[4][64];
+  const int col = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  const int e = blockIdx.x * 64 + col;
   float acc = 0.f;
-  for (int c = 0; c < nparts; ++c) acc += partial[(size_t)c * n + e];
-  grads[e] = acc;
-  if (e == P + PPO_STAT_LOSS) {  // total loss from the (already reduced on the fly) component means
+  if (e < n)
+    for (int c = grp; c < nparts; c += 4) acc += partial[(size_t)c * n + e];
+  sm[grp][col] = acc;
+  __syncthreads();
+  if (grp == 0 && e < n) {
+    float v = (sm[0][col] + sm[1][col]) + (sm[2][col] + sm[3][col]);
+    grads[e] = v;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {  // total loss from the component means
     float a = 0.f, cl = 0.f, en = 0.f, b = 0.f;
     for (int c = 0; c < nparts; ++c) {
       const float* q = partial + (size_t)c * n + P;
       a += q[PPO_STAT_A_LOSS]; cl += q[PPO_STAT_C_LOSS]; en += q[PPO_STAT_ENTROPY]; b += q[PPO_STAT_B_LOSS];
     }
-    grads[e] = a + 0.5f * cl * lp.critic_coef - en * lp.entropy_coef + b * lp.bounds_loss_coef;
+    grads[P + PPO_STAT_LOSS] = a + 0.5f * cl * lp.critic_coef - en * lp.entropy_coef + b * lp.bounds_loss_coef;
   }
 }
 
-// clip_grad_norm_ + Adam + adaptive-KL lr, one CTA (P ~ 2e4)
-__global__ void __launch_bounds__(1024) adam_kernel(float* __restrict__ prm, float* __restrict__ g, float* __restrict__ m,
-                                                    float* __restrict__ v, float* __restrict__ lr_p, int* __restrict__ step_p,
-                                                    int P, PpoAdamParams ap) {
-  __shared__ float red[32];
+// clip_grad_norm_ + Adam + adaptive-KL lr.  Multi-CTA: every CTA recomputes the global gradient norm from the (L2-resident)
+// 75 KB gradient in the same fixed order (deterministic, no atomics, no second launch), then updates its own slice.
+// lr/step live in device memory: read by every CTA at entry; the LAST launch-ordered writer is CTA 0, and the next
+// kernel that reads them is a later launch, so there is no intra-kernel hazard (they are written from *_in copies).
+constexpr int kAdamThreads = 256;
+__global__ void __launch_bounds__(kAdamThreads) adam_kernel(float* __restrict__ prm, float* __restrict__ g, float* __restrict__ m,
+                                                            float* __restrict__ v, const float* __restrict__ lr_in,
+                                                            const int* __restrict__ step_in, float* __restrict__ lr_out,
+                                                            int* __restrict__ step_out, int P, PpoAdamParams ap) {
+  __shared__ float red[kAdamThreads / 32];
   __shared__ float s_coef;
   const int t = threadIdx.x;
-  // all-reduce delivered the SUM over ranks: average gradients and statistics  [ref a2c_common.py:311-323]
+  // all-reduce delivered the SUM over ranks: average  [ref a2c_common.py:311-323]
   float ss = 0.f;
-  for (int e = t; e < P + PPO_STAT_COUNT; e += blockDim.x) {
+  for (int e = t; e < P; e += kAdamThreads) {
     const float x = g[e] * ap.inv_world;
-    g[e] = x;
-    if (e < P) ss = fmaf(x, x, ss);
+    ss = fmaf(x, x, ss);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
   if ((t & 31) == 0) red[t >> 5] = ss;
   __syncthreads();
-  if (t < 32) {
-    float x = (t < (int)(blockDim.x >> 5)) ? red[t] : 0.f;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-    if (t == 0) {
-      const float norm = sqrtf(x);
-      // torch.nn.utils.clip_grad_norm_: coef = max_norm/(norm+1e-6), clamped to 1
-      s_coef = (ap.grad_norm > 0.f) ? fminf(ap.grad_norm / (norm + 1e-6f), 1.0f) : 1.0f;
-      g[P + PPO_STAT_GRAD_NORM] = norm;
-    }
+  if (t == 0) {
+    float x = 0.f;
+    for (int w = 0; w < kAdamThreads / 32; ++w) x += red[w];
+    const float norm = sqrtf(x);
+    // torch.nn.utils.clip_grad_norm_: coef = max_norm/(norm+1e-6), clamped to 1
+    s_coef = (ap.grad_norm > 0.f) ? fminf(ap.grad_norm / (norm + 1e-6f), 1.0f) : 1.0f;
+    red[0] = norm;
   }
   __syncthreads();
-  const float coef = s_coef;
-  const float lr = *lr_p;
-  const int step = *step_p + 1;
-  // torch.optim.Adam (amsgrad=False, weight_decay=0): bias corrections in double as torch's scalar path does
+  const float coef = s_coef * ap.inv_world;
+  const float lr = *lr_in;
+  const int step = *step_in + 1;
+  // torch.optim.Adam (amsgrad=False, weight_decay=0); bias corrections evaluated in double like torch's scalar path
   const double bc1 = 1.0 - pow((double)ap.beta1, (double)step), bc2 = 1.0 - pow((double)ap.beta2, (double)step);
   const float step_size = (float)((double)lr / bc1);
   const float bc2_sqrt = (float)sqrt(bc2);
-  for (int e = t; e < P; e += blockDim.x) {
+  const int e = blockIdx.x * kAdamThreads + t;
+  if (e < P) {
     const float gr = g[e] * coef;
-    g[e] = gr;
     const float mm = m[e] + (gr - m[e]) * (1.0f - ap.beta1);           // exp_avg.lerp_(grad, 1-beta1)
     const float vv = v[e] * ap.beta2 + (1.0f - ap.beta2) * gr * gr;    // exp_avg_sq.mul_(beta2).addcmul_(g,g,1-beta2)
     m[e] = mm;
@@ -519,16 +528,21 @@ __global__ void __launch_bounds__(1024) adam_kernel(float* __restrict__ prm, flo
     const float denom = sqrtf(vv) / bc2_sqrt + ap.eps;
     prm[e] = prm[e] - step_size * (mm / denom);
   }
-  __syncthreads();
-  if (t == 0) {
-    *step_p = step;
-    g[P + PPO_STAT_LR] = lr;
-    if (ap.adaptive_lr) {  // AdaptiveScheduler.update, 'legacy' per-minibatch schedule  [ref schedulers.py:26-32]
-      const float kl = g[P + PPO_STAT_KL];
-      float nl = lr;
-      if (kl > 2.0f * ap.kl_threshold) nl = fmaxf(lr / 1.5f, ap.min_lr);
-      if (kl < 0.5f * ap.kl_threshold) nl = fminf(lr * 1.5f, ap.max_lr);
-      *lr_p = nl;
+  if (blockIdx.x == gridDim.x - 1) {   // the last CTA owns the statistics tail (no other CTA touches g[P..])
+    if (t < PPO_STAT_COUNT) {
+      float x = g[P + t] * ap.inv_world;
+      if (t == PPO_STAT_GRAD_NORM) x = red[0];
+      if (t == PPO_STAT_LR) x = lr;
+      g[P + t] = x;
+      if (t == PPO_STAT_KL) {
+        float nl = lr;
+        if (ap.adaptive_lr) {  // AdaptiveScheduler.update, 'legacy' per-minibatch schedule  [ref schedulers.py:26-32]
+          if (x > 2.0f * ap.kl_threshold) nl = fmaxf(lr / 1.5f, ap.min_lr);
+          if (x < 0.5f * ap.kl_threshold) nl = fminf(lr * 1.5f, ap.max_lr);
+        }
+        *lr_out = nl;
+        *step_out = step;
+      }
     }
   }
 }
@@ -589,7 +603,7 @@ int ppo_minibatch_grad_f32(const float* params, const float* obs, int32_t obs_di
   LossIn in{actions, old_neglogp, advantages, old_values, returns, old_mu, old_sigma};
   train_kernel<<<grid, NT, smem, (cudaStream_t)stream>>>(params, obs, obs_dim, obs_mean, obs_var, in, *lp, scratch, M);
   const int n = L.P + PPO_STAT_COUNT;
-  reduce_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(scratch, grid, n, grads, *lp, L.P);
+  reduce_kernel<<<(n + 63) / 64, 256, 0, (cudaStream_t)stream>>>(scratch, grid, n, grads, *lp, L.P);
   return usv::finish_launch(2);
 }
 
@@ -597,7 +611,11 @@ int ppo_adam_step_f32(float* params, float* grads, float* exp_avg, float* exp_av
                       const PpoAdamParams* ap, void* stream) {
   if (P <= 0) return USV_E_SIZE;
   if (!params || !grads || !exp_avg || !exp_avg_sq || !lr || !step || !ap) return USV_E_NULL;
-  adam_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, lr, step, (int)P, *ap);
+  // lr/step are double-buffered ([0] = current, [1] = next) so that no CTA can observe the update of another CTA
+  adam_kernel<<<(int)((P + kAdamThreads - 1) / kAdamThreads), kAdamThreads, 0, (cudaStream_t)stream>>>(
+      params, grads, exp_avg, exp_avg_sq, lr, step, lr + 1, step + 1, (int)P, *ap);
+  cudaMemcpyAsync(lr, lr + 1, sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+  cudaMemcpyAsync(step, step + 1, sizeof(int32_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
   return usv::finish_launch();
 }
 

@@ -68,12 +68,13 @@ def gae(rewards, values, dones, last_values, last_dones, gamma, tau, adv, ret):
 
 
 class A2CAgent:
-    def __init__(self, vec_env, cfg: PPOConfig, device="cuda:0", rank: int = 0, world_size: int = 1):
+    def __init__(self, vec_env, cfg: PPOConfig, device="cuda:0", rank: int = 0, world_size: int = 1, use_cuda_graph: bool = True):
         """`vec_env` follows the rl_games IVecEnv contract (step/reset/get_env_info), e.g. RLGPUEnv(VecEnvRLGames)."""
         self.vec_env, self.cfg = vec_env, cfg
         self.device = torch.device(device)
         self.rank, self.world = rank, world_size
         self.multi_gpu = world_size > 1
+        self.use_cuda_graph, self._graph = use_cuda_graph, None
         info = vec_env.get_env_info()
         self.obs_dim = int(info["observation_space"]["state"].shape[0])
         self.num_actors = int(vec_env.env.num_envs)
@@ -151,23 +152,40 @@ class A2CAgent:
                        mu=flat(b["mus"]), sigma=flat(b["sigmas"]))
 
     # ---- update  [ref: a2c_common.py:1197-1245 ; a2c_continuous.py:78-196] -----------------------------
+    def update(self):
+        """prepare_dataset + mini_epochs x num_minibatches PPO steps.  Touches only static buffers and device-side
+        scalars (lr, Adam step, normaliser moments), so the whole phase is captured once into a CUDA graph
+        (~800 launches, one NCCL all-reduce per minibatch) and replayed every epoch."""
+        self.prepare_dataset()
+        ds, pol, mb = self.ds, self.policy, self.minibatch_size
+        for mini_ep in range(self.cfg.mini_epochs):
+            for i in range(self.num_minibatches):
+                s = slice(i * mb, (i + 1) * mb)
+                if self.cfg.normalize_input and mini_ep == 0:
+                    pol.obs_rms.update(ds["obs"][s])                    # train-mode forward updates the normaliser first
+                pol.minibatch_grad(ds["obs"][s], ds["actions"][s], ds["old_logp_actions"][s], ds["advantages"][s],
+                                   ds["old_values"][s], ds["returns"][s], ds["mu"][s], ds["sigma"][s])
+                if self.multi_gpu:
+                    dist.all_reduce(pol.grads, op=dist.ReduceOp.SUM)     # gradient + KL + loss stats in one span
+                pol.optimizer_step()
+
     def train_epoch(self):
         t0 = time.perf_counter()
         with torch.no_grad():
             self.play_steps()
             t1 = time.perf_counter()
-            self.prepare_dataset()
-            ds, pol, mb = self.ds, self.policy, self.minibatch_size
-            for mini_ep in range(self.cfg.mini_epochs):
-                for i in range(self.num_minibatches):
-                    s = slice(i * mb, (i + 1) * mb)
-                    if self.cfg.normalize_input and mini_ep == 0:
-                        pol.obs_rms.update(ds["obs"][s])                    # train-mode forward updates the normaliser first
-                    pol.minibatch_grad(ds["obs"][s], ds["actions"][s], ds["old_logp_actions"][s], ds["advantages"][s],
-                                       ds["old_values"][s], ds["returns"][s], ds["mu"][s], ds["sigma"][s])
-                    if self.multi_gpu:
-                        dist.all_reduce(pol.grads, op=dist.ReduceOp.SUM)     # gradient + KL + loss stats in one span
-                    pol.optimizer_step()
+            if not self.use_cuda_graph:
+                self.update()
+            elif self._graph is None and self.epoch_num < 2:
+                self.update()                                            # eager warm-up (allocator, NCCL communicators)
+            elif self._graph is None:
+                torch.cuda.synchronize(self.device)
+                self._graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._graph):
+                    self.update()
+                self._graph.replay()
+            else:
+                self._graph.replay()
         self.epoch_num += 1
         self.frame += self.batch_size * self.world
         return t1 - t0, time.perf_counter() - t1

@@ -47,11 +47,14 @@ class RunningMeanStd:
         self.update_from_moments(bm, bv, bc)
 
     def update_from_moments(self, bm, bv, bc) -> None:
+        # in place: the buffers keep their addresses, so the update can live inside a captured CUDA graph
         delta = bm - self.mean
         tot = self.count + bc
-        self.mean = self.mean + delta * bc / tot
-        self.var = (self.var * self.count + bv * bc + delta ** 2 * self.count * bc / tot) / tot
-        self.count = tot
+        new_mean = self.mean + delta * bc / tot
+        new_var = (self.var * self.count + bv * bc + delta ** 2 * self.count * bc / tot) / tot
+        self.mean.copy_(new_mean)
+        self.var.copy_(new_var)
+        self.count.copy_(tot)
         self._sync()
 
     def normalize(self, x):
@@ -70,7 +73,7 @@ class RunningMeanStd:
 class PolicyMLP:
     def __init__(self, obs_dim: int, device="cuda:0", seed: int = 0, lr: float = 1e-4, e_clip: float = 0.2, critic_coef: float = 0.5,
                  entropy_coef: float = 0.0, bounds_loss_coef: float = 1e-4, clip_value: bool = True, grad_norm: float = 1.0,
-                 kl_threshold: float = 0.016, adaptive_lr: bool = True, world_size: int = 1):
+                 kl_threshold: float = 0.016, adaptive_lr: bool = True, world_size: int = 1, tensor_cores: bool = True):
         self.lib = _lib.lib()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -83,12 +86,15 @@ class PolicyMLP:
         self.exp_avg_sq = torch.zeros(self.P, **f32)
         self.grads = torch.zeros(self.P + N_STAT, **f32)          # gradient followed by the statistics: one all-reduce span
         self.scratch = torch.empty(int(self.lib.ppo_train_scratch_floats(ctypes.c_int32(self.D))), **f32)
-        self.lr = torch.full((1,), lr, **f32)
-        self.step = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._lr2 = torch.full((2,), lr, **f32)             # [0] current, [1] scratch of the Adam kernel
+        self._step2 = torch.zeros(2, dtype=torch.int32, device=self.device)
+        self.lr, self.step = self._lr2[:1], self._step2[:1]
         self.obs_rms = RunningMeanStd(self.D, self.device)
         self.val_rms = RunningMeanStd(1, self.device)
         self.seed = int(seed)
         self.sample_counter = 0
+        # tcgen05/TMEM kernels (TF32) when the obs fit their padded K tile; the fp32 SIMT kernels are the numerics reference
+        self.tensor_cores = bool(tensor_cores) and self.D <= 15
         self.loss_params = _lib.PpoLossParams(e_clip, critic_coef, entropy_coef, bounds_loss_coef, 1.1, int(clip_value))
         self.adam_params = _lib.PpoAdamParams(0.9, 0.999, 1e-8, grad_norm, 1.0 / world_size, int(adaptive_lr), kl_threshold, 1e-6, 1e-2)
         self.reset_parameters(seed)
@@ -150,7 +156,8 @@ class PolicyMLP:
         return v
 
     def _forward(self, obs, actions, neglogp, values, mus, sigmas, row_offset):
-        rc = self.lib.ppo_policy_forward_f32(
+        fn = self.lib.ppo_policy_forward_tc if self.tensor_cores else self.lib.ppo_policy_forward_f32
+        rc = fn(
             _lib.ptr(self.params), _lib.ptr(obs, torch.float32), ctypes.c_int32(self.D), _lib.ptr(self.obs_rms.mean32),
             _lib.ptr(self.obs_rms.var32), _lib.ptr(self.val_rms.mean32), _lib.ptr(self.val_rms.var32), ctypes.c_uint64(self.seed),
             ctypes.c_uint64(self.sample_counter), ctypes.c_int64(row_offset), _lib.ptr(actions), _lib.ptr(neglogp), _lib.ptr(values),
@@ -172,7 +179,7 @@ class PolicyMLP:
     def optimizer_step(self) -> None:
         """trancate_gradients_and_step (+ the adaptive-KL lr update), on device."""
         rc = self.lib.ppo_adam_step_f32(_lib.ptr(self.params), _lib.ptr(self.grads), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
-                                        _lib.ptr(self.lr), _lib.ptr(self.step), ctypes.c_int64(self.P), ctypes.byref(self.adam_params),
+                                        _lib.ptr(self._lr2), _lib.ptr(self._step2), ctypes.c_int64(self.P), ctypes.byref(self.adam_params),
                                         _lib.stream())
         _lib.check(rc, "ppo_adam_step_f32")
 

@@ -116,3 +116,25 @@ def test_minibatch_grad_vs_oracle_autograd_large():
     assert_close(torch.tensor(s["kl"]), st["kl"], 1e-4, 1e-6, "kl")
     assert_close(g[: pol.P], params.grad, 2e-4, 3e-7, "grads (fp32 sums over 8k samples)")
     assert_close(mu, st["mu"], 1e-5, 2e-6, "new mu")
+
+
+def test_tensor_core_forward_vs_fp32(golden):
+    """tcgen05/TMEM forward (TF32 operands, tanh.approx) against the fp32 SIMT kernel: ~1e-3 class agreement, identical
+    sampling noise (same Philox keys), and against the reference golden at the same tolerance."""
+    G = golden("ppo")
+    tc, ref = _policy(G, tensor_cores=True), _policy(G, tensor_cores=False)
+    assert tc.tensor_cores and not ref.tensor_cores
+    for M in (200, 128, 1, 16384 + 77):
+        obs = cu(G["obs"]) if M == 200 else torch.randn((M, D), device=DEV) * 3
+        a, b = tc.act(obs), ref.act(obs)
+        # hidden activations carry ~5e-4 relative error each; mu/value are O(0.1-1) sums of 128 terms
+        assert_close(a["mus"], b["mus"], 5e-3, 5e-3, f"tc mus M={M}")
+        assert_close(a["values"], b["values"], 5e-3, 1e-2, f"tc values M={M}")
+        assert torch.equal(a["sigmas"], b["sigmas"])
+        assert_close(a["actions"] - a["mus"], b["actions"] - b["mus"], 1e-6, 1e-6, "same noise")
+        sg = a["sigmas"].cpu()
+        assert_close(a["neglogpacs"], P.neglogp(a["actions"].cpu(), a["mus"].cpu(), sg, torch.log(sg)), 1e-5, 1e-5, "neglogp self-consistent")
+        assert_close(tc.values(obs), b["values"], 5e-3, 1e-2, "tc get_values")
+    out = tc.act(cu(G["obs"]))
+    assert_close(out["mus"], G["inf_mus"], 5e-3, 5e-3, "tc mus vs reference")
+    assert_close(out["values"], G["inf_values"], 5e-3, 1e-2, "tc values vs reference")
