@@ -301,7 +301,11 @@ int ppo_policy_forward_f32(const float* params, const float* obs /*[M,D]*/, int3
 
 /* the same contract on the tcgen05 tensor cores (TF32 operands, fp32 accumulation in TMEM, tanh.approx): ~1e-3 relative
  * of the fp32 entry point above; requires obs_dim <= 15 (one padded K column carries the first-layer bias) */
-int ppo_policy_forward_tc(const float* params, const float* obs, int32_t obs_dim, const float* obs_mean, const float* obs_var,
+int64_t ppo_packed_weight_floats(void);
+/* params -> weight operand tiles pre-arranged in the kernels' shared-memory order (staged by TMA bulk copies); call after
+ * every parameter update.  `packed`: ppo_packed_weight_floats() floats, 16 B aligned */
+int ppo_pack_weights_tc(const float* params, int32_t obs_dim, float* packed, void* stream);
+int ppo_policy_forward_tc(const float* params, const float* packed, const float* obs, int32_t obs_dim, const float* obs_mean, const float* obs_var,
                           const float* value_mean, const float* value_var, uint64_t seed, uint64_t counter, int64_t row_offset,
                           float* actions, float* neglogp, float* values, float* mus, float* sigmas, int64_t M, void* stream);
 
@@ -331,6 +335,15 @@ int ppo_minibatch_grad_f32(const float* params, const float* obs /*[M,D]*/, int3
                            const PpoLossParams* lp, float* grads /*[P+PPO_STAT_COUNT]*/, float* scratch,
                            int64_t M, void* stream);
 
+/* the same minibatch step with every GEMM (forward, dH, and the weight gradients, which accumulate in TMEM across the
+ * CTA's tiles) on the tcgen05 tensor cores in TF32; obs_dim <= 15 */
+int ppo_minibatch_grad_tc(const float* params, const float* packed, const float* obs, int32_t obs_dim, const float* obs_mean, const float* obs_var,
+                          const float* actions, const float* old_neglogp, const float* advantages, const float* old_values,
+                          const float* returns, float* old_mu, float* old_sigma, const PpoLossParams* lp, float* grads,
+                          float* scratch, float* workspace /*ppo_train_tc_workspace_floats(M) floats, 16 B aligned*/,
+                          int64_t M, void* stream);
+int64_t ppo_train_tc_workspace_floats(int64_t M);
+
 /* gradient-norm clip + Adam + adaptive-KL learning rate, all on device (no kl.item() host sync)                  */
 /*   [ref: RLG/common/a2c_common.py:308-330 ; torch.optim.Adam ; RLG/common/schedulers.py:19-32]                  */
 typedef struct {
@@ -344,6 +357,11 @@ int ppo_adam_step_f32(float* params, float* grads /*[P+PPO_STAT_COUNT], scaled i
                       float* lr /*device float[2]: [0] current lr (updated), [1] scratch*/,
                       int32_t* step /*device int32[2]: [0] Adam step count (incremented), [1] scratch*/,
                       int64_t P, const PpoAdamParams* ap, void* stream);
+
+/* RunningMeanStd training-mode update, fused: batch moments of x[M,D] + Chan merge into the fp64 running state + fp32 copies
+ *   [ref: RLG/algos_torch/running_mean_std.py:69-89] */
+int ppo_rms_update_f64(const float* x /*[M,D]*/, int64_t M, int32_t D, double* mean /*[D]*/, double* var /*[D]*/, double* count /*[1]*/,
+                       float* mean32 /*[D]*/, float* var32 /*[D]*/, void* stream);
 
 #ifdef __cplusplus
 }

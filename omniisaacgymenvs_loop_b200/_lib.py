@@ -23,7 +23,7 @@ _CTYPES = {
     "float": ctypes.c_float, "int32_t": ctypes.c_int32, "uint32_t": ctypes.c_uint32,
     "int64_t": ctypes.c_int64, "uint64_t": ctypes.c_uint64,
     "float*": ctypes.c_void_p, "const float*": ctypes.c_void_p, "int64_t*": ctypes.c_void_p,
-    "uint32_t*": ctypes.c_void_p, "int32_t*": ctypes.c_void_p,
+    "uint32_t*": ctypes.c_void_p, "int32_t*": ctypes.c_void_p, "double*": ctypes.c_void_p,
 }
 
 
@@ -118,6 +118,8 @@ def lib() -> ctypes.CDLL:
     L.usv_b200_sizeof.argtypes = [ctypes.c_char_p]
     L.ppo_param_count.restype = ctypes.c_int64
     L.ppo_train_scratch_floats.restype = ctypes.c_int64
+    L.ppo_train_tc_workspace_floats.restype = ctypes.c_int64
+    L.ppo_packed_weight_floats.restype = ctypes.c_int64
     for name, st in STRUCTS.items():
         want = L.usv_b200_sizeof(name.encode())
         if want != ctypes.sizeof(st):

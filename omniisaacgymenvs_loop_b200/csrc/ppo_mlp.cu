@@ -547,6 +547,50 @@ __global__ void __launch_bounds__(kAdamThreads) adam_kernel(float* __restrict__ 
   }
 }
 
+// RunningMeanStd.forward in training mode, fused: batch mean / unbiased variance per feature (fp32 inputs, fp64 accumulation)
+// + the Chan parallel-variance merge into the fp64 running moments + the fp32 copies the network kernels read.
+// One CTA per feature.  [ref: RLG/algos_torch/running_mean_std.py:69-89]
+__global__ void __launch_bounds__(256) rms_update_kernel(const float* __restrict__ x, int64_t M, int D, double* __restrict__ mean,
+                                                         double* __restrict__ var, double* __restrict__ count,
+                                                         float* __restrict__ mean32, float* __restrict__ var32) {
+  __shared__ double sh[2][8];
+  const int d = blockIdx.x, t = threadIdx.x;
+  // pass 1: mean
+  double s = 0.0;
+  for (int64_t r = t; r < M; r += 256) s += (double)x[r * D + d];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((t & 31) == 0) sh[0][t >> 5] = s;
+  __syncthreads();
+  double bm = 0.0;
+  for (int w = 0; w < 8; ++w) bm += sh[0][w];
+  bm /= (double)M;
+  // pass 2: centred sum of squares (the batch is L2-resident)
+  double q = 0.0;
+  for (int64_t r = t; r < M; r += 256) {
+    const double c = (double)x[r * D + d] - bm;
+    q += c * c;
+  }
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  if ((t & 31) == 0) sh[1][t >> 5] = q;
+  __syncthreads();
+  if (t == 0) {
+    double ss = 0.0;
+    for (int w = 0; w < 8; ++w) ss += sh[1][w];
+    // torch computes the batch moments in fp32 (input.mean / input.var) before they are promoted: round-trip through float
+    const double bmean = (double)(float)bm, bvar = (double)(float)(M > 1 ? ss / (double)(M - 1) : 0.0);
+    const double cnt = *count, bc = (double)M, tot = cnt + bc;
+    const double delta = bmean - mean[d];
+    const double new_mean = mean[d] + delta * bc / tot;
+    const double M2 = var[d] * cnt + bvar * bc + delta * delta * cnt * bc / tot;
+    mean[d] = new_mean;
+    var[d] = M2 / tot;
+    mean32[d] = (float)new_mean;
+    var32[d] = (float)(M2 / tot);
+  }
+}
+__global__ void rms_count_kernel(double* count, double add) { *count += add; }
+__global__ void adam_roll_kernel(float* lr, int* step) { lr[0] = lr[1]; step[0] = step[1]; }
+
 static int g_num_sms = 0;
 static int num_sms() {
   if (!g_num_sms) {
@@ -558,6 +602,10 @@ static int num_sms() {
   return g_num_sms;
 }
 constexpr int kMaxParts = 160;
+
+void launch_reduce(const float* scratch, int nparts, int n, float* grads, const PpoLossParams& lp, int P, cudaStream_t s) {
+  reduce_kernel<<<(n + 63) / 64, 256, 0, s>>>(scratch, nparts, n, grads, lp, P);
+}
 
 }  // namespace ppo
 
@@ -614,9 +662,17 @@ int ppo_adam_step_f32(float* params, float* grads, float* exp_avg, float* exp_av
   // lr/step are double-buffered ([0] = current, [1] = next) so that no CTA can observe the update of another CTA
   adam_kernel<<<(int)((P + kAdamThreads - 1) / kAdamThreads), kAdamThreads, 0, (cudaStream_t)stream>>>(
       params, grads, exp_avg, exp_avg_sq, lr, step, lr + 1, step + 1, (int)P, *ap);
-  cudaMemcpyAsync(lr, lr + 1, sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
-  cudaMemcpyAsync(step, step + 1, sizeof(int32_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
-  return usv::finish_launch();
+  adam_roll_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(lr, step);
+  return usv::finish_launch(2);
+}
+
+int ppo_rms_update_f64(const float* x, int64_t M, int32_t D, double* mean, double* var, double* count, float* mean32, float* var32,
+                       void* stream) {
+  if (M <= 0 || D < 1) return USV_E_SIZE;
+  if (!x || !mean || !var || !count || !mean32 || !var32) return USV_E_NULL;
+  rms_update_kernel<<<D, 256, 0, (cudaStream_t)stream>>>(x, M, D, mean, var, count, mean32, var32);
+  rms_count_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(count, (double)M);   // after every feature has read the old count
+  return usv::finish_launch(2);
 }
 
 }  // extern "C"

@@ -152,25 +152,66 @@ __device__ __forceinline__ void gemm_kmajor(uint32_t tmem_d, const float* a_tile
   }
 }
 
+
+// ---- packed weights ---------------------------------------------------------------------------------------------
+// The four weight operand tiles live pre-arranged ("packed") in global memory in exactly the byte order of the shared-
+// memory tiles, so a CTA stages all of them with a few TMA bulk copies (cp.async.bulk + mbarrier complete_tx) issued by ONE
+// thread instead of ~50 dependent LDG/STS rounds per thread (the first version of these kernels spent half its time there).
+//   [ W2 tile 128x128 | W2^T tile 128x128 | W1 tile 128x16 (col D = b1) | heads tile 16x128 | b2[128] | b3[16] ]
+constexpr int PK_W2 = 0, PK_W2T = PK_W2 + H * H, PK_W1 = PK_W2T + H * H, PK_W3 = PK_W1 + H * DP, PK_B2 = PK_W3 + 16 * H,
+              PK_B3 = PK_B2 + H, PK_TOTAL = PK_B3 + 16;
+
+__device__ __forceinline__ void tile_inv(int e, int kc, int& outer, int& inner) {
+  const int og = e / (kc * 32), rem = e - og * (kc * 32);
+  outer = og * 8 + ((rem & 31) >> 2);
+  inner = (rem >> 5) * 4 + (rem & 3);
+}
+__global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ prm, int D, float* __restrict__ pk) {
+  const Layout L(D);
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= PK_TOTAL) return;
+  int o, i;
+  float v = 0.f;
+  if (e < PK_W2T) { tile_inv(e - PK_W2, H / 4, o, i); v = prm[L.w2 + o * H + i]; }
+  else if (e < PK_W1) { tile_inv(e - PK_W2T, H / 4, o, i); v = prm[L.w2 + i * H + o]; }          // outer = in-feature, inner = out-feature
+  else if (e < PK_W3) { tile_inv(e - PK_W1, DP / 4, o, i); v = i < D ? prm[L.w1 + o * D + i] : (i == D ? prm[L.b1 + o] : 0.f); }
+  else if (e < PK_B2) { tile_inv(e - PK_W3, H / 4, o, i); v = o < 2 ? prm[L.wmu + o * H + i] : (o == 2 ? prm[L.wv + i] : 0.f); }
+  else if (e < PK_B3) { v = prm[L.b2 + (e - PK_B2)]; }
+  else { const int j = e - PK_B3; v = j < 2 ? prm[L.bmu + j] : (j == 2 ? prm[L.bv] : 0.f); }
+  pk[e] = v;
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(mbar))
+               : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
+
 struct FwdSmem {
   float *w1, *w2, *w3, *x, *act, *b2, *b3;
   uint64_t* mbar;
   uint32_t* tmem_slot;
 };
 __host__ __device__ inline size_t fwd_smem_bytes() {
-  return (size_t)(H * DP + H * H + 16 * H + TM * DP + TM * H + H + 16) * sizeof(float) + 64;
+  return (size_t)(H * DP + H * H + 16 * H + TM * DP + TM * H + H + 16) * sizeof(float) + 96;
 }
 __device__ inline FwdSmem carve_fwd(float* base) {
   FwdSmem s;
   float* p = base;
   s.w2 = p; p += H * H;
-  s.act = p; p += TM * H;
-  s.w1 = p; p += H * DP;
+  s.w1 = p; p += H * DP;          // w1 | w3 | b2 | b3 contiguous: one bulk copy from the packed buffer
   s.w3 = p; p += 16 * H;
-  s.x = p; p += TM * DP;
   s.b2 = p; p += H;
   s.b3 = p; p += 16;
-  s.mbar = reinterpret_cast<uint64_t*>(p); p += 2;
+  s.act = p; p += TM * H;
+  s.x = p; p += TM * DP;
+  s.mbar = reinterpret_cast<uint64_t*>(p); p += 4;   // [0] MMA completion, [1] weight bulk copies
   s.tmem_slot = reinterpret_cast<uint32_t*>(p);
   return s;
 }
@@ -220,7 +261,7 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t tmem_acc, float* act, c
 }
 
 __global__ void __launch_bounds__(NT, 1) forward_tc_kernel(
-    const float* __restrict__ prm, const float* __restrict__ obs, int D, const float* __restrict__ omean,
+    const float* __restrict__ prm, const float* __restrict__ pk, const float* __restrict__ obs, int D, const float* __restrict__ omean,
     const float* __restrict__ ovar, const float* __restrict__ vmean, const float* __restrict__ vvar, uint64_t seed,
     uint64_t counter, int64_t row_offset, float* __restrict__ actions, float* __restrict__ neglogp,
     float* __restrict__ values, float* __restrict__ mus, float* __restrict__ sigmas, int64_t M) {
@@ -228,36 +269,22 @@ __global__ void __launch_bounds__(NT, 1) forward_tc_kernel(
   const Layout L(D);
   const FwdSmem s = carve_fwd(smem);
   const int t = threadIdx.x;
-  // ---- one-time set-up: weights -> operand tiles, TMEM, mbarrier ----------------------------------------
-  stage_matrix(s.w2, prm + L.w2, H, H, H);
-  for (int e = t; e < H * (DP / 4); e += NT) {   // W1 [128][D] + bias column D, zero padded to 16
-    const int r = e >> 2, c4 = (e & 3) * 4;
-    float v[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int d = c4 + q;
-      v[q] = d < D ? prm[L.w1 + r * D + d] : (d == D ? prm[L.b1 + r] : 0.f);
-    }
-    *reinterpret_cast<float4*>(s.w1 + tile_off(r, c4, DP / 4)) = make_float4(v[0], v[1], v[2], v[3]);
-  }
-  for (int e = t; e < 16 * (H / 4); e += NT) {   // heads: rows 0,1 = mu, 2 = value, rest 0
-    const int r = e / (H / 4), c4 = (e - r * (H / 4)) * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r < 2) v = make_float4(prm[L.wmu + r * H + c4], prm[L.wmu + r * H + c4 + 1], prm[L.wmu + r * H + c4 + 2], prm[L.wmu + r * H + c4 + 3]);
-    else if (r == 2) v = make_float4(prm[L.wv + c4], prm[L.wv + c4 + 1], prm[L.wv + c4 + 2], prm[L.wv + c4 + 3]);
-    *reinterpret_cast<float4*>(s.w3 + tile_off(r, c4, H / 4)) = v;
-  }
-  for (int e = t; e < H; e += NT) s.b2[e] = prm[L.b2 + e];
-  if (t < 16) s.b3[t] = t < 2 ? prm[L.bmu + t] : (t == 2 ? prm[L.bv] : 0.f);
+  // ---- one-time set-up: packed weight tiles by TMA bulk copy, TMEM, mbarriers ---------------------------------
   if (t == 0) {
     mbar_init(s.mbar, 1);
+    mbar_init(s.mbar + 1, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    constexpr uint32_t b_w2 = H * H * 4, b_rest = (H * DP + 16 * H + H + 16) * 4;
+    mbar_expect_tx(s.mbar + 1, b_w2 + b_rest);
+    bulk_g2s(s.w2, pk + PK_W2, b_w2, s.mbar + 1);
+    bulk_g2s(s.w1, pk + PK_W1, b_rest, s.mbar + 1);
   }
   if (t < 32) tmem_alloc(s.tmem_slot, 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *s.tmem_slot;
+  mbar_wait(s.mbar + 1, 0);        // weights have landed (async proxy writes: visible to the MMA without a proxy fence)
   const uint32_t acc_h = tmem, acc_o = tmem + 128;
   const float ls0 = prm[L.sigma], ls1 = prm[L.sigma + 1];
   const float sg0 = expf(ls0), sg1 = expf(ls1);
@@ -337,6 +364,380 @@ __global__ void __launch_bounds__(NT, 1) forward_tc_kernel(
   if (t < 32) tmem_dealloc(tmem, 256);
 }
 
+
+// =====================================================================================================================
+// Training on the tensor cores: two kernels per minibatch.
+//
+// tcgen05.mma.kind::tf32 only takes K-major shared-memory operands (the transpose bits of the instruction descriptor
+// return zeros for tf32 -- scripts/probes/tc_probe.cu), and the weight gradients contract over the SAMPLE index, so their
+// operands must be sample-contiguous while the forward / dH operands are feature-contiguous.  Instead of transposing
+// 64 KB tiles inside one CTA (shared memory cannot hold both orientations of H1, H2, dz2 plus W2 and W2^T), the work is
+// split where the orientation changes:
+//
+//  T1 train_fwd_bwd_tc_kernel (one CTA per 128-sample tile):
+//       forward (3 UMMA GEMMs) -> per-sample PPO losses -> dz3 -> dz2 = (dz3.W3)(1-H2^2) -> dH1 = dz2.W2 (UMMA, W2^T tile)
+//       -> dz1 = dH1 (1-H1^2).  H1, H2, dz2, dz1, X, dz3 are written to global FEATURE-major ([feature][sample]): each
+//       store instruction of a warp covers 32 consecutive samples of one feature, i.e. one full 128 B line.
+//  T2 wgrad_tc_kernel (one CTA per 64-sample chunk): loads the feature-major slabs straight into K-major operand tiles
+//       (float4 along the sample axis, no transposition) and runs dW2 = dz2^T.H1, [dW1|db1] = dz1^T.X, dW3^T = H2^T.dz3,
+//       db2 = dz2^T.1 as UMMA GEMMs with K = samples; accumulators in TMEM; partial gradients per CTA.
+//  The slabs (4 x 4 MB at the reference's 8192-sample minibatch) stay in the 126 MB L2 between the two kernels.
+struct LossInTc {
+  const float *actions, *old_nlp, *adv, *old_v, *ret;
+  float *old_mu, *old_sigma;
+};
+struct TrainWs {   // feature-major workspaces, leading dimension ld (samples, multiple of 128)
+  float *h1t, *h2t, *dz2t, *dz1t, *xt, *dz3t;
+  int64_t ld;
+};
+
+struct TrainSmem {
+  float *w1, *w2, *w2t, *w3, *x, *act, *dz3, *b2, *b3, *red;
+  uint64_t* mbar;
+  uint32_t* tmem_slot;
+};
+__host__ __device__ inline size_t train_smem_bytes() {
+  return (size_t)(H * DP + 2 * H * H + 16 * H + TM * DP + TM * H + TM * 4 + H + 16 + 64) * sizeof(float) + 96;
+}
+__device__ inline TrainSmem carve_train(float* base) {
+  TrainSmem s;
+  float* p = base;
+  s.w2 = p; p += H * H;           // w2 | w2t | w1 | w3 | b2 | b3: the packed-buffer order
+  s.w2t = p; p += H * H;
+  s.w1 = p; p += H * DP;
+  s.w3 = p; p += 16 * H;
+  s.b2 = p; p += H;
+  s.b3 = p; p += 16;
+  s.act = p; p += TM * H;
+  s.x = p; p += TM * DP;
+  s.dz3 = p; p += TM * 4;
+  s.red = p; p += 64;
+  s.mbar = reinterpret_cast<uint64_t*>(p); p += 4;
+  s.tmem_slot = reinterpret_cast<uint32_t*>(p);
+  return s;
+}
+
+// hidden-layer epilogue that also stores the activation feature-major to global (ht[col][sample])
+__device__ __forceinline__ void hidden_epilogue_store(uint32_t tmem_acc, float* act, const float* bias, float* __restrict__ ht,
+                                                     int64_t ld, int64_t sample) {
+  const int t = threadIdx.x, row = t & 127, half = t >> 7;
+  const uint32_t lane_base = (uint32_t)((t >> 5) & 3) * 32u;
+#pragma unroll
+  for (int c0 = 0; c0 < 64; c0 += 32) {
+    const int col = half * 64 + c0;
+    float v[32];
+    tmem_ld32(tmem_acc + (lane_base << 16) + (uint32_t)col, v);
+#pragma unroll
+    for (int q = 0; q < 32; ++q) v[q] = tanh_fast(v[q] + (bias ? bias[col + q] : 0.f));
+#pragma unroll
+    for (int q = 0; q < 32; q += 4)
+      *reinterpret_cast<float4*>(act + tile_off(row, col + q, H / 4)) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+#pragma unroll
+    for (int q = 0; q < 32; ++q) ht[(int64_t)(col + q) * ld + sample] = v[q];   // warp: 32 consecutive samples of one feature
+  }
+}
+
+__global__ void __launch_bounds__(NT, 1) train_fwd_bwd_tc_kernel(const float* __restrict__ prm, const float* __restrict__ pk,
+                                                                const float* __restrict__ obs, int D,
+                                                                const float* __restrict__ omean, const float* __restrict__ ovar,
+                                                                LossInTc in, PpoLossParams lp, TrainWs ws, float* __restrict__ partial,
+                                                                int64_t M) {
+  extern __shared__ __align__(1024) float smem[];
+  const Layout L(D);
+  const TrainSmem s = carve_train(smem);
+  const int t = threadIdx.x, row = t & 127, half = t >> 7;
+  const uint32_t lane_base = (uint32_t)((t >> 5) & 3) * 32u;
+  // ---- one-time set-up: packed weight tiles by TMA bulk copy, TMEM, mbarriers ---------------------------------
+  if (t == 0) {
+    mbar_init(s.mbar, 1);
+    mbar_init(s.mbar + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    constexpr uint32_t b_w = H * H * 4, b_rest = (H * DP + 16 * H + H + 16) * 4;
+    mbar_expect_tx(s.mbar + 1, 2 * b_w + b_rest);
+    bulk_g2s(s.w2, pk + PK_W2, b_w, s.mbar + 1);
+    bulk_g2s(s.w2t, pk + PK_W2T, b_w, s.mbar + 1);
+    bulk_g2s(s.w1, pk + PK_W1, b_rest, s.mbar + 1);
+  }
+  if (t < 32) tmem_alloc(s.tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s.tmem_slot;
+  mbar_wait(s.mbar + 1, 0);
+  const uint32_t acc_h = tmem, acc_o = tmem + 128;
+  const float ls0 = prm[L.sigma], ls1 = prm[L.sigma + 1];
+  const float sg0 = expf(ls0), sg1 = expf(ls1);
+  const float invM = 1.0f / (float)M;
+  float st_a = 0.f, st_c = 0.f, st_e = 0.f, st_b = 0.f, st_kl = 0.f, g_ls0 = 0.f, g_ls1 = 0.f, g_b3[3] = {0.f, 0.f, 0.f};
+  uint32_t phase = 0;
+  const int64_t ntiles = (M + TM - 1) / TM;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t row0 = tile * TM;
+    const int64_t sample = row0 + row;          // < ws.ld always (ld is padded to a multiple of 128)
+    // ---------------- forward ----------------
+    stage_obs(s.x, obs, D, omean, ovar, row0, M);
+    __syncthreads();
+    if (t < 128) {                              // X^T to global for the weight-gradient kernel (zero rows beyond M)
+#pragma unroll
+      for (int d = 0; d < DP; ++d) ws.xt[(int64_t)d * ws.ld + sample] = (row0 + t < M) ? s.x[tile_off(t, d, DP / 4)] : 0.f;
+    }
+    fence_async_smem(); tc_fence_before(); __syncthreads();
+    if (t == 0) { tc_fence_after(); gemm_kmajor(acc_h, s.x, DP / 4, s.w1, DP / 4, DP, H); umma_commit(s.mbar); }
+    mbar_wait(s.mbar, phase); phase ^= 1; tc_fence_after();
+    hidden_epilogue_store(acc_h, s.act, nullptr, ws.h1t, ws.ld, sample);
+    fence_async_smem(); tc_fence_before(); __syncthreads();
+    if (t == 0) { tc_fence_after(); gemm_kmajor(acc_h, s.act, H / 4, s.w2, H / 4, H, H); umma_commit(s.mbar); }
+    mbar_wait(s.mbar, phase); phase ^= 1; tc_fence_after();
+    hidden_epilogue_store(acc_h, s.act, s.b2, ws.h2t, ws.ld, sample);
+    fence_async_smem(); tc_fence_before(); __syncthreads();
+    if (t == 0) { tc_fence_after(); gemm_kmajor(acc_o, s.act, H / 4, s.w3, H / 4, H, 16); umma_commit(s.mbar); }
+    mbar_wait(s.mbar, phase); phase ^= 1; tc_fence_after();
+    // ---------------- per-sample losses -> dz3 (threads 0..127, one row each) ----------------
+    if (t < 128) {
+      const int64_t r = row0 + t;
+      float o[16];
+      tmem_ld16(acc_o + (lane_base << 16), o);
+      const float mu0 = o[0] + s.b3[0], mu1 = o[1] + s.b3[1], v = o[2] + s.b3[2];
+      float d_mu0 = 0.f, d_mu1 = 0.f, d_v = 0.f;
+      if (r < M) {
+        const float a0 = in.actions[r * 2], a1 = in.actions[r * 2 + 1];
+        const float e0 = (a0 - mu0) / sg0, e1 = (a1 - mu1) / sg1;
+        const float nlp = 0.5f * (e0 * e0 + e1 * e1) + kHalfLog2Pi2 + (ls0 + ls1);
+        const float adv = in.adv[r];
+        const float ratio = expf(in.old_nlp[r] - nlp);
+        const float s1 = adv * ratio;
+        const float s2 = adv * fminf(fmaxf(ratio, 1.0f - lp.e_clip), 1.0f + lp.e_clip);
+        const float a_loss = fmaxf(-s1, -s2);
+        const float g_nlp = (-s1 >= -s2) ? s1 : 0.f;
+        const float ov = in.old_v[r], ret = in.ret[r];
+        float c_loss, g_v;
+        if (lp.clip_value) {
+          const float dvc = fminf(fmaxf(v - ov, -lp.e_clip), lp.e_clip);
+          const float vpc = ov + dvc;
+          const float l1 = (v - ret) * (v - ret), l2 = (vpc - ret) * (vpc - ret);
+          c_loss = fmaxf(l1, l2);
+          const bool inside = fabsf(v - ov) <= lp.e_clip;
+          g_v = (l1 >= l2) ? 2.0f * (v - ret) : (inside ? 2.0f * (vpc - ret) : 0.f);
+        } else {
+          c_loss = (ret - v) * (ret - v);
+          g_v = 2.0f * (v - ret);
+        }
+        const float h0 = fmaxf(mu0 - lp.bound_soft, 0.f), l0 = fminf(mu0 + lp.bound_soft, 0.f);
+        const float h1v = fmaxf(mu1 - lp.bound_soft, 0.f), l1v = fminf(mu1 + lp.bound_soft, 0.f);
+        const float b_loss = (l0 * l0 + h0 * h0) + (l1v * l1v + h1v * h1v);
+        const float ent = (0.5f + 0.5f * 1.8378770664093453f + ls0) + (0.5f + 0.5f * 1.8378770664093453f + ls1);
+        const float om0 = in.old_mu[r * 2], om1 = in.old_mu[r * 2 + 1];
+        const float os0 = in.old_sigma[r * 2], os1 = in.old_sigma[r * 2 + 1];
+        const float kl0 = logf(os0 / sg0 + 1e-5f) + (sg0 * sg0 + (om0 - mu0) * (om0 - mu0)) / (2.0f * (os0 * os0 + 1e-5f)) - 0.5f;
+        const float kl1 = logf(os1 / sg1 + 1e-5f) + (sg1 * sg1 + (om1 - mu1) * (om1 - mu1)) / (2.0f * (os1 * os1 + 1e-5f)) - 0.5f;
+        st_a += a_loss; st_c += c_loss; st_e += ent; st_b += b_loss; st_kl += kl0 + kl1;
+        const float wa = invM, wc = 0.5f * lp.critic_coef * invM, wb = lp.bounds_loss_coef * invM, we = lp.entropy_coef * invM;
+        d_mu0 = wa * g_nlp * (-(a0 - mu0) / (sg0 * sg0)) + wb * 2.0f * (h0 + l0);
+        d_mu1 = wa * g_nlp * (-(a1 - mu1) / (sg1 * sg1)) + wb * 2.0f * (h1v + l1v);
+        d_v = wc * g_v;
+        g_ls0 += wa * g_nlp * (1.0f - e0 * e0) - we;
+        g_ls1 += wa * g_nlp * (1.0f - e1 * e1) - we;
+        g_b3[0] += d_mu0; g_b3[1] += d_mu1; g_b3[2] += d_v;
+        in.old_mu[r * 2] = mu0; in.old_mu[r * 2 + 1] = mu1;
+        in.old_sigma[r * 2] = sg0; in.old_sigma[r * 2 + 1] = sg1;
+      }
+      *reinterpret_cast<float4*>(s.dz3 + t * 4) = make_float4(d_mu0, d_mu1, d_v, 0.f);
+      ws.dz3t[0 * ws.ld + sample] = d_mu0;
+      ws.dz3t[1 * ws.ld + sample] = d_mu1;
+      ws.dz3t[2 * ws.ld + sample] = d_v;
+    }
+    __syncthreads();
+    // ---------------- dz2 = (dz3 . W3) * (1 - H2^2), in place over H2 (operand tile) + feature-major to global -------------
+    {
+      const float4 g = *reinterpret_cast<const float4*>(s.dz3 + row * 4);
+#pragma unroll 4
+      for (int c = half * 64; c < half * 64 + 64; c += 4) {
+        float* hp = s.act + tile_off(row, c, H / 4);
+        const float4 h = *reinterpret_cast<const float4*>(hp);
+        const float4 wa = *reinterpret_cast<const float4*>(s.w3 + tile_off(0, c, H / 4));
+        const float4 wb = *reinterpret_cast<const float4*>(s.w3 + tile_off(1, c, H / 4));
+        const float4 wc = *reinterpret_cast<const float4*>(s.w3 + tile_off(2, c, H / 4));
+        float4 o;
+        o.x = (g.x * wa.x + g.y * wb.x + g.z * wc.x) * (1.0f - h.x * h.x);
+        o.y = (g.x * wa.y + g.y * wb.y + g.z * wc.y) * (1.0f - h.y * h.y);
+        o.z = (g.x * wa.z + g.y * wb.z + g.z * wc.z) * (1.0f - h.z * h.z);
+        o.w = (g.x * wa.w + g.y * wb.w + g.z * wc.w) * (1.0f - h.w * h.w);
+        *reinterpret_cast<float4*>(hp) = o;
+        ws.dz2t[(int64_t)(c + 0) * ws.ld + sample] = o.x;
+        ws.dz2t[(int64_t)(c + 1) * ws.ld + sample] = o.y;
+        ws.dz2t[(int64_t)(c + 2) * ws.ld + sample] = o.z;
+        ws.dz2t[(int64_t)(c + 3) * ws.ld + sample] = o.w;
+      }
+    }
+    // ---------------- dH1 = dz2 . W2   (A = dz2 tile, B = W2^T tile, both K-major) ----------------
+    fence_async_smem(); tc_fence_before(); __syncthreads();
+    if (t == 0) { tc_fence_after(); gemm_kmajor(acc_h, s.act, H / 4, s.w2t, H / 4, H, H); umma_commit(s.mbar); }
+    mbar_wait(s.mbar, phase); phase ^= 1; tc_fence_after();
+    // ---------------- dz1 = dH1 * (1 - H1^2): H1 re-read feature-major from global (L2), dz1 stored feature-major ----------
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 32) {
+      const int col = half * 64 + c0;
+      float v[32];
+      tmem_ld32(acc_h + (lane_base << 16) + (uint32_t)col, v);
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        const float h = ws.h1t[(int64_t)(col + q) * ws.ld + sample];
+        ws.dz1t[(int64_t)(col + q) * ws.ld + sample] = v[q] * (1.0f - h * h);
+      }
+    }
+    tc_fence_before();
+    __syncthreads();   // X / ACT / dz3 and the TMEM accumulators are reused by the next tile
+  }
+  // ---- this CTA's share of the scalar-parameter gradients and the statistics: compact 16-float slot --------------
+  float* out = partial + (size_t)blockIdx.x * 16;
+  float vals[10] = {st_a, st_c, st_e, st_b, st_kl, g_ls0, g_ls1, g_b3[0], g_b3[1], g_b3[2]};
+  float* red = s.red;   // [10][4] (threads 0..127 hold the data: 4 warps)
+#pragma unroll
+  for (int q = 0; q < 10; ++q) {
+    float v = vals[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((t & 31) == 0 && t < 128) red[q * 4 + (t >> 5)] = v;
+  }
+  __syncthreads();
+  if (t == 0) {   // slot: [a, c, ent, b, kl (means)] [dlogstd0, dlogstd1, dbmu0, dbmu1, dbv]
+    for (int q = 0; q < 10; ++q) {
+      const float v = (red[q * 4] + red[q * 4 + 1]) + (red[q * 4 + 2] + red[q * 4 + 3]);
+      out[q] = q < 5 ? v * invM : v;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (t < 32) tmem_dealloc(tmem, 256);
+}
+
+// second stage for the tensor-core path: matrix gradients from the wgrad slots, scalar gradients + statistics from T1's slots
+__global__ void __launch_bounds__(256) reduce_tc_kernel(const float* __restrict__ scal, int g1, const float* __restrict__ mat, int g2,
+                                                       int D, float* __restrict__ grads, PpoLossParams lp) {
+  __shared__ float sm[4][64];
+  __shared__ float sc[16];
+  const Layout L(D);
+  const int col = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  const int e = blockIdx.x * 64 + col;
+  float acc = 0.f;
+  if (e < L.P)
+    for (int c = grp; c < g2; c += 4) acc += mat[(size_t)c * L.P + e];
+  sm[grp][col] = acc;
+  __syncthreads();
+  const bool scalar_entry = e < L.w1 || e >= L.bmu || e == L.bv;
+  if (grp == 0 && e < L.P && !scalar_entry) grads[e] = (sm[0][col] + sm[1][col]) + (sm[2][col] + sm[3][col]);
+  if (blockIdx.x == 0 && threadIdx.x < 10) {
+    float v = 0.f;
+    for (int c = 0; c < g1; ++c) v += scal[c * 16 + threadIdx.x];
+    sc[threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const float* v = sc;
+    grads[L.P + PPO_STAT_A_LOSS] = v[0]; grads[L.P + PPO_STAT_C_LOSS] = v[1]; grads[L.P + PPO_STAT_ENTROPY] = v[2];
+    grads[L.P + PPO_STAT_B_LOSS] = v[3]; grads[L.P + PPO_STAT_KL] = v[4];
+    grads[L.P + PPO_STAT_LOSS] = v[0] + 0.5f * v[1] * lp.critic_coef - v[2] * lp.entropy_coef + v[3] * lp.bounds_loss_coef;
+    grads[L.P + PPO_STAT_GRAD_NORM] = 0.f; grads[L.P + PPO_STAT_LR] = 0.f;
+    grads[L.sigma] = v[5]; grads[L.sigma + 1] = v[6]; grads[L.bmu] = v[7]; grads[L.bmu + 1] = v[8]; grads[L.bv] = v[9];
+  }
+}
+
+// ---- T2: weight gradients, K = samples ------------------------------------------------------------------------------
+constexpr int WK = 64;   // samples per CTA chunk
+// feature-major global slab [rows][ld] (columns c0..c0+WK) -> K-major operand tile (outer = feature row, inner = sample)
+__device__ __forceinline__ void stage_slab(float* tile, const float* __restrict__ g, int rows, int64_t ld, int64_t c0) {
+  // walk the tile in shared-memory order (consecutive lanes -> consecutive 16 B chunks: conflict-free); the matching global
+  // reads are 8 rows x 64 B per warp instruction, i.e. whole 32 B sectors
+  for (int q = threadIdx.x; q < rows * (WK / 4); q += NT) {
+    const int og = q / (8 * (WK / 4)), rem = q - og * (8 * (WK / 4));
+    const int ic = rem >> 3, ol = rem & 7;
+    cp_async16(tile + q * 4, g + (int64_t)(og * 8 + ol) * ld + c0 + ic * 4);   // asynchronous: no register round trip
+  }
+}
+__host__ __device__ inline size_t wgrad_smem_bytes() { return (size_t)(4 * H * WK + 2 * 16 * WK) * sizeof(float) + 64; }
+
+__global__ void __launch_bounds__(NT, 1) wgrad_tc_kernel(TrainWs ws, int D, float* __restrict__ partial, int part0, int64_t nchunks) {
+  extern __shared__ __align__(1024) float smem[];
+  const Layout L(D);
+  float* dz2 = smem;
+  float* h1 = dz2 + H * WK;
+  float* dz1 = h1 + H * WK;
+  float* h2 = dz1 + H * WK;
+  float* xt = h2 + H * WK;
+  float* dz3 = xt + 16 * WK;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(dz3 + 16 * WK);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(mbar + 1);
+  const int t = threadIdx.x, row = t & 127, half = t >> 7;
+  const uint32_t lane_base = (uint32_t)((t >> 5) & 3) * 32u;
+  if (t == 0) {
+    mbar_init(mbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (t < 32) tmem_alloc(slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *slot;
+  const uint32_t acc_w2 = tmem, acc_w1 = tmem + 128, acc_w3 = tmem + 160, acc_b2 = tmem + 192;
+  uint32_t phase = 0, first = 0;
+  for (int64_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x, first = 1) {
+    const int64_t c0 = ch * WK;
+    stage_slab(dz2, ws.dz2t, H, ws.ld, c0);
+    stage_slab(h1, ws.h1t, H, ws.ld, c0);
+    stage_slab(dz1, ws.dz1t, H, ws.ld, c0);
+    stage_slab(h2, ws.h2t, H, ws.ld, c0);
+    stage_slab(xt, ws.xt, 16, ws.ld, c0);
+    stage_slab(dz3, ws.dz3t, 16, ws.ld, c0);
+    cp_async_wait_all();
+    fence_async_smem(); tc_fence_before(); __syncthreads();
+    if (t == 0) {
+      tc_fence_after();
+      const uint32_t i128 = make_idesc(128, 128, 0, 0), i16 = make_idesc(128, 16, 0, 0);
+      for (int k = 0; k < WK; k += 8) {
+        const uint32_t acc = (k > 0) ? 1u : first;
+        const uint32_t ko = (k >> 2) * 128;
+        const uint64_t d_dz2 = make_desc(smem_u32(dz2) + ko, 128, (WK / 4) * 128), d_h1 = make_desc(smem_u32(h1) + ko, 128, (WK / 4) * 128);
+        const uint64_t d_dz1 = make_desc(smem_u32(dz1) + ko, 128, (WK / 4) * 128), d_h2 = make_desc(smem_u32(h2) + ko, 128, (WK / 4) * 128);
+        const uint64_t d_x = make_desc(smem_u32(xt) + ko, 128, (WK / 4) * 128), d_dz3 = make_desc(smem_u32(dz3) + ko, 128, (WK / 4) * 128);
+        umma_tf32(acc_w2, d_dz2, d_h1, i128, acc);    // dW2[o][i]   += sum_r dz2[r][o] H1[r][i]
+        umma_tf32(acc_w1, d_dz1, d_x, i16, acc);      // dW1[o][d]   += sum_r dz1[r][o] X[r][d]   (column D: db1)
+        umma_tf32(acc_w3, d_h2, d_dz3, i16, acc);     // dW3^T[k][j] += sum_r H2[r][k] dz3[r][j]
+        umma_tf32(acc_b2, d_dz2, d_x, i16, acc);      // column D: db2[o] = sum_r dz2[r][o]
+      }
+      umma_commit(mbar);
+    }
+    mbar_wait(mbar, phase); phase ^= 1; tc_fence_after();
+    tc_fence_before();
+    __syncthreads();
+  }
+  // ---- accumulators -> this CTA's partial-gradient slot ----
+  float* out = partial + (size_t)part0 + (size_t)blockIdx.x * L.P;   // matrix gradients only; scalars come from the T1 slots
+  tc_fence_after();
+#pragma unroll
+  for (int c0 = 0; c0 < 64; c0 += 32) {
+    const int col = half * 64 + c0;
+    float v[32];
+    tmem_ld32(acc_w2 + (lane_base << 16) + (uint32_t)col, v);
+#pragma unroll
+    for (int q = 0; q < 32; ++q) out[L.w2 + row * H + col + q] = v[q];
+  }
+  if (t < 128) {
+    float v[16];
+    tmem_ld16(acc_w1 + (lane_base << 16), v);
+    for (int d = 0; d < D; ++d) out[L.w1 + t * D + d] = v[d];
+    out[L.b1 + t] = v[D];
+    tmem_ld16(acc_w3 + (lane_base << 16), v);
+    out[L.wmu + t] = v[0];
+    out[L.wmu + H + t] = v[1];
+    out[L.wv + t] = v[2];
+    tmem_ld16(acc_b2 + (lane_base << 16), v);
+    out[L.b2 + t] = v[D];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (t < 32) tmem_dealloc(tmem, 256);
+}
+
 static int num_sms() {
   static int n = 0;
   if (!n) {
@@ -352,19 +753,68 @@ static int num_sms() {
 
 using namespace ppotc;
 
-extern "C" int ppo_policy_forward_tc(const float* params, const float* obs, int32_t obs_dim, const float* obs_mean,
+extern "C" int64_t ppo_packed_weight_floats(void) { return PK_TOTAL; }
+
+// params -> packed operand tiles; call after every parameter update (the policy host class does)
+extern "C" int ppo_pack_weights_tc(const float* params, int32_t obs_dim, float* packed, void* stream) {
+  if (!params || !packed) return USV_E_NULL;
+  if (obs_dim < 1 || obs_dim >= DP) return USV_E_SIZE;
+  if ((uintptr_t)packed & 15) return USV_E_ALIGN;
+  pack_weights_kernel<<<(PK_TOTAL + 255) / 256, 256, 0, (cudaStream_t)stream>>>(params, obs_dim, packed);
+  return usv::finish_launch();
+}
+
+extern "C" int ppo_policy_forward_tc(const float* params, const float* packed, const float* obs, int32_t obs_dim, const float* obs_mean,
                                      const float* obs_var, const float* value_mean, const float* value_var, uint64_t seed,
                                      uint64_t counter, int64_t row_offset, float* actions, float* neglogp, float* values,
                                      float* mus, float* sigmas, int64_t M, void* stream) {
   if (M < 0 || obs_dim < 1 || obs_dim >= DP) return USV_E_SIZE;   // one padded column is reserved for the bias
   if (M == 0) return USV_OK;
-  if (!params || !obs || !obs_mean || !obs_var) return USV_E_NULL;
+  if (!params || !packed || !obs || !obs_mean || !obs_var) return USV_E_NULL;
   if ((value_mean == nullptr) != (value_var == nullptr)) return USV_E_NULL;
+  if ((uintptr_t)packed & 15) return USV_E_ALIGN;
   const size_t smem = fwd_smem_bytes();
   cudaFuncSetAttribute(forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int64_t ntiles = (M + TM - 1) / TM;
   const int grid = (int)(ntiles < num_sms() ? ntiles : num_sms());
-  forward_tc_kernel<<<grid, NT, smem, (cudaStream_t)stream>>>(params, obs, obs_dim, obs_mean, obs_var, value_mean, value_var, seed,
+  forward_tc_kernel<<<grid, NT, smem, (cudaStream_t)stream>>>(params, packed, obs, obs_dim, obs_mean, obs_var, value_mean, value_var, seed,
                                                               counter, row_offset, actions, neglogp, values, mus, sigmas, M);
   return usv::finish_launch();
+}
+
+namespace ppo { void launch_reduce(const float* scratch, int nparts, int n, float* grads, const PpoLossParams& lp, int P, cudaStream_t s); }
+
+extern "C" int64_t ppo_train_tc_workspace_floats(int64_t M) {
+  const int64_t ld = (M + 127) / 128 * 128;
+  return (4 * (int64_t)H + 2 * 16) * ld;
+}
+
+extern "C" int ppo_minibatch_grad_tc(const float* params, const float* packed, const float* obs, int32_t obs_dim, const float* obs_mean,
+                                     const float* obs_var, const float* actions, const float* old_neglogp, const float* advantages,
+                                     const float* old_values, const float* returns, float* old_mu, float* old_sigma,
+                                     const PpoLossParams* lp, float* grads, float* scratch, float* workspace, int64_t M, void* stream) {
+  if (M <= 0 || obs_dim < 1 || obs_dim >= DP) return USV_E_SIZE;
+  if (!params || !packed || !obs || !obs_mean || !obs_var || !actions || !old_neglogp || !advantages || !old_values || !returns ||
+      !old_mu || !old_sigma || !lp || !grads || !scratch || !workspace)
+    return USV_E_NULL;
+  if (((uintptr_t)workspace | (uintptr_t)packed) & 15) return USV_E_ALIGN;
+  const Layout L(obs_dim);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t ld = (M + 127) / 128 * 128;
+  TrainWs ws;
+  ws.ld = ld;
+  ws.h1t = workspace; ws.h2t = ws.h1t + H * ld; ws.dz2t = ws.h2t + H * ld; ws.dz1t = ws.dz2t + H * ld;
+  ws.xt = ws.dz1t + H * ld; ws.dz3t = ws.xt + 16 * ld;
+  cudaMemsetAsync(ws.dz3t, 0, sizeof(float) * 16 * ld, st);           // rows 3..15 of dz3^T are structurally zero
+  const int64_t ntiles = ld / TM, nchunks = ld / WK;
+  int g1 = (int)(ntiles < num_sms() ? ntiles : num_sms()), g2 = (int)(nchunks < num_sms() ? nchunks : num_sms());
+  if (g2 > 64) g2 = 64;                                               // fewer, longer wgrad CTAs: the second stage reads g2 x P floats
+  cudaFuncSetAttribute(train_fwd_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)train_smem_bytes());
+  cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wgrad_smem_bytes());
+  LossInTc in{actions, old_neglogp, advantages, old_values, returns, old_mu, old_sigma};
+  train_fwd_bwd_tc_kernel<<<g1, NT, train_smem_bytes(), st>>>(params, packed, obs, obs_dim, obs_mean, obs_var, in, *lp, ws, scratch, M);
+  const int mat0 = 16 * 160;                                          // scalar slots first, then the matrix slots
+  wgrad_tc_kernel<<<g2, NT, wgrad_smem_bytes(), st>>>(ws, obs_dim, scratch, mat0, nchunks);
+  reduce_tc_kernel<<<(L.P + 63) / 64, 256, 0, st>>>(scratch, g1, scratch + mat0, g2, obs_dim, grads, *lp);
+  return usv::finish_launch(3);
 }

@@ -43,8 +43,14 @@ class RunningMeanStd:
         self.var32.copy_(self.var)
 
     def update(self, x: torch.Tensor) -> None:
-        bm, bv, bc = x.mean(0), x.var(0), x.shape[0]
-        self.update_from_moments(bm, bv, bc)
+        """One fused kernel: batch moments + Chan merge + fp32 copies (in place: CUDA-graph friendly)."""
+        x = x.reshape(x.shape[0], -1)
+        if not x.is_contiguous():
+            x = x.contiguous()
+        rc = _lib.lib().ppo_rms_update_f64(_lib.ptr(x, torch.float32), ctypes.c_int64(x.shape[0]), ctypes.c_int32(x.shape[1]),
+                                           _lib.ptr(self.mean), _lib.ptr(self.var), _lib.ptr(self.count.view(1)), _lib.ptr(self.mean32),
+                                           _lib.ptr(self.var32), _lib.stream())
+        _lib.check(rc, "ppo_rms_update_f64")
 
     def update_from_moments(self, bm, bv, bc) -> None:
         # in place: the buffers keep their addresses, so the update can live inside a captured CUDA graph
@@ -95,6 +101,9 @@ class PolicyMLP:
         self.sample_counter = 0
         # tcgen05/TMEM kernels (TF32) when the obs fit their padded K tile; the fp32 SIMT kernels are the numerics reference
         self.tensor_cores = bool(tensor_cores) and self.D <= 15
+        self._ws = None
+        self.packed = torch.zeros(int(self.lib.ppo_packed_weight_floats()), **f32) if self.tensor_cores else None
+        self._packed_dirty = True
         self.loss_params = _lib.PpoLossParams(e_clip, critic_coef, entropy_coef, bounds_loss_coef, 1.1, int(clip_value))
         self.adam_params = _lib.PpoAdamParams(0.9, 0.999, 1e-8, grad_norm, 1.0 / world_size, int(adaptive_lr), kl_threshold, 1e-6, 1e-2)
         self.reset_parameters(seed)
@@ -119,6 +128,7 @@ class PolicyMLP:
                 t.copy_(((torch.rand(t.shape, generator=g) * 2 - 1) * bound).to(self.device))
             else:
                 t.zero_()
+        self._packed_dirty = True
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
         """rl_games 'model' state_dict (same keys / dtypes as the reference checkpoints)."""
@@ -133,6 +143,7 @@ class PolicyMLP:
     def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
         for k, v in self.views().items():
             v.copy_(sd[k].to(self.device))
+        self._packed_dirty = True
         self.val_rms.load(sd["value_mean_std.running_mean"], sd["value_mean_std.running_var"], sd["value_mean_std.count"])
         self.obs_rms.load(sd["running_mean_std.running_mean_std.state.running_mean"],
                           sd["running_mean_std.running_mean_std.state.running_var"],
@@ -155,10 +166,20 @@ class PolicyMLP:
         self._forward(obs, None, None, v, None, None, 0)
         return v
 
+    def pack(self) -> None:
+        """Re-arranges the parameters into the tensor-core kernels' operand tiles (after every parameter change)."""
+        if self.tensor_cores:
+            _lib.check(self.lib.ppo_pack_weights_tc(_lib.ptr(self.params), ctypes.c_int32(self.D), _lib.ptr(self.packed), _lib.stream()),
+                       "ppo_pack_weights_tc")
+        self._packed_dirty = False
+
     def _forward(self, obs, actions, neglogp, values, mus, sigmas, row_offset):
+        if self._packed_dirty:
+            self.pack()
         fn = self.lib.ppo_policy_forward_tc if self.tensor_cores else self.lib.ppo_policy_forward_f32
+        extra = (_lib.ptr(self.packed),) if self.tensor_cores else ()
         rc = fn(
-            _lib.ptr(self.params), _lib.ptr(obs, torch.float32), ctypes.c_int32(self.D), _lib.ptr(self.obs_rms.mean32),
+            _lib.ptr(self.params), *extra, _lib.ptr(obs, torch.float32), ctypes.c_int32(self.D), _lib.ptr(self.obs_rms.mean32),
             _lib.ptr(self.obs_rms.var32), _lib.ptr(self.val_rms.mean32), _lib.ptr(self.val_rms.var32), ctypes.c_uint64(self.seed),
             ctypes.c_uint64(self.sample_counter), ctypes.c_int64(row_offset), _lib.ptr(actions), _lib.ptr(neglogp), _lib.ptr(values),
             _lib.ptr(mus), _lib.ptr(sigmas), ctypes.c_int64(obs.shape[0]), _lib.stream())
@@ -168,11 +189,21 @@ class PolicyMLP:
     def minibatch_grad(self, obs, actions, old_neglogp, advantages, old_values, returns, mu, sigma) -> torch.Tensor:
         """calc_gradients up to backward(): fills self.grads = [dLoss/dparams | stats]; mu/sigma are updated in place
         (dataset.update_mu_sigma)."""
-        rc = self.lib.ppo_minibatch_grad_f32(
-            _lib.ptr(self.params), _lib.ptr(obs, torch.float32), ctypes.c_int32(self.D), _lib.ptr(self.obs_rms.mean32),
-            _lib.ptr(self.obs_rms.var32), _lib.ptr(actions), _lib.ptr(old_neglogp), _lib.ptr(advantages), _lib.ptr(old_values),
-            _lib.ptr(returns), _lib.ptr(mu), _lib.ptr(sigma), ctypes.byref(self.loss_params), _lib.ptr(self.grads), _lib.ptr(self.scratch),
-            ctypes.c_int64(obs.shape[0]), _lib.stream())
+        M = obs.shape[0]
+        common = (_lib.ptr(self.params), _lib.ptr(obs, torch.float32), ctypes.c_int32(self.D), _lib.ptr(self.obs_rms.mean32),
+                  _lib.ptr(self.obs_rms.var32), _lib.ptr(actions), _lib.ptr(old_neglogp), _lib.ptr(advantages), _lib.ptr(old_values),
+                  _lib.ptr(returns), _lib.ptr(mu), _lib.ptr(sigma), ctypes.byref(self.loss_params), _lib.ptr(self.grads),
+                  _lib.ptr(self.scratch))
+        if self.tensor_cores:
+            need = int(self.lib.ppo_train_tc_workspace_floats(ctypes.c_int64(M)))
+            if self._ws is None or self._ws.numel() < need:
+                self._ws = torch.empty(need, dtype=torch.float32, device=self.device)
+            if self._packed_dirty:
+                self.pack()
+            rc = self.lib.ppo_minibatch_grad_tc(common[0], _lib.ptr(self.packed), *common[1:], _lib.ptr(self._ws), ctypes.c_int64(M),
+                                                _lib.stream())
+        else:
+            rc = self.lib.ppo_minibatch_grad_f32(*common, ctypes.c_int64(M), _lib.stream())
         _lib.check(rc, "ppo_minibatch_grad_f32")
         return self.grads
 
@@ -182,6 +213,7 @@ class PolicyMLP:
                                         _lib.ptr(self._lr2), _lib.ptr(self._step2), ctypes.c_int64(self.P), ctypes.byref(self.adam_params),
                                         _lib.stream())
         _lib.check(rc, "ppo_adam_step_f32")
+        self.pack()          # same stream, right behind the update: the packed tiles are never stale
 
     def stats(self) -> Dict[str, float]:
         s = self.grads[self.P:].tolist()

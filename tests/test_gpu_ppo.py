@@ -15,8 +15,9 @@ D = 13
 cu = lambda a: torch.as_tensor(a).to(DEV).contiguous()
 
 
-def _policy(G, **kw):
-    pol = PolicyMLP(D, DEV, lr=3e-4, **kw)
+def _policy(G, tensor_cores=False, **kw):
+    """fp32 SIMT kernels by default: they carry the 1e-5 parity bar; the tensor-core path has its own tests below."""
+    pol = PolicyMLP(D, DEV, lr=3e-4, tensor_cores=tensor_cores, **kw)
     pol.params.copy_(cu(G["params0"]))
     pol.obs_rms.load(G["obs_mean"], G["obs_var"], G["obs_count"])
     pol.val_rms.load(G["val_mean"], G["val_var"], G["val_count"])
@@ -96,7 +97,7 @@ def test_minibatch_grad_vs_oracle_autograd_large():
     """8192-sample minibatch (the reference's minibatch_size) against torch autograd on the oracle."""
     torch.manual_seed(3)
     M = 8192 + 50
-    pol = PolicyMLP(D, DEV, seed=5)
+    pol = PolicyMLP(D, DEV, seed=5, tensor_cores=False)
     pol.params.add_(0.02 * torch.randn(pol.P, device=DEV))
     obs = torch.randn((M, D)) * 2
     pol.obs_rms.update(cu(obs[:500]))
@@ -138,3 +139,59 @@ def test_tensor_core_forward_vs_fp32(golden):
     out = tc.act(cu(G["obs"]))
     assert_close(out["mus"], G["inf_mus"], 5e-3, 5e-3, "tc mus vs reference")
     assert_close(out["values"], G["inf_values"], 5e-3, 1e-2, "tc values vs reference")
+
+
+def test_tensor_core_minibatch_grad_vs_fp32():
+    """tcgen05 training kernel (all GEMMs incl. the TMEM-resident weight-gradient accumulators) vs the fp32 SIMT kernel."""
+    torch.manual_seed(11)
+    for M in (200, 8192, 8192 * 3 + 5):      # ragged single tile / the reference minibatch / several tiles per CTA
+        tc, ref = PolicyMLP(D, DEV, seed=5, tensor_cores=True), PolicyMLP(D, DEV, seed=5, tensor_cores=False)
+        delta = 0.02 * torch.randn(tc.P, device=DEV)
+        tc.params.add_(delta); ref.params.add_(delta)
+        obs = torch.randn((M, D), device=DEV) * 2
+        for p in (tc, ref):
+            p.obs_rms.update(obs[:150])
+        inf = ref.act(obs)
+        act = (inf["actions"] + 0.2 * torch.randn((M, 2), device=DEV)).contiguous()
+        old_nlp = (inf["neglogpacs"] + 0.1 * torch.randn(M, device=DEV)).contiguous()
+        adv, old_v, ret = torch.randn(M, device=DEV), torch.randn(M, device=DEV) * 0.3, torch.randn(M, device=DEV) * 0.5
+        mu0 = (inf["mus"] + 0.02 * torch.randn((M, 2), device=DEV)).contiguous()
+        mu_a, sg_a, mu_b, sg_b = mu0.clone(), inf["sigmas"].clone(), mu0.clone(), inf["sigmas"].clone()
+        ga = tc.minibatch_grad(obs, act, old_nlp, adv, old_v, ret, mu_a, sg_a).clone()
+        gb = ref.minibatch_grad(obs, act, old_nlp, adv, old_v, ret, mu_b, sg_b).clone()
+        sa, sb = tc.stats(), ref.stats()
+        for k in ("a_loss", "c_loss", "b_loss", "kl", "loss", "entropy"):
+            assert abs(sa[k] - sb[k]) <= 5e-3 * abs(sb[k]) + 2e-4, (M, k, sa[k], sb[k])
+        P_ = tc.P
+        # TF32 + tanh.approx: compare per parameter block relative to that block's gradient scale
+        off = 0
+        for name, shp in zip(["sigma", "w1", "b1", "w2", "b2", "wv", "bv", "wmu", "bmu"], [(2,), (128, D), (128,), (128, 128), (128,), (1, 128), (1,), (2, 128), (2,)]):
+            n = int(np.prod(shp))
+            a, b = ga[off:off + n], gb[off:off + n]
+            scale = float(b.abs().max()) + 1e-12
+            err = float((a - b).abs().max())
+            # 2% of the block's scale; + 5e-5 absolute for the scalar blocks (bias gradients are means of sign-alternating
+            # per-sample terms, so TF32 noise does not shrink with the cancelling sum)
+            assert err <= 2e-2 * scale + 5e-5, (M, name, err, scale)
+            if n > 2:
+                cos = float(torch.nn.functional.cosine_similarity(a, b, dim=0))
+                assert cos > 0.999, (M, name, cos)
+            off += n
+        assert_close(mu_a, mu_b, 5e-3, 5e-3, "new mu")
+        tc.optimizer_step(); ref.optimizer_step()
+        assert float((tc.params - ref.params).abs().max()) < 2.1e-4       # one Adam step moves each weight by <= lr
+
+
+def test_ppo_loop_learns_on_tensor_cores():
+    from omniisaacgymenvs_loop_b200.config import UsvEnvConfig
+    from omniisaacgymenvs_loop_b200.rl.a2c import A2CAgent, PPOConfig
+    from scripts.train_usv import make_env
+    cfg = UsvEnvConfig(num_envs=2048, max_episode_length=400)
+    agent = A2CAgent(make_env(cfg.to_task_cfg(), DEV, seed=3, collect_stats=False), PPOConfig(seed=3), DEV)
+    assert agent.policy.tensor_cores
+    rewards = []
+    for chunk in range(4):
+        for _ in range(15):
+            agent.train_epoch()
+        rewards.append(agent.episode_stats()[0])
+    assert torch.isfinite(agent.policy.params).all() and rewards[-1] > rewards[0], rewards
