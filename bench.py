@@ -143,7 +143,7 @@ def cpu_port(budget_s: float, steps: int | None = None, warmup: int = 1, envs: i
                       f"{threads} of {os.cpu_count()} host threads), full DR, 5 sub-steps"}, dt / steps
 
 
-def run_reference(args):
+def run_reference(args, emit):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -156,7 +156,7 @@ def run_reference(args):
                                       "(the Python reference needs Isaac Sim and cannot travel to the GPU box); each step is a bounded sample"),
             "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(envs, note=None):
@@ -280,6 +280,14 @@ def bench_ppo(args, rank, world, device, dist_on):
 
 
 def main():
+    # exactly ONE line on stdout: libraries (NCCL's version banner, ...) write to fd 1 too, so park fd 1 on stderr while we
+    # run and print the JSON line to the real stdout at the end
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line: dict):
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)
@@ -295,7 +303,7 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, emit)
         return
 
     import torch.distributed as dist
@@ -382,7 +390,7 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
 
 
 if __name__ == "__main__":

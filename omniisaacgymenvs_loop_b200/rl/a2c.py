@@ -74,7 +74,9 @@ class A2CAgent:
         self.device = torch.device(device)
         self.rank, self.world = rank, world_size
         self.multi_gpu = world_size > 1
-        self.use_cuda_graph, self._graph = use_cuda_graph, None
+        # NCCL collectives inside a captured graph deadlocked on the 2-GPU box (r01 notes in DESIGN.md): graphs are used on the
+        # single-rank path, multi-rank runs launch the update phase eagerly
+        self.use_cuda_graph, self._graph = (use_cuda_graph and world_size == 1), None
         info = vec_env.get_env_info()
         self.obs_dim = int(info["observation_space"]["state"].shape[0])
         self.num_actors = int(vec_env.env.num_envs)
