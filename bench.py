@@ -279,6 +279,53 @@ def bench_ppo(args, rank, world, device, dist_on):
             "mlp": ("tcgen05 TF32 UMMA + TMEM (csrc/ppo_mlp_tc.cu)" if agent.policy.tensor_cores else "fp32 SIMT fused kernels (csrc/ppo_mlp.cu)"), "kl": st["kl"], "lr": st["lr"]}
 
 
+def bench_gae_mlp(device):
+    """Secondary kernels of the north_star's ncu evidence: GAE (HBM-bound) and the policy MLP (tensor pipe)."""
+    import ctypes
+    from omniisaacgymenvs_loop_b200 import _lib
+    from omniisaacgymenvs_loop_b200.rl.a2c import gae
+    from omniisaacgymenvs_loop_b200.rl.policy import PolicyMLP
+
+    out = {}
+    T, n = 16, 1 << 22                                      # 4M envs x 16: 1.16 GB touched per launch (>> L2)
+    g = torch.Generator(device=device).manual_seed(0)
+    rew, val = torch.randn((T, n), device=device, generator=g), torch.randn((T, n), device=device, generator=g)
+    dones = (torch.rand((T, n), device=device, generator=g) < 0.1).to(torch.uint8)
+    lv, ld = torch.randn(n, device=device, generator=g), torch.zeros(n, dtype=torch.uint8, device=device)
+    adv, ret = torch.empty_like(rew), torch.empty_like(rew)
+    for _ in range(3):
+        gae(rew, val, dones, lv, ld, 0.99, 0.95, adv, ret)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        gae(rew, val, dones, lv, ld, 0.99, 0.95, adv, ret)
+    e1.record()
+    torch.cuda.synchronize(device)
+    ms = e0.elapsed_time(e1) / 20
+    peak, _ = measured_peak()
+    gbs = 277.0 * n / (ms * 1e-3) / 1e9                     # 149 B read + 128 B written per env per rollout (SURVEY 8(d))
+    out["gae"] = {"kernel": "usv::gae_kernel<4>", "envs": n, "horizon": T, "ms": ms, "achieved_gbs": gbs, "frac_of_measured_hbm": gbs / peak,
+                  "bytes_per_env_rollout": 277}
+    del rew, val, dones, adv, ret
+    M = 1 << 20
+    pol = PolicyMLP(13, device)
+    obs = torch.randn((M, 13), device=device, generator=g)
+    o = pol.act(obs)
+    for _ in range(3):
+        pol.act(obs, o)
+    e0.record()
+    for _ in range(10):
+        pol.act(obs, o)
+    e1.record()
+    torch.cuda.synchronize(device)
+    ms = e0.elapsed_time(e1) / 10
+    flops = 2.0 * (13 * 128 + 128 * 128 + 128 * 3) * M     # algorithmic (un-padded) forward FLOPs
+    out["mlp_forward"] = {"kernel": "ppotc::forward_tc_kernel (tcgen05 kind::tf32, TMEM accumulators)", "rows": M, "ms": ms,
+                          "rows_per_s": M / (ms * 1e-3), "algorithmic_tflops": flops / (ms * 1e-3) / 1e12,
+                          "note": "tiny-K/N GEMMs: bounded by the tanh/TMEM epilogue and operand staging, not by the tensor pipe"}
+    return out
+
+
 def main():
     # exactly ONE line on stdout: libraries (NCCL's version banner, ...) write to fd 1 too, so park fd 1 on stderr while we
     # run and print the JSON line to the real stdout at the end
@@ -383,6 +430,10 @@ def main():
                                    "latency-bound, working set L2-resident -> no HBM roofline claimed"}
     if not args.no_extra and not args.no_ppo:
         line["ppo"] = bench_ppo(args, rank, world, device, dist_on)
+    if not args.no_extra and rank == 0:
+        line["secondary_kernels"] = bench_gae_mlp(device)
+    if dist_on:
+        dist.barrier()
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         cb, _ = cpu_port(20.0)
         line["cpu_baseline"] = cb

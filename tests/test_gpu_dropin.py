@@ -87,3 +87,15 @@ def test_ppo_loop_runs_and_learns(tmp_path):
     other.restore(path)
     assert torch.equal(other.policy.params, agent.policy.params) and torch.equal(other.policy.exp_avg_sq, agent.policy.exp_avg_sq)
     assert float(other.policy.lr) == pytest.approx(float(agent.policy.lr)) and other.epoch_num == 60
+
+
+def test_reference_trained_policy_captures_in_fused_env():
+    """Closed loop with the reference's own trained classic policy (5450 epochs in Isaac Sim / PhysX, filename reward 38.55):
+    the deterministic policy must capture the goal in essentially every episode of the fused env and earn the reward the
+    checkpoint was saved at -- the end-to-end check that obs layout, reward, kills and the planar integrator reproduce the task."""
+    from scripts.eval_reference_policy import run
+    for tc in (False, True):
+        r = run(n=2048, steps=1200, tensor_cores=tc)
+        assert r["episodes"] > 10000 and r["killed"] == 0 and r["timeouts"] == 0
+        assert r["captured"] >= 0.999 * r["episodes"], r
+        assert 30.0 < r["mean_return"] < 48.0, r            # checkpoint: rew_38.55 at save time
