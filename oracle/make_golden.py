@@ -345,6 +345,81 @@ def ppo():
     print("ppo.npz")
 
 
+def variant_b():
+    """Live CaptureXY with static obstacles (Variant B): spawn + potential-field build + K steps of obs / reward / kills,
+    with a reset batch in the middle  [OIGE/tasks/USV/USV_capture_xy_static_obs.py, d_multi_gemini.py]."""
+    live, dmap = ref_shim.load_live()
+    cfg = ref_shim.live_yaml()
+    NB, K = 12, 6
+    torch.manual_seed(21)
+    g = gen()
+    with ref_shim.quiet():
+        task = live.CaptureXYTask(cfg["env"]["task_parameters"], cfg["env"]["reward_parameters"], NB, "cpu", priv_dim=8)
+    task._env = types.SimpleNamespace(_env_pos=torch.zeros((NB, 3)))
+    ids = torch.arange(NB)
+    out = {}
+    with ref_shim.quiet():
+        task.reset(ids)
+        task.get_goals(ids, torch.zeros((NB, 3)), torch.zeros((NB, 4)))
+        pos0, rot0 = task.get_spawns(ids, torch.zeros((NB, 3)), torch.zeros((NB, 4)))
+    out.update(obstacles0=task.xunlian_pos[:, :, :2].clone(), field0=task.global_potential_field.clone(), target=task._target_positions.clone(),
+               spawn_pos=pos0[:, :2].clone(), spawn_quat=rot0.clone())
+    # intermediate products of the field builder for env 0..NB (fresh call, same obstacles): occupancy, sdf, cost
+    occ, sdf = task.gpu_map.compute_occupancy_and_sdf(task.xunlian_pos[:, :, :2])
+    cost = task.gpu_map.compute_cost_field_wavefront(occ, task._target_positions)
+    out.update(occupancy0=occ.to(torch.uint8), sdf0=sdf.clone(), cost0=cost.clone())
+    pos = pos0[:, :2].clone()
+    yaw = (torch.rand(NB, generator=g) * 2 - 1) * math.pi
+    vel = torch.rand((NB, 2), generator=g) * 2 - 1
+    w = torch.rand(NB, generator=g) * 1.2 - 0.6
+    # crafted rows: next to an obstacle (collision), inside the goal tolerance, far away, high-potential region
+    obs_xy = task.xunlian_pos[:, :, :2]
+    pos[0] = obs_xy[0, 0] + torch.tensor([0.9, 0.3])
+    pos[1] = task._target_positions[1] + torch.tensor([0.3, -0.2])
+    pos[2] = torch.tensor([-20.5, 1.0])
+    pos[3] = obs_xy[3, 1] + torch.tensor([1.6, 0.2])
+    S = {k: [] for k in ("pos", "yaw", "vel", "w", "prev_action", "priv", "obs", "reward", "die", "goal_reached", "done_success", "done_collision",
+                         "distance_reward", "alignment_reward", "potential_shaping", "turn_hazard", "speed_reward", "angular_reward",
+                         "heading_improve", "collision_penalty", "goal_reward", "danger", "potential")}
+    reset_ids = torch.tensor([2, 5, 9])
+    for k in range(K):
+        if k == 3:
+            with ref_shim.quiet():
+                task.reset(reset_ids)
+                p_new, _ = task.get_spawns(reset_ids, torch.zeros((NB, 3)), torch.zeros((NB, 4)))
+            pos[reset_ids] = p_new[reset_ids, :2]
+            out.update(obstacles1=task.xunlian_pos[:, :, :2].clone(), field1=task.global_potential_field.clone())
+        heading = torch.stack([torch.cos(yaw), torch.sin(yaw)], 1)
+        state = {"position": pos.clone(), "orientation": heading, "linear_velocity": vel.clone(), "angular_velocity": w.clone()}
+        prev_action = torch.rand((NB, 2), generator=g) * 2 - 1
+        priv = torch.rand((NB, 8), generator=g) * 2 - 1
+        actions = torch.rand((NB, 2), generator=g)
+        with ref_shim.quiet():
+            obs = task.get_state_observations(state, "local", prev_action=prev_action, priv_tail=priv).clone()
+            r = task.compute_reward(state, actions).clone()
+            die = task.update_kills(0, state).clone()
+        for name, v in (("pos", pos), ("yaw", yaw), ("vel", vel), ("w", w), ("prev_action", prev_action), ("priv", priv), ("obs", obs), ("reward", r),
+                        ("die", die), ("goal_reached", task._goal_reached), ("done_success", task._done_success), ("done_collision", task._done_collision),
+                        ("distance_reward", task.distance_reward), ("alignment_reward", task.alignment_reward),
+                        ("potential_shaping", task.potential_shaping_reward), ("turn_hazard", task._turn_hazard_penalty),
+                        ("speed_reward", task._speed_reward), ("angular_reward", task._angular_reward), ("heading_improve", task._heading_improve_reward),
+                        ("collision_penalty", task.collision_penalty), ("goal_reward", task._goal_reward), ("danger", task._danger_factor),
+                        ("potential", task._get_potential_values(state["position"]))):
+            S[name].append(v.clone())
+        pos = pos + 0.15 * vel
+        yaw = yaw + 0.15 * w
+        vel = vel * 0.9 + 0.1 * (torch.rand((NB, 2), generator=g) * 2 - 1)
+        w = w * 0.8 + 0.2 * (torch.rand(NB, generator=g) * 1.2 - 0.6)
+    out.update({k: torch.stack(v) for k, v in S.items()})
+    out["reset_step"] = np.int64(3)
+    out["reset_ids"] = reset_ids
+    d = t2n(out)
+    for k in ("field0", "field1", "sdf0", "cost0"):
+        d[k] = d[k].astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "capture_xy_live.npz"), **d)
+    print("capture_xy_live.npz")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)
@@ -353,6 +428,7 @@ def main():
     classic_task()
     gae()
     ppo()
+    variant_b()
 
 
 if __name__ == "__main__":

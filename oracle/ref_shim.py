@@ -258,6 +258,28 @@ def load_classic():
     return core, rew, cap
 
 
+def load_live():
+    """The live (Variant B) task: CaptureXYTask with static obstacles + BatchedMapGPU; returns (task_module, map_module)."""
+    install()
+    for k in ("omniisaacgymenvs.tasks.USV.USV_core", "omniisaacgymenvs.tasks.USV.USV_task_rewards"):
+        sys.modules.pop(k, None)                 # make sure the LIVE core/rewards are imported, not the snapshot aliases
+    with quiet():
+        import omniisaacgymenvs.tasks.USV.USV_capture_xy_static_obs as live
+        import omniisaacgymenvs.tasks.USV.d_multi_gemini as dmap
+    return live, dmap
+
+
+def live_yaml() -> dict:
+    import re
+    import yaml
+
+    path = os.path.join(REFERENCE_ROOT, "omniisaacgymenvs", "cfg", "task", "USV", "IROS2024", "USV_Virtual_CaptureXY_SysID-TEST.yaml")
+    with open(path) as f:
+        txt = f.read()
+    txt = re.sub(r"\$\{resolve_default:([^,]+),\$\{[^}]*\}\}", r"\1", txt)
+    return yaml.safe_load(txt)
+
+
 def load_rl_games():
     """Returns the reference rl_games modules used on the PPO path."""
     install()

@@ -1,0 +1,64 @@
+"""CPU suite: the Variant-B (live CaptureXY, static obstacles) oracle vs goldens produced by the reference's own task and
+BatchedMapGPU (oracle/make_golden.py:variant_b)."""
+import numpy as np
+import torch
+
+from oracle import usv_oracle_b as B
+
+T = torch.from_numpy
+
+
+def test_potential_field_builder_vs_reference(golden):
+    G = golden("capture_xy_live")
+    obst, target = T(G["obstacles0"]), T(G["target"])
+    occ, sdf = B.occupancy_and_sdf(obst)
+    assert torch.equal(occ.to(torch.uint8), T(G["occupancy0"])) and torch.allclose(sdf, T(G["sdf0"]), rtol=1e-6, atol=1e-6)
+    cost = B.cost_to_go(occ, target)
+    assert torch.equal(cost, T(G["cost0"]))                       # bit-exact incl. the +inf cells
+    field = B.potential_field(cost, T(G["sdf0"]))
+    assert torch.allclose(field, T(G["field0"]), rtol=1e-6, atol=1e-7)
+
+
+def test_grid_sample_restatement(golden):
+    G = golden("capture_xy_live")
+    field = T(G["field0"])
+    for k in range(3):
+        pos = T(G["pos"][k])
+        got = B.sample_potential(field, pos)
+        want = torch.nn.functional.grid_sample(field.unsqueeze(1), (2.0 * pos / 30.0).view(-1, 1, 1, 2), align_corners=False,
+                                               padding_mode="border").view(-1)
+        assert torch.allclose(got, want, rtol=1e-6, atol=1e-7)
+        assert torch.allclose(got, T(G["potential"][k]), rtol=1e-6, atol=1e-7)
+
+
+def test_live_task_vs_reference(golden):
+    """obs (33) / reward terms / kills / outcome latches over 6 steps with a reset batch (prev_potential=None quirk)."""
+    G = golden("capture_xy_live")
+    c = B.LiveTaskConfig()
+    K, n = G["pos"].shape[:2]
+    S = B.LiveRewardState(n)
+    obst, field, target = T(G["obstacles0"]).clone(), T(G["field0"]).clone(), T(G["target"])
+    for k in range(K):
+        if k == int(G["reset_step"]):
+            ids = T(G["reset_ids"])
+            S.reset(ids)
+            obst, field = T(G["obstacles1"]).clone(), T(G["field1"]).clone()
+        yaw = T(G["yaw"][k])
+        state = {"position": T(G["pos"][k]), "orientation": torch.stack([torch.cos(yaw), torch.sin(yaw)], 1),
+                 "linear_velocity": T(G["vel"][k]), "angular_velocity": T(G["w"][k])}
+        obs, aux = B.live_observation(state, target, obst, T(G["prev_action"][k]), T(G["priv"][k]))
+        assert torch.allclose(obs, T(G["obs"][k]), rtol=1e-6, atol=1e-6), k
+        out = B.live_reward(c, S, aux, state, obst, field)
+        for name in ("distance_reward", "alignment_reward", "potential_shaping", "turn_hazard", "speed_reward", "angular_reward",
+                     "heading_improve", "collision_penalty", "goal_reward", "danger"):
+            # the shaping term is 100 x (difference of two nearly equal potentials): 1e-7 relative on the potential -> 1e-5 absolute
+            atol = 5e-5 if name == "potential_shaping" else 1e-6
+            assert torch.allclose(out[name], T(G[name][k]), rtol=1e-5, atol=atol), (k, name)
+        assert torch.allclose(out["reward"], T(G["reward"][k]), rtol=1e-5, atol=1e-4), k
+        die = B.live_kills(c, S, aux["d"], state["position"], obst)
+        assert torch.equal(die, T(G["die"][k])) and torch.equal(S.goal_reached, T(G["goal_reached"][k]))
+        assert torch.equal(S.done_success, T(G["done_success"][k])) and torch.equal(S.done_collision, T(G["done_collision"][k]))
+    # the crafted rows did their job: a collision, a goal capture, a distance kill
+    assert G["done_collision"][0][0] == 1 and G["done_success"][0][1] == 1 and G["die"][0][2] == 1
+    # quirk 8: on the step after the reset batch the potential shaping is exactly zero for EVERY env
+    assert np.all(G["potential_shaping"][int(G["reset_step"])] == 0.0)
