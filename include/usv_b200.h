@@ -224,6 +224,10 @@ typedef struct {
   /* ---- reset-time randomisation (A3, A6, A10, A11, A14, A19) ---- */
   float goal_random_position; int32_t retarget_on_reset;
   float spawn_min_dist, spawn_max_dist;    /* after curriculum, set by host     */
+  int32_t spawn_about_origin;              /* live task: the spawn annulus is centred on the env origin, not the target */
+  int32_t reset_pose_external;             /* scene replay (OIGE/tasks/USV_Virtual.py:1395-1458): pose, velocity and target of a
+                                              resetting env were written by the host; the kernel only re-draws the dynamics
+                                              randomisation and clears the episode bookkeeping */
   float spawn_vel_range;                   /* 1.5: vx,vy ~ U(-1.5,1.5)          */
   int32_t mass_rand; float mass_min, mass_max, mass_base;
   int32_t drag_rand; float lin_base[3], quad_base[3], lin_rand[3], quad_rand[3];
@@ -265,6 +269,95 @@ int usv_rollout_fused_f32(const UsvEnvBuffers* b, const float* actions /*[T,n,2]
  * returns the body-frame drag (u,v,r), thrust wrench and world accelerations of ONE sub-step.  */
 int usv_planar_forces_f32(const UsvEnvBuffers* b, float* out /*[n,8]: du,dv,dr,Fx,Fy,Tz,ax,ay*/,
                           int64_t n, const UsvStepParams* p, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* Variant B: live CaptureXY with 16 static obstacles and a per-env potential field            */
+/*     [ref: OIGE/tasks/USV/USV_capture_xy_static_obs.py ; OIGE/tasks/USV/d_multi_gemini.py ;                      */
+/*           OIGE/tasks/USV_Virtual.py:771-1101,1223-1240,1502-1662 ; OIGE/tasks/USV/USV_core.py:55-125]           */
+#define USV_B_OBS 33          /* 3 + 20 (5 task scalars + 5 nearest obstacles x 3) + prev_action 2 + priv 8        */
+#define USV_B_OBSTACLES 16    /* CaptureXYTask.big                                                                 */
+#define USV_B_CLOSEST 5
+#define USV_B_GRID 150        /* BatchedMapGPU: 150 x 150 cells of 0.2 m over a 30 m map, row = y, column = x      */
+
+/* extra dynamic per-env fields of the live task (AoSoA like the base state) */
+enum {
+  USV_BS_PREV_H = 0,          /* prev_heading_error                                                                */
+  USV_BS_PREV_POT,            /* prev_potential                                                                    */
+  USV_BS_OUTCOME,             /* int32 bit pattern: bit0 _done_success, bit1 _done_collision                       */
+  USV_BS_COUNT
+};
+/* extra per-episode constants of the live task */
+enum {
+  USV_BC_COM_X = 0, USV_BC_COM_Y, USV_BC_COM_Z,   /* MDD.platforms_CoM (observed only)                             */
+  USV_BC_OBST = 3,            /* xunlian_pos[:, j, 0:2] at USV_BC_OBST + 2*j, +1   (env-local frame)               */
+  USV_BC_COUNT = USV_BC_OBST + 2 * USV_B_OBSTACLES
+};
+/* optional episode_sums of the live task [ref: USV_capture_xy_static_obs.py:130-187,720-765 ;                     */
+/* OIGE/tasks/USV/USV_task_rewards.py Penalties.update_statistics ; OIGE/tasks/USV_Virtual.py:1187-1220]           */
+enum {
+  USV_BST_TOTAL_REWARD = 0, USV_BST_DISTANCE_REWARD, USV_BST_ALIGNMENT_REWARD, USV_BST_HEADING_IMPROVE_REWARD,
+  USV_BST_POTENTIAL_SHAPING_REWARD, USV_BST_SPEED_REWARD, USV_BST_ANGULAR_REWARD, USV_BST_TURN_HAZARD_PENALTY,
+  USV_BST_GOAL_REWARD, USV_BST_COLLISION_REWARD, USV_BST_TIME_REWARD, USV_BST_POSITION_ERROR, USV_BST_BOUNDARY_PENALTY,
+  USV_BST_DANGER_MEAN, USV_BST_DANGER_HI_RATE, USV_BST_G_GATE_MEAN,
+  USV_BST_LINEAR_VEL_PENALTY, USV_BST_ANGULAR_VEL_PENALTY, USV_BST_ANGULAR_VEL_VARIATION_PENALTY,
+  USV_BST_ENERGY_PENALTY, USV_BST_ACTION_VARIATION_PENALTY,
+  USV_BST_NORMED_LINEAR_VEL, USV_BST_NORMED_ANGULAR_VEL, USV_BST_ACTIONS_SUM,
+  USV_BST_CMD_NEG_RATE, USV_BST_THRUSTER_FORCE_NEG_RATE, USV_BST_U_MEAN, USV_BST_U_LOW_RATE, USV_BST_U_SUM,
+  USV_BST_COUNT      /* "success" / "collision" are read from USV_BS_OUTCOME before the reset (USV_Virtual.py:1508-1516,1581-1588) */
+};
+
+enum { USV_PRIV_RAW = 0, USV_PRIV_CENTERED = 1, USV_PRIV_MINMAX = 2 };
+
+typedef struct {
+  /* privileged tail [ref: OIGE/tasks/USV_Virtual.py:837-984 ; USV_disturbances.py:153-194] */
+  int32_t priv_mode;            /* USV_PRIV_*                                                       */
+  int32_t mass_obs_relative;    /* 1: (m - base)/max(|base|,eps) ; 0: raw                            */
+  int32_t com_obs_scaled;       /* 1: com / (scale + eps)                                            */
+  float com_scale_eps[3];       /* fp32 (scale + 1e-6)                                               */
+  /* [k_drag, thr_L, thr_R, k_Iz]: raw -> x ; centered -> clamp((x - a)/b, +-1) with a = nominal, b = max(|min-nom|,|max-nom|,eps) ;
+   * minmax -> active ? clamp(2*((x - a)/b) - 1, +-1) : 0 with a = min, b = max - min  (USV_Virtual.py:97-151,905-970) */
+  float priv_a[4], priv_b[4]; int32_t priv_active[4];
+  /* CoM re-draw at reset [ref: USV_disturbances.py:88-124] (observation only: the planar integrator has no CoM offset) */
+  int32_t com_rand; float com_base[3], com_disp[3];
+  /* task */
+  float collision_threshold;    /* 1.2  (:103)                                                       */
+  float map_size;               /* 30.0                                                              */
+  int32_t fixed_horizon_eval;   /* is_done ignores `die` (USV_Virtual.py:1229-1233)                  */
+} UsvLiveParams;
+
+typedef struct {
+  float* bstate;  int64_t bstate_stride;   /* [stride/32][USV_BS_COUNT][32]                              */
+  float* bconsts; int64_t bconsts_stride;  /* [stride/32][USV_BC_COUNT][32]                              */
+  float* bstats;  int64_t bstats_stride;   /* [stride/32][USV_BST_COUNT][32] or NULL                     */
+  float* field;                            /* [n][150][150] global_potential_field                       */
+  /* "a reset happened" epoch words, uint64[2] (reference quirk: reset() sets prev_potential=None for EVERY env, so the
+   * potential shaping of the next reward is zero for all envs).  The step kernel of control step s stores s+1 into word
+   * (s+1)&1 when any env finishes; the kernel of step s+1 treats word[(s+1)&1] == its step_counter as "some env was reset
+   * on entry" (two words: readers and writers of one launch never share a word).  The host stores step_counter into word
+   * step_counter&1 when it sets reset_buf itself. */
+  uint64_t* reset_epoch;
+} UsvLiveBuffers;
+
+/* one control step of the live task for n envs.  Same dynamics / action path as usv_step_fused_f32 (p->action_affine etc.);
+ * env resets are split: the in-kernel part re-draws the episode constants and the spawn pose, obstacles + potential field of
+ * the envs flagged in reset_buf must have been rebuilt by usv_live_reset_scene_f32 BEFORE this call.                        */
+int usv_step_live_f32(const UsvEnvBuffers* b, const UsvLiveBuffers* lb, const float* actions /*[n,2]*/,
+                      float* obs /*[n,33]*/, float* rew /*[n]*/, int64_t n, const UsvStepParams* p,
+                      const UsvLiveParams* lp, void* stream);
+
+/* B5 + B6: for every env flagged in b->reset_buf re-draw the 16 obstacles (rejection sampling against the spawn point the
+ * step kernel will draw for the same (seed, env, step) and against the CURRENT target) and rebuild its potential field.
+ * The batch-global maxima of the reference's builder (d_multi_gemini.py:204-210,257-260) are taken over the envs that reset
+ * in this call.  Call before usv_step_live_f32 with the same p->step_counter.  cell_centres = torch.linspace(-14.9,14.9,150);
+ * workspace: usv_live_scene_workspace_bytes(n) bytes, 16 B aligned.
+ *     [ref: USV_capture_xy_static_obs.py:936-1060 ; d_multi_gemini.py:66-271]                                               */
+int64_t usv_live_scene_workspace_bytes(int64_t n);
+int usv_live_reset_scene_f32(const UsvEnvBuffers* b, const UsvLiveBuffers* lb, const float* cell_centres /*[150]*/,
+                             void* workspace, int64_t n, const UsvStepParams* p, void* stream);
+/* B6 alone on a dense batch (BatchedMapGPU.compute_occupancy_and_sdf -> compute_cost_field_wavefront -> compute_potential_field) */
+int usv_live_build_fields_f32(const float* obstacles /*[m,16,2]*/, const float* targets /*[m,2]*/,
+                              const float* cell_centres /*[150]*/, float* field /*[m,150,150]*/,
+                              float* cost_out /*[m,150,150] raw cost-to-go or NULL*/, void* workspace, int64_t m, void* stream);
 
 /* ------------------------------------------------------------------------- */
 /* P1  A2CBase.discount_values (GAE) + returns                                */

@@ -24,6 +24,7 @@ _CTYPES = {
     "int64_t": ctypes.c_int64, "uint64_t": ctypes.c_uint64,
     "float*": ctypes.c_void_p, "const float*": ctypes.c_void_p, "int64_t*": ctypes.c_void_p,
     "uint32_t*": ctypes.c_void_p, "int32_t*": ctypes.c_void_p, "double*": ctypes.c_void_p,
+    "uint64_t*": ctypes.c_void_p, "const int32_t*": ctypes.c_void_p,
 }
 
 
@@ -66,6 +67,8 @@ def _parse_structs(src: str) -> Dict[str, type]:
 def _parse_enums(src: str) -> Dict[str, int]:
     src = _strip_comments(src)
     vals: Dict[str, int] = {}
+    for m in re.finditer(r"#define\s+((?:USV|PPO)_\w+)\s+(\d+)", src):
+        vals[m.group(1)] = int(m.group(2))
     for m in re.finditer(r"enum\s*\{(.*?)\}\s*;", src, flags=re.S):
         cur = -1
         for item in m.group(1).split(","):
@@ -74,12 +77,11 @@ def _parse_enums(src: str) -> Dict[str, int]:
                 continue
             if "=" in item:
                 k, v = [x.strip() for x in item.split("=")]
-                cur = int(v, 0)
+                # integer literal or an arithmetic expression over earlier constants of this header
+                cur = int(eval(v, {"__builtins__": {}}, dict(vals)))
             else:
                 k, cur = item, cur + 1
             vals[k] = cur
-    for m in re.finditer(r"#define\s+((?:USV|PPO)_\w+)\s+(\d+)", src):
-        vals[m.group(1)] = int(m.group(2))
     return vals
 
 
@@ -92,6 +94,8 @@ UsvHydrodynamicsParams = STRUCTS["UsvHydrodynamicsParams"]
 UsvPenaltyTerm = STRUCTS["UsvPenaltyTerm"]
 UsvStepParams = STRUCTS["UsvStepParams"]
 UsvEnvBuffers = STRUCTS["UsvEnvBuffers"]
+UsvLiveParams = STRUCTS["UsvLiveParams"]
+UsvLiveBuffers = STRUCTS["UsvLiveBuffers"]
 PpoLossParams = STRUCTS["PpoLossParams"]
 PpoAdamParams = STRUCTS["PpoAdamParams"]
 
@@ -120,6 +124,8 @@ def lib() -> ctypes.CDLL:
     L.ppo_train_scratch_floats.restype = ctypes.c_int64
     L.ppo_train_tc_workspace_floats.restype = ctypes.c_int64
     L.ppo_packed_weight_floats.restype = ctypes.c_int64
+    L.usv_live_scene_workspace_bytes.restype = ctypes.c_int64
+    L.usv_live_scene_workspace_bytes.argtypes = [ctypes.c_int64]
     for name, st in STRUCTS.items():
         want = L.usv_b200_sizeof(name.encode())
         if want != ctypes.sizeof(st):

@@ -93,6 +93,7 @@ class UsvEnvConfig:
     action_noise_min: float = -0.05
     action_noise_max: float = 0.05
     action_bias: float = 0.0
+    action_bias_steps: int = 0       # live: the bias is applied to the first N control steps only (host-side counter)
     penalties_use_u: bool = False
     noise_pos: bool = False
     pos_noise_min: float = -0.03
@@ -131,6 +132,8 @@ class UsvEnvConfig:
     retarget_on_reset: bool = False
     spawn_min_dist: float = 0.3
     spawn_max_dist: float = 12.0
+    spawn_about_origin: bool = False   # live task (Variant B): annulus around the env origin, not the target
+    reset_pose_external: bool = False  # scene replay: the host writes pose / velocity / target of resetting envs
     spawn_vel_range: float = 1.5
     mass_rand: bool = False
     mass_min: float = 34.96
@@ -368,6 +371,106 @@ class UsvEnvConfig:
             torque_min_shift=t["torque_min_shift"], torque_max_shift=t["torque_max_shift"],
         )
         return dataclasses.replace(cfg, **overrides)
+
+
+@dataclass
+class UsvLiveConfig:
+    """Mirror of UsvLiveParams: what the live task (Variant B, CaptureXY with static obstacles) adds on top of UsvEnvConfig
+    [ref: OIGE/tasks/USV_Virtual.py:97-151,440-527,837-984 ; OIGE/tasks/USV/USV_disturbances.py:88-124,153-194 ;
+    OIGE/tasks/USV/USV_capture_xy_static_obs.py:30-32,103].  Defaults = IROS2024/USV_Virtual_CaptureXY_SysID-TEST.yaml."""
+    priv_mode: int = 2                       # 0 raw, 1 centered, 2 minmax
+    mass_obs_relative: bool = True
+    com_obs_scaled: bool = True
+    com_scale: Tuple[float, float, float] = (1.3, 1.0, 1.0)   # box_length, box_width, max(heron_zero_height, 1)
+    priv_a: Tuple[float, float, float, float] = (1.0, 0.5, 0.5, 1.0)
+    priv_b: Tuple[float, float, float, float] = (0.5, 0.5, 0.5, 0.5)
+    priv_active: Tuple[bool, bool, bool, bool] = (True, True, True, True)
+    com_rand: bool = True
+    com_base: Tuple[float, float, float] = (0.0, 0.0, 0.0)
+    com_disp: Tuple[float, float, float] = (0.15, 0.05, 0.02)
+    collision_threshold: float = 1.2
+    map_size: float = 30.0
+    fixed_horizon_eval: bool = False
+
+    def to_params(self):
+        lp = _lib.UsvLiveParams()
+        lp.priv_mode, lp.mass_obs_relative, lp.com_obs_scaled = int(self.priv_mode), int(self.mass_obs_relative), int(self.com_obs_scaled)
+        for j in range(3):
+            # `com / (scale_t + eps)` with scale_t an fp32 tensor  [ref: USV_disturbances.py:183-190]
+            lp.com_scale_eps[j] = float(np.float32(self.com_scale[j]) + np.float32(1e-6))
+            lp.com_base[j], lp.com_disp[j] = float(self.com_base[j]), float(self.com_disp[j])
+        for j in range(4):
+            lp.priv_a[j], lp.priv_b[j], lp.priv_active[j] = float(self.priv_a[j]), float(self.priv_b[j]), int(self.priv_active[j])
+        lp.com_rand = int(self.com_rand)
+        lp.collision_threshold, lp.map_size, lp.fixed_horizon_eval = self.collision_threshold, self.map_size, int(self.fixed_horizon_eval)
+        return lp
+
+    @classmethod
+    def from_task_cfg(cls, task_cfg: dict) -> "UsvLiveConfig":
+        env = task_cfg["env"]
+        dist = env["disturbances"]
+        m, dr, th, inr = dist["mass"], dist.get("drag", {}) or {}, dist.get("thruster", {}) or {}, dist.get("inertia", {}) or {}
+        hs = task_cfg["dynamics"]["hydrostatics"]
+        cp = (dist.get("coupling", {}) or {}).get("mass_driven", {}) or {}
+        targets = set(cp.get("targets", []) or []) if cp.get("enabled", False) else set()
+        pp = env.get("privileged_params", {}) or {}
+        mode = {"raw": 0, "centered": 1, "minmax": 2}[str(pp.get("mode", "raw"))]
+        nominal = float(pp.get("nominal", 1.0))
+        a = float(th.get("thruster_rand", 0.0))
+        rng = [(float(dr.get("k_drag_min", 1.0)), float(dr.get("k_drag_max", 1.0))),
+               (1.0 - a, 1.0 if "thruster" in targets else 1.0 + a), (1.0 - a, 1.0 if "thruster" in targets else 1.0 + a),
+               (float(inr.get("k_Iz_min", 1.0)), float(inr.get("k_Iz_max", 1.0)))]
+        active = [bool(dr.get("use_drag_scale_randomization", False)) or "drag_scale" in targets,
+                  bool(th.get("use_thruster_randomization", False)) or "thruster" in targets,
+                  bool(th.get("use_thruster_randomization", False)) or "thruster" in targets,
+                  bool(inr.get("use_yaw_inertia_randomization", False)) or "yaw_inertia" in targets]
+        if mode == 1:
+            pa = [nominal] * 4
+            pb = [max(abs(lo - nominal), abs(hi - nominal), 1e-6) for lo, hi in rng]
+        else:
+            pa = [lo for lo, _ in rng]
+            pb = [hi - lo for lo, hi in rng]
+            active = [act and (hi - lo) > 1e-6 for act, (lo, hi) in zip(active, rng)]   # degenerate range -> neutral 0
+            pb = [b if b > 1e-6 else 1.0 for b in pb]
+        if str(m.get("masscom_obs_source", "sim")) != "sim":
+            raise NotImplementedError("masscom_obs_source='base' (ablation mode) is not built into the fused live step")
+        disp = m.get("com_displacement_xyz", None)
+        if disp is None and float(m.get("CoM_max_displacement", 0.0) or 0.0) > 0.0:
+            raise NotImplementedError("legacy disc-shaped CoM randomisation is not built into the fused live step")
+        scale = m.get("com_obs_scale", None) or [hs["box_length"], hs["box_width"], max(hs["heron_zero_height"], 1.0)]
+        return cls(priv_mode=mode, mass_obs_relative=str(m.get("mass_obs_mode", "raw")) == "relative",
+                   com_obs_scaled=str(m.get("com_obs_mode", "raw")) == "scaled", com_scale=tuple(float(x) for x in scale),
+                   priv_a=tuple(pa), priv_b=tuple(pb), priv_active=tuple(active),
+                   com_rand=bool(m.get("add_mass_disturbances", False)) and disp is not None,
+                   com_base=tuple(float(x) for x in m.get("base_com", [0.0, 0.0, 0.0])),
+                   com_disp=tuple(float(x) for x in (disp or [0.0, 0.0, 0.0])),
+                   fixed_horizon_eval=bool(env.get("fixed_horizon_eval", False)))
+
+
+def live_env_config(task_cfg: dict, **overrides) -> "UsvEnvConfig":
+    """UsvEnvConfig for the LIVE USVVirtual (OIGE/tasks/USV_Virtual.py): from_task_cfg + the keys only the live file reads
+    (action_processing :590-615, mass-driven coupling :415-438, live reward dataclass defaults USV_task_rewards.py:27-32)."""
+    env = task_cfg["env"]
+    dist = env["disturbances"]
+    ap = env.get("action_processing", {}) or {}
+    cp = (dist.get("coupling", {}) or {}).get("mass_driven", {}) or {}
+    targets = set(cp.get("targets", []) or []) if cp.get("enabled", False) else set()
+    if targets and targets != {"drag_scale", "thruster", "yaw_inertia"}:
+        raise NotImplementedError("mass-driven coupling is built for the full target set [drag_scale, thruster, yaw_inertia]")
+    rp, m, dr, th, inr = env["reward_parameters"], dist["mass"], dist["drag"], dist["thruster"], dist.get("inertia", {}) or {}
+    if bool(inr.get("use_yaw_inertia_randomization", False)) and not targets:
+        raise NotImplementedError("independent k_Iz randomisation is not built into the fused step (coupled mode is)")
+    live = dict(
+        action_affine=bool(ap.get("use_affine_thrust_mapping", True)), penalties_use_u=bool(ap.get("penalties_use_thrust_u", False)),
+        action_bias=float(ap.get("initial_action_bias", 0.0)), action_bias_steps=int(ap.get("initial_action_bias_steps", 0)),
+        spawn_about_origin=True, retarget_on_reset=True, goal_speed_gate=float("inf"),
+        position_scale=rp.get("position_scale", 1.5), align_la1=rp.get("align_la1", 0.04),
+        mass_coupling=bool(targets), couple_mass_max=float(m.get("max_mass", 0.0)), couple_thr_a=float(th.get("thruster_rand", 0.0)),
+        couple_kiz_min=float(inr.get("k_Iz_min", 1.0)), couple_kiz_max=float(inr.get("k_Iz_max", 1.0)),
+        use_drag_scale=bool(dr.get("use_drag_scale_randomization", False)) or "drag_scale" in targets,
+    )
+    live.update(overrides)
+    return UsvEnvConfig.from_task_cfg(task_cfg, **live)
 
 
 def load_task_yaml(path: str, num_envs: Optional[int] = None) -> dict:

@@ -11,10 +11,12 @@ from typing import Optional
 import torch
 
 from . import _lib
-from .config import UsvEnvConfig
+from .config import UsvEnvConfig, UsvLiveConfig
 
 E = _lib.ENUMS
 OBS_DIM = 13
+LIVE_OBS_DIM = E["USV_B_OBS"]
+GRID = E["USV_B_GRID"]
 
 
 def _round_up(n: int, m: int) -> int:
@@ -139,6 +141,8 @@ class FusedUsvEnv:
             p = self._params = self.cfg.to_params(0, self.env_id_offset, False)
         p.step_counter = self.step_counter
         p.first_call = int(self.first_call)
+        # live action path: the initial bias applies to the first N control steps only  [ref: OIGE/tasks/USV_Virtual.py:1070-1077]
+        p.action_bias = self.cfg.action_bias if self.step_counter < self.cfg.action_bias_steps else 0.0
         return p
 
     # ---- the hot path ------------------------------------------------------------------
@@ -182,3 +186,107 @@ class FusedUsvEnv:
         if flag != 0:
             what = "+".join(w for bit, w in ((1, "obs/reward"), (2, "actions(clamped)")) if flag & bit)
             raise RuntimeError(f"[USV_NAN_PROBE] non-finite detected: {what} of the fused env step")
+
+
+class FusedUsvLiveEnv(FusedUsvEnv):
+    """Variant B: the live CaptureXY task with 16 static obstacles and a per-env potential field
+    [ref: OIGE/tasks/USV/USV_capture_xy_static_obs.py ; OIGE/tasks/USV/d_multi_gemini.py].  Per control step: one scene
+    rebuild pass over the envs that reset (obstacle placement + potential field, usv_reset_b.cu) and one fused step kernel
+    (usv_step_b.cu).  The potential fields cost 90 KB of HBM per env (16 384 envs = 1.5 GB)."""
+
+    def __init__(self, cfg: UsvEnvConfig, live: Optional[UsvLiveConfig] = None, num_envs: Optional[int] = None, device="cuda:0",
+                 env_id_offset: int = 0, collect_stats: bool = False):
+        super().__init__(cfg, num_envs, device, env_id_offset, collect_stats=False)
+        self.live = live if live is not None else UsvLiveConfig()
+        n, nt = self.num_envs, self.stride // 32
+        f32 = dict(dtype=torch.float32, device=self.device)
+        self.bstate = torch.zeros((nt, E["USV_BS_COUNT"], 32), **f32)
+        self.bconsts = torch.zeros((nt, E["USV_BC_COUNT"], 32), **f32)
+        self.bstats = torch.zeros((nt, E["USV_BST_COUNT"], 32), **f32) if collect_stats else None
+        for j in range(3):
+            self.bconsts[:, E["USV_BC_COM_X"] + j] = self.live.com_base[j]
+        self.potential = torch.zeros((n, GRID, GRID), **f32)     # task.global_potential_field
+        self.obs = torch.zeros((n, LIVE_OBS_DIM), **f32)
+        # BatchedMapGPU.__init__: cell-centre coordinates  [ref: d_multi_gemini.py:15-19]
+        ms = self.live.map_size
+        cell = ms / GRID
+        self.cell_centres = torch.linspace(-ms / 2 + cell / 2, ms / 2 - cell / 2, GRID, device=self.device)
+        self.reset_epoch = torch.zeros(2, dtype=torch.int64, device=self.device)   # every env starts flagged: epoch 0 == step 0
+        self.workspace = torch.zeros(int(self.lib.usv_live_scene_workspace_bytes(n)) // 4 + 4, dtype=torch.int32, device=self.device)
+        self._live_params = self.live.to_params()
+        lb = _lib.UsvLiveBuffers()
+        lb.bstate, lb.bstate_stride = self.bstate.data_ptr(), self.stride
+        lb.bconsts, lb.bconsts_stride = self.bconsts.data_ptr(), self.stride
+        lb.bstats = self.bstats.data_ptr() if self.bstats is not None else None
+        lb.bstats_stride = self.stride
+        lb.field = self.potential.data_ptr()
+        lb.reset_epoch = self.reset_epoch.data_ptr()
+        self._live_buffers = lb
+
+    def _src(self, name: str) -> torch.Tensor:
+        if name.startswith("USV_BS_"):
+            return self.bstate
+        if name.startswith("USV_BC_"):
+            return self.bconsts
+        if name.startswith("USV_BST_"):
+            return self.bstats
+        return super()._src(name)
+
+    # ---- host access to the live buffers -------------------------------------------------
+    @property
+    def obstacles(self) -> torch.Tensor:
+        """(N,16,2) copy of xunlian_pos[:, :, :2] (env-local frame)."""
+        o = self.bconsts[:, E["USV_BC_OBST"]:, :].permute(0, 2, 1).reshape(-1, E["USV_B_OBSTACLES"], 2)
+        return o[: self.num_envs].clone()
+
+    def set_obstacles(self, obstacles: torch.Tensor) -> None:
+        o = torch.zeros((self.stride, E["USV_B_OBSTACLES"] * 2), dtype=torch.float32, device=self.device)
+        o[: self.num_envs] = obstacles.to(self.device, torch.float32).reshape(self.num_envs, -1)
+        self.bconsts[:, E["USV_BC_OBST"]:, :] = o.view(-1, 32, E["USV_B_OBSTACLES"] * 2).permute(0, 2, 1)
+
+    def episode_outcomes(self):
+        """(success, collision) latches  [ref: USV_capture_xy_static_obs.py:708-713]."""
+        oc = self.int_field("USV_BS_OUTCOME")
+        return (oc & 1).float(), ((oc >> 1) & 1).float()
+
+    def mark_host_reset(self) -> None:
+        """Call after writing reset_buf from the host (keeps the prev_potential=None quirk exact, see usv_b200.h)."""
+        self.reset_epoch[self.step_counter & 1] = self.step_counter
+
+    def bstats_matrix(self) -> torch.Tensor:
+        return self.bstats.permute(1, 0, 2).reshape(E["USV_BST_COUNT"], -1)[:, : self.num_envs]
+
+    def build_fields(self, obstacles: torch.Tensor, targets: torch.Tensor, want_cost: bool = False):
+        """BatchedMapGPU on a dense batch: (m,16,2), (m,2) -> field (m,150,150) [, raw cost-to-go]."""
+        m = int(obstacles.shape[0])
+        obstacles = obstacles.to(self.device, torch.float32).contiguous()
+        targets = targets.to(self.device, torch.float32).contiguous()
+        field = torch.empty((m, GRID, GRID), dtype=torch.float32, device=self.device)
+        cost = torch.empty_like(field) if want_cost else None
+        _lib.check(self.lib.usv_live_build_fields_f32(_lib.ptr(obstacles), _lib.ptr(targets), _lib.ptr(self.cell_centres),
+                                                      _lib.ptr(field), _lib.ptr(cost), _lib.ptr(self.workspace),
+                                                      ctypes.c_int64(m), _lib.stream()), "usv_live_build_fields_f32")
+        return (field, cost) if want_cost else field
+
+    # ---- the hot path ------------------------------------------------------------------
+    def step(self, actions: torch.Tensor, obs: Optional[torch.Tensor] = None, rew: Optional[torch.Tensor] = None,
+             rebuild_scene: bool = True):
+        """One control step of every env (== VecEnvRLGames.step over the live task).  Returns (obs (N,33), rew, reset_buf)."""
+        obs = self.obs if obs is None else obs
+        rew = self.rew if rew is None else rew
+        p = self.params()
+        n = ctypes.c_int64(self.num_envs)
+        if rebuild_scene:
+            _lib.check(self.lib.usv_live_reset_scene_f32(ctypes.byref(self._buffers), ctypes.byref(self._live_buffers),
+                                                         _lib.ptr(self.cell_centres), _lib.ptr(self.workspace), n, ctypes.byref(p),
+                                                         _lib.stream()), "usv_live_reset_scene_f32")
+        _lib.check(self.lib.usv_step_live_f32(ctypes.byref(self._buffers), ctypes.byref(self._live_buffers),
+                                              _lib.ptr(actions, torch.float32), _lib.ptr(obs), _lib.ptr(rew), n, ctypes.byref(p),
+                                              ctypes.byref(self._live_params), _lib.stream()), "usv_step_live_f32")
+        self.step_counter += 1
+        self.first_call = False
+        return obs, rew, self.reset_buf
+
+    def rollout(self, *a, **k):
+        raise NotImplementedError("the multi-step rollout kernel exists for the classic task only (the live task's "
+                                  "prev_potential quirk needs a grid-wide flag between control steps)")

@@ -18,6 +18,8 @@ MASK = np.uint64(0xFFFFFFFF)
 RS_STEP_A, RS_STEP_B = 0, 1
 RS_RESET = [2, 3, 4, 5, 6, 7, 8, 9, 10]
 RS_ROWS = 64
+RS_RESET_COM = 11
+RS_OBST = 0x1000      # + round*8 + j//2 ; obstacle j takes words (0,1) if j even else (2,3)
 
 
 def philox4x32_10(c0, c1, c2, c3, k0, k1):

@@ -206,6 +206,7 @@ class EnvConfig:
     action_noise_min: float = -0.05
     action_noise_max: float = 0.05
     action_bias: float = 0.0
+    action_bias_steps: int = 0      # the bias is applied while the control-step counter is below this [OIGE/tasks/USV_Virtual.py:1070-1077]
     penalties_use_u: bool = False
     noise_pos: bool = False
     pos_noise_min: float = -0.03
@@ -244,6 +245,8 @@ class EnvConfig:
     retarget_on_reset: bool = False
     spawn_min_dist: float = 0.3
     spawn_max_dist: float = 12.0
+    spawn_about_origin: bool = False
+    reset_pose_external: bool = False
     spawn_vel_range: float = 1.5
     mass_rand: bool = False
     mass_min: float = 34.96
@@ -419,19 +422,24 @@ class ClassicEnvOracle:
             self.thr_mult_left[ids] = s
             self.thr_mult_right[ids] = s
             self.k_iz[ids] = c.couple_kiz_min + rr * (c.couple_kiz_max - c.couple_kiz_min)
-        if c.retarget_on_reset:                                             # get_goals [SNAP/USV_capture_xy.py:312-326]
-            self.target[ids, 0] = r0[:, 0] * c.goal_random_position * 2 - c.goal_random_position
-            self.target[ids, 1] = r0[:, 1] * c.goal_random_position * 2 - c.goal_random_position
-        # get_spawns  [SNAP/USV_capture_xy.py:330-394]
-        sr = r0[:, 2] * (c.spawn_max_dist - c.spawn_min_dist) + c.spawn_min_dist
-        th = r0[:, 3] * 2 * math.pi
-        self.pos[ids, 0] = sr * torch.cos(th) + self.target[ids, 0]
-        self.pos[ids, 1] = sr * torch.sin(th) + self.target[ids, 1]
-        self.psi[ids] = r1[:, 0] * math.pi
-        # [SNAP/USV_Virtual.py:786-794]
-        self.vel[ids, 0] = r1[:, 1] * (2 * c.spawn_vel_range) - c.spawn_vel_range
-        self.vel[ids, 1] = r1[:, 2] * (2 * c.spawn_vel_range) - c.spawn_vel_range
-        self.r[ids] = 0
+        if not c.reset_pose_external:
+            if c.retarget_on_reset:                                             # get_goals [SNAP/USV_capture_xy.py:312-326]
+                self.target[ids, 0] = r0[:, 0] * c.goal_random_position * 2 - c.goal_random_position
+                self.target[ids, 1] = r0[:, 1] * c.goal_random_position * 2 - c.goal_random_position
+            # get_spawns  [SNAP/USV_capture_xy.py:330-394]
+            sr = r0[:, 2] * (c.spawn_max_dist - c.spawn_min_dist) + c.spawn_min_dist
+            th = r0[:, 3] * 2 * math.pi
+            if c.spawn_about_origin:                                            # live task: OIGE/tasks/USV/USV_capture_xy_static_obs.py:955-956
+                self.pos[ids, 0] = sr * torch.cos(th)
+                self.pos[ids, 1] = sr * torch.sin(th)
+            else:
+                self.pos[ids, 0] = sr * torch.cos(th) + self.target[ids, 0]
+                self.pos[ids, 1] = sr * torch.sin(th) + self.target[ids, 1]
+            self.psi[ids] = r1[:, 0] * math.pi
+            # [SNAP/USV_Virtual.py:786-794]
+            self.vel[ids, 0] = r1[:, 1] * (2 * c.spawn_vel_range) - c.spawn_vel_range
+            self.vel[ids, 1] = r1[:, 2] * (2 * c.spawn_vel_range) - c.spawn_vel_range
+            self.r[ids] = 0
         self.reset_buf[ids] = 0
         self.progress_buf[ids] = 0
 
@@ -484,7 +492,8 @@ class ClassicEnvOracle:
         self.psi = self.psi + c.dt * self.r
 
     # ---- VecEnvRLGames.step  [OIGE/envs/vec_env_rlgames.py:120-217] --------------------------
-    def step(self, actions: torch.Tensor):
+    def dynamics(self, actions: torch.Tensor):
+        """pre_physics_step + the physics sub-steps + update_state; shared by the classic and the live (Variant B) task."""
         c = self.cfg
         n = self.n
         step = self.step_counter
@@ -494,18 +503,22 @@ class ClassicEnvOracle:
         # pre_physics_step  [SNAP/USV_Virtual.py:571-617]
         reset_ids = self.reset_buf.nonzero(as_tuple=False).squeeze(-1)
         self.reset_idx(reset_ids, step)
+        raw_actions = actions.clone()
         if not c.action_affine:
             if c.action_noise:
                 actions = actions + _u(nz[:, 0:2], c.action_noise_min, c.action_noise_max)
             pen_actions = actions
             cmd = torch.clamp(actions, -1.0, 1.0)
+            before_rect = cmd.clone()
         else:                                                               # [OIGE/tasks/USV_Virtual.py:1064-1097]
-            t = actions + c.action_bias
+            t = actions + (c.action_bias if self.step_counter < c.action_bias_steps else 0.0)
             if c.action_noise:
                 t = t + _u(nz[:, 0:2], c.action_noise_min, c.action_noise_max)
             t = torch.clamp(t, -1.0, 1.0)
+            before_rect = t.clone()
             cmd = torch.clamp(0.5 * (t + 1.0), 0.0, 1.0)
             pen_actions = cmd.clone() if c.penalties_use_u else actions
+        unit = cmd.clone()
         cmd[reset_ids] = 0
         _, target = thruster_target(cmd, self.lut_left, self.lut_right, self.thr_mult_left, self.thr_mult_right)
         for _ in range(c.n_substeps):
@@ -525,6 +538,13 @@ class ClassicEnvOracle:
             yaw = yaw + _u(nz[:, 5], c.heading_noise_min, c.heading_noise_max)
         heading = torch.stack([torch.cos(yaw), torch.sin(yaw)], 1)
         state = {"position": pos, "orientation": heading, "linear_velocity": vel, "angular_velocity": w}
+        return state, {"pen_actions": pen_actions, "reset_ids": reset_ids, "raw_actions": raw_actions, "before_rect": before_rect,
+                       "unit": unit}
+
+    def step(self, actions: torch.Tensor):
+        c = self.cfg
+        state, dyn = self.dynamics(actions)
+        pen_actions, reset_ids, w = dyn["pen_actions"], dyn["reset_ids"], state["angular_velocity"]
         obs, aux = capture_xy_observation(state, self.target)
         out = capture_xy_reward(c, aux, state, self.goal_reached, self.prev_d, reset_ids)
         self.prev_d = aux["d"]

@@ -9,7 +9,11 @@ from __future__ import annotations
 import math
 from dataclasses import dataclass
 
+import numpy as np
 import torch
+
+from . import philox
+from .usv_oracle import ClassicEnvOracle, EnvConfig, penalties
 
 GRID, MAP_SIZE, OBST_R = 150, 30.0, 0.5          # :30-32
 CELL = MAP_SIZE / GRID
@@ -186,7 +190,9 @@ def live_reward(c: LiveTaskConfig, S: LiveRewardState, aux, state, obstacles, fi
     total = (dist_rew * 0.5 + align * 0.5 + shaping * 2.0 + hazard + goal_rew + c.time_reward + coll + speed_rew + ang_rew + h_imp_rew)
     return {"reward": total, "distance_reward": dist_rew, "alignment_reward": align, "potential_shaping": shaping, "turn_hazard": hazard,
             "speed_reward": speed_rew, "angular_reward": ang_rew, "heading_improve": h_imp_rew, "collision_penalty": coll,
-            "goal_reward": goal_rew, "danger": danger, "potential": pot}
+            "goal_reward": goal_rew, "danger": danger, "potential": pot, "g_gate": gate_pos, "danger_hi": (danger > 0.5).float(),
+            # :349-351 (diagnostic only)
+            "boundary_penalty": -torch.expm1(torch.clamp(torch.clamp(d - c.kill_dist, min=0.0) / 0.25, max=20.0)) * c.boundary_cost}
 
 
 # B4  update_kills :661-706
@@ -211,7 +217,7 @@ def occupancy_and_sdf(obstacles):
     xg, yg = grid_coords()
     dx = xg[None, :, :, None] - obstacles[:, None, None, :, 0]
     dy = yg[None, :, :, None] - obstacles[:, None, None, :, 1]
-    sdf = torch.sqrt(dx * dx + dy * dy).min(dim=-1).values - OBST_R
+    sdf = torch.norm(torch.stack([dx, dy], dim=-1), dim=-1).min(dim=-1).values - OBST_R   # ATen: sqrt(fma(y, y, x*x))
     occ = (sdf <= 0).float()
     occ[:, 0, :] = 1; occ[:, -1, :] = 1; occ[:, :, 0] = 1; occ[:, :, -1] = 1   # border walls
     return occ, sdf
@@ -263,3 +269,142 @@ def potential_field(cost, sdf, influence=0.7, eta=20.0):
 def build_field(obstacles, target):
     occ, sdf = occupancy_and_sdf(obstacles)
     return potential_field(cost_to_go(occ, target), sdf), occ, sdf
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Full live env step: the shared dynamics of ClassicEnvOracle + the Variant-B task, resets included (B5 with the CUDA
+# path's Philox streams; RNG parity with torch's generator is statistical only, as for the classic task).
+@dataclass
+class LivePrivConfig:
+    """Privileged tail + CoM randomisation  [OIGE/tasks/USV_Virtual.py:97-151,837-984 ; USV_disturbances.py:88-124,153-194]."""
+    priv_mode: int = 2                       # 0 raw, 1 centered, 2 minmax
+    mass_obs_relative: bool = True
+    com_obs_scaled: bool = True
+    com_scale: tuple = (1.3, 1.0, 1.0)       # (box_length, box_width, max(heron_zero_height, 1))
+    priv_a: tuple = (1.0, 0.5, 0.5, 1.0)     # minmax: min of [k_drag, thr_L, thr_R, k_Iz]
+    priv_b: tuple = (0.5, 0.5, 0.5, 0.5)     # minmax: max - min
+    priv_active: tuple = (True, True, True, True)
+    com_rand: bool = True
+    com_base: tuple = (0.0, 0.0, 0.0)
+    com_disp: tuple = (0.15, 0.05, 0.02)
+    collision_threshold: float = COLLISION_TH
+    fixed_horizon_eval: bool = False
+
+
+def priv_encode(pc: LivePrivConfig, j: int, x: torch.Tensor) -> torch.Tensor:
+    if pc.priv_mode == 0:
+        return x
+    if pc.priv_mode == 1:
+        return torch.clamp((x - pc.priv_a[j]) / pc.priv_b[j], -1.0, 1.0)
+    if not pc.priv_active[j]:
+        return torch.zeros_like(x)
+    z = (x - pc.priv_a[j]) / pc.priv_b[j]
+    return torch.clamp(2.0 * z - 1.0, -1.0, 1.0)
+
+
+def place_obstacles(seed: int, env_ids: np.ndarray, step: int, start: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """get_spawns :970-1047: 16 centres ~ U(target +- 12), <= 20 rounds of re-drawing the invalid ones (within 3 m of start /
+    target, or < 2.5 m from a lower-index obstacle), leftovers -> (999, 999)."""
+    m = len(env_ids)
+    mn = target - 12.0
+    span = (target + 12.0) - mn
+
+    def draw(rnd):
+        out = torch.zeros((m, N_OBST, 2), dtype=F32)
+        for pair in range(N_OBST // 2):
+            u = torch.from_numpy(philox.uniform4(seed, env_ids, step, philox.RS_OBST + rnd * 8 + pair))
+            out[:, 2 * pair] = u[:, 0:2] * span + mn
+            out[:, 2 * pair + 1] = u[:, 2:4] * span + mn
+        return out
+
+    def invalid(obs):
+        ds = obs - start.unsqueeze(1)
+        dt = obs - target.unsqueeze(1)
+        inv = (torch.norm(ds, dim=-1) < 3.0) | (torch.norm(dt, dim=-1) < 3.0)
+        valid = obs[..., 0] < 900.0
+        delta = obs.unsqueeze(2) - obs.unsqueeze(1)                  # [n, a, b] = obs[a] - obs[b]
+        d2 = delta[..., 0] * delta[..., 0] + delta[..., 1] * delta[..., 1]
+        triu = torch.triu(torch.ones((N_OBST, N_OBST), dtype=torch.bool), diagonal=1).unsqueeze(0)
+        conf = (d2 < 2.5 * 2.5) & valid.unsqueeze(2) & valid.unsqueeze(1) & triu
+        return inv | conf.any(dim=1)
+
+    obs = draw(0)
+    active = torch.ones(m, dtype=torch.bool)                         # per-env early exit == the batch-wide one: valid ones never move
+    for it in range(20):
+        inv = invalid(obs) & active.unsqueeze(1)
+        active = inv.any(dim=1)
+        if not active.any():
+            break
+        obs = torch.where(inv.unsqueeze(-1), draw(it + 1), obs)
+    obs = torch.where(invalid(obs).unsqueeze(-1), torch.tensor([999.0, 999.0]), obs)
+    return obs
+
+
+class LiveEnvOracle(ClassicEnvOracle):
+    """VecEnvRLGames.step over the live USVVirtual + CaptureXYTask (static obstacles)."""
+
+    def __init__(self, cfg: EnvConfig, task: LiveTaskConfig, priv: LivePrivConfig, num_envs: int, env_id_offset: int = 0):
+        super().__init__(cfg, num_envs, env_id_offset)
+        self.task, self.priv = task, priv
+        n = num_envs
+        self.obstacles = torch.zeros((n, N_OBST, 2), dtype=F32)
+        self.field = torch.zeros((n, GRID, GRID), dtype=F32)
+        self.com = torch.tensor([priv.com_base] * n, dtype=F32)
+        self.S = LiveRewardState(n)
+        self.outcome_at_reset = {"success": torch.zeros(0), "collision": torch.zeros(0)}
+
+    def reset_idx(self, ids: torch.Tensor, step: int):
+        if ids.numel() == 0:
+            return
+        c = self.cfg
+        gids = self.env_ids[ids.numpy()]
+        self.outcome_at_reset = {"success": self.S.done_success[ids].float(), "collision": self.S.done_collision[ids].float()}
+        self.S.reset(ids)
+        if self.priv.com_rand:
+            rc = torch.from_numpy(philox.uniform4(c.seed, gids, step, philox.RS_RESET_COM))
+            self.com[ids] = torch.tensor(self.priv.com_base, dtype=F32) + (rc[:, 0:3] * 2 - 1) * torch.tensor(self.priv.com_disp, dtype=F32)
+        # scene: spawn point of this reset (same draw as ClassicEnvOracle.reset_idx) and the CURRENT target
+        r0 = torch.from_numpy(philox.uniform4(c.seed, gids, step, philox.RS_RESET[0]))
+        sr = r0[:, 2] * (c.spawn_max_dist - c.spawn_min_dist) + c.spawn_min_dist
+        th = r0[:, 3] * 2 * math.pi
+        start = torch.stack([sr * torch.cos(th), sr * torch.sin(th)], 1)
+        if not c.spawn_about_origin:
+            start = start + self.target[ids]
+        tgt = self.target[ids].clone()
+        self.obstacles[ids] = place_obstacles(c.seed, gids, step, start, tgt)
+        self.field[ids] = build_field(self.obstacles[ids], tgt)[0]
+        super().reset_idx(ids, step)
+
+    def priv_tail(self):
+        c, pc = self.cfg, self.priv
+        mass = (self.mass - c.mass_base) / max(abs(c.mass_base), 1e-6) if pc.mass_obs_relative else self.mass
+        com = self.com / (torch.tensor(pc.com_scale, dtype=F32) + 1e-6) if pc.com_obs_scaled else self.com
+        cols = [mass.unsqueeze(1), com] + [priv_encode(pc, j, x).unsqueeze(1) for j, x in
+                                           enumerate((self.drag_scale[:, 0], self.thr_mult_left, self.thr_mult_right, self.k_iz))]
+        return torch.cat(cols, dim=1)
+
+    def step(self, actions: torch.Tensor):
+        c, t = self.cfg, self.task
+        state, dyn = self.dynamics(actions)
+        reset_ids, w = dyn["reset_ids"], state["angular_velocity"]
+        prev_action = dyn["raw_actions"].clone()
+        prev_action[reset_ids] = 0.0
+        obs, aux = live_observation(state, self.target, self.obstacles, prev_action, self.priv_tail())
+        out = live_reward(t, self.S, aux, state, self.obstacles, self.field)
+        pen = penalties(c, state, dyn["pen_actions"], self.prev_w, self.prev_asum, self.first_call)
+        self.prev_w = w
+        self.prev_asum = pen["asum"]
+        self.first_call = False
+        rew = out["reward"] + pen["total"]
+        self.goal_reached = self.S.goal_reached
+        self.prev_d = aux["d"]
+        die = live_kills(t, self.S, aux["d"], state["position"], self.obstacles)
+        if self.priv.fixed_horizon_eval:
+            die = torch.zeros_like(die)
+        ones = torch.ones_like(self.reset_buf)
+        self.reset_buf = torch.where(self.progress_buf >= c.max_episode_length - 1, ones, die)
+        obs = torch.clamp(obs, -c.clip_obs, c.clip_obs)
+        self.step_counter += 1
+        self.last = {**out, **pen, **aux, "reset_ids": reset_ids, "before_rect": dyn["before_rect"], "unit": dyn["unit"],
+                     "raw_actions": dyn["raw_actions"], "state": state}
+        return obs, rew, self.reset_buf.clone()

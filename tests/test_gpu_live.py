@@ -1,0 +1,241 @@
+"""GPU parity tests of Variant B (live CaptureXY with static obstacles), through the C ABI:
+(i) against the goldens produced by the reference's own CaptureXYTask / BatchedMapGPU (tests/golden/capture_xy_live.npz) and
+(ii) against the CPU oracle (oracle/usv_oracle_b.py) on the same seeded inputs, resets and scene rebuilds included.
+Bars: obs / reward terms 1e-5 relative (atol written at each assert), kills / outcome latches / obstacle placement and the
+cost-to-go field bit-exact."""
+import dataclasses
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from omniisaacgymenvs_loop_b200.config import PenaltyTerm, UsvEnvConfig, UsvLiveConfig  # noqa: E402
+from omniisaacgymenvs_loop_b200.engine import FusedUsvLiveEnv  # noqa: E402
+from oracle import usv_oracle_b as B  # noqa: E402
+from tests.util import assert_close, engine_state, oracle_cfg, oracle_state, push_oracle_state  # noqa: E402
+
+DEV = "cuda:0"
+T = torch.from_numpy
+OFF = PenaltyTerm()
+
+LIVE_CFG = UsvEnvConfig(
+    dt=0.01, n_substeps=10, max_episode_length=200, action_affine=True, penalties_use_u=True, action_noise=False,
+    spawn_about_origin=True, retarget_on_reset=True, spawn_min_dist=9.0, spawn_max_dist=12.0,
+    position_tolerance=1.0, kill_after_n_steps_in_tolerance=1, kill_dist=20.0, goal_reward=20.0, time_reward=-0.05,
+    position_scale=1.5, align_la1=0.04, mass_rand=True, mass_min=34.96, mass_max=54.96, mass_base=34.96,
+    mass_coupling=True, couple_mass_max=54.96, couple_thr_a=0.5, kdrag_min=1.0, kdrag_max=1.5, use_drag_scale=True,
+    pen_energy=PenaltyTerm(1, 0.005, 0.0, 0.0), pen_angular_vel=PenaltyTerm(4, 0.02, 0.0, 0.4),
+    pen_angular_vel_variation=PenaltyTerm(4, 0.005, 0.0, 0.10))
+
+
+def oracle_live(live: UsvLiveConfig):
+    return B.LivePrivConfig(priv_mode=live.priv_mode, mass_obs_relative=live.mass_obs_relative, com_obs_scaled=live.com_obs_scaled,
+                            com_scale=live.com_scale, priv_a=live.priv_a, priv_b=live.priv_b, priv_active=live.priv_active,
+                            com_rand=live.com_rand, com_base=live.com_base, com_disp=live.com_disp,
+                            collision_threshold=live.collision_threshold, fixed_horizon_eval=live.fixed_horizon_eval)
+
+
+def oracle_task(cfg: UsvEnvConfig):
+    return B.LiveTaskConfig(position_tolerance=cfg.position_tolerance, kill_after_n_steps_in_tolerance=cfg.kill_after_n_steps_in_tolerance,
+                            kill_dist=cfg.kill_dist, boundary_cost=cfg.boundary_cost, goal_reward=cfg.goal_reward,
+                            time_reward=cfg.time_reward, position_scale=cfg.position_scale, align_la1=cfg.align_la1,
+                            align_la2=cfg.align_la2, align_la3=cfg.align_la3, spawn_min_dist=cfg.spawn_min_dist,
+                            spawn_max_dist=cfg.spawn_max_dist, goal_random_position=cfg.goal_random_position)
+
+
+# ------------------------------------------------------------------------------------------
+def test_potential_field_builder_vs_reference_golden(golden):
+    """B6: occupancy/SDF -> wavefront cost-to-go (bit-exact, +inf cells included) -> potential field, batch-global maxima."""
+    G = golden("capture_xy_live")
+    env = FusedUsvLiveEnv(LIVE_CFG, UsvLiveConfig(), 32, DEV)
+    field, cost = env.build_fields(T(G["obstacles0"]), T(G["target"]), want_cost=True)
+    assert torch.equal(cost.cpu(), T(G["cost0"]))
+    assert_close(field, G["field0"], 1e-6, 1e-6, "potential field")
+    # a batch of one: the global maxima change, the raw cost does not
+    f1, c1 = env.build_fields(T(G["obstacles0"][3:4]), T(G["target"][3:4]), want_cost=True)
+    assert torch.equal(c1.cpu()[0], T(G["cost0"][3]))
+    want = B.potential_field(T(G["cost0"][3:4]), T(G["sdf0"][3:4]))
+    assert_close(f1, want, 1e-6, 1e-6, "potential field (batch of one)")
+
+
+def test_live_task_vs_reference_golden(golden):
+    """B1-B4 on the states the reference task was driven with (n_substeps=0: the kernel's physics is a no-op, the host writes
+    pose / velocity every step = the reference's scene-replay mode): obs(33), reward, kills, outcome latches."""
+    G = golden("capture_xy_live")
+    K, n = G["pos"].shape[:2]
+    cfg = dataclasses.replace(LIVE_CFG, n_substeps=0, max_episode_length=10_000, mass_rand=False, mass_coupling=False, use_drag_scale=False,
+                              reset_pose_external=True, retarget_on_reset=False, noise_vel=False, noise_heading=False, noise_pos=False,
+                              pen_energy=OFF, pen_angular_vel=OFF, pen_angular_vel_variation=OFF)
+    live = UsvLiveConfig(priv_mode=0, mass_obs_relative=False, com_obs_scaled=False, com_rand=False)
+    env = FusedUsvLiveEnv(cfg, live, n, DEV)
+    env.set_obstacles(T(G["obstacles0"]))
+    env.potential.copy_(T(G["field0"]).to(DEV))
+    env.set_field("USV_C_TX", T(G["target"][:, 0])); env.set_field("USV_C_TY", T(G["target"][:, 1]))
+    reset_ids = T(G["reset_ids"])
+    for k in range(K):
+        was_reset = torch.zeros(n, dtype=torch.bool)
+        env.reset_buf.zero_()
+        env.reset_epoch.fill_(-1)
+        if k == 0:
+            was_reset[:] = True
+        elif k == int(G["reset_step"]):
+            was_reset[reset_ids] = True
+            env.set_obstacles(T(G["obstacles1"]))
+            env.potential.copy_(T(G["field1"]).to(DEV))
+        if was_reset.any():
+            env.reset_buf.copy_(was_reset.long().to(DEV))
+            env.mark_host_reset()
+        for name, v in (("USV_S_X", G["pos"][k][:, 0]), ("USV_S_Y", G["pos"][k][:, 1]), ("USV_S_PSI", G["yaw"][k]),
+                        ("USV_S_VX", G["vel"][k][:, 0]), ("USV_S_VY", G["vel"][k][:, 1]), ("USV_S_R", G["w"][k]),
+                        ("USV_C_MASS", G["priv"][k][:, 0]), ("USV_BC_COM_X", G["priv"][k][:, 1]), ("USV_BC_COM_Y", G["priv"][k][:, 2]),
+                        ("USV_BC_COM_Z", G["priv"][k][:, 3]), ("USV_C_KDRAG", G["priv"][k][:, 4]), ("USV_C_THR_ML", G["priv"][k][:, 5]),
+                        ("USV_C_THR_MR", G["priv"][k][:, 6]), ("USV_C_KIZ", G["priv"][k][:, 7])):
+            env.set_field(name, T(np.ascontiguousarray(v)))
+        obs, rew, done = env.step(T(G["prev_action"][k]).to(DEV), rebuild_scene=False)
+        obs, want = obs.cpu().clone(), T(G["obs"][k]).clone()
+        # a resetting env sees prev_action = 0 and the nominal mass (reset_idx zeroes / re-draws them before the step; the
+        # golden drove get_state_observations directly with random values): those three columns are checked separately
+        assert torch.all(obs[was_reset][:, 23:25] == 0) and torch.all(obs[was_reset][:, 25] == min(np.float32(cfg.mass_base), np.float32(cfg.clip_obs)))
+        obs[was_reset, 23:26] = want[was_reset, 23:26]
+        want = want.clamp(-cfg.clip_obs, cfg.clip_obs)          # VecEnvRLGames._process_data; the golden is the task's raw buffer
+        assert_close(obs, want, 1e-5, 2e-6, f"obs step {k}")
+        # the shaping term is 2 x 100 x (difference of two nearly equal potentials): 1e-7 relative on the potential -> 1e-4
+        assert_close(rew, G["reward"][k], 1e-5, 1.5e-4, f"reward step {k}")
+        assert torch.equal(done.cpu(), T(G["die"][k])), k
+        assert torch.equal(env.goal_reached.cpu(), T(G["goal_reached"][k]))
+        succ, coll = env.episode_outcomes()
+        assert torch.equal(succ.cpu().int(), T(G["done_success"][k])) and torch.equal(coll.cpu().int(), T(G["done_collision"][k]))
+    env.check_finite()
+
+
+# ------------------------------------------------------------------------------------------
+LIVE_STATE = [("USV_BS_PREV_H", lambda o: o.S.prev_h), ("USV_BS_PREV_POT", lambda o: o.S.prev_pot)]
+
+
+def push_live_state(orc, env):
+    push_oracle_state(orc, env)
+    z = torch.zeros(orc.n)
+    for name, get in LIVE_STATE:
+        v = get(orc)
+        env.set_field(name, (z if v is None else v).to(DEV))
+    env.set_field("USV_BS_OUTCOME", (orc.S.done_success + 2 * orc.S.done_collision).to(torch.int32).to(DEV))
+    for j in range(3):
+        env.set_field(("USV_BC_COM_X", "USV_BC_COM_Y", "USV_BC_COM_Z")[j], orc.com[:, j].to(DEV))
+    env.set_obstacles(orc.obstacles)
+    env.potential.copy_(orc.field.to(DEV))
+    env.reset_epoch.fill_(-1)
+    if bool(orc.reset_buf.any()):
+        env.mark_host_reset()
+
+
+def _lockstep(cfg, live, n, steps, seed=7, sync=True, collect_stats=False):
+    env = FusedUsvLiveEnv(cfg, live, n, DEV, collect_stats=collect_stats)
+    orc = B.LiveEnvOracle(oracle_cfg(cfg), oracle_task(cfg), oracle_live(live), n)
+    g = torch.Generator().manual_seed(seed)
+    for k in range(steps):
+        act = torch.rand((n, 2), generator=g) * 2.4 - 1.2
+        if sync:
+            push_live_state(orc, env)
+        o_out = orc.step(act)
+        obs, rew, done = env.step(act.to(DEV))
+        yield k, env, orc, (obs.cpu(), rew.cpu(), done.cpu()), o_out
+
+
+def test_live_step_vs_oracle_lockstep():
+    """Full control steps (dynamics + live task + resets with scene rebuild) from identical state each step."""
+    cfg = dataclasses.replace(LIVE_CFG, max_episode_length=7, kill_dist=12.5, action_bias=-0.6, action_bias_steps=5)
+    live = UsvLiveConfig()
+    n = 96 + 5
+    n_done = 0
+    for k, env, orc, (obs, rew, done), (o_obs, o_rew, o_done) in _lockstep(cfg, live, n, 12):
+        assert obs.shape == (n, 33) and done.dtype == torch.int64
+        # B5: the same Philox draws -> the same obstacles, bit for bit; B6: the fields rebuilt for exactly the envs that reset
+        assert torch.equal(env.obstacles.cpu(), orc.obstacles), f"obstacles step {k}"
+        assert_close(env.potential, orc.field, 1e-6, 1e-6, f"fields step {k}")
+        assert_close(obs, o_obs, 1e-5, 2e-5, f"obs step {k}")
+        assert_close(rew, o_rew, 1e-5, 2e-4, f"reward step {k}")
+        assert torch.equal(done, o_done), f"done mismatch at step {k}"
+        es, os_ = engine_state(env), oracle_state(orc)
+        assert torch.equal(es["goal"], os_["goal"]) and torch.equal(es["progress"], os_["progress"])
+        for name in es:
+            if name not in ("goal", "progress", "reset"):
+                assert_close(es[name], os_[name], 1e-5, 2e-5, f"{name} step {k}")
+        succ, coll = env.episode_outcomes()
+        assert torch.equal(succ.cpu().int(), orc.S.done_success) and torch.equal(coll.cpu().int(), orc.S.done_collision)
+        assert_close(env.field("USV_BS_PREV_POT"), orc.S.prev_pot, 1e-6, 1e-6, f"prev_potential step {k}")
+        n_done += int(done.sum())
+    assert n_done > n
+    env.check_finite()
+
+
+def test_live_step_free_running_vs_oracle():
+    """No re-sync: resets, obstacle re-draws and field rebuilds happen on the same steps for the same envs."""
+    cfg = dataclasses.replace(LIVE_CFG, max_episode_length=9)
+    n = 64
+    for k, env, orc, (obs, rew, done), (o_obs, o_rew, o_done) in _lockstep(cfg, UsvLiveConfig(), n, 22, sync=False):
+        assert torch.equal(done, o_done), f"done mismatch at step {k}"
+        assert torch.equal(env.obstacles.cpu(), orc.obstacles), f"obstacles step {k}"
+        assert_close(obs, o_obs, 1e-4, 2e-3, f"free-running obs step {k}")
+        assert_close(rew, o_rew, 1e-4, 5e-3, f"free-running reward step {k}")
+
+
+def test_live_stats_vs_oracle():
+    cfg = dataclasses.replace(LIVE_CFG, max_episode_length=6)
+    n = 64
+    E = __import__("omniisaacgymenvs_loop_b200._lib", fromlist=["ENUMS"]).ENUMS
+    sums = None
+    for k, env, orc, _, _ in _lockstep(cfg, UsvLiveConfig(), n, 9, sync=True, collect_stats=True):
+        L = orc.last
+        st = L["state"]
+        thr = orc.current_forces
+        rows = {
+            "TOTAL_REWARD": L["reward"], "DISTANCE_REWARD": L["distance_reward"], "ALIGNMENT_REWARD": L["alignment_reward"],
+            "HEADING_IMPROVE_REWARD": L["heading_improve"], "POTENTIAL_SHAPING_REWARD": L["potential_shaping"],
+            "SPEED_REWARD": L["speed_reward"], "ANGULAR_REWARD": L["angular_reward"], "TURN_HAZARD_PENALTY": L["turn_hazard"],
+            "GOAL_REWARD": L["goal_reward"], "COLLISION_REWARD": L["collision_penalty"], "TIME_REWARD": torch.full((n,), cfg.time_reward),
+            "POSITION_ERROR": L["d"], "BOUNDARY_PENALTY": L["boundary_penalty"], "DANGER_MEAN": L["danger"], "DANGER_HI_RATE": L["danger_hi"],
+            "G_GATE_MEAN": L["g_gate"], "LINEAR_VEL_PENALTY": L["pen_lin"], "ANGULAR_VEL_PENALTY": L["pen_ang"],
+            "ANGULAR_VEL_VARIATION_PENALTY": L["pen_angvar"], "ENERGY_PENALTY": L["pen_energy"], "ACTION_VARIATION_PENALTY": L["pen_actvar"],
+            "NORMED_LINEAR_VEL": torch.norm(st["linear_velocity"], dim=-1), "NORMED_ANGULAR_VEL": st["angular_velocity"].abs(),
+            "ACTIONS_SUM": L["raw_actions"].sum(-1), "CMD_NEG_RATE": (L["before_rect"] < 0).float().mean(1),
+            "THRUSTER_FORCE_NEG_RATE": (thr < 0).float().mean(1), "U_MEAN": L["unit"].mean(1), "U_LOW_RATE": (L["unit"] < 0.05).float().mean(1),
+            "U_SUM": L["unit"].sum(1)}
+        terms = torch.zeros((E["USV_BST_COUNT"], n))
+        for name, v in rows.items():
+            terms[E["USV_BST_" + name]] = v
+        assert len(rows) == E["USV_BST_COUNT"]
+        if sums is None:
+            sums = torch.zeros_like(terms)
+        sums[:, L["reset_ids"]] = 0
+        sums += terms
+        assert_close(env.bstats_matrix().cpu(), sums, 1e-5, 5e-4, f"episode sums step {k}")
+
+
+def test_live_full_size_properties():
+    """4096 envs, 40 free-running steps with random actions: finite, bounded, outcomes consistent, obstacles legal."""
+    cfg = dataclasses.replace(LIVE_CFG, max_episode_length=30)
+    n = 4096
+    env = FusedUsvLiveEnv(cfg, UsvLiveConfig(), n, DEV)
+    g = torch.Generator(device=DEV).manual_seed(3)
+    resets = 0
+    for k in range(40):
+        obs, rew, done = env.step(torch.rand((n, 2), generator=g, device=DEV) * 2 - 1)
+        resets += int(done.sum())
+        assert bool(torch.isfinite(obs).all()) and bool(torch.isfinite(rew).all())
+        assert float(obs.abs().max()) <= cfg.clip_obs
+    env.check_finite()
+    assert resets >= n
+    ob = env.obstacles                                        # (n,16,2)
+    valid = ob[..., 0] < 900
+    tgt = torch.stack([env.field("USV_C_TX"), env.field("USV_C_TY")], 1)
+    assert bool((((ob - tgt[:, None]).norm(dim=-1) >= 3.0) | ~valid).all())
+    d2 = ((ob[:, :, None] - ob[:, None]) ** 2).sum(-1)
+    pair = valid[:, :, None] & valid[:, None] & ~torch.eye(16, dtype=torch.bool, device=DEV)
+    assert bool(((d2 >= 2.5 * 2.5 - 1e-4) | ~pair).all())
+    assert bool((((ob - tgt[:, None]).abs() <= 12.0 + 1e-4) | ~valid[..., None]).all())
+    f = env.potential
+    assert bool(torch.isfinite(f).all()) and float(f.min()) >= 0.0 and float(f.max()) <= 1.5 + 1e-5
+    succ, coll = env.episode_outcomes()
+    assert bool(((succ + coll) <= 1).all())
