@@ -420,6 +420,118 @@ def variant_b():
     print("capture_xy_live.npz")
 
 
+def live_virtual():
+    """The live USVVirtual's own host-side chains that sit around the task (driven on a bare instance, no Isaac Sim):
+    pre_physics_step action path (A12), get_observations privileged tail (B1), _apply_mass_driven_coupling (A11)
+    [OIGE/tasks/USV_Virtual.py:837-1101]."""
+    ref_shim.install()
+    ref_shim.load_live()
+    hs, hd, td = ref_shim.load_force_modules()
+    dist = ref_shim.load_disturbances()
+    with ref_shim.quiet():
+        import omniisaacgymenvs.tasks.USV_Virtual as V
+    cfg = ref_shim.live_yaml()
+    env, dyn = cfg["env"], cfg["dynamics"]
+    d = env["disturbances"]
+    n = 24
+    g = gen()
+    out = {}
+
+    def bare():
+        me = object.__new__(V.USVVirtual)
+        me._device, me._num_envs = "cpu", n
+        me._task_cfg = cfg
+        return me
+
+    thr = dyn["thrusters"]
+    def thrusters():
+        with ref_shim.quiet():
+            return td.DynamicsFirstOrder(d["thruster"], n, "cpu", thr["timeConstant"], cfg["sim"]["dt"],
+                                         thr["interpolation"]["numberOfPointsForInterpolation"],
+                                         thr["interpolation"]["interpolationPointsFromRealDataLeft"],
+                                         thr["interpolation"]["interpolationPointsFromRealDataRight"],
+                                         thr["leastSquareMethod"]["neg_cmd_coeff"], thr["leastSquareMethod"]["pos_cmd_coeff"],
+                                         thr["cmd_lower_range"], thr["cmd_upper_range"])
+
+    # ---- A12: action path, with and without the initial bias, with a reset subset ----------------------------------------
+    for tag, count in (("bias", 0), ("nobias", 10 ** 9)):
+        me = bare()
+        me._env = types.SimpleNamespace(_world=types.SimpleNamespace(is_playing=lambda: True))
+        me.reset_buf = torch.zeros(n, dtype=torch.long)
+        me.reset_buf[[1, 7, 20]] = 1
+        me.reset_idx = lambda ids: None
+        me._discrete_actions = "Continuous"
+        me.prev_thrust_cmds = torch.full((n, 2), 9.0)
+        ap = env["action_processing"]
+        me._initial_action_bias, me._initial_action_bias_steps = float(ap["initial_action_bias"]), int(ap["initial_action_bias_steps"])
+        me._action_bias_step_count = count
+        me._use_affine_thrust_mapping = bool(ap["use_affine_thrust_mapping"])
+        me.AN = dist.NoisyActions(dict(d["actions"], add_noise_on_act=False))
+        me.thrust_cmds_before_rect = torch.zeros((n, 2))
+        me.thrust_cmds_unit = torch.zeros((n, 2))
+        me.thrusters_dynamics = thrusters()
+        actions = torch.rand((n, 2), generator=g) * 2 - 1           # VecEnvRLGames has already clamped to +-1
+        with ref_shim.quiet():
+            V.USVVirtual.pre_physics_step(me, actions.clone())
+        out.update({f"act_{tag}_in": actions, f"act_{tag}_prev": me.prev_thrust_cmds.clone(), f"act_{tag}_before_rect": me.thrust_cmds_before_rect.clone(),
+                    f"act_{tag}_unit": me.thrust_cmds_unit.clone(), f"act_{tag}_target": me.thrusters_dynamics.thruster_forces_before_dynamics.clone()})
+    out["act_reset_ids"] = torch.tensor([1, 7, 20])
+    out.update(lut_points_left=torch.tensor(thr["interpolation"]["interpolationPointsFromRealDataLeft"], dtype=torch.float64),
+               lut_points_right=torch.tensor(thr["interpolation"]["interpolationPointsFromRealDataRight"], dtype=torch.float64),
+               n_lut=torch.tensor(int(thr["interpolation"]["numberOfPointsForInterpolation"])),
+               act_bias=torch.tensor(float(env["action_processing"]["initial_action_bias"]), dtype=torch.float64))
+
+    # ---- A11 + B1: mass -> coupling -> privileged tail, for the three encodings ------------------------------------------
+    for mode in ("minmax", "centered", "raw"):
+        me = bare()
+        with ref_shim.quiet():
+            me.MDD = dist.MassDistributionDisturbances(d["mass"], n, "cpu")
+            me.hydrodynamics = hd.HydrodynamicsObject(d["drag"], n, "cpu", 1000, -9.81, dyn["hydrodynamics"]["linear_damping"],
+                                                      dyn["hydrodynamics"]["quadratic_damping"], dyn["hydrodynamics"]["linear_damping_forward_speed"],
+                                                      0.0, 0.0, 0.0, 1.0, 0.0, 1.0, 0.3, -10.0)
+            me.thrusters_dynamics = thrusters()
+        ids = torch.arange(n)
+        torch.manual_seed(33)
+        me.MDD.randomize_masses(ids, n)
+        me.MDD.platforms_mass[0, 0] = me.MDD._base_mass
+        me.MDD.platforms_mass[1, 0] = me.MDD._max_mass
+        me._mass_driven_coupling_enabled = True
+        me._mass_driven_couple_drag = me._mass_driven_couple_thruster = me._mass_driven_couple_yaw_inertia = True
+        me._k_drag_min, me._k_drag_max = float(d["drag"]["k_drag_min"]), float(d["drag"]["k_drag_max"])
+        me._thruster_rand_for_priv = float(d["thruster"]["thruster_rand"])
+        me._k_iz_min, me._k_iz_max = float(d["inertia"]["k_Iz_min"]), float(d["inertia"]["k_Iz_max"])
+        me.mass_ratio_r = torch.zeros((n, 1))
+        me.k_Iz = torch.ones((n, 1))
+        me._base_inertias0 = torch.ones((n, 9))
+        me._maybe_init_base_inertias0 = lambda: None
+        me._heron = types.SimpleNamespace(name="heron")
+        with ref_shim.quiet():
+            V.USVVirtual._apply_mass_driven_coupling(me, ids)
+        captured = {}
+        me.update_state = lambda: None
+        me.current_state = None
+        me._masscom_obs_source, me._mass_obs_mode, me._com_obs_mode = "sim", d["mass"]["mass_obs_mode"], d["mass"]["com_obs_mode"]
+        hsd = dyn["hydrostatics"]
+        me._com_obs_scale = [float(hsd["box_length"]), float(hsd["box_width"]), float(max(hsd["heron_zero_height"], 1.0))]
+        me._priv_dim = 8
+        me._privileged_params_mode, me._privileged_params_nominal = mode, 1.0
+        me._use_drag_scale_randomization_priv = me._use_thruster_randomization_priv = me._use_yaw_inertia_randomization = True
+        me.obs_buf = {}
+        me._observation_frame = "local"
+        me.prev_thrust_cmds = torch.zeros((n, 2))
+        me.task = types.SimpleNamespace(get_state_observations=lambda st, fr, mass, com, prev_action=None, priv_tail=None:
+                                        captured.update(priv=priv_tail.clone()) or torch.zeros((n, 33)))
+        with ref_shim.quiet():
+            V.USVVirtual.get_observations(me)
+        out.update({f"priv_{mode}": captured["priv"]})
+        if mode == "minmax":
+            out.update(cpl_mass=me.MDD.platforms_mass[:, 0].clone(), cpl_com=me.MDD.platforms_CoM.clone(), cpl_kdrag=me.hydrodynamics.drag_scale[:, 0].clone(),
+                       cpl_thr=me.thrusters_dynamics.thruster_multiplier[:, 0].clone(), cpl_kiz=me.k_Iz[:, 0].clone(),
+                       cpl_com_scale=torch.tensor(me._com_obs_scale))
+    np.savez_compressed(os.path.join(OUT, "live_virtual.npz"), **t2n(out))
+    print("live_virtual.npz")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)
@@ -429,6 +541,7 @@ def main():
     gae()
     ppo()
     variant_b()
+    live_virtual()
 
 
 if __name__ == "__main__":

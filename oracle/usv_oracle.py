@@ -312,6 +312,16 @@ class EnvConfig:
             mass_rand=True, drag_rand=True, thr_rand=True, thr_rand_frac=0.5, envs_per_row=0)
 
 
+def mass_coupling(c: "EnvConfig", mass: torch.Tensor):
+    """_apply_mass_driven_coupling  [OIGE/tasks/USV_Virtual.py:988-1040]: mass -> r in [0,1] -> (k_drag, thruster scale, k_Iz)."""
+    denom = max(c.couple_mass_max - c.mass_base, 1e-6)
+    rr = torch.clamp((mass - c.mass_base) / denom, 0.0, 1.0)
+    kd = c.kdrag_min + rr * (c.kdrag_max - c.kdrag_min)
+    sthr = torch.clamp(1.0 - rr * c.couple_thr_a, 1.0 - c.couple_thr_a, 1.0)
+    kiz = c.couple_kiz_min + rr * (c.couple_kiz_max - c.couple_kiz_min)
+    return kd, sthr, kiz
+
+
 def _u(u, lo, hi):
     return u * (hi - lo) + lo
 
@@ -414,14 +424,12 @@ class ClassicEnvOracle:
                 m = r3[:, 3] * 2 * c.thr_rand_frac + (1 - c.thr_rand_frac)
                 self.thr_mult_left[ids] = m
                 self.thr_mult_right[ids] = m
-        if c.mass_coupling:                                                 # [OIGE/tasks/USV_Virtual.py:988-1040]
-            denom = max(c.couple_mass_max - c.mass_base, 1e-6)
-            rr = torch.clamp((self.mass[ids] - c.mass_base) / denom, 0.0, 1.0)
-            self.drag_scale[ids, 0] = c.kdrag_min + rr * (c.kdrag_max - c.kdrag_min)
-            s = torch.clamp(1.0 - rr * c.couple_thr_a, 1.0 - c.couple_thr_a, 1.0)
-            self.thr_mult_left[ids] = s
-            self.thr_mult_right[ids] = s
-            self.k_iz[ids] = c.couple_kiz_min + rr * (c.couple_kiz_max - c.couple_kiz_min)
+        if c.mass_coupling:
+            kd, sthr, kiz = mass_coupling(c, self.mass[ids])
+            self.drag_scale[ids, 0] = kd
+            self.thr_mult_left[ids] = sthr
+            self.thr_mult_right[ids] = sthr
+            self.k_iz[ids] = kiz
         if not c.reset_pose_external:
             if c.retarget_on_reset:                                             # get_goals [SNAP/USV_capture_xy.py:312-326]
                 self.target[ids, 0] = r0[:, 0] * c.goal_random_position * 2 - c.goal_random_position
@@ -539,7 +547,7 @@ class ClassicEnvOracle:
         heading = torch.stack([torch.cos(yaw), torch.sin(yaw)], 1)
         state = {"position": pos, "orientation": heading, "linear_velocity": vel, "angular_velocity": w}
         return state, {"pen_actions": pen_actions, "reset_ids": reset_ids, "raw_actions": raw_actions, "before_rect": before_rect,
-                       "unit": unit}
+                       "unit": unit, "target": target}
 
     def step(self, actions: torch.Tensor):
         c = self.cfg

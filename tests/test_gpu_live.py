@@ -239,3 +239,49 @@ def test_live_full_size_properties():
     assert bool(torch.isfinite(f).all()) and float(f.min()) >= 0.0 and float(f.max()) <= 1.5 + 1e-5
     succ, coll = env.episode_outcomes()
     assert bool(((succ + coll) <= 1).all())
+
+
+# ------------------------------------------------------------------------------------------
+# the live USVVirtual's host chains around the task, against goldens produced by the reference class itself
+def _golden_live_cfg(G, **kw):
+    return dataclasses.replace(
+        LIVE_CFG, n_lut=int(G["n_lut"]), lut_points_left=tuple(G["lut_points_left"].tolist()), lut_points_right=tuple(G["lut_points_right"].tolist()),
+        reset_pose_external=True, retarget_on_reset=False, mass_rand=False, mass_coupling=False, use_drag_scale=False, noise_vel=False,
+        noise_heading=False, pen_energy=OFF, pen_angular_vel=OFF, pen_angular_vel_variation=OFF, **kw)
+
+
+def test_live_action_path_vs_reference_golden(golden):
+    """A12: the thrust target the kernel feeds the lag filter and the prev_action observation, with / without the initial bias."""
+    from oracle.usv_oracle import lag_alpha, thruster_lag
+    G = golden("live_virtual")
+    ids = T(G["act_reset_ids"])
+    for tag, steps in (("bias", 5), ("nobias", 0)):
+        n = G[f"act_{tag}_in"].shape[0]
+        cfg = _golden_live_cfg(G, n_substeps=1, action_bias=float(G["act_bias"]), action_bias_steps=steps)
+        env = FusedUsvLiveEnv(cfg, UsvLiveConfig(), n, DEV)
+        env.reset_buf.zero_()
+        env.reset_buf[ids.to(DEV)] = 1
+        env.mark_host_reset()
+        obs, _, _ = env.step(T(G[f"act_{tag}_in"]).to(DEV), rebuild_scene=False)
+        assert torch.equal(obs[:, 23:25].cpu(), T(G[f"act_{tag}_prev"]))
+        want = thruster_lag(torch.zeros((n, 2)), T(G[f"act_{tag}_target"]), lag_alpha(cfg.dt, cfg.time_constant))
+        got = torch.stack([env.field("USV_S_THR_L"), env.field("USV_S_THR_R")], 1).cpu()
+        assert torch.equal(got, want), tag
+
+
+def test_live_priv_tail_vs_reference_golden(golden):
+    """B1 privileged tail [m_rel, com/scale, enc(k_drag), enc(thr_L), enc(thr_R), enc(k_Iz)] in the three encodings."""
+    G = golden("live_virtual")
+    n = G["cpl_mass"].shape[0]
+    scale = tuple(float(x) for x in G["cpl_com_scale"])
+    for mode, code, a, b in (("minmax", 2, (1.0, 0.5, 0.5, 1.0), (0.5, 0.5, 0.5, 0.5)), ("centered", 1, (1.0,) * 4, (0.5,) * 4),
+                             ("raw", 0, (0.0,) * 4, (1.0,) * 4)):
+        env = FusedUsvLiveEnv(_golden_live_cfg(G, n_substeps=0), UsvLiveConfig(priv_mode=code, priv_a=a, priv_b=b, com_scale=scale, com_rand=False), n, DEV)
+        env.reset_buf.zero_()
+        env.reset_epoch.fill_(-1)
+        for name, v in (("USV_C_MASS", G["cpl_mass"]), ("USV_C_KDRAG", G["cpl_kdrag"]), ("USV_C_THR_ML", G["cpl_thr"]), ("USV_C_THR_MR", G["cpl_thr"]),
+                        ("USV_C_KIZ", G["cpl_kiz"]), ("USV_BC_COM_X", G["cpl_com"][:, 0]), ("USV_BC_COM_Y", G["cpl_com"][:, 1]),
+                        ("USV_BC_COM_Z", G["cpl_com"][:, 2])):
+            env.set_field(name, T(np.ascontiguousarray(v)))
+        obs, _, _ = env.step(torch.zeros((n, 2), device=DEV), rebuild_scene=False)
+        assert_close(obs[:, 25:33], G[f"priv_{mode}"], 1e-6, 1e-7, f"priv tail ({mode})")

@@ -62,3 +62,51 @@ def test_live_task_vs_reference(golden):
     assert G["done_collision"][0][0] == 1 and G["done_success"][0][1] == 1 and G["die"][0][2] == 1
     # quirk 8: on the step after the reset batch the potential shaping is exactly zero for EVERY env
     assert np.all(G["potential_shaping"][int(G["reset_step"])] == 0.0)
+
+
+# ---- the live USVVirtual's own host chains (goldens: oracle/make_golden.py:live_virtual) -------------------------------------
+def _live_oracle_cfg(G, **kw):
+    import dataclasses
+    from oracle.usv_oracle import EnvConfig
+    return dataclasses.replace(
+        EnvConfig(), action_affine=True, penalties_use_u=True, action_noise=False, noise_vel=False, noise_heading=False, n_substeps=0,
+        reset_pose_external=True, n_lut=int(G["n_lut"]), lut_points_left=tuple(G["lut_points_left"].tolist()),
+        lut_points_right=tuple(G["lut_points_right"].tolist()), mass_base=34.96, couple_mass_max=54.96, couple_thr_a=0.5,
+        kdrag_min=1.0, kdrag_max=1.5, couple_kiz_min=1.0, couple_kiz_max=1.5, **kw)
+
+
+def test_live_action_path_vs_reference(golden):
+    """A12: bias (first N steps) -> clamp -> affine map to [0,1] -> LUT, resets zero the command and prev_action."""
+    from oracle.usv_oracle import ClassicEnvOracle
+    G = golden("live_virtual")
+    ids = T(G["act_reset_ids"])
+    for tag, steps in (("bias", 5), ("nobias", 0)):
+        n = G[f"act_{tag}_in"].shape[0]
+        orc = ClassicEnvOracle(_live_oracle_cfg(G, action_bias=float(G["act_bias"]), action_bias_steps=steps), n)
+        orc.reset_buf[:] = 0
+        orc.reset_buf[ids] = 1
+        _, dyn = orc.dynamics(T(G[f"act_{tag}_in"]))
+        prev = dyn["raw_actions"].clone()
+        prev[ids] = 0
+        assert torch.equal(prev, T(G[f"act_{tag}_prev"]))
+        assert torch.equal(dyn["before_rect"], T(G[f"act_{tag}_before_rect"]))
+        assert torch.equal(dyn["unit"], T(G[f"act_{tag}_unit"]))
+        assert torch.equal(dyn["target"], T(G[f"act_{tag}_target"]))
+    # a reset env commands u = 0, i.e. the LUT entry of the mid-range command (not exactly 0 N)
+    assert len(np.unique(G["act_bias_target"][G["act_reset_ids"]], axis=0)) == 1
+
+
+def test_mass_coupling_and_priv_tail_vs_reference(golden):
+    from oracle.usv_oracle import mass_coupling
+    G = golden("live_virtual")
+    n = G["cpl_mass"].shape[0]
+    cfg = _live_oracle_cfg(G)
+    kd, sthr, kiz = mass_coupling(cfg, T(G["cpl_mass"]))
+    assert torch.equal(kd, T(G["cpl_kdrag"])) and torch.equal(sthr, T(G["cpl_thr"])) and torch.equal(kiz, T(G["cpl_kiz"]))
+    scale = tuple(float(x) for x in G["cpl_com_scale"])
+    for mode, code, a, b in (("minmax", 2, (1.0, 0.5, 0.5, 1.0), (0.5, 0.5, 0.5, 0.5)), ("centered", 1, (1.0,) * 4, (0.5,) * 4),
+                             ("raw", 0, (0.0,) * 4, (1.0,) * 4)):
+        orc = B.LiveEnvOracle(cfg, B.LiveTaskConfig(), B.LivePrivConfig(priv_mode=code, priv_a=a, priv_b=b, com_scale=scale), n)
+        orc.mass, orc.com = T(G["cpl_mass"]).clone(), T(G["cpl_com"]).clone()
+        orc.drag_scale[:, 0], orc.thr_mult_left, orc.thr_mult_right, orc.k_iz = kd, sthr.clone(), sthr.clone(), kiz
+        assert torch.allclose(orc.priv_tail(), T(G[f"priv_{mode}"]), rtol=1e-6, atol=1e-7), mode
