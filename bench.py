@@ -326,6 +326,81 @@ def bench_gae_mlp(device):
     return out
 
 
+def bench_variant_b(device, envs=16384, steps=400, warmup=50):
+    """SURVEY rows B1-B6 (live CaptureXY, 16 obstacles, potential field): the fused live step alone, the steady state with the
+    scene rebuilds of the envs that reset (episodes of <= 200 steps), and the scene builder on a dense batch; the CPU oracle's
+    step / field build beside them (bounded samples)."""
+    import time
+
+    from omniisaacgymenvs_loop_b200.config import UsvLiveConfig, live_default_config
+    from omniisaacgymenvs_loop_b200.engine import FusedUsvLiveEnv
+
+    cfg = live_default_config(num_envs=envs)
+    env = FusedUsvLiveEnv(cfg, UsvLiveConfig(), envs, device)
+    g = torch.Generator(device=device).manual_seed(99)
+    acts = [torch.rand((envs, 2), device=device, generator=g) * 2 - 1 for _ in range(8)]
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    # steady state: step + scene rebuild; the first step resets (and builds) every env, so warm up past the first episodes
+    for w in range(max(warmup, 210)):
+        env.step(acts[w % 8])
+    torch.cuda.synchronize(device)
+    r0 = 0
+    e0, e1 = ev(), ev()
+    e0.record()
+    for k in range(steps):
+        env.step(acts[k % 8])
+    e1.record()
+    torch.cuda.synchronize(device)
+    full_ms = e0.elapsed_time(e1) / steps
+    resets = float(env.reset_buf.float().mean())
+    # step kernel alone (scene rebuild skipped: the fields of resetting envs go stale, which does not change the kernel's work)
+    e0, e1 = ev(), ev()
+    e0.record()
+    for k in range(steps):
+        env.step(acts[k % 8], rebuild_scene=False)
+    e1.record()
+    torch.cuda.synchronize(device)
+    step_ms = e0.elapsed_time(e1) / steps
+    env.check_finite()
+    # scene builder on a dense batch of 8 waves of CTAs
+    m = 1184
+    ob, tg = env.obstacles[:m].contiguous(), torch.zeros((m, 2), device=device)
+    env.build_fields(ob, tg)
+    torch.cuda.synchronize(device)
+    e0, e1 = ev(), ev()
+    e0.record()
+    env.build_fields(ob, tg)
+    e1.record()
+    torch.cuda.synchronize(device)
+    build_ms = e0.elapsed_time(e1)
+    out = {"envs_per_gpu": envs, "obs_dim": 33, "substeps": cfg.n_substeps, "step_kernel_us": step_ms * 1e3,
+           "step_kernel_env_steps_per_s": envs / (step_ms * 1e-3), "steady_state_us_per_step": full_ms * 1e3,
+           "steady_state_env_steps_per_s": envs / (full_ms * 1e-3), "reset_fraction_per_step": resets,
+           "scene_build": {"batch": m, "ms": build_ms, "us_per_env": build_ms * 1e3 / m},
+           "bytes_per_env_step": 610, "step_kernel_gbps": 610 * envs / (step_ms * 1e-3) / 1e9,
+           "note": "steady state = usv_live_reset_scene_f32 (obstacle placement + 150x150 wavefront + potential field for the envs "
+                   "that reset) + usv_step_live_f32 per control step; random actions, episodes <= 200 steps"}
+    try:
+        from oracle import usv_oracle_b as B
+        from tests.test_gpu_live import oracle_live, oracle_task
+        from tests.util import oracle_cfg
+        torch.set_num_threads(min(8, os.cpu_count() or 1))
+        nb = 32
+        orc = B.LiveEnvOracle(oracle_cfg(cfg), oracle_task(cfg), oracle_live(UsvLiveConfig()), nb)
+        t0 = time.perf_counter()
+        orc.step(torch.zeros((nb, 2)))                       # first step: resets + builds all 32 scenes
+        t_reset = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        for _ in range(5):
+            orc.step(torch.rand((nb, 2)) * 2 - 1)
+        t_step = (time.perf_counter() - t0) / 5
+        out["cpu_oracle"] = {"envs": nb, "threads": torch.get_num_threads(), "step_ms": t_step * 1e3, "env_steps_per_s": nb / t_step,
+                             "first_step_with_32_scene_builds_s": t_reset, "kind": "port"}
+    except Exception as ex:   # the oracle is optional for this leg
+        out["cpu_oracle"] = {"error": repr(ex)}
+    return out
+
+
 def main():
     # exactly ONE line on stdout: libraries (NCCL's version banner, ...) write to fd 1 too, so park fd 1 on stderr while we
     # run and print the JSON line to the real stdout at the end
@@ -344,6 +419,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the 4096-env and e2e legs (profiling runs)")
     ap.add_argument("--no-ppo", action="store_true", help="skip the PPO frames/s leg")
+    ap.add_argument("--no-variant-b", action="store_true", help="skip the live-task (Variant B) leg")
     ap.add_argument("--ppo-envs", type=int, default=16384, help="envs per GPU of the PPO leg (BASELINE config[2])")
     ap.add_argument("--ppo-epochs", type=int, default=10)
     args = ap.parse_args()
@@ -432,6 +508,8 @@ def main():
         line["ppo"] = bench_ppo(args, rank, world, device, dist_on)
     if not args.no_extra and rank == 0:
         line["secondary_kernels"] = bench_gae_mlp(device)
+    if not args.no_extra and not args.no_variant_b and rank == 0:
+        line["variant_b"] = bench_variant_b(device)
     if dist_on:
         dist.barrier()
     if rank == 0 and not args.no_cpu_baseline and world == 1:

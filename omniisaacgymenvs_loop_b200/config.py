@@ -185,7 +185,8 @@ class UsvEnvConfig:
     @property
     def lag_alpha(self) -> float:
         # torch.exp(torch.tensor(-dt/tau)) evaluated in fp32 [ref: OIGE/envs/USV/ThrusterDynamics.py:132]
-        return float(np.exp(np.float32(-self.dt / self.time_constant), dtype=np.float32))
+        import torch
+        return float(torch.exp(torch.tensor(-self.dt / self.time_constant)))
 
     def to_params(self, step_counter: int = 0, env_id_offset: int = 0, first_call: bool = False):
         p = _lib.UsvStepParams()
@@ -471,6 +472,46 @@ def live_env_config(task_cfg: dict, **overrides) -> "UsvEnvConfig":
     )
     live.update(overrides)
     return UsvEnvConfig.from_task_cfg(task_cfg, **live)
+
+
+_LIVE_LUT = (0.0,) * 11 + (8.0, 16.0, 24.0, 32.0, 40.0, 48.0, 56.0, 64.0, 72.0, 80.0)
+
+
+def live_default_config(**overrides) -> "UsvEnvConfig":
+    """UsvEnvConfig of the live task as shipped  [ref: OIGE/cfg/task/USV/IROS2024/USV_Virtual_CaptureXY_SysID-TEST.yaml]."""
+    base = dict(
+        n_substeps=10, max_episode_length=200, env_spacing=20.0, use_drag_scale=True, lut_points_left=_LIVE_LUT, lut_points_right=_LIVE_LUT,
+        action_affine=True, action_noise=False, action_bias=-0.6, action_bias_steps=20000, penalties_use_u=True,
+        position_tolerance=1.0, goal_reward=20.0, time_reward=-0.05, goal_speed_gate=float("inf"), position_scale=1.5,
+        exponential_reward_coeff=0.15, align_la1=0.04, pen_angular_vel=PenaltyTerm(PEN_NEG_DEADZONE, 0.02, 0.0, 0.4),
+        pen_angular_vel_variation=PenaltyTerm(PEN_NEG_DEADZONE, 0.005, 0.0, 0.1), pen_energy=PenaltyTerm(PEN_NEG_SUM, 0.005, 0.0, 0.0),
+        retarget_on_reset=True, spawn_min_dist=9.0, spawn_about_origin=True, mass_rand=True, mass_max=54.96, mass_base=34.96,
+        kdrag_max=1.5, mass_coupling=True)
+    base.update(overrides)
+    return UsvEnvConfig(**base)
+
+
+def live_task_cfg(cfg: Optional["UsvEnvConfig"] = None, live: Optional["UsvLiveConfig"] = None) -> dict:
+    """The live task-YAML tree for (cfg, live): to_task_cfg() plus the keys only the live USVVirtual reads."""
+    cfg = cfg if cfg is not None else live_default_config()
+    live = live if live is not None else UsvLiveConfig()
+    t = cfg.to_task_cfg()
+    env, dist = t["env"], t["env"]["disturbances"]
+    env["mass_dim"] = 8
+    env["privileged_params"] = {"mode": ("raw", "centered", "minmax")[live.priv_mode], "nominal": 1.0}
+    env["fixed_horizon_eval"] = live.fixed_horizon_eval
+    env["action_processing"] = {"use_affine_thrust_mapping": cfg.action_affine, "initial_action_bias": cfg.action_bias,
+                                "initial_action_bias_steps": cfg.action_bias_steps, "penalties_use_thrust_u": cfg.penalties_use_u}
+    dist["coupling"] = {"mass_driven": {"enabled": cfg.mass_coupling, "targets": ["drag_scale", "thruster", "yaw_inertia"]}}
+    dist["mass"].update(com_displacement_xyz=list(live.com_disp) if live.com_rand else None, base_com=list(live.com_base),
+                        apply_com_to_sim=True, mass_obs_mode="relative" if live.mass_obs_relative else "raw",
+                        com_obs_mode="scaled" if live.com_obs_scaled else "raw", masscom_obs_source="sim")
+    dist["drag"]["use_drag_scale_randomization"] = cfg.kdrag_rand
+    dist["thruster"]["thruster_rand"] = cfg.couple_thr_a if cfg.mass_coupling else cfg.thr_rand_frac
+    dist["inertia"] = {"use_yaw_inertia_randomization": False, "k_Iz_min": cfg.couple_kiz_min, "k_Iz_max": cfg.couple_kiz_max,
+                       "k_Iz_sample_space": "linear"}
+    t["dynamics"]["hydrostatics"].update(box_length=live.com_scale[0], box_width=live.com_scale[1])
+    return t
 
 
 def load_task_yaml(path: str, num_envs: Optional[int] = None) -> dict:

@@ -26,6 +26,8 @@ constexpr int kRowIters = (kG + 31) / 32;  // 5
 constexpr int kColIters = (kG + 31) / 32;  // 5
 constexpr int kMaxSweeps = (int)(kG * 1.5);  // 225  (d_multi_gemini.py:160)
 constexpr float kObstR = 0.5f;
+constexpr int kChunks = 5, kBands = 6, kBandRows = 25, kTiles = kChunks * kBands;  // wavefront tiles: 32 columns x 25 rows
+constexpr float kReach = 1.7f + 1e-3f;  // an obstacle matters to a cell only within 0.5 (radius) + 0.5 + 0.7 (influence) of its centre
 
 // counters (uint32[8]) in the workspace
 enum { CW_COUNT = 0, CW_MAXCOST = 1, CW_MAXJ = 2, CW_INSIDE = 3, CW_HAVE = 4, CW_WORDS = 8 };
@@ -68,6 +70,26 @@ __device__ __forceinline__ float cell_sdf(float cx, float cy, const float* s_ox,
   float best = CUDART_INF_F;
 #pragma unroll
   for (int j = 0; j < USV_B_OBSTACLES; ++j) {
+    const float dx = __fsub_rn(cx, s_ox[j]), dy = __fsub_rn(cy, s_oy[j]);
+    best = fminf(best, sqrtf(__fmaf_rn(dy, dy, __fmul_rn(dx, dx))));
+  }
+  return __fsub_rn(best, kObstR);
+}
+
+// bit j set: obstacle j is within kReach of grid row cy (|dy| <= dist), i.e. it can make a cell of that row occupied / repelled
+__device__ __forceinline__ uint32_t row_obstacle_mask(float cy, const float* s_oy) {
+  uint32_t m = 0;
+#pragma unroll
+  for (int j = 0; j < USV_B_OBSTACLES; ++j) m |= (fabsf(cy - s_oy[j]) <= kReach) ? (1u << j) : 0u;
+  return m;
+}
+// cell_sdf over the obstacles of `mask` only: exact wherever the result is below kReach - 0.5, +inf-ish (>= that) elsewhere --
+// every consumer only distinguishes values below 1.2 (occupancy: <= 0; repulsion: sdf - 0.5 < 0.7)
+__device__ __forceinline__ float cell_sdf_masked(float cx, float cy, const float* s_ox, const float* s_oy, uint32_t mask) {
+  float best = CUDART_INF_F;
+  while (mask) {
+    const int j = __ffs(mask) - 1;
+    mask &= mask - 1;
     const float dx = __fsub_rn(cx, s_ox[j]), dy = __fsub_rn(cy, s_oy[j]);
     best = fminf(best, sqrtf(__fmaf_rn(dy, dy, __fmul_rn(dx, dx))));
   }
@@ -142,6 +164,8 @@ __global__ void __launch_bounds__(kSceneThreads, 1) scene_cost_kernel(SceneIO io
   float* bufB = smem + kGP * kGP;
   float* s_sc = bufB + kGP * kGP;     // 34 floats
   float* s_red = s_sc + 64;           // 32 floats
+  int* s_act = reinterpret_cast<int*>(s_red + 32);        // [2][32] tile-active flags of the current / next sweep
+  uint32_t* s_rowmask = reinterpret_cast<uint32_t*>(s_act + 64);  // [150] obstacles that can matter on a grid row
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t total = scene_count(io);
   for (int64_t j = blockIdx.x; j < total; j += gridDim.x) {
@@ -167,56 +191,87 @@ __global__ void __launch_bounds__(kSceneThreads, 1) scene_cost_kernel(SceneIO io
     }
     // both buffers +inf (halo included)
     for (int q = threadIdx.x; q < kGP * kGP; q += kSceneThreads) { bufA[q] = CUDART_INF_F; bufB[q] = CUDART_INF_F; }
+    if (threadIdx.x < 64) s_act[threadIdx.x] = 0;
     __syncthreads();
-    // free mask of this thread's <= 25 cells: bit (ri*5 + ci)
-    uint32_t freemask = 0;
-#pragma unroll 1
-    for (int ri = 0; ri < kRowIters; ++ri) {
-      const int y = warp + 32 * ri;
-#pragma unroll
-      for (int ci = 0; ci < kColIters; ++ci) {
-        const int x = lane + 32 * ci;
-        if (y < kG && x < kG) {
-          const bool border = (y == 0) || (y == kG - 1) || (x == 0) || (x == kG - 1);
-          const float sdf = cell_sdf(io.lin[x], io.lin[y], s_sc, s_sc + 16);
-          if (!border && !(sdf <= 0.0f)) freemask |= 1u << (ri * kColIters + ci);
-        }
-      }
-    }
+    if (threadIdx.x < kG) s_rowmask[threadIdx.x] = row_obstacle_mask(io.lin[threadIdx.x], s_sc + 16);
     if (threadIdx.x == 0) {
-      // target cell: ((pos + map/2) / cell).long().clamp(0, 149)   (d_multi_gemini.py:148-155)
+      // target cell: ((pos + map/2) / cell).long().clamp(0, 149)   (d_multi_gemini.py:148-155).  It is written into BOTH buffers:
+      // the tile-skipping below relies on "a tile that is not swept holds the same values in both buffers"
       const int txi = min(max((int)__fdiv_rn(s_sc[32] + 15.0f, 0.2f), 0), kG - 1);
       const int tyi = min(max((int)__fdiv_rn(s_sc[33] + 15.0f, 0.2f), 0), kG - 1);
       bufA[(tyi + 1) * kGP + txi + 1] = 0.0f;
+      bufB[(tyi + 1) * kGP + txi + 1] = 0.0f;
+      const int tc = txi >> 5, tb = tyi / kBandRows;
+      for (int db = -1; db <= 1; ++db)
+        for (int dc = -1; dc <= 1; ++dc)
+          if (tc + dc >= 0 && tc + dc < kChunks && tb + db >= 0 && tb + db < kBands) s_act[(tb + db) * kChunks + tc + dc] = 1;
     }
     __syncthreads();
+    // warp w < 30 owns the tile (chunk = w % 5: 32 columns, band = w / 5: 25 rows); a lane walks down its column with a rolling
+    // 3x3 window in registers: 3 shared loads + 1 store per cell instead of 9 + 1 (the r01 kernel ran the shared-memory pipe
+    // at 84 % of peak: profiles/r01_live_kernels.md)
+    const bool has_tile = warp < kTiles;
+    const int chunk = warp % kChunks, band = warp / kChunks;
+    const int x = chunk * 32 + lane, y0 = band * kBandRows;
+    const bool xin = has_tile && x < kG;
+    const int xc = min(x, kG - 1);
+    uint32_t freemask = 0;   // bit i: cell (y0 + i, x) is free
+    if (xin) {
+#pragma unroll 1
+      for (int i = 0; i < kBandRows; ++i) {
+        const int y = y0 + i;
+        const bool border = (y == 0) || (y == kG - 1) || (x == 0) || (x == kG - 1);
+        const float sdf = cell_sdf_masked(io.lin[x], io.lin[y], s_sc, s_sc + 16, s_rowmask[y]);
+        if (!border && !(sdf <= 0.0f)) freemask |= 1u << i;
+      }
+    }
     float* cur = bufA;
     float* nxt = bufB;
     for (int sweep = 0; sweep < kMaxSweeps; ++sweep) {
-      int changed = 0;
-#pragma unroll 1
-      for (int ri = 0; ri < kRowIters; ++ri) {
-        const int y = warp + 32 * ri;
-        if (y < kG) {
-#pragma unroll
-          for (int ci = 0; ci < kColIters; ++ci) {
-            const int x = lane + 32 * ci;
-            if (x < kG) {
-              const int q = (y + 1) * kGP + x + 1;
-              const float old = cur[q];
-              float best = CUDART_INF_F;
-              if (freemask & (1u << (ri * kColIters + ci))) {
-                const float a = fminf(fminf(cur[q - 1], cur[q + 1]), fminf(cur[q - kGP], cur[q + kGP])) + 1.0f;
-                const float b = fminf(fminf(cur[q - kGP - 1], cur[q - kGP + 1]), fminf(cur[q + kGP - 1], cur[q + kGP + 1])) + 1.414f;
-                best = fminf(old, fminf(a, b));
-              }
-              nxt[q] = best;
-              changed |= (best != old) ? 1 : 0;
-            }
+      int* act_cur = s_act + (sweep & 1) * 32;
+      int* act_nxt = s_act + ((sweep + 1) & 1) * 32;
+      int any_change = 0;
+      if (has_tile && act_cur[warp]) {
+        __syncwarp();
+        if (lane == 0) act_cur[warp] = 0;  // consumed; writers of this sweep only touch act_nxt
+        const float* c0 = cur + y0 * kGP + xc + 1;  // (row y0 - 1, column x) in padded coordinates
+        float* n0 = nxt + (y0 + 1) * kGP + xc + 1;
+        float ul = c0[-1], uc = c0[0], ur = c0[1];
+        float ml = c0[kGP - 1], mc = c0[kGP], mr = c0[kGP + 1];
+        uint32_t chg = 0;
+#pragma unroll 5
+        for (int i = 0; i < kBandRows; ++i) {
+          const float* d = c0 + (i + 2) * kGP;
+          const float dl = d[-1], dc = d[0], dr = d[1];
+          float best = CUDART_INF_F;
+          if ((freemask >> i) & 1u) {
+            const float a = fminf(fminf(ml, mr), fminf(uc, dc)) + 1.0f;
+            const float b = fminf(fminf(ul, ur), fminf(dl, dr)) + 1.414f;
+            best = fminf(mc, fminf(a, b));
+          }
+          if (xin) {
+            n0[i * kGP] = best;
+            chg |= (best != mc) ? (1u << i) : 0u;
+          }
+          ul = ml; uc = mc; ur = mr;
+          ml = dl; mc = dc; mr = dr;
+        }
+        // activate for the next sweep exactly the tiles whose inputs changed: this one, and a neighbour only when a cell on the
+        // shared edge changed
+        const uint32_t any_b = __ballot_sync(0xffffffffu, chg != 0u);
+        if (any_b) {
+          any_change = 1;
+          const bool left = any_b & 1u, right = (any_b >> 31) & 1u;
+          const bool up = __any_sync(0xffffffffu, chg & 1u), down = __any_sync(0xffffffffu, (chg >> (kBandRows - 1)) & 1u);
+          if (lane < 9) {
+            const int dc = lane % 3 - 1, db = lane / 3 - 1;
+            const bool need = (dc == 0 || (dc < 0 ? left : right)) && (db == 0 || (db < 0 ? up : down));
+            const int c2 = chunk + dc, b2 = band + db;
+            if (need && c2 >= 0 && c2 < kChunks && b2 >= 0 && b2 < kBands) act_nxt[b2 * kChunks + c2] = 1;
           }
         }
       }
-      const int any = __syncthreads_or(changed);
+      const int any = __syncthreads_or(any_change);
       float* t = cur; cur = nxt; nxt = t;
       if (!any) break;
     }
@@ -273,11 +328,14 @@ __device__ __forceinline__ float global_vis_inf(const uint32_t* counters, int ha
 __global__ void __launch_bounds__(kSceneThreads, 1) scene_jmax_kernel(SceneIO io, uint32_t* __restrict__ counters) {
   __shared__ float s_sc[64];
   __shared__ float s_red[32];
+  __shared__ uint32_t s_rowmask[160];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t total = scene_count(io);
   const float vis_inf = global_vis_inf(counters, counters[CW_HAVE] != 0u);
   for (int64_t j = blockIdx.x; j < total; j += gridDim.x) {
     const int64_t env = load_scene(io, j, s_sc);
+    __syncthreads();
+    if (threadIdx.x < kG) s_rowmask[threadIdx.x] = row_obstacle_mask(io.lin[threadIdx.x], s_sc + 16);
     __syncthreads();
     const float* f = io.field + env * (int64_t)kCells;
     float mj = 0.0f;
@@ -290,7 +348,7 @@ __global__ void __launch_bounds__(kSceneThreads, 1) scene_jmax_kernel(SceneIO io
         for (int ci = 0; ci < kColIters; ++ci) {
           const int x = lane + 32 * ci;
           if (x < kG) {
-            const CellTerms t = cell_terms(f[y * kG + x], cell_sdf(io.lin[x], io.lin[y], s_sc, s_sc + 16), vis_inf);
+            const CellTerms t = cell_terms(f[y * kG + x], cell_sdf_masked(io.lin[x], io.lin[y], s_sc, s_sc + 16, s_rowmask[y]), vis_inf);
             mj = fmaxf(mj, t.J);
             inside |= (t.edge <= 0.0f) ? 1 : 0;
           }
@@ -310,6 +368,7 @@ __global__ void __launch_bounds__(kSceneThreads, 1) scene_jmax_kernel(SceneIO io
 __global__ void __launch_bounds__(kSceneThreads, 1) scene_field_kernel(SceneIO io, const uint32_t* __restrict__ counters) {
   __shared__ float s_sc[64];
   __shared__ float s_red[32];
+  __shared__ uint32_t s_rowmask[160];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t total = scene_count(io);
   const float vis_inf = global_vis_inf(counters, counters[CW_HAVE] != 0u);
@@ -318,6 +377,8 @@ __global__ void __launch_bounds__(kSceneThreads, 1) scene_field_kernel(SceneIO i
   const float high = (cur_max > 1e-6f) ? __fmul_rn(cur_max, 10.0f) : 100.0f;
   for (int64_t j = blockIdx.x; j < total; j += gridDim.x) {
     const int64_t env = load_scene(io, j, s_sc);
+    __syncthreads();
+    if (threadIdx.x < kG) s_rowmask[threadIdx.x] = row_obstacle_mask(io.lin[threadIdx.x], s_sc + 16);
     __syncthreads();
     float* f = io.field + env * (int64_t)kCells;
     float gmn = CUDART_INF_F, gmx = -CUDART_INF_F, jmn = CUDART_INF_F, jmx = -CUDART_INF_F;
@@ -329,7 +390,7 @@ __global__ void __launch_bounds__(kSceneThreads, 1) scene_field_kernel(SceneIO i
         for (int ci = 0; ci < kColIters; ++ci) {
           const int x = lane + 32 * ci;
           if (x < kG) {
-            CellTerms t = cell_terms(f[y * kG + x], cell_sdf(io.lin[x], io.lin[y], s_sc, s_sc + 16), vis_inf);
+            CellTerms t = cell_terms(f[y * kG + x], cell_sdf_masked(io.lin[x], io.lin[y], s_sc, s_sc + 16, s_rowmask[y]), vis_inf);
             if (any_inside && t.edge <= 0.0f) t.J = high;
             gmn = fminf(gmn, t.vis); gmx = fmaxf(gmx, t.vis);
             jmn = fminf(jmn, t.J); jmx = fmaxf(jmx, t.J);
@@ -350,7 +411,7 @@ __global__ void __launch_bounds__(kSceneThreads, 1) scene_field_kernel(SceneIO i
         for (int ci = 0; ci < kColIters; ++ci) {
           const int x = lane + 32 * ci;
           if (x < kG) {
-            CellTerms t = cell_terms(f[y * kG + x], cell_sdf(io.lin[x], io.lin[y], s_sc, s_sc + 16), vis_inf);
+            CellTerms t = cell_terms(f[y * kG + x], cell_sdf_masked(io.lin[x], io.lin[y], s_sc, s_sc + 16, s_rowmask[y]), vis_inf);
             if (any_inside && t.edge <= 0.0f) t.J = high;
             const float gn = __fdiv_rn(__fsub_rn(t.vis, gmn), gden);
             const float jn = __fdiv_rn(__fsub_rn(t.J, jmn), jden);
@@ -371,7 +432,7 @@ __global__ void compact_resets_kernel(const int64_t* __restrict__ reset_buf, int
   }
 }
 
-static size_t cost_smem_bytes() { return (size_t)(2 * kGP * kGP + 64 + 32) * sizeof(float); }
+static size_t cost_smem_bytes() { return (size_t)(2 * kGP * kGP + 64 + 32 + 64 + 160) * sizeof(float); }
 
 static int scene_grid() {
   static int sms = 0;

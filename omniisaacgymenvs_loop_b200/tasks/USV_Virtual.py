@@ -15,8 +15,8 @@ import numpy as np
 import torch
 
 from .. import _lib
-from ..config import UsvEnvConfig
-from ..engine import FusedUsvEnv, OBS_DIM
+from ..config import UsvEnvConfig, UsvLiveConfig, live_env_config
+from ..engine import FusedUsvEnv, FusedUsvLiveEnv, LIVE_OBS_DIM, OBS_DIM
 from ..envs.USV.Hydrodynamics import HydrodynamicsObject
 from ..envs.USV.Hydrostatics import HydrostaticsObject
 from ..envs.USV.ThrusterDynamics import DynamicsFirstOrder
@@ -31,6 +31,18 @@ _PENALTY_FLAGS = {"linear_vel_penalty": "pen_linear_vel", "angular_vel_penalty":
                   "action_variation_penalty": "pen_action_variation"}
 
 
+# live task (Variant B): episode_sums keys in the order of the kernel's USV_BST_* rows  [ref: OIGE/tasks/USV/
+# USV_capture_xy_static_obs.py:130-187 ; OIGE/tasks/USV/USV_task_rewards.py Penalties.create_stats ; OIGE/tasks/USV_Virtual.py:586-601]
+_LIVE_STAT_KEYS = [k[len("USV_BST_"):].lower() for k, _ in sorted(((k, v) for k, v in E.items() if k.startswith("USV_BST_") and k != "USV_BST_COUNT"),
+                                                                 key=lambda kv: kv[1])]
+
+
+def is_live_task_cfg(task_cfg: dict) -> bool:
+    """The live USVVirtual reads env.action_processing / env.mass_dim / env.privileged_params; the classic snapshot has none."""
+    env = task_cfg["env"]
+    return any(k in env for k in ("action_processing", "mass_dim", "privileged_params"))
+
+
 class SimConfig:
     """Minimal stand-in for omniisaacgymenvs.utils.config_utils.sim_config.SimConfig: `.config` and `.task_config`."""
 
@@ -40,7 +52,7 @@ class SimConfig:
 
 
 class USVVirtual:
-    def __init__(self, name: str, sim_config, env, offset=None, collect_stats: bool = True) -> None:
+    def __init__(self, name: str, sim_config, env, offset=None, collect_stats: bool = True, variant: Optional[str] = None) -> None:
         self._sim_config = sim_config
         self._cfg = sim_config.config
         self._task_cfg = sim_config.task_config
@@ -49,7 +61,16 @@ class USVVirtual:
         self._device = self._cfg.get("sim_device", "cuda:0")
         self.device = self._device
         self.rl_device = self._cfg.get("rl_device", self._device)
-        self.cfg = UsvEnvConfig.from_task_cfg(self._task_cfg, seed=int(self._cfg.get("seed", 1234)))
+        # which USVVirtual this YAML belongs to: the classic snapshot (13-dim CaptureXY) or the live file (33-dim, obstacles)
+        self._live = (variant == "live") if variant is not None else is_live_task_cfg(self._task_cfg)
+        seed = int(self._cfg.get("seed", 1234))
+        if self._live:
+            self.cfg = live_env_config(self._task_cfg, seed=seed)
+            self.live_cfg = UsvLiveConfig.from_task_cfg(self._task_cfg)
+            if int(self._task_cfg["env"].get("mass_dim", 8)) != 8:
+                raise NotImplementedError("the fused live step builds the 8-wide privileged tail (env.mass_dim: 8)")
+        else:
+            self.cfg = UsvEnvConfig.from_task_cfg(self._task_cfg, seed=seed)
         envc = self._task_cfg["env"]
         self._num_envs = self.num_envs = int(self.cfg.num_envs)
         self._max_episode_length = self.cfg.max_episode_length
@@ -65,7 +86,7 @@ class USVVirtual:
         self.clip_actions = self.cfg.clip_actions
         self.randomize_actions = False
         self.randomize_observations = False
-        self._num_observations = self.num_observations = OBS_DIM
+        self._num_observations = self.num_observations = LIVE_OBS_DIM if self._live else OBS_DIM
         self._num_actions = self.num_actions = 2
         self._max_actions = 2
         self.num_states = 0
@@ -74,8 +95,11 @@ class USVVirtual:
         self._nan_probe = os.getenv("USV_NAN_PROBE", "1") != "0"
         self._nan_probe_interval = int(self._cfg.get("nan_probe_interval", self.cfg.horizon_length))
         self._calls = 0
-        self.engine = FusedUsvEnv(self.cfg, self._num_envs, self._device, env_id_offset=int(self._cfg.get("env_id_offset", 0)),
-                                  collect_stats=collect_stats)
+        off = int(self._cfg.get("env_id_offset", 0))
+        if self._live:
+            self.engine = FusedUsvLiveEnv(self.cfg, self.live_cfg, self._num_envs, self._device, env_id_offset=off, collect_stats=collect_stats)
+        else:
+            self.engine = FusedUsvEnv(self.cfg, self._num_envs, self._device, env_id_offset=off, collect_stats=collect_stats)
         self.set_action_and_observation_spaces()
         self.cleanup()
         self.actions = torch.zeros((self._num_envs, 2), device=self._device, dtype=torch.float32)
@@ -102,7 +126,7 @@ class USVVirtual:
 
     def _stat_names(self):
         on = lambda k: k not in _PENALTY_FLAGS or getattr(self.cfg, _PENALTY_FLAGS[k]).form != 0
-        return [k for k in _STAT_KEYS if on(k)]
+        return [k for k in (_LIVE_STAT_KEYS if self._live else _STAT_KEYS) if on(k)]
 
     # ---- force-layer objects kept as attributes  [ref: SNAP/USV_Virtual.py:419-468] -------------------
     def get_USV_dynamics(self):
@@ -128,6 +152,8 @@ class USVVirtual:
     def reset(self):
         """RLTask.reset: flag every env for reset  [ref: OIGE/tasks/base/rl_task.py:268-270]."""
         self.reset_buf.fill_(1)
+        if self._live:
+            self.engine.mark_host_reset()
 
     def pre_physics_step(self, actions: torch.Tensor) -> None:
         """Records the (already clamped) actions; resets of flagged envs, action noise, LUT lookup run inside the fused kernel
@@ -176,12 +202,15 @@ class USVVirtual:
         """Flags `env_ids`; the kernel performs reset_idx for them at the start of the next step, in the reference's position
         (pre_physics_step)  [ref: SNAP/USV_Virtual.py:750-817]."""
         self.reset_buf[env_ids] = 1
+        if self._live:
+            self.engine.mark_host_reset()
 
     # ---- extras["episode"]: mean over the envs being reset of episode_sums / maxEpisodeLength -----------
     def _fill_episode_extras(self) -> None:
-        st = self.engine.stats
+        st = self.engine.bstats if self._live else self.engine.stats
         if st is None:
             return
+        prefix = "USV_BST_" if self._live else "USV_ST_"
         n = self._num_envs
         mask = torch.zeros(self.engine.stride, dtype=torch.float32, device=self._device)
         mask[:n] = (self.reset_buf != 0).float()
@@ -191,6 +220,14 @@ class USVVirtual:
         prev = self.extras.get("episode")
         ep = {}
         for k in self._stat_names():
-            v = new[E["USV_ST_" + k.upper()]]
+            v = new[E[prefix + k.upper()]]
             ep[k] = torch.where(cnt > 0, v, prev[k]) if prev is not None else v
+        if self._live:
+            # episode outcome events: plain means over the envs being reset, read BEFORE the reset clears the latches
+            # [ref: OIGE/tasks/USV_Virtual.py:1508-1516,1581-1596]; "g_safe_mean" is declared but never fed (:497 commented out)
+            oc = self.engine.bstate[:, E["USV_BS_OUTCOME"], :].reshape(-1).view(torch.int32)
+            for k, bit in (("success", 0), ("collision", 1)):
+                v = (((oc >> bit) & 1).float() * mask).sum() / cnt.clamp(min=1.0)
+                ep[k] = torch.where(cnt > 0, v, prev[k]) if prev is not None else v
+            ep["g_safe_mean"] = torch.zeros((), device=self._device)
         self.extras["episode"] = ep                                               # [ref: SNAP/USV_Virtual.py:810-817]

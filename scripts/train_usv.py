@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.distributed as dist
 
-from omniisaacgymenvs_loop_b200.config import UsvEnvConfig, load_task_yaml
+from omniisaacgymenvs_loop_b200.config import UsvEnvConfig, live_default_config, live_task_cfg, load_task_yaml
 from omniisaacgymenvs_loop_b200.envs.vec_env_rlgames import VecEnvRLGames
 from omniisaacgymenvs_loop_b200.rl.a2c import A2CAgent, PPOConfig
 from omniisaacgymenvs_loop_b200.tasks.USV_Virtual import SimConfig, USVVirtual
@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--num-envs", type=int, default=4096)
     ap.add_argument("--epochs", type=int, default=100)
     ap.add_argument("--full-dr", action="store_true")
+    ap.add_argument("--live", action="store_true", help="built-in LIVE CaptureXY (16 static obstacles, 33-dim obs) instead of the classic task")
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--checkpoint", default=None)
     ap.add_argument("--save", default=None)
@@ -43,6 +44,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(device))
     if args.task_yaml:
         task_cfg = load_task_yaml(args.task_yaml, num_envs=args.num_envs)
+    elif args.live:
+        task_cfg = live_task_cfg(live_default_config(num_envs=args.num_envs))
     else:
         cfg = UsvEnvConfig(num_envs=args.num_envs)
         task_cfg = (cfg.full_dr() if args.full_dr else cfg).to_task_cfg()

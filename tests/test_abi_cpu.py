@@ -80,3 +80,22 @@ def test_reference_yamls_parse():
     for y in glob.glob("/root/reference/omniisaacgymenvs/cfg/task/USV/IROS2024/USV_Virtual_CaptureXY_*DR50.yaml"):
         c = UsvEnvConfig.from_task_cfg(load_task_yaml(y, num_envs=64))
         assert c.num_envs == 64 and c.use_sin_force and c.drag_rand and c.thr_rand and c.n_substeps == 5
+
+
+def test_live_task_cfg_round_trip():
+    """live_task_cfg() emits the YAML tree the live USVVirtual reads; parsing it back gives the same configs."""
+    from omniisaacgymenvs_loop_b200.config import UsvLiveConfig, live_default_config, live_env_config, live_task_cfg
+    cfg, live = live_default_config(num_envs=96), UsvLiveConfig()
+    t = live_task_cfg(cfg, live)
+    assert dataclasses.asdict(live_env_config(t)) == dataclasses.asdict(cfg)
+    assert UsvLiveConfig.from_task_cfg(t) == live
+    lp = live.to_params()
+    assert lp.priv_mode == 2 and list(lp.priv_a) == [1.0, 0.5, 0.5, 1.0] and list(lp.priv_active) == [1, 1, 1, 1]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference YAMLs only exist in the build container")
+def test_reference_live_yaml_parses_to_the_shipped_defaults():
+    from omniisaacgymenvs_loop_b200.config import UsvLiveConfig, live_default_config, live_env_config
+    y = load_task_yaml("/root/reference/omniisaacgymenvs/cfg/task/USV/IROS2024/USV_Virtual_CaptureXY_SysID-TEST.yaml", num_envs=128)
+    assert dataclasses.asdict(live_env_config(y)) == dataclasses.asdict(live_default_config(num_envs=128))
+    assert UsvLiveConfig.from_task_cfg(y) == UsvLiveConfig()

@@ -99,3 +99,45 @@ def test_reference_trained_policy_captures_in_fused_env():
         assert r["episodes"] > 10000 and r["killed"] == 0 and r["timeouts"] == 0
         assert r["captured"] >= 0.999 * r["episodes"], r
         assert 30.0 < r["mean_return"] < 48.0, r            # checkpoint: rew_38.55 at save time
+
+
+def test_live_vecenv_matches_oracle_and_contract():
+    """The live USVVirtual (Variant B: 33-dim obs, obstacles, potential field) behind VecEnvRLGames, from the live YAML tree."""
+    from omniisaacgymenvs_loop_b200.config import UsvLiveConfig, live_default_config, live_task_cfg
+    from oracle import usv_oracle_b as B
+    from tests.test_gpu_live import oracle_live, oracle_task
+    n = 80
+    cfg = live_default_config(num_envs=n, max_episode_length=8, seed=11, action_bias_steps=6)
+    env = make_env(live_task_cfg(cfg), DEV, seed=11)
+    info = env.get_env_info()
+    assert info["observation_space"]["state"].shape == (33,) and info["action_space"].shape == (2,)
+    orc = B.LiveEnvOracle(oracle_cfg(cfg), oracle_task(cfg), oracle_live(UsvLiveConfig()), n)
+    obs = env.reset()
+    o_obs, _, _ = orc.step(torch.zeros((n, 2)))
+    assert obs["obs"]["state"].shape == (n, 33)
+    assert_close(obs["obs"]["state"], o_obs, 1e-5, 2e-5, "reset obs")
+    g = torch.Generator().manual_seed(1)
+    for k in range(18):
+        act = torch.rand((n, 2), generator=g) * 3 - 1.5
+        od, rew, done, extras = env.step(act.to(DEV))
+        o_obs, o_rew, o_done = orc.step(act)
+        assert_close(od["obs"]["state"], o_obs, 1e-4, 2e-3, f"obs {k}"); assert_close(rew, o_rew, 1e-4, 5e-3, f"rew {k}")
+        assert torch.equal(done.cpu(), o_done), k
+    ep = extras["episode"]
+    assert {"total_reward", "potential_shaping_reward", "collision_reward", "success", "collision", "danger_mean", "u_mean",
+            "energy_penalty", "g_safe_mean"} <= set(ep)
+    assert "linear_vel_penalty" not in ep and all(torch.isfinite(v) for v in ep.values())
+    assert 0.0 <= float(ep["success"]) <= 1.0 and 0.0 <= float(ep["collision"]) <= 1.0
+
+
+def test_live_ppo_loop_runs():
+    """PPO on the 33-dim live task (fp32 SIMT policy kernels: the tcgen05 path packs obs_dim <= 15): finite and moving."""
+    from omniisaacgymenvs_loop_b200.config import live_default_config, live_task_cfg
+    env = make_env(live_task_cfg(live_default_config(num_envs=1024)), DEV, seed=5, collect_stats=False)
+    agent = A2CAgent(env, PPOConfig(seed=5, minibatch_size=8192), DEV)
+    p0 = agent.policy.params.clone()
+    for _ in range(6):
+        agent.train_epoch()
+    st = agent.policy.stats()
+    assert all(v == v for v in st.values()), st
+    assert torch.isfinite(agent.policy.params).all() and not torch.equal(p0, agent.policy.params)
