@@ -20,7 +20,15 @@ struct LiveState {
 };
 
 struct LiveOut {
-  float obs[kObsB];
+  float* sw;     // this lane's row of the warp's shared-memory observation tile (stride 33: conflict-free)
+  float chk;     // NaN probe accumulator: x*0 is 0 for finite x, NaN otherwise
+  float clip;
+  // observations go straight to the staging tile, clamped, as they are produced: holding all 33 in registers until the end
+  // cost ~30 registers (113 -> 2 CTAs/SM in the r01 profile)
+  __device__ __forceinline__ void put(int j, float v) {
+    chk = fmaf(v, 0.0f, chk);
+    sw[j] = fminf(fmaxf(v, -clip), clip);
+  }
   float rew;
   int done;
   bool finite;
@@ -106,37 +114,37 @@ __device__ __forceinline__ void post_live(EnvState& e, const EnvConst& k, LiveSt
     }
   }
   // Core.update_observation_tensor  [ref OIGE/tasks/USV/USV_core.py:55-125]
-  o.obs[0] = hc * vxn + hs * vyn;
-  o.obs[1] = -hs * vxn + hc * vyn;
-  o.obs[2] = wn;
-  o.obs[3] = ca;
-  o.obs[4] = sa;
-  o.obs[5] = d_obs;
-  o.obs[6] = 0.0f;
-  o.obs[7] = 0.0f;
+  o.put(0, hc * vxn + hs * vyn);
+  o.put(1, -hs * vxn + hc * vyn);
+  o.put(2, wn);
+  o.put(3, ca);
+  o.put(4, sa);
+  o.put(5, d_obs);
+  o.put(6, 0.0f);
+  o.put(7, 0.0f);
 #pragma unroll
   for (int q = 0; q < USV_B_CLOSEST; ++q) {
     const float xb = bx[q] * hc + by[q] * hs;
     const float yb = -bx[q] * hs + by[q] * hc;
     const float nf = sqrtf(xb * xb + yb * yb + 1e-6f);
-    o.obs[8 + 3 * q] = bd[q] - 0.5f;
-    o.obs[9 + 3 * q] = __fdiv_rn(-xb, nf);
-    o.obs[10 + 3 * q] = __fdiv_rn(-yb, nf);
+    o.put(8 + 3 * q, bd[q] - 0.5f);
+    o.put(9 + 3 * q, __fdiv_rn(-xb, nf));
+    o.put(10 + 3 * q, __fdiv_rn(-yb, nf));
   }
   // prev_thrust_cmds: the raw policy command of THIS control step, zero for an env reset in it (USV_Virtual.py:1063-1066)
-  o.obs[23] = do_reset ? 0.0f : s.raw0;
-  o.obs[24] = do_reset ? 0.0f : s.raw1;
+  o.put(23, do_reset ? 0.0f : s.raw0);
+  o.put(24, do_reset ? 0.0f : s.raw1);
   // privileged tail  (USV_Virtual.py:837-984)
-  o.obs[25] = lp.mass_obs_relative ? __fdiv_rn(k.mass - p.mass_base, fmaxf(fabsf(p.mass_base), 1e-6f)) : k.mass;
+  o.put(25, lp.mass_obs_relative ? __fdiv_rn(k.mass - p.mass_base, fmaxf(fabsf(p.mass_base), 1e-6f)) : k.mass);
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
     const float c = bc[(USV_BC_COM_X + j) * kTile];
-    o.obs[26 + j] = lp.com_obs_scaled ? __fdiv_rn(c, lp.com_scale_eps[j]) : c;
+    o.put(26 + j, lp.com_obs_scaled ? __fdiv_rn(c, lp.com_scale_eps[j]) : c);
   }
-  o.obs[29] = priv_encode(lp, 0, k.kdrag);
-  o.obs[30] = priv_encode(lp, 1, k.mL);
-  o.obs[31] = priv_encode(lp, 2, k.mR);
-  o.obs[32] = priv_encode(lp, 3, k.kiz);
+  o.put(29, priv_encode(lp, 0, k.kdrag));
+  o.put(30, priv_encode(lp, 1, k.mL));
+  o.put(31, priv_encode(lp, 2, k.mR));
+  o.put(32, priv_encode(lp, 3, k.kiz));
 
   // ---- compute_reward (:335-657) ----------------------------------------------------------------
   const int goal = (d < p.position_tolerance) ? 1 : 0;  // no speed gate in the live task
@@ -253,23 +261,14 @@ __device__ __forceinline__ void post_live(EnvState& e, const EnvConst& k, LiveSt
     o.st[USV_BST_U_SUM] = s.c0 + s.c1;
   }
   // NaN probe on the un-clamped obs and the reward, then _process_data's clamp  [ref vec_env_rlgames.py:82-95,187-192]
-  float chk = o.rew * 0.0f;
-#pragma unroll
-  for (int j = 0; j < kObsB; ++j) chk = fmaf(o.obs[j], 0.0f, chk);
-  o.finite = (chk == 0.0f);
-#pragma unroll
-  for (int j = 0; j < kObsB; ++j) o.obs[j] = fminf(fmaxf(o.obs[j], -p.clip_obs), p.clip_obs);
+  o.finite = (fmaf(o.rew, 0.0f, o.chk) == 0.0f);
 }
 
 // each warp stages its 32 x 33 observation tile (stride 33: conflict-free) and writes one contiguous 4224 B run
-__device__ __forceinline__ void write_obs_tile_b(float* s_obs, const LiveOut& o, bool active, float* __restrict__ obs,
+__device__ __forceinline__ void write_obs_tile_b(float* s_obs, float* __restrict__ obs,
                                                  int64_t block_start, int64_t n) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* sw = s_obs + warp * (32 * kObsB);
-  if (active) {
-#pragma unroll
-    for (int j = 0; j < kObsB; ++j) sw[lane * kObsB + j] = o.obs[j];
-  }
   __syncwarp();
   const int64_t warp_start = block_start + (int64_t)warp * 32;
   if (warp_start >= n) return;
@@ -287,7 +286,7 @@ __device__ __forceinline__ void write_obs_tile_b(float* s_obs, const LiveOut& o,
 }
 
 template <bool kDisturb, bool kStats>
-__global__ void __launch_bounds__(kBlock, 2) step_live_kernel(UsvEnvBuffers b, UsvLiveBuffers lb, const float2* __restrict__ actions,
+__global__ void __launch_bounds__(kBlock, 3) step_live_kernel(UsvEnvBuffers b, UsvLiveBuffers lb, const float2* __restrict__ actions,
                                                               float* __restrict__ obs, float* __restrict__ rew, int64_t n,
                                                               const __grid_constant__ UsvStepParams p,
                                                               const __grid_constant__ UsvLiveParams lp) {
@@ -297,6 +296,9 @@ __global__ void __launch_bounds__(kBlock, 2) step_live_kernel(UsvEnvBuffers b, U
   const bool active = i < n;
   const bool any_reset = (lb.reset_epoch[p.step_counter & 1] == p.step_counter);
   LiveOut o;
+  o.sw = smem + (threadIdx.x >> 5) * (32 * kObsB) + (threadIdx.x & 31) * kObsB;
+  o.chk = 0.0f;
+  o.clip = p.clip_obs;
   if (active) {
     EnvState e;
     EnvConst k;
@@ -338,7 +340,7 @@ __global__ void __launch_bounds__(kBlock, 2) step_live_kernel(UsvEnvBuffers b, U
       if (!isfinite(act.x) || !isfinite(act.y)) atomicOr(b.nonfinite_flag, 2u);
     }
   }
-  write_obs_tile_b(smem, o, active, obs, block_start, n);
+  write_obs_tile_b(smem, obs, block_start, n);
 }
 
 }  // namespace usv
