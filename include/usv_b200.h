@@ -225,6 +225,8 @@ typedef struct {
   float goal_random_position; int32_t retarget_on_reset;
   float spawn_min_dist, spawn_max_dist;    /* after curriculum, set by host     */
   int32_t spawn_about_origin;              /* live task: the spawn annulus is centred on the env origin, not the target */
+  int32_t retarget_after_spawn;            /* live reset_idx order: get_spawns (around the OLD target) first, set_targets last
+                                              (OIGE/tasks/USV_Virtual.py:1542,1622); classic: target first */
   int32_t reset_pose_external;             /* scene replay (OIGE/tasks/USV_Virtual.py:1395-1458): pose, velocity and target of a
                                               resetting env were written by the host; the kernel only re-draws the dynamics
                                               randomisation and clears the episode bookkeeping */
@@ -307,6 +309,12 @@ enum {
 };
 
 enum { USV_PRIV_RAW = 0, USV_PRIV_CENTERED = 1, USV_PRIV_MINMAX = 2 };
+/* tasks behind the live USVVirtual's 33-dim observation (task_data = obs[3:23]); 1-3 are SURVEY row T (Tier 3):
+ *   [ref: OIGE/tasks/USV/USV_go_to_pose.py:81-209 ; USV_keep_xy.py:80-179 ; USV_track_xy_velocity.py:64-128 ;
+ *         OIGE/tasks/USV/USV_task_rewards.py:170-325 ; USV_task_parameters.py:95-177]                                    */
+enum { USV_TASK_CAPTURE_OBSTACLES = 0, USV_TASK_GO_TO_POSE = 1, USV_TASK_KEEP_XY = 2, USV_TASK_TRACK_XY_VELOCITY = 3 };
+/* per-episode task constants of tasks 1-3 live in the (otherwise unused) obstacle slots of bconsts */
+enum { USV_BC_TARGET_HEADING = 3 /* GoToPose: _target_headings */, USV_BC_TARGET_VX = 3, USV_BC_TARGET_VY = 4 /* TrackXYVelocity */ };
 
 typedef struct {
   /* privileged tail [ref: OIGE/tasks/USV_Virtual.py:837-984 ; USV_disturbances.py:153-194] */
@@ -323,6 +331,12 @@ typedef struct {
   float collision_threshold;    /* 1.2  (:103)                                                       */
   float map_size;               /* 30.0                                                              */
   int32_t fixed_horizon_eval;   /* is_done ignores `die` (USV_Virtual.py:1229-1233)                  */
+  /* Tier-3 tasks (task != 0): no obstacles / potential field; UsvStepParams.reward_mode, exponential_reward_coeff and
+   * position_scale parameterise the position (or velocity) reward                                    */
+  int32_t task;                 /* USV_TASK_*                                                        */
+  int32_t heading_reward_mode;  /* GoToPoseReward.heading_reward_mode (USV_REWARD_*)                  */
+  float heading_exponential_reward_coeff, heading_scale, sig_gain;
+  float goal_random_velocity, lin_vel_tolerance;   /* TrackXYVelocityParameters                       */
 } UsvLiveParams;
 
 typedef struct {

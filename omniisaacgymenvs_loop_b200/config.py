@@ -133,6 +133,7 @@ class UsvEnvConfig:
     spawn_min_dist: float = 0.3
     spawn_max_dist: float = 12.0
     spawn_about_origin: bool = False   # live task (Variant B): annulus around the env origin, not the target
+    retarget_after_spawn: bool = False # live reset order: spawn around the old target, re-draw the target last
     reset_pose_external: bool = False  # scene replay: the host writes pose / velocity / target of resetting envs
     spawn_vel_range: float = 1.5
     mass_rand: bool = False
@@ -392,9 +393,21 @@ class UsvLiveConfig:
     collision_threshold: float = 1.2
     map_size: float = 30.0
     fixed_horizon_eval: bool = False
+    # Tier-3 tasks behind the same live step: 0 CaptureXY+obstacles, 1 GoToPose, 2 KeepXY, 3 TrackXYVelocity
+    # [ref: OIGE/tasks/USV/USV_task_rewards.py:170-325 ; USV_task_parameters.py:95-177]
+    task: int = 0
+    heading_reward_mode: int = 2             # GoToPoseReward.heading_reward_mode: exponential
+    heading_exponential_reward_coeff: float = 0.25
+    heading_scale: float = 5.0
+    sig_gain: float = 3.0
+    goal_random_velocity: float = 0.75       # TrackXYVelocityParameters
+    lin_vel_tolerance: float = 0.01
 
     def to_params(self):
         lp = _lib.UsvLiveParams()
+        lp.task, lp.heading_reward_mode = int(self.task), int(self.heading_reward_mode)
+        lp.heading_exponential_reward_coeff, lp.heading_scale, lp.sig_gain = self.heading_exponential_reward_coeff, self.heading_scale, self.sig_gain
+        lp.goal_random_velocity, lp.lin_vel_tolerance = self.goal_random_velocity, self.lin_vel_tolerance
         lp.priv_mode, lp.mass_obs_relative, lp.com_obs_scaled = int(self.priv_mode), int(self.mass_obs_relative), int(self.com_obs_scaled)
         for j in range(3):
             # `com / (scale_t + eps)` with scale_t an fp32 tensor  [ref: USV_disturbances.py:183-190]
@@ -464,7 +477,7 @@ def live_env_config(task_cfg: dict, **overrides) -> "UsvEnvConfig":
     live = dict(
         action_affine=bool(ap.get("use_affine_thrust_mapping", True)), penalties_use_u=bool(ap.get("penalties_use_thrust_u", False)),
         action_bias=float(ap.get("initial_action_bias", 0.0)), action_bias_steps=int(ap.get("initial_action_bias_steps", 0)),
-        spawn_about_origin=True, retarget_on_reset=True, goal_speed_gate=float("inf"),
+        spawn_about_origin=True, retarget_on_reset=True, retarget_after_spawn=True, goal_speed_gate=float("inf"),
         position_scale=rp.get("position_scale", 1.5), align_la1=rp.get("align_la1", 0.04),
         mass_coupling=bool(targets), couple_mass_max=float(m.get("max_mass", 0.0)), couple_thr_a=float(th.get("thruster_rand", 0.0)),
         couple_kiz_min=float(inr.get("k_Iz_min", 1.0)), couple_kiz_max=float(inr.get("k_Iz_max", 1.0)),
@@ -485,7 +498,7 @@ def live_default_config(**overrides) -> "UsvEnvConfig":
         position_tolerance=1.0, goal_reward=20.0, time_reward=-0.05, goal_speed_gate=float("inf"), position_scale=1.5,
         exponential_reward_coeff=0.15, align_la1=0.04, pen_angular_vel=PenaltyTerm(PEN_NEG_DEADZONE, 0.02, 0.0, 0.4),
         pen_angular_vel_variation=PenaltyTerm(PEN_NEG_DEADZONE, 0.005, 0.0, 0.1), pen_energy=PenaltyTerm(PEN_NEG_SUM, 0.005, 0.0, 0.0),
-        retarget_on_reset=True, spawn_min_dist=9.0, spawn_about_origin=True, mass_rand=True, mass_max=54.96, mass_base=34.96,
+        retarget_on_reset=True, retarget_after_spawn=True, spawn_min_dist=9.0, spawn_about_origin=True, mass_rand=True, mass_max=54.96, mass_base=34.96,
         kdrag_max=1.5, mass_coupling=True)
     base.update(overrides)
     return UsvEnvConfig(**base)

@@ -78,7 +78,8 @@ enum : uint32_t {
   RS_RESET_6 = 8,  // force_x_shift, force_y_shift, force_amp, force_const_r
   RS_RESET_7 = 9,  // force_const_theta, torque_freq, torque_shift, torque_amp
   RS_RESET_8 = 10, // torque_const_r, torque_sign, -, -
-  RS_RESET_COM = 11,  // live: com_x, com_y, com_z, -
+  RS_RESET_COM = 11,  // live: com_x, com_y, com_z, target_heading (GoToPose)
+  RS_RESET_TASK = 12, // TrackXYVelocity: target_vx, target_vy, -, -
   RS_OBST = 0x1000, // live scene builder: stream RS_OBST + round*8 + j/2 (round 0..20); obstacle j takes (a,b) if j even else (c,d)
   RS_ROWS = 64     // usv_randomize_rows_f32: stream = RS_ROWS + stream_id*16 + col/4
 };

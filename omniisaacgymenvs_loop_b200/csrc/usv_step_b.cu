@@ -72,6 +72,31 @@ __device__ __forceinline__ float priv_encode(const UsvLiveParams& lp, int j, flo
   return fminf(fmaxf(__fsub_rn(__fmul_rn(2.0f, z), 1.0f), -1.0f), 1.0f);
 }
 
+// Core.update_observation_tensor, "local" frame  [ref OIGE/tasks/USV/USV_core.py:55-125]: obs[0:3] body-frame velocity + yaw rate
+__device__ __forceinline__ void obs_head(LiveOut& o, const DynOut& s) {
+  o.put(0, s.hc * s.vxn + s.hs * s.vyn);
+  o.put(1, -s.hs * s.vxn + s.hc * s.vyn);
+  o.put(2, s.wn);
+}
+// obs[23:25] previous action, obs[25:33] privileged tail
+__device__ __forceinline__ void obs_tail(LiveOut& o, const DynOut& s, const EnvConst& k, const float* __restrict__ bc,
+                                         const UsvStepParams& p, const UsvLiveParams& lp, bool do_reset) {
+  // prev_thrust_cmds: the raw policy command of THIS control step, zero for an env reset in it (USV_Virtual.py:1063-1066)
+  o.put(23, do_reset ? 0.0f : s.raw0);
+  o.put(24, do_reset ? 0.0f : s.raw1);
+  // privileged tail  (USV_Virtual.py:837-984)
+  o.put(25, lp.mass_obs_relative ? __fdiv_rn(k.mass - p.mass_base, fmaxf(fabsf(p.mass_base), 1e-6f)) : k.mass);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const float c = bc[(USV_BC_COM_X + j) * kTile];
+    o.put(26 + j, lp.com_obs_scaled ? __fdiv_rn(c, lp.com_scale_eps[j]) : c);
+  }
+  o.put(29, priv_encode(lp, 0, k.kdrag));
+  o.put(30, priv_encode(lp, 1, k.mL));
+  o.put(31, priv_encode(lp, 2, k.mR));
+  o.put(32, priv_encode(lp, 3, k.kiz));
+}
+
 // Variant B task part of a control step.  `any_reset`: some env of the batch was reset on entry to this control step
 // (reference quirk: CaptureXYTask.reset sets prev_potential = None for EVERY env, :773, :448-452).
 template <bool kStats>
@@ -114,9 +139,7 @@ __device__ __forceinline__ void post_live(EnvState& e, const EnvConst& k, LiveSt
     }
   }
   // Core.update_observation_tensor  [ref OIGE/tasks/USV/USV_core.py:55-125]
-  o.put(0, hc * vxn + hs * vyn);
-  o.put(1, -hs * vxn + hc * vyn);
-  o.put(2, wn);
+  obs_head(o, s);
   o.put(3, ca);
   o.put(4, sa);
   o.put(5, d_obs);
@@ -131,20 +154,7 @@ __device__ __forceinline__ void post_live(EnvState& e, const EnvConst& k, LiveSt
     o.put(9 + 3 * q, __fdiv_rn(-xb, nf));
     o.put(10 + 3 * q, __fdiv_rn(-yb, nf));
   }
-  // prev_thrust_cmds: the raw policy command of THIS control step, zero for an env reset in it (USV_Virtual.py:1063-1066)
-  o.put(23, do_reset ? 0.0f : s.raw0);
-  o.put(24, do_reset ? 0.0f : s.raw1);
-  // privileged tail  (USV_Virtual.py:837-984)
-  o.put(25, lp.mass_obs_relative ? __fdiv_rn(k.mass - p.mass_base, fmaxf(fabsf(p.mass_base), 1e-6f)) : k.mass);
-#pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    const float c = bc[(USV_BC_COM_X + j) * kTile];
-    o.put(26 + j, lp.com_obs_scaled ? __fdiv_rn(c, lp.com_scale_eps[j]) : c);
-  }
-  o.put(29, priv_encode(lp, 0, k.kdrag));
-  o.put(30, priv_encode(lp, 1, k.mL));
-  o.put(31, priv_encode(lp, 2, k.mR));
-  o.put(32, priv_encode(lp, 3, k.kiz));
+  obs_tail(o, s, k, bc, p, lp, do_reset);
 
   // ---- compute_reward (:335-657) ----------------------------------------------------------------
   const int goal = (d < p.position_tolerance) ? 1 : 0;  // no speed gate in the live task
@@ -343,6 +353,166 @@ __global__ void __launch_bounds__(kBlock, 3) step_live_kernel(UsvEnvBuffers b, U
   write_obs_tile_b(smem, obs, block_start, n);
 }
 
+// ---- Tier-3 tasks behind the same 33-dim observation -------------------------------------------------
+__device__ __forceinline__ float mode_reward(int mode, float err, float coeff) {
+  // 1/(1+e) | 1/(1+e^2) | exp(-e/coeff)   [ref OIGE/tasks/USV/USV_task_rewards.py:206-325]
+  if (mode == USV_REWARD_LINEAR) return __fdiv_rn(1.0f, 1.0f + err);
+  if (mode == USV_REWARD_SQUARE) return __fdiv_rn(1.0f, 1.0f + err * err);
+  return expf(-__fdiv_rn(err, coeff));
+}
+
+__device__ __forceinline__ void penalties_live(EnvState& e, const UsvStepParams& p, const DynOut& s, bool first_call, float speed,
+                                               float& total) {
+  const float pa0_ = s.pa0, pa1_ = s.pa1, wn = s.wn;
+  const float asum = pa0_ + pa1_;
+  const float dw = first_call ? 0.0f : (wn - e.prev_w);
+  const float dasum = first_call ? 0.0f : (asum - e.prev_asum);
+  float pen_lin = 0.0f, pen_ang = 0.0f, pen_angvar = 0.0f, pen_energy = 0.0f, pen_actvar = 0.0f;
+  if (p.pen_linear_vel.form != USV_PEN_OFF) pen_lin = penalty_scalar(p.pen_linear_vel, speed);
+  if (p.pen_angular_vel.form != USV_PEN_OFF) pen_ang = penalty_scalar(p.pen_angular_vel, wn);
+  if (p.pen_angular_vel_variation.form != USV_PEN_OFF) pen_angvar = penalty_scalar(p.pen_angular_vel_variation, dw);
+  if (p.pen_energy.form == USV_PEN_NEG_SUM) pen_energy = -(pa0_ + pa1_) * p.pen_energy.c1 + p.pen_energy.c2;
+  else if (p.pen_energy.form == USV_PEN_EXP_NEG_SUMSQ) pen_energy = (__expf(-(pa0_ * pa0_ + pa1_ * pa1_)) - 1.0f) * p.pen_energy.c1;
+  if (p.pen_action_variation.form != USV_PEN_OFF) pen_actvar = penalty_scalar(p.pen_action_variation, dasum);
+  e.prev_w = wn;
+  e.prev_asum = asum;
+  total = pen_lin + pen_ang + pen_angvar + pen_energy + pen_actvar;
+}
+
+template <int kTask>
+__device__ __forceinline__ void post_task(EnvState& e, const EnvConst& k, const float* __restrict__ bc, const UsvStepParams& p,
+                                          const UsvLiveParams& lp, bool do_reset, bool first_call, const DynOut& s, LiveOut& o) {
+  const float pxn = s.pxn, pyn = s.pyn, vxn = s.vxn, vyn = s.vyn;
+  obs_head(o, s);
+  float task_rew;
+  int die;
+  const float speed = sqrtf(__fmaf_rn(vyn, vyn, __fmul_rn(vxn, vxn)));  // torch.norm(linear_velocity, dim=-1)
+  if (kTask == USV_TASK_TRACK_XY_VELOCITY) {
+    // [ref USV_track_xy_velocity.py:64-128]
+    const float evx = bc[USV_BC_TARGET_VX * kTile] - vxn, evy = bc[USV_BC_TARGET_VY * kTile] - vyn;
+    o.put(3, evx);
+    o.put(4, evy);
+#pragma unroll
+    for (int j = 5; j < 23; ++j) o.put(j, 0.0f);
+    const float pd = sqrtf(__fadd_rn(__fmul_rn(pxn, pxn), __fmul_rn(pyn, pyn)));   // _position_error = position
+    const float vd = sqrtf(__fadd_rn(__fmul_rn(evx, evx), __fmul_rn(evy, evy)));
+    const int goal = (vd < lp.lin_vel_tolerance) ? 1 : 0;
+    e.goal_cnt = e.goal_cnt * goal + goal;
+    task_rew = mode_reward(p.reward_mode, vd, p.exponential_reward_coeff);
+    die = (pd > p.kill_dist) ? 1 : 0;
+    if (e.goal_cnt > p.kill_after_n_steps_in_tolerance) die = 1;      // strict '>' in this task (:123)
+  } else {
+    // GoToPose [ref USV_go_to_pose.py:81-209] / KeepXY [ref USV_keep_xy.py:80-179]
+    const float ex = k.tx - pxn, ey = k.ty - pyn;
+    const float theta = wrap_pi(s.yawn);
+    const float beta = atan2f(ey, ex);
+    const float xa = beta - theta + USV_PI_F;
+    const float alpha = ((xa >= USV_2PI_F) ? xa - USV_2PI_F : xa) - USV_PI_F;
+    float sa, ca;
+    fsincos(alpha, &sa, &ca);
+    const float d = sqrtf(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)));
+    o.put(3, ca);
+    o.put(4, sa);
+    o.put(5, sqrtf(__fmaf_rn(ey, ey, __fmul_rn(ex, ex))));
+    float herr = 0.0f;
+    if (kTask == USV_TASK_GO_TO_POSE) {
+      // heading error: fmod(target - theta + pi, 2pi) - pi, then atan2(sin, cos)
+      const float xh = bc[USV_BC_TARGET_HEADING * kTile] - theta + USV_PI_F;   // in (-pi, 4pi): C fmod keeps the sign of the dividend
+      const float hr = fmodf(xh, USV_2PI_F) - USV_PI_F;
+      float sh, ch;
+      fsincos(hr, &sh, &ch);
+      herr = atan2f(sh, ch);
+      float sh2, ch2;
+      fsincos(herr, &sh2, &ch2);
+      o.put(6, ch2);
+      o.put(7, sh2);
+    } else {
+      o.put(6, 0.0f);
+      o.put(7, 0.0f);
+    }
+#pragma unroll
+    for (int j = 8; j < 23; ++j) o.put(j, 0.0f);
+    if (kTask == USV_TASK_GO_TO_POSE) {
+      if (do_reset) e.prev_d = 0.0f;                                    // reset(): prev_position_dist[env_ids] = 0  (:226)
+      const float progress = 2.0f * fminf(fmaxf(e.prev_d - d, -2.0f), 2.0f);
+      e.prev_d = d;
+      const int goal = ((d < p.position_tolerance) && (speed < 0.1f)) ? 1 : 0;
+      e.goal_cnt = e.goal_cnt * goal + goal;
+      // GoToPoseReward.compute_reward  [ref USV_task_rewards.py:206-255]
+      const float hw = 1.0f - __fdiv_rn(1.0f, 1.0f + expf(-lp.sig_gain * (d - 2.0f)));
+      const float pos_rew = p.position_scale * mode_reward(p.reward_mode, d, p.exponential_reward_coeff);
+      const float head_rew = hw * lp.heading_scale * mode_reward(lp.heading_reward_mode, fabsf(herr), lp.heading_exponential_reward_coeff);
+      const float act_pen = -0.05f * (fabsf(s.raw0) + fabsf(s.raw1));
+      task_rew = pos_rew + head_rew + progress + 2.0f * (float)goal + act_pen;
+    } else {
+      task_rew = mode_reward(p.reward_mode, d, p.exponential_reward_coeff);   // KeepXYReward; the goal counter is never fed (:118-141)
+    }
+    die = (d > p.kill_dist) ? 1 : 0;
+    if (e.goal_cnt >= p.kill_after_n_steps_in_tolerance) die = 1;
+  }
+  obs_tail(o, s, k, bc, p, lp, do_reset);
+  float pen;
+  penalties_live(e, p, s, first_call, speed, pen);
+  o.rew = task_rew + pen;
+  if (lp.fixed_horizon_eval) die = 0;
+  o.done = (e.progress >= p.max_episode_length - 1) ? 1 : die;
+  o.finite = (fmaf(o.rew, 0.0f, o.chk) == 0.0f);
+}
+
+template <int kTask, bool kDisturb>
+__global__ void __launch_bounds__(kBlock, 3) step_task_kernel(UsvEnvBuffers b, UsvLiveBuffers lb, const float2* __restrict__ actions,
+                                                              float* __restrict__ obs, float* __restrict__ rew, int64_t n,
+                                                              const __grid_constant__ UsvStepParams p,
+                                                              const __grid_constant__ UsvLiveParams lp) {
+  extern __shared__ __align__(16) float smem[];
+  const int64_t block_start = (int64_t)blockIdx.x * kBlock;
+  const int64_t i = block_start + threadIdx.x;
+  const bool active = i < n;
+  LiveOut o;
+  o.sw = smem + (threadIdx.x >> 5) * (32 * kObsB) + (threadIdx.x & 31) * kObsB;
+  o.chk = 0.0f;
+  o.clip = p.clip_obs;
+  if (active) {
+    EnvState e;
+    EnvConst k;
+    load_state(b.state, b.state_stride, i, e);
+    load_consts<kDisturb>(b.consts, b.consts_stride, i, k);
+    float* __restrict__ bc = lb.bconsts + tile_base(i, USV_BC_COUNT);
+    const bool do_reset = b.reset_buf[i] != 0;
+    const float2 act = actions[i];
+    const uint64_t gid = (uint64_t)(p.env_id_offset + i);
+    if (do_reset) {
+      const Uniform4 rc = philox_uniform4(p.seed, gid, p.step_counter, RS_RESET_COM);
+      if (lp.com_rand) {
+        bc[USV_BC_COM_X * kTile] = lp.com_base[0] + (rc.a * 2.0f - 1.0f) * lp.com_disp[0];
+        bc[USV_BC_COM_Y * kTile] = lp.com_base[1] + (rc.b * 2.0f - 1.0f) * lp.com_disp[1];
+        bc[USV_BC_COM_Z * kTile] = lp.com_base[2] + (rc.c * 2.0f - 1.0f) * lp.com_disp[2];
+      }
+      if (!p.reset_pose_external) {
+        // task.get_goals at the end of reset_idx  [ref USV_go_to_pose.py:244-246 ; USV_track_xy_velocity.py:141-146]
+        if (kTask == USV_TASK_GO_TO_POSE) bc[USV_BC_TARGET_HEADING * kTile] = rc.d * USV_PI_F * 2.0f;
+        if (kTask == USV_TASK_TRACK_XY_VELOCITY) {
+          const Uniform4 rt = philox_uniform4(p.seed, gid, p.step_counter, RS_RESET_TASK);
+          bc[USV_BC_TARGET_VX * kTile] = rt.a * lp.goal_random_velocity * 2.0f - lp.goal_random_velocity;
+          bc[USV_BC_TARGET_VY * kTile] = rt.b * lp.goal_random_velocity * 2.0f - lp.goal_random_velocity;
+        }
+      }
+    }
+    DynOut s;
+    step_dynamics<kDisturb, true>(e, k, p, do_reset, act, gid, i, p.step_counter, b.lut_left, b.lut_right, s);
+    post_task<kTask>(e, k, bc, p, lp, do_reset, p.first_call != 0, s, o);
+    store_state(b.state, b.state_stride, i, e);
+    if (do_reset) store_consts<kDisturb>(b.consts, b.consts_stride, i, k);
+    rew[i] = o.rew;
+    b.reset_buf[i] = (int64_t)o.done;
+    if (b.nonfinite_flag) {
+      if (!o.finite) atomicOr(b.nonfinite_flag, 1u);
+      if (!isfinite(act.x) || !isfinite(act.y)) atomicOr(b.nonfinite_flag, 2u);
+    }
+  }
+  write_obs_tile_b(smem, obs, block_start, n);
+}
+
 }  // namespace usv
 
 using namespace usv;
@@ -352,9 +522,12 @@ extern "C" int usv_step_live_f32(const UsvEnvBuffers* b, const UsvLiveBuffers* l
   if (!b || !lb || !p || !lp) return USV_E_NULL;
   if (n < 0) return USV_E_SIZE;
   if (!b->state || !b->consts || !b->reset_buf || !b->lut_left || !b->lut_right) return USV_E_NULL;
-  if (!lb->bstate || !lb->bconsts || !lb->field || !lb->reset_epoch) return USV_E_NULL;
+  if (lp->task < USV_TASK_CAPTURE_OBSTACLES || lp->task > USV_TASK_TRACK_XY_VELOCITY) return USV_E_PARAM;
+  const bool obst = lp->task == USV_TASK_CAPTURE_OBSTACLES;
+  if (!lb->bconsts || (obst && (!lb->bstate || !lb->field || !lb->reset_epoch))) return USV_E_NULL;
   if (b->state_stride < n || b->consts_stride < n || (b->state_stride & 31) || (b->consts_stride & 31)) return USV_E_SIZE;
-  if (lb->bstate_stride < n || lb->bconsts_stride < n || (lb->bstate_stride & 31) || (lb->bconsts_stride & 31)) return USV_E_SIZE;
+  if (lb->bconsts_stride < n || (lb->bconsts_stride & 31)) return USV_E_SIZE;
+  if (obst && (lb->bstate_stride < n || (lb->bstate_stride & 31))) return USV_E_SIZE;
   if (lb->bstats && (lb->bstats_stride < n || (lb->bstats_stride & 31))) return USV_E_SIZE;
   if (p->n_lut < 2 || p->n_lut > 8192) return USV_E_PARAM;
   if (p->n_substeps < 0 || p->n_substeps > 1024) return USV_E_PARAM;
@@ -370,10 +543,15 @@ extern "C" int usv_step_live_f32(const UsvEnvBuffers* b, const UsvLiveBuffers* l
   const bool st = lb->bstats != nullptr;
   cudaStream_t s = (cudaStream_t)stream;
 #define USV_LAUNCH_LIVE(D, S) step_live_kernel<D, S><<<grid, kBlock, smem, s>>>(*b, *lb, (const float2*)actions, obs, rew, n, *p, *lp)
-  if (dis && st) USV_LAUNCH_LIVE(true, true);
+#define USV_LAUNCH_TASK(T, D) step_task_kernel<T, D><<<grid, kBlock, smem, s>>>(*b, *lb, (const float2*)actions, obs, rew, n, *p, *lp)
+  if (lp->task == USV_TASK_GO_TO_POSE) { if (dis) USV_LAUNCH_TASK(USV_TASK_GO_TO_POSE, true); else USV_LAUNCH_TASK(USV_TASK_GO_TO_POSE, false); }
+  else if (lp->task == USV_TASK_KEEP_XY) { if (dis) USV_LAUNCH_TASK(USV_TASK_KEEP_XY, true); else USV_LAUNCH_TASK(USV_TASK_KEEP_XY, false); }
+  else if (lp->task == USV_TASK_TRACK_XY_VELOCITY) { if (dis) USV_LAUNCH_TASK(USV_TASK_TRACK_XY_VELOCITY, true); else USV_LAUNCH_TASK(USV_TASK_TRACK_XY_VELOCITY, false); }
+  else if (dis && st) USV_LAUNCH_LIVE(true, true);
   else if (dis) USV_LAUNCH_LIVE(true, false);
   else if (st) USV_LAUNCH_LIVE(false, true);
   else USV_LAUNCH_LIVE(false, false);
 #undef USV_LAUNCH_LIVE
+#undef USV_LAUNCH_TASK
   return finish_launch();
 }

@@ -319,12 +319,13 @@ __device__ __forceinline__ void reset_env(EnvState& e, EnvConst& k, const UsvSte
     k.kiz = p.couple_kiz_min + rr * (p.couple_kiz_max - p.couple_kiz_min);
   }
   if (!p.reset_pose_external) {
-    // goals (live calls set_targets at the end of reset_idx; classic only at post_reset)
-    if (p.retarget_on_reset) {  // [ref SNAP/USV_capture_xy.py:312-326]
+    // goals [ref SNAP/USV_capture_xy.py:312-326]: the live reset_idx spawns around the OLD target and re-draws the target last
+    if (p.retarget_after_spawn) spawn_xy(p, r0, k.tx, k.ty, e.x, e.y);
+    if (p.retarget_on_reset) {
       k.tx = r0.a * p.goal_random_position * 2.0f - p.goal_random_position;
       k.ty = r0.b * p.goal_random_position * 2.0f - p.goal_random_position;
     }
-    spawn_xy(p, r0, k.tx, k.ty, e.x, e.y);
+    if (!p.retarget_after_spawn) spawn_xy(p, r0, k.tx, k.ty, e.x, e.y);
     // quaternion (cos(a/2),0,0,sin(a/2)) with a ~ U[0,pi)  ->  yaw = a
     e.psi = r1.a * USV_PI_F;
     // root velocities: zero, then vx,vy ~ U(-1.5,1.5) in the world frame  [ref SNAP/USV_Virtual.py:786-794]

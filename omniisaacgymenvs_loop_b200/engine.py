@@ -205,7 +205,9 @@ class FusedUsvLiveEnv(FusedUsvEnv):
         self.bstats = torch.zeros((nt, E["USV_BST_COUNT"], 32), **f32) if collect_stats else None
         for j in range(3):
             self.bconsts[:, E["USV_BC_COM_X"] + j] = self.live.com_base[j]
-        self.potential = torch.zeros((n, GRID, GRID), **f32)     # task.global_potential_field
+        self.task = int(self.live.task)
+        # task.global_potential_field (only the obstacle task has one)
+        self.potential = torch.zeros((n, GRID, GRID), **f32) if self.task == 0 else torch.zeros((1, GRID, GRID), **f32)
         self.obs = torch.zeros((n, LIVE_OBS_DIM), **f32)
         # BatchedMapGPU.__init__: cell-centre coordinates  [ref: d_multi_gemini.py:15-19]
         ms = self.live.map_size
@@ -276,7 +278,7 @@ class FusedUsvLiveEnv(FusedUsvEnv):
         rew = self.rew if rew is None else rew
         p = self.params()
         n = ctypes.c_int64(self.num_envs)
-        if rebuild_scene:
+        if rebuild_scene and self.task == 0:
             _lib.check(self.lib.usv_live_reset_scene_f32(ctypes.byref(self._buffers), ctypes.byref(self._live_buffers),
                                                          _lib.ptr(self.cell_centres), _lib.ptr(self.workspace), n, ctypes.byref(p),
                                                          _lib.stream()), "usv_live_reset_scene_f32")

@@ -532,6 +532,80 @@ def live_virtual():
     print("live_virtual.npz")
 
 
+def tier3():
+    """GoToPose / KeepXY / TrackXYVelocity: the tasks cannot run end-to-end in the reference (broken wiring), so
+    their methods are called one by one on a bare task object with `_task_data` pre-allocated (N,20), as SURVEY 8(c) prescribes.
+    KeepXYTask.compute_reward reads an undefined `self.positionposition` (USV_keep_xy.py:137): the attribute is set on the instance,
+    the source is not touched."""
+    ref_shim.install()
+    ref_shim.load_live()
+    with ref_shim.quiet():
+        import omniisaacgymenvs.tasks.USV.USV_go_to_pose as gtp
+        import omniisaacgymenvs.tasks.USV.USV_keep_xy as kxy
+        import omniisaacgymenvs.tasks.USV.USV_track_xy_velocity as txv
+    n, K = 16, 5
+    g = gen()
+    out = {}
+    specs = [("gotopose", gtp.GoToPoseTask, dict(name="GoToPose", position_tolerance=0.5, kill_after_n_steps_in_tolerance=3, max_spawn_dist=3.0,
+                                                 min_spawn_dist=0.3, kill_dist=10.0),
+              dict(name="GoToPose", position_reward_mode="exponential", heading_reward_mode="exponential", position_exponential_reward_coeff=0.25,
+                   heading_exponential_reward_coeff=0.25, position_scale=1.0, heading_scale=5.0, sig_gain=3.0)),
+             ("gotopose_sq", gtp.GoToPoseTask, dict(name="GoToPose", position_tolerance=0.5, kill_after_n_steps_in_tolerance=3, kill_dist=10.0),
+              dict(name="GoToPose", position_reward_mode="square", heading_reward_mode="linear", position_scale=2.0, heading_scale=3.0, sig_gain=2.0)),
+             ("keepxy", kxy.KeepXYTask, dict(name="KeepXY", position_tolerance=0.1, kill_after_n_steps_in_tolerance=500, kill_dist=8.0, boundary_cost=25.0),
+              dict(name="KeepXY", reward_mode="exponential", exponential_reward_coeff=0.25)),
+             ("keepxy_lin", kxy.KeepXYTask, dict(name="KeepXY", kill_dist=8.0), dict(name="KeepXY", reward_mode="linear")),
+             ("trackxyvel", txv.TrackXYVelocityTask, dict(name="TrackXYVelocity", lin_vel_tolerance=0.3, kill_after_n_steps_in_tolerance=2, kill_dist=9.0,
+                                                          goal_random_velocity=0.75),
+              dict(name="TrackXYVelocity", reward_mode="exponential", exponential_reward_coeff=0.25))]
+    for tag, cls, tp, rp in specs:
+        with ref_shim.quiet():
+            task = cls(tp, rp, n, "cpu", priv_dim=8)
+        task._task_data = torch.zeros((n, 20))
+        task.positionposition = None
+        ids = torch.arange(n)
+        target = torch.rand((n, 2), generator=g) * 2 - 1
+        if hasattr(task, "_target_positions"):
+            task._target_positions[:] = target
+        if hasattr(task, "_target_headings"):
+            task._target_headings[:] = torch.rand(n, generator=g) * 2 * math.pi
+            out[f"{tag}_target_heading"] = task._target_headings.clone()
+        if hasattr(task, "_target_velocities"):
+            task._target_velocities[:] = torch.rand((n, 2), generator=g) * 1.5 - 0.75
+            out[f"{tag}_target_vel"] = task._target_velocities.clone()
+        task.reset(ids)
+        pos = torch.rand((n, 2), generator=g) * 8 - 4
+        pos[0] = target[0] + torch.tensor([0.1, 0.05])          # inside the tolerance
+        pos[1] = target[1] + torch.tensor([11.0, 0.0])          # beyond kill_dist
+        yaw = (torch.rand(n, generator=g) * 2 - 1) * math.pi
+        vel = torch.rand((n, 2), generator=g) * 2 - 1
+        vel[0] = torch.tensor([0.02, -0.03])
+        if tag == "trackxyvel":
+            vel[2] = task._target_velocities[2] + torch.tensor([0.05, -0.05])   # inside lin_vel_tolerance
+        w = torch.rand(n, generator=g) * 1.2 - 0.6
+        S = {k: [] for k in ("pos", "yaw", "vel", "w", "prev_action", "priv", "actions", "obs", "reward", "die", "goal_reached")}
+        for k in range(K):
+            state = {"position": pos.clone(), "orientation": torch.stack([torch.cos(yaw), torch.sin(yaw)], 1),
+                     "linear_velocity": vel.clone(), "angular_velocity": w.clone()}
+            actions = torch.rand((n, 2), generator=g) * 2 - 1
+            priv = torch.rand((n, 8), generator=g) * 2 - 1
+            with ref_shim.quiet():
+                obs = task.get_state_observations(state, "local", prev_action=actions, priv_tail=priv).clone()
+                r = task.compute_reward(state, actions).clone()
+                die = (task.update_kills() if tag == "trackxyvel" else task.update_kills(0)).clone()
+            for name, v in (("pos", pos), ("yaw", yaw), ("vel", vel), ("w", w), ("prev_action", actions), ("priv", priv), ("actions", actions),
+                            ("obs", obs), ("reward", r), ("die", die), ("goal_reached", task._goal_reached)):
+                S[name].append(v.clone())
+            pos = pos + 0.1 * vel
+            yaw = yaw + 0.1 * w
+            vel = vel * 0.95
+            vel[3:] = vel[3:] + 0.05 * (torch.rand((n - 3, 2), generator=g) * 2 - 1)
+        out.update({f"{tag}_{k}": torch.stack(v) for k, v in S.items()})
+        out[f"{tag}_target"] = target
+    np.savez_compressed(os.path.join(OUT, "tier3_tasks.npz"), **t2n(out))
+    print("tier3_tasks.npz")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)
@@ -542,6 +616,7 @@ def main():
     ppo()
     variant_b()
     live_virtual()
+    tier3()
 
 
 if __name__ == "__main__":

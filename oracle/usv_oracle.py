@@ -246,6 +246,7 @@ class EnvConfig:
     spawn_min_dist: float = 0.3
     spawn_max_dist: float = 12.0
     spawn_about_origin: bool = False
+    retarget_after_spawn: bool = False
     reset_pose_external: bool = False
     spawn_vel_range: float = 1.5
     mass_rand: bool = False
@@ -431,18 +432,24 @@ class ClassicEnvOracle:
             self.thr_mult_right[ids] = sthr
             self.k_iz[ids] = kiz
         if not c.reset_pose_external:
+            sr = r0[:, 2] * (c.spawn_max_dist - c.spawn_min_dist) + c.spawn_min_dist
+            th = r0[:, 3] * 2 * math.pi
+
+            def spawn():                                                        # get_spawns  [SNAP/USV_capture_xy.py:330-394]
+                if c.spawn_about_origin:                                        # live CaptureXY: USV_capture_xy_static_obs.py:955-956
+                    self.pos[ids, 0] = sr * torch.cos(th)
+                    self.pos[ids, 1] = sr * torch.sin(th)
+                else:
+                    self.pos[ids, 0] = sr * torch.cos(th) + self.target[ids, 0]
+                    self.pos[ids, 1] = sr * torch.sin(th) + self.target[ids, 1]
+
+            if c.retarget_after_spawn:                                          # live reset_idx: get_spawns first, set_targets last
+                spawn()
             if c.retarget_on_reset:                                             # get_goals [SNAP/USV_capture_xy.py:312-326]
                 self.target[ids, 0] = r0[:, 0] * c.goal_random_position * 2 - c.goal_random_position
                 self.target[ids, 1] = r0[:, 1] * c.goal_random_position * 2 - c.goal_random_position
-            # get_spawns  [SNAP/USV_capture_xy.py:330-394]
-            sr = r0[:, 2] * (c.spawn_max_dist - c.spawn_min_dist) + c.spawn_min_dist
-            th = r0[:, 3] * 2 * math.pi
-            if c.spawn_about_origin:                                            # live task: OIGE/tasks/USV/USV_capture_xy_static_obs.py:955-956
-                self.pos[ids, 0] = sr * torch.cos(th)
-                self.pos[ids, 1] = sr * torch.sin(th)
-            else:
-                self.pos[ids, 0] = sr * torch.cos(th) + self.target[ids, 0]
-                self.pos[ids, 1] = sr * torch.sin(th) + self.target[ids, 1]
+            if not c.retarget_after_spawn:
+                spawn()
             self.psi[ids] = r1[:, 0] * math.pi
             # [SNAP/USV_Virtual.py:786-794]
             self.vel[ids, 0] = r1[:, 1] * (2 * c.spawn_vel_range) - c.spawn_vel_range
