@@ -93,7 +93,7 @@ def test_tier3_step_vs_oracle(tag, sync):
     n_done = 0
     for k in range(20):
         act = torch.rand((n, 2), generator=g) * 2.4 - 1.2
-        if sync:
+        if sync or k == 0:          # free-running: only the initial state (post_reset targets) is shared
             push_task_state(orc, env)
         o_obs, o_rew, o_done = orc.step(act)
         obs, rew, done = env.step(act.to(DEV))
