@@ -237,7 +237,8 @@ def time_e2e(env, steps, warmup, dist_on, device):
 
 
 def bench_ppo(args, rank, world, device, dist_on):
-    """BASELINE config[2]: CaptureXY + USV_PPOcontinuous_MLP, 16384 envs/GPU, env-sharded, NCCL grad all-reduce.
+    """BASELINE config[2]: CaptureXY + USV_PPOcontinuous_MLP, 16384 envs/GPU, env-sharded; gradient all-reduce = one kernel over NVLink
+    peer memory per minibatch (rl/peer.py), update phase replayed as one CUDA graph per rank.
     PPO frames/s = horizon * envs * world / epoch time (rollout + GAE + dataset + 8 mini-epochs x 32 minibatches)."""
     import torch.distributed as dist
     from omniisaacgymenvs_loop_b200 import _lib
@@ -272,10 +273,13 @@ def bench_ppo(args, rank, world, device, dist_on):
         ms = float(t.item())
     frames = agent.batch_size * world * args.ppo_epochs
     st = agent.policy.stats()
+    if agent.peer is not None:
+        agent.peer.check()
     return {"metric": "PPO frames/sec", "value": frames / (ms * 1e-3), "unit": "frames/s", "envs_per_gpu": n, "horizon": agent.T,
             "minibatch": agent.minibatch_size, "mini_epochs": agent.cfg.mini_epochs, "epochs_timed": args.ppo_epochs,
             "ms_per_epoch": ms / args.ppo_epochs, "host_play_s": play, "host_update_s": upd,
             "our_kernel_launches_per_epoch": (_lib.launch_count() - l0) / args.ppo_epochs,
+            "collective": agent.collective, "update_in_cuda_graph": agent._graph is not None,
             "mlp": ("tcgen05 TF32 UMMA + TMEM (csrc/ppo_mlp_tc.cu)" if agent.policy.tensor_cores else "fp32 SIMT fused kernels (csrc/ppo_mlp.cu)"), "kl": st["kl"], "lr": st["lr"]}
 
 

@@ -465,6 +465,26 @@ int ppo_adam_step_f32(float* params, float* grads /*[P+PPO_STAT_COUNT], scaled i
                       int32_t* step /*device int32[2]: [0] Adam step count (incremented), [1] scratch*/,
                       int64_t P, const PpoAdamParams* ap, void* stream);
 
+/* ------------------------------------------------------------------------- */
+/* Gradient all-reduce over NVLink peer memory (SURVEY 8(e) collective (1)+(2)): replaces dist.all_reduce(grads) of
+ *   [ref: RLG/common/a2c_common.py:308-323] with ONE kernel per minibatch that exchanges the span through CUDA-IPC mapped
+ *   windows (P2P stores / loads, release / acquire flags), sums in rank order (bit-identical on every rank) and never leaves the
+ *   stream -- so the PPO update phase stays one CUDA graph on every rank.  Windows are the one thing this library allocates
+ *   itself (cudaMalloc: IPC handles need whole allocations); the 64-byte handles travel through torch.distributed. */
+typedef struct {
+  float* windows[16];          /* windows[r] = rank r's window mapped into THIS process (windows[rank] = the local one) */
+  int64_t cap;                 /* floats per payload buffer (>= count)                                          */
+  int32_t world, rank;
+} PpoPeerComm;
+int64_t ppo_peer_window_bytes(int64_t cap);
+int ppo_peer_window_alloc(int64_t cap, void** window_out, unsigned char* handle64_out);
+int ppo_peer_window_open(const unsigned char* handle64, void** window_out);
+int ppo_peer_window_close(void* window, int32_t owned);
+/* dst[i] = sum over ranks of src_r[i]; seq_dev: device uint32 sequence counter (starts at 0, same on every rank);
+ * err_flag: device word OR-ed with 1 if a peer did not arrive within the spin bound (result then undefined)          */
+int ppo_peer_allreduce_f32(const PpoPeerComm* c, const float* src, float* dst, int64_t count, uint32_t* seq_dev,
+                           uint32_t* err_flag, void* stream);
+
 /* RunningMeanStd training-mode update, fused: batch moments of x[M,D] + Chan merge into the fp64 running state + fp32 copies
  *   [ref: RLG/algos_torch/running_mean_std.py:69-89] */
 int ppo_rms_update_f64(const float* x /*[M,D]*/, int64_t M, int32_t D, double* mean /*[D]*/, double* var /*[D]*/, double* count /*[1]*/,

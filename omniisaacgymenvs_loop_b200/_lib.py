@@ -98,6 +98,7 @@ UsvLiveParams = STRUCTS["UsvLiveParams"]
 UsvLiveBuffers = STRUCTS["UsvLiveBuffers"]
 PpoLossParams = STRUCTS["PpoLossParams"]
 PpoAdamParams = STRUCTS["PpoAdamParams"]
+PpoPeerComm = STRUCTS["PpoPeerComm"]
 
 _lib = None
 
@@ -125,6 +126,7 @@ def lib() -> ctypes.CDLL:
     L.ppo_train_tc_workspace_floats.restype = ctypes.c_int64
     L.ppo_packed_weight_floats.restype = ctypes.c_int64
     L.usv_live_scene_workspace_bytes.restype = ctypes.c_int64
+    L.ppo_peer_window_bytes.restype = ctypes.c_int64
     L.usv_live_scene_workspace_bytes.argtypes = [ctypes.c_int64]
     for name, st in STRUCTS.items():
         want = L.usv_b200_sizeof(name.encode())

@@ -203,6 +203,7 @@ int64_t usv_b200_sizeof(const char* name) {
   USV_SZ(UsvLiveBuffers);
   USV_SZ(PpoLossParams);
   USV_SZ(PpoAdamParams);
+  USV_SZ(PpoPeerComm);
 #undef USV_SZ
   return -1;
 }

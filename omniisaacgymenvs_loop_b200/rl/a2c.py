@@ -68,15 +68,17 @@ def gae(rewards, values, dones, last_values, last_dones, gamma, tau, adv, ret):
 
 
 class A2CAgent:
-    def __init__(self, vec_env, cfg: PPOConfig, device="cuda:0", rank: int = 0, world_size: int = 1, use_cuda_graph: bool = True):
+    def __init__(self, vec_env, cfg: PPOConfig, device="cuda:0", rank: int = 0, world_size: int = 1, use_cuda_graph: bool = True,
+                 collective: str = "peer"):
         """`vec_env` follows the rl_games IVecEnv contract (step/reset/get_env_info), e.g. RLGPUEnv(VecEnvRLGames)."""
         self.vec_env, self.cfg = vec_env, cfg
         self.device = torch.device(device)
         self.rank, self.world = rank, world_size
         self.multi_gpu = world_size > 1
-        # NCCL collectives inside a captured graph deadlocked on the 2-GPU box (r01 notes in DESIGN.md): graphs are used on the
-        # single-rank path, multi-rank runs launch the update phase eagerly
-        self.use_cuda_graph, self._graph = (use_cuda_graph and world_size == 1), None
+        # gradient collective: "peer" = one-shot all-reduce over NVLink peer memory (rl/peer.py; stays inside the captured graph),
+        # "nccl" = dist.all_reduce launched eagerly (NCCL inside a captured graph deadlocked on the 2-GPU box, r01 notes in DESIGN.md)
+        self.collective = collective if world_size > 1 else "none"
+        self.use_cuda_graph, self._graph = (use_cuda_graph and (world_size == 1 or collective == "peer")), None
         info = vec_env.get_env_info()
         self.obs_dim = int(info["observation_space"]["state"].shape[0])
         self.num_actors = int(vec_env.env.num_envs)
@@ -90,8 +92,12 @@ class A2CAgent:
                                 clip_value=cfg.clip_value, grad_norm=cfg.grad_norm if cfg.truncate_grads else 0.0,
                                 kl_threshold=cfg.kl_threshold, adaptive_lr=cfg.lr_schedule == "adaptive", world_size=world_size)
         self.policy.seed = cfg.seed + rank                                  # [ref: RLG/torch_runner.py:74-75]
+        self.peer = None
         if self.multi_gpu:                                                  # [ref: a2c_common.py:1350-1355]
             dist.broadcast(self.policy.params, 0)
+            if self.collective == "peer":
+                from .peer import PeerAllReduce
+                self.peer = PeerAllReduce(self.policy.grads.numel(), self.device, rank, world_size)
         N, T, D = self.num_actors, self.T, self.obs_dim
         f32 = dict(dtype=torch.float32, device=self.device)
         self.buf = dict(obses=torch.zeros((T, N, D), **f32), rewards=torch.zeros((T, N), **f32), values=torch.zeros((T, N, 1), **f32),
@@ -167,8 +173,10 @@ class A2CAgent:
                     pol.obs_rms.update(ds["obs"][s])                    # train-mode forward updates the normaliser first
                 pol.minibatch_grad(ds["obs"][s], ds["actions"][s], ds["old_logp_actions"][s], ds["advantages"][s],
                                    ds["old_values"][s], ds["returns"][s], ds["mu"][s], ds["sigma"][s])
-                if self.multi_gpu:
-                    dist.all_reduce(pol.grads, op=dist.ReduceOp.SUM)     # gradient + KL + loss stats in one span
+                if self.peer is not None:
+                    self.peer(pol.grads)                                 # gradient + KL + loss stats in one span, over NVLink peer memory
+                elif self.multi_gpu:
+                    dist.all_reduce(pol.grads, op=dist.ReduceOp.SUM)
                 pol.optimizer_step()
 
     def train_epoch(self):

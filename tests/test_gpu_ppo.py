@@ -195,3 +195,25 @@ def test_ppo_loop_learns_on_tensor_cores():
             agent.train_epoch()
         rewards.append(agent.episode_stats()[0])
     assert torch.isfinite(agent.policy.params).all() and rewards[-1] > rewards[0], rewards
+
+
+def test_peer_allreduce_world1_and_abi():
+    """The NVLink peer all-reduce with a single rank degenerates to a copy through the IPC window: exercises window allocation,
+    the flag protocol (own flag), sequence numbers across calls and graph capture.  Multi-rank: scripts/test_peer_allreduce.py."""
+    from omniisaacgymenvs_loop_b200.rl.peer import PeerAllReduce
+    ar = PeerAllReduce(5000, DEV, 0, 1)
+    x = torch.randn(4097, device=DEV)
+    for k in range(5):
+        y = ar(x * (k + 1), torch.empty_like(x))
+        assert torch.equal(y, x * (k + 1))
+    g = torch.cuda.CUDAGraph()
+    out = torch.empty_like(x)
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g):
+        for _ in range(4):
+            ar(x, out)
+    g.replay(); g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, x) and int(ar.seq.item()) == 5 + 8
+    ar.check()
+    ar.close()
