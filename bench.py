@@ -278,7 +278,8 @@ def bench_ppo(args, rank, world, device, dist_on):
     return {"metric": "PPO frames/sec", "value": frames / (ms * 1e-3), "unit": "frames/s", "envs_per_gpu": n, "horizon": agent.T,
             "minibatch": agent.minibatch_size, "mini_epochs": agent.cfg.mini_epochs, "epochs_timed": args.ppo_epochs,
             "ms_per_epoch": ms / args.ppo_epochs, "host_play_s": play, "host_update_s": upd,
-            "our_kernel_launches_per_epoch": (_lib.launch_count() - l0) / args.ppo_epochs,
+            "our_kernel_launches_per_epoch": (_lib.launch_count() - l0) / args.ppo_epochs + sum(agent.graph_launches.values()),
+            "rollout_in_cuda_graph": agent._graph_play is not None,
             "collective": agent.collective, "update_in_cuda_graph": agent._graph is not None,
             "mlp": ("tcgen05 TF32 UMMA + TMEM (csrc/ppo_mlp_tc.cu)" if agent.policy.tensor_cores else "fp32 SIMT fused kernels (csrc/ppo_mlp.cu)"), "kl": st["kl"], "lr": st["lr"]}
 

@@ -251,6 +251,9 @@ typedef struct {
   const float* lut_left;                     /* [n_lut]                                        */
   const float* lut_right;                    /* [n_lut]                                        */
   uint32_t* nonfinite_flag;                  /* device word, OR-ed with 1 on NaN/Inf obs/rew, or NULL */
+  /* optional device-side addend to UsvStepParams.step_counter (NULL = 0): lets a captured CUDA graph of control steps advance
+   * its Philox step index between replays.  Honoured by usv_step_fused_f32 / usv_rollout_fused_f32 (classic task). */
+  const uint64_t* step_offset;
 } UsvEnvBuffers;
 
 /* one control step for n envs: reset-if-flagged, action -> thrust target, n_substeps of
@@ -402,7 +405,8 @@ int64_t ppo_param_count(int32_t obs_dim);
 int ppo_policy_forward_f32(const float* params, const float* obs /*[M,D]*/, int32_t obs_dim,
                            const float* obs_mean /*[D] fp32 copy of the fp64 running mean*/, const float* obs_var /*[D]*/,
                            const float* value_mean /*[1]*/, const float* value_var /*[1]*/,
-                           uint64_t seed, uint64_t counter, int64_t row_offset,
+                           uint64_t seed, uint64_t counter, const uint64_t* counter_offset /*device addend to `counter` or NULL (graph replay)*/,
+                           int64_t row_offset,
                            float* actions /*[M,2]*/, float* neglogp /*[M]*/, float* values /*[M] de-normalised*/,
                            float* mus /*[M,2]*/, float* sigmas /*[M,2]*/, int64_t M, void* stream);
 
@@ -413,8 +417,8 @@ int64_t ppo_packed_weight_floats(void);
  * every parameter update.  `packed`: ppo_packed_weight_floats() floats, 16 B aligned */
 int ppo_pack_weights_tc(const float* params, int32_t obs_dim, float* packed, void* stream);
 int ppo_policy_forward_tc(const float* params, const float* packed, const float* obs, int32_t obs_dim, const float* obs_mean, const float* obs_var,
-                          const float* value_mean, const float* value_var, uint64_t seed, uint64_t counter, int64_t row_offset,
-                          float* actions, float* neglogp, float* values, float* mus, float* sigmas, int64_t M, void* stream);
+                          const float* value_mean, const float* value_var, uint64_t seed, uint64_t counter, const uint64_t* counter_offset,
+                          int64_t row_offset, float* actions, float* neglogp, float* values, float* mus, float* sigmas, int64_t M, void* stream);
 
 typedef struct {
   float e_clip;            /* 0.2  */
@@ -451,6 +455,7 @@ int ppo_minibatch_grad_tc(const float* params, const float* packed, const float*
                           int64_t M, void* stream);
 int64_t ppo_train_tc_workspace_floats(int64_t M);
 
+
 /* gradient-norm clip + Adam + adaptive-KL learning rate, all on device (no kl.item() host sync)                  */
 /*   [ref: RLG/common/a2c_common.py:308-330 ; torch.optim.Adam ; RLG/common/schedulers.py:19-32]                  */
 typedef struct {
@@ -464,6 +469,13 @@ int ppo_adam_step_f32(float* params, float* grads /*[P+PPO_STAT_COUNT], scaled i
                       float* lr /*device float[2]: [0] current lr (updated), [1] scratch*/,
                       int32_t* step /*device int32[2]: [0] Adam step count (incremented), [1] scratch*/,
                       int64_t P, const PpoAdamParams* ap, void* stream);
+/* one whole minibatch step on a single rank: ppo_minibatch_grad_tc + ppo_adam_step_f32 + ppo_pack_weights_tc with the second-stage
+ * reduction, clip, Adam, adaptive lr and re-pack fused into ONE cooperative launch (3 launches per minibatch instead of 7) */
+int ppo_minibatch_step_tc(float* params, float* packed, const float* obs, int32_t obs_dim, const float* obs_mean, const float* obs_var,
+                          const float* actions, const float* old_neglogp, const float* advantages, const float* old_values,
+                          const float* returns, float* old_mu, float* old_sigma, const PpoLossParams* lp, float* grads, float* scratch,
+                          float* workspace, float* exp_avg, float* exp_avg_sq, float* lr, int32_t* step, const PpoAdamParams* ap,
+                          int64_t M, void* stream);
 
 /* ------------------------------------------------------------------------- */
 /* Gradient all-reduce over NVLink peer memory (SURVEY 8(e) collective (1)+(2)): replaces dist.all_reduce(grads) of

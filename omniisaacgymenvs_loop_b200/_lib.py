@@ -24,7 +24,7 @@ _CTYPES = {
     "int64_t": ctypes.c_int64, "uint64_t": ctypes.c_uint64,
     "float*": ctypes.c_void_p, "const float*": ctypes.c_void_p, "int64_t*": ctypes.c_void_p,
     "uint32_t*": ctypes.c_void_p, "int32_t*": ctypes.c_void_p, "double*": ctypes.c_void_p,
-    "uint64_t*": ctypes.c_void_p, "const int32_t*": ctypes.c_void_p,
+    "uint64_t*": ctypes.c_void_p, "const int32_t*": ctypes.c_void_p, "const uint64_t*": ctypes.c_void_p,
 }
 
 

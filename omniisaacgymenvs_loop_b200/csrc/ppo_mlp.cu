@@ -162,12 +162,13 @@ __device__ inline float head_out(const Smem& s, int r, int j) {
 __global__ void __launch_bounds__(NT, 1) forward_kernel(
     const float* __restrict__ prm, const float* __restrict__ obs, int D, const float* __restrict__ omean,
     const float* __restrict__ ovar, const float* __restrict__ vmean, const float* __restrict__ vvar, uint64_t seed,
-    uint64_t counter, int64_t row_offset, float* __restrict__ actions, float* __restrict__ neglogp,
+    uint64_t counter_in, const uint64_t* __restrict__ counter_offset, int64_t row_offset, float* __restrict__ actions, float* __restrict__ neglogp,
     float* __restrict__ values, float* __restrict__ mus, float* __restrict__ sigmas, int64_t M) {
   extern __shared__ __align__(16) float smem[];
   const Layout L(D);
   const Smem s = carve(smem, D, false);
   load_weights(s, prm, L);
+  const uint64_t counter = counter_in + (counter_offset ? *counter_offset : 0ull);
   const float ls0 = prm[L.sigma], ls1 = prm[L.sigma + 1];
   const float sg0 = expf(ls0), sg1 = expf(ls1);
   const int64_t ntiles = (M + TM - 1) / TM;
@@ -618,8 +619,9 @@ int64_t ppo_param_count(int32_t obs_dim) { return Layout(obs_dim).P; }
 int64_t ppo_train_scratch_floats(int32_t obs_dim) { return (int64_t)kMaxParts * (Layout(obs_dim).P + PPO_STAT_COUNT); }
 
 int ppo_policy_forward_f32(const float* params, const float* obs, int32_t obs_dim, const float* obs_mean, const float* obs_var,
-                           const float* value_mean, const float* value_var, uint64_t seed, uint64_t counter, int64_t row_offset,
-                           float* actions, float* neglogp, float* values, float* mus, float* sigmas, int64_t M, void* stream) {
+                           const float* value_mean, const float* value_var, uint64_t seed, uint64_t counter, const uint64_t* counter_offset,
+                           int64_t row_offset, float* actions, float* neglogp, float* values, float* mus, float* sigmas, int64_t M,
+                           void* stream) {
   if (M < 0 || obs_dim < 1 || obs_dim > PPO_MAX_OBS) return USV_E_SIZE;
   if (M == 0) return USV_OK;
   if (!params || !obs || !obs_mean || !obs_var) return USV_E_NULL;
@@ -629,7 +631,7 @@ int ppo_policy_forward_f32(const float* params, const float* obs, int32_t obs_di
   const int64_t ntiles = (M + TM - 1) / TM;
   const int grid = (int)(ntiles < num_sms() ? ntiles : num_sms());
   forward_kernel<<<grid, NT, smem, (cudaStream_t)stream>>>(params, obs, obs_dim, obs_mean, obs_var, value_mean, value_var, seed,
-                                                           counter, row_offset, actions, neglogp, values, mus, sigmas, M);
+                                                           counter, counter_offset, row_offset, actions, neglogp, values, mus, sigmas, M);
   return usv::finish_launch();
 }
 

@@ -16,6 +16,7 @@
 //
 // TF32 inputs (10-bit mantissa) + tanh.approx (2^-11) put this path at ~1e-3 relative of the fp32 kernels in ppo_mlp.cu,
 // which remain the numerics reference.
+#include <cooperative_groups.h>
 #include <math_constants.h>
 #include "philox.cuh"
 #include "usv_common.cuh"
@@ -263,12 +264,13 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t tmem_acc, float* act, c
 __global__ void __launch_bounds__(NT, 1) forward_tc_kernel(
     const float* __restrict__ prm, const float* __restrict__ pk, const float* __restrict__ obs, int D, const float* __restrict__ omean,
     const float* __restrict__ ovar, const float* __restrict__ vmean, const float* __restrict__ vvar, uint64_t seed,
-    uint64_t counter, int64_t row_offset, float* __restrict__ actions, float* __restrict__ neglogp,
+    uint64_t counter_in, const uint64_t* __restrict__ counter_offset, int64_t row_offset, float* __restrict__ actions, float* __restrict__ neglogp,
     float* __restrict__ values, float* __restrict__ mus, float* __restrict__ sigmas, int64_t M) {
   extern __shared__ __align__(1024) float smem[];
   const Layout L(D);
   const FwdSmem s = carve_fwd(smem);
   const int t = threadIdx.x;
+  const uint64_t counter = counter_in + (counter_offset ? *counter_offset : 0ull);
   // ---- one-time set-up: packed weight tiles by TMA bulk copy, TMEM, mbarriers ---------------------------------
   if (t == 0) {
     mbar_init(s.mbar, 1);
@@ -642,6 +644,120 @@ __global__ void __launch_bounds__(256) reduce_tc_kernel(const float* __restrict_
   }
 }
 
+// ---- fused tail of a minibatch step (single rank): second-stage gradient reduction + clip_grad_norm_ + Adam + adaptive-KL lr +
+// re-packing of the operand tiles, ONE cooperative launch instead of reduce / adam / roll / pack (4 dependent launches were
+// ~1/3 of the 65 us minibatch step in the r01 launch list).  Phases are separated by grid-wide barriers:
+//   A  every CTA sums its 64 gradient entries over the partial slots (as reduce_tc_kernel) and publishes their sum of squares
+//   B  every CTA rebuilds the global norm from the per-CTA partials in a fixed order (deterministic), applies clip + Adam to its
+//      own entries; lr / step are read from slot [0], the new values go to slot [1]
+//   C  slot [1] -> [0]; all CTAs re-pack the parameters into the tensor-core operand tiles
+namespace cgx = cooperative_groups;
+__global__ void __launch_bounds__(256) finish_tc_kernel(const float* __restrict__ scal, int g1, const float* __restrict__ mat, int g2, int D,
+                                                       float* __restrict__ grads, PpoLossParams lp, float* __restrict__ prm,
+                                                       float* __restrict__ m, float* __restrict__ v, float* __restrict__ lr,
+                                                       int* __restrict__ step, PpoAdamParams ap, float* __restrict__ pk,
+                                                       float* __restrict__ part_ss) {
+  cgx::grid_group grid = cgx::this_grid();
+  __shared__ float sm[4][64];
+  __shared__ float sc[16];
+  __shared__ float s_red[8];
+  __shared__ float s_coef, s_norm;
+  const Layout L(D);
+  const int col = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  const int e = blockIdx.x * 64 + col;
+  // ---- A: reduce --------------------------------------------------------------------------------------------------------
+  float acc = 0.f;
+  if (e < L.P)
+    for (int c = grp; c < g2; c += 4) acc += mat[(size_t)c * L.P + e];
+  sm[grp][col] = acc;
+  __syncthreads();
+  const bool scalar_entry = e < L.w1 || e >= L.bmu || e == L.bv;
+  float gval = 0.f;
+  if (grp == 0 && e < L.P && !scalar_entry) {
+    gval = (sm[0][col] + sm[1][col]) + (sm[2][col] + sm[3][col]);
+    grads[e] = gval;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < 10) {
+    float x = 0.f;
+    for (int c = 0; c < g1; ++c) x += scal[c * 16 + threadIdx.x];
+    sc[threadIdx.x] = x;
+  }
+  __syncthreads();
+  float ss = gval * gval;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const float* q = sc;
+    grads[L.P + PPO_STAT_A_LOSS] = q[0]; grads[L.P + PPO_STAT_C_LOSS] = q[1]; grads[L.P + PPO_STAT_ENTROPY] = q[2];
+    grads[L.P + PPO_STAT_B_LOSS] = q[3]; grads[L.P + PPO_STAT_KL] = q[4];
+    grads[L.P + PPO_STAT_LOSS] = q[0] + 0.5f * q[1] * lp.critic_coef - q[2] * lp.entropy_coef + q[3] * lp.bounds_loss_coef;
+    grads[L.sigma] = q[5]; grads[L.sigma + 1] = q[6]; grads[L.bmu] = q[7]; grads[L.bmu + 1] = q[8]; grads[L.bv] = q[9];
+    ss += (q[5] * q[5] + q[6] * q[6]) + (q[7] * q[7] + q[8] * q[8]) + q[9] * q[9];
+  }
+  if (grp == 0) {   // 64 threads = 2 warps hold the squares
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = ss;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) part_ss[blockIdx.x] = s_red[0] + s_red[1];
+  __threadfence();
+  grid.sync();
+  // ---- B: norm, clip, Adam ------------------------------------------------------------------------------------------------
+  if (threadIdx.x < 32) {
+    float x = 0.f;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += 32) x += part_ss[b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (threadIdx.x == 0) {
+      const float norm = sqrtf(x) * ap.inv_world;
+      s_norm = norm;
+      s_coef = (ap.grad_norm > 0.f) ? fminf(ap.grad_norm / (norm + 1e-6f), 1.0f) : 1.0f;
+    }
+  }
+  __syncthreads();
+  const float coef = s_coef * ap.inv_world;
+  const float lr0 = lr[0];
+  const int stp = step[0] + 1;
+  if (grp == 0 && e < L.P) {
+    const double bc1 = 1.0 - pow((double)ap.beta1, (double)stp), bc2 = 1.0 - pow((double)ap.beta2, (double)stp);
+    const float step_size = (float)((double)lr0 / bc1);
+    const float bc2_sqrt = (float)sqrt(bc2);
+    const float gr = (scalar_entry ? grads[e] : gval) * coef;
+    const float mm = m[e] + (gr - m[e]) * (1.0f - ap.beta1);
+    const float vv = v[e] * ap.beta2 + (1.0f - ap.beta2) * gr * gr;
+    m[e] = mm;
+    v[e] = vv;
+    prm[e] = prm[e] - step_size * (mm / (sqrtf(vv) / bc2_sqrt + ap.eps));
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const float kl = grads[L.P + PPO_STAT_KL] * ap.inv_world;
+    for (int q = 0; q < PPO_STAT_COUNT; ++q) grads[L.P + q] *= ap.inv_world;
+    grads[L.P + PPO_STAT_GRAD_NORM] = s_norm;
+    grads[L.P + PPO_STAT_LR] = lr0;
+    float nl = lr0;
+    if (ap.adaptive_lr) {
+      if (kl > 2.0f * ap.kl_threshold) nl = fmaxf(lr0 / 1.5f, ap.min_lr);
+      if (kl < 0.5f * ap.kl_threshold) nl = fminf(lr0 * 1.5f, ap.max_lr);
+    }
+    lr[1] = nl;
+    step[1] = stp;
+  }
+  __threadfence();
+  grid.sync();
+  // ---- C: roll lr / step, re-pack -------------------------------------------------------------------------------------------
+  if (blockIdx.x == 0 && threadIdx.x == 0) { lr[0] = lr[1]; step[0] = step[1]; }
+  for (int q = blockIdx.x * 256 + threadIdx.x; q < PK_TOTAL; q += gridDim.x * 256) {
+    int o, i;
+    float x = 0.f;
+    if (q < PK_W2T) { tile_inv(q - PK_W2, H / 4, o, i); x = prm[L.w2 + o * H + i]; }
+    else if (q < PK_W1) { tile_inv(q - PK_W2T, H / 4, o, i); x = prm[L.w2 + i * H + o]; }
+    else if (q < PK_W3) { tile_inv(q - PK_W1, DP / 4, o, i); x = i < D ? prm[L.w1 + o * D + i] : (i == D ? prm[L.b1 + o] : 0.f); }
+    else if (q < PK_B2) { tile_inv(q - PK_W3, H / 4, o, i); x = o < 2 ? prm[L.wmu + o * H + i] : (o == 2 ? prm[L.wv + i] : 0.f); }
+    else if (q < PK_B3) { x = prm[L.b2 + (q - PK_B2)]; }
+    else { const int j = q - PK_B3; x = j < 2 ? prm[L.bmu + j] : (j == 2 ? prm[L.bv] : 0.f); }
+    pk[q] = x;
+  }
+}
+
 // ---- T2: weight gradients, K = samples ------------------------------------------------------------------------------
 constexpr int WK = 64;   // samples per CTA chunk
 // feature-major global slab [rows][ld] (columns c0..c0+WK) -> K-major operand tile (outer = feature row, inner = sample)
@@ -766,7 +882,7 @@ extern "C" int ppo_pack_weights_tc(const float* params, int32_t obs_dim, float* 
 
 extern "C" int ppo_policy_forward_tc(const float* params, const float* packed, const float* obs, int32_t obs_dim, const float* obs_mean,
                                      const float* obs_var, const float* value_mean, const float* value_var, uint64_t seed,
-                                     uint64_t counter, int64_t row_offset, float* actions, float* neglogp, float* values,
+                                     uint64_t counter, const uint64_t* counter_offset, int64_t row_offset, float* actions, float* neglogp, float* values,
                                      float* mus, float* sigmas, int64_t M, void* stream) {
   if (M < 0 || obs_dim < 1 || obs_dim >= DP) return USV_E_SIZE;   // one padded column is reserved for the bias
   if (M == 0) return USV_OK;
@@ -778,7 +894,7 @@ extern "C" int ppo_policy_forward_tc(const float* params, const float* packed, c
   const int64_t ntiles = (M + TM - 1) / TM;
   const int grid = (int)(ntiles < num_sms() ? ntiles : num_sms());
   forward_tc_kernel<<<grid, NT, smem, (cudaStream_t)stream>>>(params, packed, obs, obs_dim, obs_mean, obs_var, value_mean, value_var, seed,
-                                                              counter, row_offset, actions, neglogp, values, mus, sigmas, M);
+                                                              counter, counter_offset, row_offset, actions, neglogp, values, mus, sigmas, M);
   return usv::finish_launch();
 }
 
@@ -787,6 +903,49 @@ namespace ppo { void launch_reduce(const float* scratch, int nparts, int n, floa
 extern "C" int64_t ppo_train_tc_workspace_floats(int64_t M) {
   const int64_t ld = (M + 127) / 128 * 128;
   return (4 * (int64_t)H + 2 * 16) * ld;
+}
+
+// T1 + T2 + the fused cooperative tail: one whole PPO minibatch step (gradient, clip, Adam, adaptive lr, re-pack) in 3 launches
+extern "C" int ppo_minibatch_step_tc(float* params, float* packed, const float* obs, int32_t obs_dim, const float* obs_mean,
+                                     const float* obs_var, const float* actions, const float* old_neglogp, const float* advantages,
+                                     const float* old_values, const float* returns, float* old_mu, float* old_sigma,
+                                     const PpoLossParams* lp, float* grads, float* scratch, float* workspace, float* exp_avg,
+                                     float* exp_avg_sq, float* lr, int32_t* step, const PpoAdamParams* ap, int64_t M, void* stream) {
+  if (M <= 0 || obs_dim < 1 || obs_dim >= DP) return USV_E_SIZE;
+  if (!params || !packed || !obs || !obs_mean || !obs_var || !actions || !old_neglogp || !advantages || !old_values || !returns ||
+      !old_mu || !old_sigma || !lp || !grads || !scratch || !workspace || !exp_avg || !exp_avg_sq || !lr || !step || !ap)
+    return USV_E_NULL;
+  if (((uintptr_t)workspace | (uintptr_t)packed) & 15) return USV_E_ALIGN;
+  const Layout L(obs_dim);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t ld = (M + 127) / 128 * 128;
+  TrainWs ws;
+  ws.ld = ld;
+  ws.h1t = workspace; ws.h2t = ws.h1t + H * ld; ws.dz2t = ws.h2t + H * ld; ws.dz1t = ws.dz2t + H * ld;
+  ws.xt = ws.dz1t + H * ld; ws.dz3t = ws.xt + 16 * ld;
+  cudaMemsetAsync(ws.dz3t + 3 * ld, 0, sizeof(float) * 13 * ld, st);  // rows 3..15 of dz3^T are structurally zero
+  const int64_t ntiles = ld / TM, nchunks = ld / WK;
+  int g1 = (int)(ntiles < num_sms() ? ntiles : num_sms()), g2 = (int)(nchunks < num_sms() ? nchunks : num_sms());
+  if (g2 > 64) g2 = 64;
+  cudaFuncSetAttribute(train_fwd_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)train_smem_bytes());
+  cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wgrad_smem_bytes());
+  LossInTc in{actions, old_neglogp, advantages, old_values, returns, old_mu, old_sigma};
+  train_fwd_bwd_tc_kernel<<<g1, NT, train_smem_bytes(), st>>>(params, packed, obs, obs_dim, obs_mean, obs_var, in, *lp, ws, scratch, M);
+  const int mat0 = 16 * 160;
+  wgrad_tc_kernel<<<g2, NT, wgrad_smem_bytes(), st>>>(ws, obs_dim, scratch, mat0, nchunks);
+  // the per-CTA sum-of-squares partials live behind the matrix slots of `scratch` (ppo_train_scratch_floats covers 160 slots)
+  const int fgrid = (L.P + 63) / 64;
+  float* part_ss = scratch + mat0 + (size_t)64 * L.P;
+  const float* scal = scratch;
+  const float* mat = scratch + mat0;
+  int D = obs_dim;
+  PpoLossParams lpv = *lp;
+  PpoAdamParams apv = *ap;
+  void* args[] = {(void*)&scal, (void*)&g1, (void*)&mat, (void*)&g2, (void*)&D, (void*)&grads, (void*)&lpv, (void*)&params,
+                  (void*)&exp_avg, (void*)&exp_avg_sq, (void*)&lr, (void*)&step, (void*)&apv, (void*)&packed, (void*)&part_ss};
+  cudaError_t e = cudaLaunchCooperativeKernel((void*)finish_tc_kernel, dim3(fgrid), dim3(256), args, 0, st);
+  if (e != cudaSuccess) return (int)e;
+  return usv::finish_launch(3);
 }
 
 extern "C" int ppo_minibatch_grad_tc(const float* params, const float* packed, const float* obs, int32_t obs_dim, const float* obs_mean,

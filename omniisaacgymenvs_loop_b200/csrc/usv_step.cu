@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(kBlock, USV_MINB) step_fused_kernel(UsvEnvBuff
   }
   StepOut o;
   if (active) {
-    control_step<kDisturb, true>(e, k, p, do_reset, act, (uint64_t)(p.env_id_offset + i), i, p.step_counter,
+    control_step<kDisturb, true>(e, k, p, do_reset, act, (uint64_t)(p.env_id_offset + i), i, p.step_counter + (b.step_offset ? *b.step_offset : 0ull),
                                  p.first_call != 0, s_lutL, s_lutR, o);
     store_state(b.state, b.state_stride, i, e);
     if (do_reset) store_consts<kDisturb>(b.consts, b.consts_stride, i, k);
@@ -239,11 +239,12 @@ __global__ void __launch_bounds__(kBlock) rollout_fused_kernel(UsvEnvBuffers b, 
   __syncthreads();
   bool first_call = p.first_call != 0;
   bool bad = false;
+  const uint64_t step0 = p.step_counter + (b.step_offset ? *b.step_offset : 0ull);
   for (int t = 0; t < T; ++t) {
     StepOut o;
     if (active) {
       const float2 act = actions[(int64_t)t * n + i];
-      control_step<kDisturb, false>(e, k, p, do_reset, act, (uint64_t)(p.env_id_offset + i), i, p.step_counter + (uint64_t)t,
+      control_step<kDisturb, false>(e, k, p, do_reset, act, (uint64_t)(p.env_id_offset + i), i, step0 + (uint64_t)t,
                              first_call, s_lutL, s_lutR, o);
       consts_dirty |= do_reset;
       if (kStats) accumulate_stats(b.stats, b.stats_stride, i, do_reset, o, p);

@@ -45,6 +45,10 @@ class FusedUsvEnv:
         self.rew = torch.zeros(n, **f32)
         self.nonfinite = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.step_counter = 0
+        # device-side part of the Philox step index: a captured graph of control steps adds to it at the end of each replay
+        # (advance_step_offset); the kernels see  p.step_counter + *step_offset  == self.step_counter  at every launch
+        self.step_offset = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self._step_offset_host = 0
         self.first_call = True
         # per-episode constants start at their nominal values (reset_idx rewrites them)
         c = self.consts
@@ -80,6 +84,7 @@ class FusedUsvEnv:
         b.reset_buf = self.reset_buf.data_ptr()
         b.lut_left, b.lut_right = self.lut_left.data_ptr(), self.lut_right.data_ptr()
         b.nonfinite_flag = self.nonfinite.data_ptr()
+        b.step_offset = self.step_offset.data_ptr()
         return b
 
     def _src(self, name: str) -> torch.Tensor:
@@ -139,11 +144,20 @@ class FusedUsvEnv:
         p = getattr(self, "_params", None)
         if p is None:
             p = self._params = self.cfg.to_params(0, self.env_id_offset, False)
-        p.step_counter = self.step_counter
+        p.step_counter = self.step_counter - self._step_offset_host
         p.first_call = int(self.first_call)
         # live action path: the initial bias applies to the first N control steps only  [ref: OIGE/tasks/USV_Virtual.py:1070-1077]
         p.action_bias = self.cfg.action_bias if self.step_counter < self.cfg.action_bias_steps else 0.0
         return p
+
+    def advance_step_offset(self, steps: int) -> None:
+        """Inside a CUDA-graph capture of `steps` control steps: make the next replay continue the Philox step sequence."""
+        self.step_offset += steps
+
+    def note_graph_replay(self, steps: int) -> None:
+        """Host bookkeeping after a replay of a graph that contains `steps` control steps and one advance_step_offset(steps)."""
+        self.step_counter += steps
+        self._step_offset_host += steps
 
     # ---- the hot path ------------------------------------------------------------------
     def step(self, actions: torch.Tensor, obs: Optional[torch.Tensor] = None, rew: Optional[torch.Tensor] = None):
@@ -198,6 +212,7 @@ class FusedUsvLiveEnv(FusedUsvEnv):
                  env_id_offset: int = 0, collect_stats: bool = False):
         super().__init__(cfg, num_envs, device, env_id_offset, collect_stats=False)
         self.live = live if live is not None else UsvLiveConfig()
+        self._buffers.step_offset = None          # the live kernels take the step index from UsvStepParams only
         n, nt = self.num_envs, self.stride // 32
         f32 = dict(dtype=torch.float32, device=self.device)
         self.bstate = torch.zeros((nt, E["USV_BS_COUNT"], 32), **f32)

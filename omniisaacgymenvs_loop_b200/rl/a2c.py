@@ -79,6 +79,9 @@ class A2CAgent:
         # "nccl" = dist.all_reduce launched eagerly (NCCL inside a captured graph deadlocked on the 2-GPU box, r01 notes in DESIGN.md)
         self.collective = collective if world_size > 1 else "none"
         self.use_cuda_graph, self._graph = (use_cuda_graph and (world_size == 1 or collective == "peer")), None
+        self._graph_play, self._probe_after_replay = None, False
+        self.graph_launches = {"play": 0, "update": 0}
+        self.fused_step = True      # single rank + tensor cores: use PolicyMLP.minibatch_step (fused reduce / Adam / re-pack tail)
         info = vec_env.get_env_info()
         self.obs_dim = int(info["observation_space"]["state"].shape[0])
         self.num_actors = int(vec_env.env.num_envs)
@@ -118,19 +121,22 @@ class A2CAgent:
 
     # ---- rollout  [ref: a2c_common.py:670-774] -------------------------------------------------------
     def play_steps(self):
+        """T control steps of every env + policy inference, with no host sync and only static buffers across calls, so the whole
+        rollout is capturable in a CUDA graph (train_epoch)."""
         b, pol, T = self.buf, self.policy, self.T
         if self.obs is None:
-            self.obs = self.vec_env.reset()["obs"]["state"]
+            self.obs = self.vec_env.reset()["obs"]["state"].clone()       # static across epochs (graph replays read it in place)
+        obs, dones_u8 = self.obs, self.dones
         for n in range(T):
-            b["obses"][n].copy_(self.obs)
-            b["dones"][n].copy_(self.dones)
+            b["obses"][n].copy_(obs)
+            b["dones"][n].copy_(dones_u8)
             out = dict(actions=b["actions"][n], neglogpacs=b["neglogpacs"][n], values=b["values"][n], mus=b["mus"][n], sigmas=b["sigmas"][n])
             pol.act(b["obses"][n], out, row_offset=self.rank * self.num_actors)
             # preprocess_actions: clamp to [-1, 1]  [ref: a2c_common.py:1134-1144] (the stored action stays unclamped)
             obs_dict, rew, dones, infos = self.vec_env.step(torch.clamp(b["actions"][n], -1.0, 1.0))
-            self.obs = obs_dict["obs"]["state"]
+            obs = obs_dict["obs"]["state"]
             b["rewards"][n] = rew * self.cfg.reward_scale                    # DefaultRewardsShaper [ref: tr_helpers.py:33-42]
-            self.dones = dones.to(torch.uint8)
+            dones_u8 = dones.to(torch.uint8)
             # episode bookkeeping without host syncs  [ref: a2c_common.py:720-747]
             self.current_rewards += rew
             self.current_lengths += 1
@@ -138,6 +144,8 @@ class A2CAgent:
             self.episode_acc += torch.stack([(self.current_rewards * d).sum(), (self.current_lengths * d).sum(), d.sum()]).double()
             self.current_rewards *= 1.0 - d
             self.current_lengths *= 1.0 - d
+        self.obs.copy_(obs)
+        self.dones.copy_(dones_u8)
         pol.values(self.obs, self.last_values)
         gae(b["rewards"], b["values"].view(T, -1), b["dones"], self.last_values.view(-1), self.dones, self.cfg.gamma, self.cfg.tau,
             self.advs, self.returns)
@@ -171,18 +179,59 @@ class A2CAgent:
                 s = slice(i * mb, (i + 1) * mb)
                 if self.cfg.normalize_input and mini_ep == 0:
                     pol.obs_rms.update(ds["obs"][s])                    # train-mode forward updates the normaliser first
-                pol.minibatch_grad(ds["obs"][s], ds["actions"][s], ds["old_logp_actions"][s], ds["advantages"][s],
-                                   ds["old_values"][s], ds["returns"][s], ds["mu"][s], ds["sigma"][s])
+                args = (ds["obs"][s], ds["actions"][s], ds["old_logp_actions"][s], ds["advantages"][s], ds["old_values"][s],
+                        ds["returns"][s], ds["mu"][s], ds["sigma"][s])
+                if not self.multi_gpu and pol.tensor_cores and self.fused_step:
+                    pol.minibatch_step(*args)                            # gradient + clip + Adam + lr + re-pack: 3 launches
+                    continue
+                pol.minibatch_grad(*args)
                 if self.peer is not None:
                     self.peer(pol.grads)                                 # gradient + KL + loss stats in one span, over NVLink peer memory
                 elif self.multi_gpu:
                     dist.all_reduce(pol.grads, op=dist.ReduceOp.SUM)
                 pol.optimizer_step()
 
+    def _rollout_graph_ok(self) -> bool:
+        """The rollout is captured when the env is the classic fused engine (its kernels take a device-side step offset) and the
+        NaN probe can be deferred to one flag read per epoch."""
+        task = getattr(getattr(self.vec_env, "env", None), "_task", None)
+        eng = getattr(task, "engine", None)
+        return (self.use_cuda_graph and eng is not None and getattr(eng, "_buffers", None) is not None
+                and bool(eng._buffers.step_offset) and not getattr(task, "_live", False))
+
+    def _play(self):
+        if not self._rollout_graph_ok() or self.epoch_num < 2:
+            self.play_steps()                                            # eager (first epochs: reset, allocator warm-up)
+            return
+        task = self.vec_env.env._task
+        eng, pol, T = task.engine, self.policy, self.T
+        if self._graph_play is None:
+            probe, task._nan_probe = task._nan_probe, False              # no host sync inside the capture: checked after replay
+            saved = (eng.step_counter, eng.first_call, pol.sample_counter, task.step, task._calls)
+            pol._packed_dirty = True                                     # the captured rollout re-packs the weights on every replay
+            torch.cuda.synchronize(self.device)
+            l0 = _lib.launch_count()
+            self._graph_play = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph_play):
+                self.play_steps()
+                eng.advance_step_offset(T)
+                pol.advance_counter_offset(T)
+            self.graph_launches["play"] = _lib.launch_count() - l0        # kernels of this library inside one replay
+            # the capture ran the host code once without executing anything: rewind the host-side counters
+            eng.step_counter, eng.first_call, pol.sample_counter, task.step, task._calls = saved
+            self._probe_after_replay = probe
+        self._graph_play.replay()
+        eng.note_graph_replay(T)
+        pol.note_graph_replay(T)
+        task.step += T / task.cfg.horizon_length
+        task._calls += T
+        if self._probe_after_replay:
+            eng.check_finite()
+
     def train_epoch(self):
         t0 = time.perf_counter()
         with torch.no_grad():
-            self.play_steps()
+            self._play()
             t1 = time.perf_counter()
             if not self.use_cuda_graph:
                 self.update()
@@ -190,9 +239,11 @@ class A2CAgent:
                 self.update()                                            # eager warm-up (allocator, NCCL communicators)
             elif self._graph is None:
                 torch.cuda.synchronize(self.device)
+                l0 = _lib.launch_count()
                 self._graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self._graph):
                     self.update()
+                self.graph_launches["update"] = _lib.launch_count() - l0
                 self._graph.replay()
             else:
                 self._graph.replay()

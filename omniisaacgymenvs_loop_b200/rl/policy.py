@@ -99,6 +99,9 @@ class PolicyMLP:
         self.val_rms = RunningMeanStd(1, self.device)
         self.seed = int(seed)
         self.sample_counter = 0
+        # device-side part of the sampling counter (advanced inside captured rollout graphs, see A2CAgent)
+        self.counter_offset = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self._counter_offset_host = 0
         # tcgen05/TMEM kernels (TF32) when the obs fit their padded K tile; the fp32 SIMT kernels are the numerics reference
         self.tensor_cores = bool(tensor_cores) and self.D <= 15
         self._ws = None
@@ -160,6 +163,14 @@ class PolicyMLP:
         self.sample_counter += 1
         return o
 
+    def advance_counter_offset(self, calls: int) -> None:
+        """Inside a CUDA-graph capture containing `calls` act() launches: the next replay draws fresh Philox samples."""
+        self.counter_offset += calls
+
+    def note_graph_replay(self, calls: int) -> None:
+        self.sample_counter += calls
+        self._counter_offset_host += calls
+
     def values(self, obs: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """get_values: de-normalised value of `obs`  [ref: RLG/common/a2c_common.py:407-437]."""
         v = out if out is not None else torch.empty((obs.shape[0], 1), dtype=torch.float32, device=self.device)
@@ -181,7 +192,8 @@ class PolicyMLP:
         rc = fn(
             _lib.ptr(self.params), *extra, _lib.ptr(obs, torch.float32), ctypes.c_int32(self.D), _lib.ptr(self.obs_rms.mean32),
             _lib.ptr(self.obs_rms.var32), _lib.ptr(self.val_rms.mean32), _lib.ptr(self.val_rms.var32), ctypes.c_uint64(self.seed),
-            ctypes.c_uint64(self.sample_counter), ctypes.c_int64(row_offset), _lib.ptr(actions), _lib.ptr(neglogp), _lib.ptr(values),
+            ctypes.c_uint64(self.sample_counter - self._counter_offset_host), _lib.ptr(self.counter_offset), ctypes.c_int64(row_offset),
+            _lib.ptr(actions), _lib.ptr(neglogp), _lib.ptr(values),
             _lib.ptr(mus), _lib.ptr(sigmas), ctypes.c_int64(obs.shape[0]), _lib.stream())
         _lib.check(rc, "ppo_policy_forward_f32")
 
@@ -206,6 +218,24 @@ class PolicyMLP:
             rc = self.lib.ppo_minibatch_grad_f32(*common, ctypes.c_int64(M), _lib.stream())
         _lib.check(rc, "ppo_minibatch_grad_f32")
         return self.grads
+
+    def minibatch_step(self, obs, actions, old_neglogp, advantages, old_values, returns, mu, sigma) -> None:
+        """minibatch_grad + optimizer_step + pack for a single rank on the tensor-core path: 3 launches (T1, T2 and one
+        cooperative kernel that reduces, clips, applies Adam / the adaptive lr and re-packs the operand tiles)."""
+        M = obs.shape[0]
+        need = int(self.lib.ppo_train_tc_workspace_floats(ctypes.c_int64(M)))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.float32, device=self.device)
+        if self._packed_dirty:
+            self.pack()
+        rc = self.lib.ppo_minibatch_step_tc(
+            _lib.ptr(self.params), _lib.ptr(self.packed), _lib.ptr(obs, torch.float32), ctypes.c_int32(self.D), _lib.ptr(self.obs_rms.mean32),
+            _lib.ptr(self.obs_rms.var32), _lib.ptr(actions), _lib.ptr(old_neglogp), _lib.ptr(advantages), _lib.ptr(old_values),
+            _lib.ptr(returns), _lib.ptr(mu), _lib.ptr(sigma), ctypes.byref(self.loss_params), _lib.ptr(self.grads), _lib.ptr(self.scratch),
+            _lib.ptr(self._ws), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq), _lib.ptr(self._lr2), _lib.ptr(self._step2),
+            ctypes.byref(self.adam_params), ctypes.c_int64(M), _lib.stream())
+        _lib.check(rc, "ppo_minibatch_step_tc")
+        self._packed_dirty = False          # the fused tail re-packed the tiles from the updated parameters
 
     def optimizer_step(self) -> None:
         """trancate_gradients_and_step (+ the adaptive-KL lr update), on device."""

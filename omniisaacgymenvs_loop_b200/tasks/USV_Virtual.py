@@ -217,17 +217,25 @@ class USVVirtual:
         cnt = mask.sum()
         tot = (st * mask.view(-1, 1, 32)).sum(dim=(0, 2))                        # (USV_ST_COUNT,)
         new = tot / cnt.clamp(min=1.0) / self._max_episode_length
-        prev = self.extras.get("episode")
-        ep = {}
+        # values live in persistent 0-dim tensors (updated in place): a step without resets keeps the previous value, and a
+        # captured rollout graph keeps reading / writing the same storage across replays
+        ep = self.extras.get("episode")
+        if ep is None:
+            ep = self.extras["episode"] = {}
+        has = cnt > 0
+
+        def put(key, value):
+            if key not in ep:
+                ep[key] = torch.zeros((), dtype=torch.float32, device=self._device)
+            ep[key].copy_(torch.where(has, value, ep[key]))
+
         for k in self._stat_names():
-            v = new[E[prefix + k.upper()]]
-            ep[k] = torch.where(cnt > 0, v, prev[k]) if prev is not None else v
+            put(k, new[E[prefix + k.upper()]])                                    # [ref: SNAP/USV_Virtual.py:810-817]
         if self._live:
             # episode outcome events: plain means over the envs being reset, read BEFORE the reset clears the latches
             # [ref: OIGE/tasks/USV_Virtual.py:1508-1516,1581-1596]; "g_safe_mean" is declared but never fed (:497 commented out)
             oc = self.engine.bstate[:, E["USV_BS_OUTCOME"], :].reshape(-1).view(torch.int32)
             for k, bit in (("success", 0), ("collision", 1)):
-                v = (((oc >> bit) & 1).float() * mask).sum() / cnt.clamp(min=1.0)
-                ep[k] = torch.where(cnt > 0, v, prev[k]) if prev is not None else v
-            ep["g_safe_mean"] = torch.zeros((), device=self._device)
-        self.extras["episode"] = ep                                               # [ref: SNAP/USV_Virtual.py:810-817]
+                put(k, (((oc >> bit) & 1).float() * mask).sum() / cnt.clamp(min=1.0))
+            if "g_safe_mean" not in ep:
+                ep["g_safe_mean"] = torch.zeros((), dtype=torch.float32, device=self._device)

@@ -217,3 +217,40 @@ def test_peer_allreduce_world1_and_abi():
     assert torch.equal(out, x) and int(ar.seq.item()) == 5 + 8
     ar.check()
     ar.close()
+
+
+def test_fused_minibatch_step_equals_unfused():
+    """ppo_minibatch_step_tc (T1 + T2 + one cooperative reduce / clip / Adam / lr / re-pack kernel) vs the unfused sequence
+    minibatch_grad -> optimizer_step -> pack on the same tensor-core kernels, eager and inside a CUDA graph."""
+    torch.manual_seed(3)
+    for M in (8192, 1000):
+        a, b = PolicyMLP(D, DEV, seed=5, tensor_cores=True), PolicyMLP(D, DEV, seed=5, tensor_cores=True)
+        obs = torch.randn((M, D), device=DEV) * 2
+        for p in (a, b):
+            p.obs_rms.update(obs[:150])
+        inf = a.act(obs)
+        act = (inf["actions"] + 0.2 * torch.randn((M, 2), device=DEV)).contiguous()
+        old_nlp = (inf["neglogpacs"] + 0.1 * torch.randn(M, device=DEV)).contiguous()
+        adv, old_v, ret = torch.randn(M, device=DEV), torch.randn(M, device=DEV) * 0.3, torch.randn(M, device=DEV) * 0.5
+        mu_a, sg_a, mu_b, sg_b = inf["mus"].clone(), inf["sigmas"].clone(), inf["mus"].clone(), inf["sigmas"].clone()
+        for it in range(4):
+            a.minibatch_grad(obs, act, old_nlp, adv, old_v, ret, mu_a, sg_a)
+            a.optimizer_step()
+            a.pack()
+            b.minibatch_step(obs, act, old_nlp, adv, old_v, ret, mu_b, sg_b)
+            # identical T1/T2 kernels; only the summation order of the gradient norm differs (clip coefficient ~1e-7 relative)
+            assert_close(b.params, a.params, 1e-6, 1e-8, f"params M={M} it={it}")
+            assert_close(b.exp_avg, a.exp_avg, 1e-5, 1e-10, "exp_avg"); assert_close(b.exp_avg_sq, a.exp_avg_sq, 1e-5, 1e-14, "exp_avg_sq")
+            assert_close(b.packed, a.packed, 1e-6, 1e-8, "packed tiles")
+            sa, sb = a.stats(), b.stats()
+            assert all(abs(sa[k] - sb[k]) <= 1e-5 * abs(sa[k]) + 1e-7 for k in sa), (sa, sb)
+            assert int(a.step) == int(b.step) == it + 1 and torch.equal(mu_a, mu_b)
+    # capturable (cooperative launch inside a graph)
+    g = torch.cuda.CUDAGraph()
+    before = b.params.clone()
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g):
+        b.minibatch_step(obs, act, old_nlp, adv, old_v, ret, mu_b, sg_b)
+    g.replay(); g.replay()
+    torch.cuda.synchronize()
+    assert int(b.step) == 6 and not torch.equal(before, b.params) and torch.isfinite(b.params).all()
