@@ -132,6 +132,13 @@ class UsvEnvConfig:
     retarget_on_reset: bool = False
     spawn_min_dist: float = 0.3
     spawn_max_dist: float = 12.0
+    # optional linear curriculum on the task's `step` (= control steps / horizon_length)  [ref: SNAP/USV_capture_xy.py:231-275,346-380]
+    spawn_curriculum: bool = False
+    spawn_curriculum_min_dist: float = 0.2
+    spawn_curriculum_max_dist: float = 3.0
+    spawn_curriculum_kill_dist: float = 30.0
+    spawn_curriculum_warmup: int = 250
+    spawn_curriculum_end: int = 1000
     spawn_about_origin: bool = False   # live task (Variant B): annulus around the env origin, not the target
     retarget_after_spawn: bool = False # live reset order: spawn around the old target, re-draw the target last
     reset_pose_external: bool = False  # scene replay: the host writes pose / velocity / target of resetting envs
@@ -182,6 +189,21 @@ class UsvEnvConfig:
         return dataclasses.replace(
             self, use_force_disturbance=True, use_const_force=True, use_sin_force=True, use_torque_disturbance=True,
             use_const_torque=True, use_sin_torque=True, noise_pos=True, mass_rand=True, drag_rand=True, thr_rand=True)
+
+    def curriculum(self, step: float):
+        """(min_spawn_dist, max_spawn_dist, kill_dist) in force at curriculum step `step`: the reference interpolates linearly between
+        the curriculum values and the final ones from `warmup` to `end` (python doubles, as the reference)."""
+        if not self.spawn_curriculum:
+            return self.spawn_min_dist, self.spawn_max_dist, self.kill_dist
+        w, e = self.spawn_curriculum_warmup, self.spawn_curriculum_end
+        if step < w:
+            return self.spawn_curriculum_min_dist, self.spawn_curriculum_max_dist, self.spawn_curriculum_kill_dist
+        if step > e:
+            return self.spawn_min_dist, self.spawn_max_dist, self.kill_dist
+        r = (step - w) / (e - w)
+        lerp = lambda a, b: r * (b - a) + a
+        return (lerp(self.spawn_curriculum_min_dist, self.spawn_min_dist), lerp(self.spawn_curriculum_max_dist, self.spawn_max_dist),
+                lerp(self.spawn_curriculum_kill_dist, self.kill_dist))
 
     @property
     def lag_alpha(self) -> float:
@@ -277,7 +299,12 @@ class UsvEnvConfig:
                                             kill_after_n_steps_in_tolerance=self.kill_after_n_steps_in_tolerance,
                                             goal_random_position=self.goal_random_position, max_spawn_dist=self.spawn_max_dist,
                                             min_spawn_dist=self.spawn_min_dist, kill_dist=self.kill_dist, boundary_cost=self.boundary_cost,
-                                            goal_reward=self.goal_reward, time_reward=self.time_reward),
+                                            goal_reward=self.goal_reward, time_reward=self.time_reward,
+                                            spawn_curriculum=self.spawn_curriculum, spawn_curriculum_min_dist=self.spawn_curriculum_min_dist,
+                                            spawn_curriculum_max_dist=self.spawn_curriculum_max_dist,
+                                            spawn_curriculum_kill_dist=self.spawn_curriculum_kill_dist,
+                                            spawn_curriculum_warmup=self.spawn_curriculum_warmup,
+                                            spawn_curriculum_end=self.spawn_curriculum_end),
                     "reward_parameters": dict(name="CaptureXY", reward_mode=inv_mode[self.reward_mode], position_scale=self.position_scale,
                                               exponential_reward_coeff=self.exponential_reward_coeff, align_la1=self.align_la1,
                                               align_la2=self.align_la2, align_la3=self.align_la3),
@@ -348,6 +375,9 @@ class UsvEnvConfig:
             goal_reward=tp.get("goal_reward", 100.0), time_reward=tp.get("time_reward", -0.1),
             goal_random_position=tp.get("goal_random_position", 0.0),
             spawn_min_dist=tp.get("min_spawn_dist", 0.5), spawn_max_dist=tp.get("max_spawn_dist", 11.0),
+            spawn_curriculum=bool(tp.get("spawn_curriculum", False)), spawn_curriculum_min_dist=tp.get("spawn_curriculum_min_dist", 0.2),
+            spawn_curriculum_max_dist=tp.get("spawn_curriculum_max_dist", 3.0), spawn_curriculum_kill_dist=tp.get("spawn_curriculum_kill_dist", 30.0),
+            spawn_curriculum_warmup=int(tp.get("spawn_curriculum_warmup", 250)), spawn_curriculum_end=int(tp.get("spawn_curriculum_end", 1000)),
             reward_mode=REWARD_MODES[str(rp.get("reward_mode", "exponential")).lower()],
             position_scale=rp.get("position_scale", 1.0), exponential_reward_coeff=rp.get("exponential_reward_coeff", 0.25),
             align_la1=rp.get("align_la1", 0.02), align_la2=rp.get("align_la2", -10.0), align_la3=rp.get("align_la3", -0.1),

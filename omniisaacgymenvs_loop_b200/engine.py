@@ -49,6 +49,7 @@ class FusedUsvEnv:
         # (advance_step_offset); the kernels see  p.step_counter + *step_offset  == self.step_counter  at every launch
         self.step_offset = torch.zeros(1, dtype=torch.int64, device=self.device)
         self._step_offset_host = 0
+        self.curriculum_step = 0.0       # the task's `step` (control steps / horizon_length); drives the optional spawn / kill curriculum
         self.first_call = True
         # per-episode constants start at their nominal values (reset_idx rewrites them)
         c = self.consts
@@ -148,6 +149,10 @@ class FusedUsvEnv:
         p.first_call = int(self.first_call)
         # live action path: the initial bias applies to the first N control steps only  [ref: OIGE/tasks/USV_Virtual.py:1070-1077]
         p.action_bias = self.cfg.action_bias if self.step_counter < self.cfg.action_bias_steps else 0.0
+        if self.cfg.spawn_curriculum:
+            # get_spawns(step) runs in pre_physics_step, update_kills(step) after calculate_metrics has advanced `step` by 1/horizon
+            p.spawn_min_dist, p.spawn_max_dist, _ = self.cfg.curriculum(self.curriculum_step)
+            p.kill_dist = self.cfg.curriculum(self.curriculum_step + 1.0 / self.cfg.horizon_length)[2]
         return p
 
     def advance_step_offset(self, steps: int) -> None:

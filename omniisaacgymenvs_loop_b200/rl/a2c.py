@@ -47,6 +47,7 @@ class PPOConfig:
     normalize_advantage: bool = True
     reward_scale: float = 0.01
     max_epochs: int = 3000
+    games_to_track: int = 100
     seed: int = 42
 
     @classmethod
@@ -65,6 +66,37 @@ def gae(rewards, values, dones, last_values, last_dones, gamma, tau, adv, ret):
                                 _lib.ptr(last_dones, torch.uint8), ctypes.c_float(gamma), ctypes.c_float(tau), _lib.ptr(adv), _lib.ptr(ret),
                                 ctypes.c_int32(T), ctypes.c_int64(n), _lib.stream())
     _lib.check(rc, "ppo_gae_f32")
+
+
+class AverageMeter:
+    """rl_games' windowed running mean [ref: RLG/algos_torch/torch_ext.py:281-307] with `current_size` kept on the device, so that
+    update() needs no host sync (the reference slices the finished envs with `dones.nonzero()` first).  update(sum, count) takes
+    the sum and the number of the values finishing at this step; the arithmetic is the reference's:
+        size = clip(count, 0, max); old = min(max - size, current); mean = (mean*old + new_mean*size) / (old + size)."""
+
+    def __init__(self, max_size: int, device):
+        self.max_size = float(max_size)
+        self.mean = torch.zeros((), dtype=torch.float32, device=device)
+        self.current_size = torch.zeros((), dtype=torch.float32, device=device)
+
+    def update(self, value_sum: torch.Tensor, count: torch.Tensor) -> None:
+        has = count > 0
+        new_mean = value_sum / count.clamp(min=1.0)
+        size = count.clamp(0.0, self.max_size)
+        old = torch.minimum(self.max_size - size, self.current_size)
+        tot = old + size
+        self.mean.copy_(torch.where(has, (self.mean * old + new_mean * size) / tot.clamp(min=1.0), self.mean))
+        self.current_size.copy_(torch.where(has, tot, self.current_size))
+
+    def clear(self) -> None:
+        self.mean.zero_()
+        self.current_size.zero_()
+
+    def get_mean(self) -> float:
+        return float(self.mean)
+
+    def __len__(self) -> int:
+        return int(self.current_size)
 
 
 class A2CAgent:
@@ -114,6 +146,11 @@ class A2CAgent:
         self.current_lengths = torch.zeros(N, **f32)
         # finished-episode accumulators: [sum of returns, sum of lengths, count] (all-reduced once per epoch)
         self.episode_acc = torch.zeros(3, dtype=torch.float64, device=self.device)
+        # the reference's meters: mean over the last `games_to_track` finished episodes  [ref: a2c_common.py:214-216,739-747]
+        self.game_rewards = AverageMeter(cfg.games_to_track, self.device)
+        self.game_lengths = AverageMeter(cfg.games_to_track, self.device)
+        # RLGPUAlgoObserver: extras['episode'] of every step, averaged per print  [ref: OIGE/utils/rlgames/rlgames_utils.py:51-99]
+        self.ep_info_sum, self.ep_info_n = {}, torch.zeros((), dtype=torch.float32, device=self.device)
         self.obs = None
         self.epoch_num = 0
         self.frame = 0
@@ -141,7 +178,17 @@ class A2CAgent:
             self.current_rewards += rew
             self.current_lengths += 1
             d = dones.to(torch.float32)
-            self.episode_acc += torch.stack([(self.current_rewards * d).sum(), (self.current_lengths * d).sum(), d.sum()]).double()
+            rs, ls, cnt = (self.current_rewards * d).sum(), (self.current_lengths * d).sum(), d.sum()
+            self.episode_acc += torch.stack([rs, ls, cnt]).double()
+            self.game_rewards.update(rs, cnt)
+            self.game_lengths.update(ls, cnt)
+            ep = infos.get("episode") if isinstance(infos, dict) else None
+            if ep:                                                       # observer.process_infos
+                for k, v in ep.items():
+                    if k not in self.ep_info_sum:
+                        self.ep_info_sum[k] = torch.zeros((), dtype=torch.float32, device=self.device)
+                    self.ep_info_sum[k] += v
+                self.ep_info_n += 1
             self.current_rewards *= 1.0 - d
             self.current_lengths *= 1.0 - d
         self.obs.copy_(obs)
@@ -197,7 +244,7 @@ class A2CAgent:
         task = getattr(getattr(self.vec_env, "env", None), "_task", None)
         eng = getattr(task, "engine", None)
         return (self.use_cuda_graph and eng is not None and getattr(eng, "_buffers", None) is not None
-                and bool(eng._buffers.step_offset) and not getattr(task, "_live", False))
+                and bool(eng._buffers.step_offset) and not getattr(task, "_live", False) and not eng.cfg.spawn_curriculum)
 
     def _play(self):
         if not self._rollout_graph_ok() or self.epoch_num < 2:
@@ -260,6 +307,15 @@ class A2CAgent:
         s, l, c = acc.tolist()
         return (s / c, l / c, int(c)) if c > 0 else (float("nan"), float("nan"), 0)
 
+    def episode_infos(self) -> dict:
+        """Episode/<key>: the mean of extras['episode'][key] over the steps since the last call (RLGPUAlgoObserver.after_print_stats)."""
+        n = float(self.ep_info_n)
+        out = {k: float(v) / n for k, v in self.ep_info_sum.items()} if n > 0 else {}
+        for v in self.ep_info_sum.values():
+            v.zero_()
+        self.ep_info_n.zero_()
+        return out
+
     def train(self, max_epochs: Optional[int] = None, log_every: int = 10, log=print):
         max_epochs = max_epochs or self.cfg.max_epochs
         while self.epoch_num < max_epochs:
@@ -272,7 +328,11 @@ class A2CAgent:
                 st = self.policy.stats()
                 if self.rank == 0 and log:
                     log(f"epoch {self.epoch_num} frames {self.frame} reward {rew:.3f} len {length:.1f} ({cnt} eps) "
+                        f"meter[{len(self.game_rewards)}] {self.game_rewards.get_mean():.3f}/{self.game_lengths.get_mean():.1f} "
                         f"kl {st['kl']:.5f} lr {st['lr']:.2e} a_loss {st['a_loss']:.4f} c_loss {st['c_loss']:.4f}")
+                    infos = self.episode_infos()
+                    if infos:
+                        log("  Episode/ " + " ".join(f"{k}={v:.4g}" for k, v in infos.items()))
         return self.mean_reward
 
     # ---- checkpoints: the reference's .pth schema  [ref: a2c_common.py:590-654] --------------------------

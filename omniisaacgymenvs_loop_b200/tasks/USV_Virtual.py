@@ -176,6 +176,7 @@ class USVVirtual:
     def post_physics_step(self):
         """ONE fused launch: reset-if-flagged, action path, sub-steps, observation, reward + penalties, kills, progress
         [ref: OIGE/tasks/base/rl_task.py:283-303]."""
+        self.engine.curriculum_step = self.step
         self.engine.step(self.actions)
         self.step += 1 / self.cfg.horizon_length                    # [ref: SNAP/USV_Virtual.py:838]
         self._calls += 1

@@ -606,6 +606,40 @@ def tier3():
     print("tier3_tasks.npz")
 
 
+def classic_curriculum():
+    """Spawn-distance / kill-distance curriculum of the classic CaptureXYTask (rows A18, A19: optional, linear in `step`)
+    [SNAP/USV_capture_xy.py:231-275,330-394]."""
+    core, rew, cap = ref_shim.load_classic()
+    cfg = ref_shim.classic_yaml()
+    tp = dict(cfg["env"]["task_parameters"], spawn_curriculum=True, spawn_curriculum_min_dist=0.2, spawn_curriculum_max_dist=3.0,
+              spawn_curriculum_kill_dist=30.0, spawn_curriculum_warmup=250, spawn_curriculum_end=1000, min_spawn_dist=0.5,
+              max_spawn_dist=11.0, kill_dist=20.0)
+    n = 64
+    with ref_shim.quiet():
+        task = cap.CaptureXYTask(tp, cfg["env"]["reward_parameters"], n, "cpu")
+    steps = [0.0, 100.0, 249.9375, 250.0, 400.5, 625.0, 1000.0, 1000.0625, 1500.0]
+    ids = torch.arange(n)
+    dist = torch.linspace(15.0, 35.0, n)
+    out = dict(steps=torch.tensor(steps, dtype=torch.float64), dist=dist, params=torch.tensor([0.2, 3.0, 30.0, 250, 1000, 0.5, 11.0, 20.0], dtype=torch.float64))
+    U, R, D = [], [], []
+    for st in steps:
+        torch.manual_seed(int(st * 16))
+        u = torch.rand(n)                                        # the first draw of get_spawns is r
+        torch.manual_seed(int(st * 16))
+        with ref_shim.quiet():
+            pos, _ = task.get_spawns(ids, torch.zeros((n, 3)), torch.zeros((n, 4)), step=st)
+        R.append(torch.norm(pos[:, :2] - task._target_positions, dim=1))
+        U.append(u)
+        task.position_dist = dist.clone()
+        task.current_state = {"linear_velocity": torch.ones((n, 2))}
+        task._goal_reached[:] = 0
+        with ref_shim.quiet():
+            D.append(task.update_kills(st).clone())
+    out.update(u=torch.stack(U), r=torch.stack(R), die=torch.stack(D))
+    np.savez(os.path.join(OUT, "classic_curriculum.npz"), **t2n(out))
+    print("classic_curriculum.npz")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)
@@ -617,6 +651,7 @@ def main():
     variant_b()
     live_virtual()
     tier3()
+    classic_curriculum()
 
 
 if __name__ == "__main__":

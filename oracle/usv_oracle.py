@@ -245,6 +245,13 @@ class EnvConfig:
     retarget_on_reset: bool = False
     spawn_min_dist: float = 0.3
     spawn_max_dist: float = 12.0
+    spawn_curriculum: bool = False
+    spawn_curriculum_min_dist: float = 0.2
+    spawn_curriculum_max_dist: float = 3.0
+    spawn_curriculum_kill_dist: float = 30.0
+    spawn_curriculum_warmup: int = 250
+    spawn_curriculum_end: int = 1000
+    horizon_length: int = 16
     spawn_about_origin: bool = False
     retarget_after_spawn: bool = False
     reset_pose_external: bool = False
@@ -313,6 +320,20 @@ class EnvConfig:
             mass_rand=True, drag_rand=True, thr_rand=True, thr_rand_frac=0.5, envs_per_row=0)
 
 
+def curriculum(c: "EnvConfig", step: float):
+    """(rmin, rmax, kill_dist) at curriculum step `step`  [SNAP/USV_capture_xy.py:238-258 (kill), :346-380 (spawn)]."""
+    if not c.spawn_curriculum:
+        return c.spawn_min_dist, c.spawn_max_dist, c.kill_dist
+    if step < c.spawn_curriculum_warmup:
+        return c.spawn_curriculum_min_dist, c.spawn_curriculum_max_dist, c.spawn_curriculum_kill_dist
+    if step > c.spawn_curriculum_end:
+        return c.spawn_min_dist, c.spawn_max_dist, c.kill_dist
+    r = (step - c.spawn_curriculum_warmup) / (c.spawn_curriculum_end - c.spawn_curriculum_warmup)
+    return (r * (c.spawn_min_dist - c.spawn_curriculum_min_dist) + c.spawn_curriculum_min_dist,
+            r * (c.spawn_max_dist - c.spawn_curriculum_max_dist) + c.spawn_curriculum_max_dist,
+            r * (c.kill_dist - c.spawn_curriculum_kill_dist) + c.spawn_curriculum_kill_dist)
+
+
 def mass_coupling(c: "EnvConfig", mass: torch.Tensor):
     """_apply_mass_driven_coupling  [OIGE/tasks/USV_Virtual.py:988-1040]: mass -> r in [0,1] -> (k_drag, thruster scale, k_Iz)."""
     denom = max(c.couple_mass_max - c.mass_base, 1e-6)
@@ -363,6 +384,7 @@ class ClassicEnvOracle:
         self.reset_buf = torch.ones(n, dtype=torch.long)       # [SNAP/USV_Virtual.py:342-344]
         self.progress_buf = torch.zeros(n, dtype=torch.long)
         self.step_counter = 0
+        self.curriculum_step = 0.0           # task `step` = control steps / horizon_length
         self.first_call = True
         self.stats = {}
         if cfg.envs_per_row > 0:
@@ -432,7 +454,10 @@ class ClassicEnvOracle:
             self.thr_mult_right[ids] = sthr
             self.k_iz[ids] = kiz
         if not c.reset_pose_external:
-            sr = r0[:, 2] * (c.spawn_max_dist - c.spawn_min_dist) + c.spawn_min_dist
+            rmin, rmax, _ = curriculum(c, self.curriculum_step)
+            # the kernel receives rmin / rmax as fp32 parameters and forms (rmax - rmin) in fp32
+            rmin32, rmax32 = torch.tensor(rmin, dtype=F32), torch.tensor(rmax, dtype=F32)
+            sr = r0[:, 2] * (rmax32 - rmin32) + rmin32
             th = r0[:, 3] * 2 * math.pi
 
             def spawn():                                                        # get_spawns  [SNAP/USV_capture_xy.py:330-394]
@@ -568,7 +593,9 @@ class ClassicEnvOracle:
         self.prev_asum = pen["asum"]
         self.first_call = False
         rew = out["reward"] + pen["total"]
-        die = capture_xy_kills(c, aux["d"], out["speed"], self.goal_reached)
+        kill_dist = curriculum(c, self.curriculum_step + 1.0 / c.horizon_length)[2]      # update_kills(step) after `step += 1/horizon`
+        die = capture_xy_kills(c, aux["d"], out["speed"], self.goal_reached, kill_dist)
+        self.curriculum_step += 1.0 / c.horizon_length
         ones = torch.ones_like(self.reset_buf)
         self.reset_buf = torch.where(self.progress_buf >= c.max_episode_length - 1, ones, die)   # is_done
         obs = torch.clamp(obs, -c.clip_obs, c.clip_obs)                     # _process_data
@@ -666,9 +693,9 @@ def penalties(c: EnvConfig, state, actions, prev_w, prev_asum, first_call: bool)
 
 
 # A18  [SNAP/USV_capture_xy.py:231-275]
-def capture_xy_kills(c: EnvConfig, d, speed, goal_reached):
+def capture_xy_kills(c: EnvConfig, d, speed, goal_reached, kill_dist=None):
     die = torch.zeros_like(goal_reached, dtype=torch.long)
     ones = torch.ones_like(goal_reached, dtype=torch.long)
-    die = torch.where(d > c.kill_dist, ones, die)
+    die = torch.where(d > (c.kill_dist if kill_dist is None else kill_dist), ones, die)
     die = torch.where((goal_reached >= c.kill_after_n_steps_in_tolerance) & (speed < c.goal_speed_gate), ones, die)
     return die

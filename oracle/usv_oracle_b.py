@@ -365,7 +365,8 @@ class LiveEnvOracle(ClassicEnvOracle):
             self.com[ids] = torch.tensor(self.priv.com_base, dtype=F32) + (rc[:, 0:3] * 2 - 1) * torch.tensor(self.priv.com_disp, dtype=F32)
         # scene: spawn point of this reset (same draw as ClassicEnvOracle.reset_idx) and the CURRENT target
         r0 = torch.from_numpy(philox.uniform4(c.seed, gids, step, philox.RS_RESET[0]))
-        sr = r0[:, 2] * (c.spawn_max_dist - c.spawn_min_dist) + c.spawn_min_dist
+        rmin32, rmax32 = torch.tensor(c.spawn_min_dist, dtype=F32), torch.tensor(c.spawn_max_dist, dtype=F32)
+        sr = r0[:, 2] * (rmax32 - rmin32) + rmin32                       # fp32 parameters, as the kernels (and ClassicEnvOracle) form it
         th = r0[:, 3] * 2 * math.pi
         start = torch.stack([sr * torch.cos(th), sr * torch.sin(th)], 1)
         if not c.spawn_about_origin:

@@ -169,3 +169,23 @@ def test_graphed_rollout_and_update_equal_eager():
     act = torch.zeros((1024, 2), device=DEV)
     oa, ob = a.vec_env.step(act), b.vec_env.step(act)
     assert torch.equal(oa[0]["obs"]["state"], ob[0]["obs"]["state"]) and torch.equal(oa[1], ob[1])
+
+
+def test_vecenv_curriculum_free_running_vs_oracle():
+    """The task-level `step` (control steps / horizon_length) drives the spawn / kill curriculum through USVVirtual."""
+    cfg = UsvEnvConfig(num_envs=512, max_episode_length=6, seed=9, spawn_curriculum=True, spawn_curriculum_min_dist=0.2,
+                       spawn_curriculum_max_dist=2.0, spawn_curriculum_kill_dist=3.0, spawn_curriculum_warmup=1, spawn_curriculum_end=2,
+                       spawn_min_dist=3.0, spawn_max_dist=9.0, kill_dist=15.0)
+    env = make_env(cfg.to_task_cfg(), DEV, seed=9)
+    orc = O.ClassicEnvOracle(oracle_cfg(cfg), 512)
+    obs = env.reset()
+    o_obs, _, _ = orc.step(torch.zeros((512, 2)))
+    assert_close(obs["obs"]["state"], o_obs, 1e-5, 2e-5, "reset obs")
+    g = torch.Generator().manual_seed(4)
+    for k in range(48):                                               # crosses warm-up (step 1) and end (step 2) of the curriculum
+        act = torch.rand((512, 2), generator=g) * 2 - 1
+        od, rew, done, _ = env.step(act.to(DEV))
+        o_obs, o_rew, o_done = orc.step(act)
+        assert torch.equal(done.cpu(), o_done), k
+        assert_close(od["obs"]["state"], o_obs, 1e-4, 2e-3, f"obs {k}")
+    assert abs(env.env._task.step - orc.curriculum_step) < 1e-9 and orc.curriculum_step > 3.0

@@ -148,12 +148,16 @@ def _lockstep(cfg, n, steps, seed=5, sync=True, collect_stats=False):
         yield k, env, orc, (obs.cpu(), rew.cpu(), done.cpu()), (o_obs, o_rew, o_done)
 
 
-@pytest.mark.parametrize("variant", ["classic", "full_dr"])
+@pytest.mark.parametrize("variant", ["classic", "full_dr", "curriculum"])
 def test_fused_step_vs_oracle_lockstep(variant):
     """Every step starts from identical state (oracle state pushed to the GPU): obs/reward 1e-5, done bit-exact,
     reset index set bit-exact, next state 1e-5."""
     cfg = UsvEnvConfig(max_episode_length=12, kill_dist=12.5)
     cfg = cfg.full_dr() if variant == "full_dr" else cfg
+    if variant == "curriculum":      # spawn annulus and kill distance move every control step (knees at step 0.25 and 0.75)
+        cfg = dataclasses.replace(cfg, spawn_curriculum=True, spawn_curriculum_min_dist=0.2, spawn_curriculum_max_dist=3.0,
+                                  spawn_curriculum_kill_dist=4.0, spawn_curriculum_warmup=0.25, spawn_curriculum_end=0.75,
+                                  spawn_min_dist=2.0, spawn_max_dist=11.0, max_episode_length=5)
     n = 4096 + 37                                                   # ragged tail block
     n_done = 0
     for k, env, orc, (obs, rew, done), (o_obs, o_rew, o_done) in _lockstep(cfg, n, 16):

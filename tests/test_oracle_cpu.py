@@ -263,3 +263,22 @@ def test_fp32_substeps_vs_float64_integration():
                       ("vy", env.vel[:, 1]), ("r", env.r)):
         err = np.abs(got.double().numpy() - ref[name])
         assert err.max() < 2e-4, (name, err.max())
+
+
+def test_spawn_and_kill_curriculum_vs_reference(golden):
+    """A18/A19 optional curriculum: spawn annulus and kill distance as functions of the task `step`, against the reference's
+    get_spawns / update_kills driven at 9 steps around the warm-up / end knees; the product's host function must agree too."""
+    import dataclasses
+    from omniisaacgymenvs_loop_b200.config import UsvEnvConfig
+    G = golden("classic_curriculum")
+    cmin, cmax, ckill, warm, end, rmin, rmax, kill = G["params"].tolist()
+    kw = dict(spawn_curriculum=True, spawn_curriculum_min_dist=cmin, spawn_curriculum_max_dist=cmax, spawn_curriculum_kill_dist=ckill,
+              spawn_curriculum_warmup=int(warm), spawn_curriculum_end=int(end), spawn_min_dist=rmin, spawn_max_dist=rmax, kill_dist=kill)
+    c, pc = dataclasses.replace(O.EnvConfig(), **kw), UsvEnvConfig(**kw)
+    for k, st in enumerate(G["steps"].tolist()):
+        lo, hi, kd = O.curriculum(c, st)
+        assert (lo, hi, kd) == pc.curriculum(st)
+        r = T(G["u"][k]) * (hi - lo) + lo
+        assert torch.allclose(r, T(G["r"][k]), rtol=1e-5, atol=1e-5), (st, lo, hi)
+        assert torch.equal((T(G["dist"]) > kd).long(), T(G["die"][k])), (st, kd)
+    assert O.curriculum(dataclasses.replace(c, spawn_curriculum=False), 10.0) == (rmin, rmax, kill)

@@ -81,3 +81,23 @@ def test_gae_oracle_vs_reference(golden):
 def test_normal_eps_statistics():
     e = P.normal_eps(1234, np.arange(200000), 7)
     assert abs(float(e.mean())) < 5e-3 and abs(float(e.std()) - 1.0) < 5e-3 and torch.isfinite(e).all()
+
+
+def test_average_meter_matches_reference_rule():
+    """A2CAgent.game_rewards / game_lengths: rl_games' AverageMeter arithmetic [RLG/algos_torch/torch_ext.py:281-307] with the
+    window size kept on the device (no `dones.nonzero()` sync)."""
+    import numpy as np
+    import torch
+    from omniisaacgymenvs_loop_b200.rl.a2c import AverageMeter
+    meter, mean, cur = AverageMeter(100, "cpu"), torch.zeros(1), 0
+    g = torch.Generator().manual_seed(0)
+    for k in range(300):
+        n = int(torch.randint(0, 70, (1,), generator=g))
+        v = torch.randn(n, generator=g)
+        meter.update(v.sum(), torch.tensor(float(n)))
+        if n:                                        # the reference's update(), restated
+            size = int(np.clip(n, 0, 100)); old = min(100 - size, cur); cur = old + size
+            mean = (mean * old + v.mean() * size) / cur
+        assert abs(meter.get_mean() - float(mean)) < 1e-5 and len(meter) == cur
+    meter.clear()
+    assert len(meter) == 0 and meter.get_mean() == 0.0

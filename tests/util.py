@@ -49,6 +49,7 @@ def push_oracle_state(orc, env):
     env.set_field("USV_S_PROGRESS", orc.progress_buf.to(torch.int32).to(dev))
     env.reset_buf.copy_(orc.reset_buf.to(dev))
     env.step_counter = orc.step_counter
+    env.curriculum_step = getattr(orc, "curriculum_step", 0.0)
     env.first_call = orc.first_call
 
 
