@@ -312,3 +312,56 @@ class FusedUsvLiveEnv(FusedUsvEnv):
     def rollout(self, *a, **k):
         raise NotImplementedError("the multi-step rollout kernel exists for the classic task only (the live task's "
                                   "prev_potential quirk needs a grid-wide flag between control steps)")
+
+
+class HostStepper:
+    """Host-buffer stepping with the PCIe copies overlapped: `submit(k)` takes one control step's actions from pinned host memory
+    and delivers that step's observations / rewards / dones into pinned host memory, asynchronously, on three streams (copy-in,
+    compute, copy-out) with `depth` device staging slots, so the host->device copy of step k+1 and the device->host copy of step k
+    run while the kernel of the step in between executes.  Dones travel as uint8 (what rl_games stores, [ref: RLG/common/
+    a2c_common.py:454]) instead of the int64 reset_buf.  Results of a submit are valid after `wait(ticket)` / `synchronize()`."""
+
+    def __init__(self, env: FusedUsvEnv, depth: int = 2):
+        self.env, self.depth = env, int(depth)
+        n, dev = env.num_envs, env.device
+        od = env.obs.shape[1]
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.d_act = [torch.empty((n, 2), **f32) for _ in range(depth)]
+        self.d_obs = [torch.empty((n, od), **f32) for _ in range(depth)]
+        self.d_rew = [torch.empty(n, **f32) for _ in range(depth)]
+        self.d_done = [torch.empty(n, dtype=torch.uint8, device=dev) for _ in range(depth)]
+        self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        self.ev_in = [torch.cuda.Event() for _ in range(depth)]
+        self.ev_step = [torch.cuda.Event() for _ in range(depth)]
+        self.ev_out = [torch.cuda.Event() for _ in range(depth)]
+        self.k = 0
+
+    def submit(self, h_act: torch.Tensor, h_obs: torch.Tensor, h_rew: torch.Tensor, h_done: torch.Tensor) -> int:
+        """All four tensors are pinned host tensors: actions (N,2) fp32 in; obs (N,D) fp32, rew (N,) fp32, done (N,) uint8 out."""
+        slot = self.k % self.depth
+        cur = torch.cuda.current_stream(self.env.device)
+        if self.k >= self.depth:
+            self.s_in.wait_event(self.ev_step[slot])      # the step that last read d_act[slot] has run
+            cur.wait_event(self.ev_out[slot])             # ... and its outputs have left d_obs / d_rew / d_done[slot]
+        with torch.cuda.stream(self.s_in):
+            self.d_act[slot].copy_(h_act, non_blocking=True)
+            self.ev_in[slot].record(self.s_in)
+        cur.wait_event(self.ev_in[slot])
+        self.env.step(self.d_act[slot], obs=self.d_obs[slot], rew=self.d_rew[slot])
+        self.d_done[slot].copy_(self.env.reset_buf)       # int64 -> uint8 on the device
+        self.ev_step[slot].record(cur)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(self.ev_step[slot])
+            h_obs.copy_(self.d_obs[slot], non_blocking=True)
+            h_rew.copy_(self.d_rew[slot], non_blocking=True)
+            h_done.copy_(self.d_done[slot], non_blocking=True)
+            self.ev_out[slot].record(self.s_out)
+        self.k += 1
+        return self.k - 1
+
+    def wait(self, ticket: int) -> None:
+        if self.k - ticket <= self.depth:                 # still tracked by a slot event
+            self.ev_out[ticket % self.depth].synchronize()
+
+    def synchronize(self) -> None:
+        self.s_out.synchronize()

@@ -415,3 +415,22 @@ def test_gae_full_size_properties():
         last = delta + 0.99 * 0.95 * nnt * last
         assert_close(a1[t, sl], last, 1e-5, 1e-5, f"gae t={t}")
         nv, nnt = V[t], 1 - D[t]
+
+
+def test_host_stepper_equals_plain_steps():
+    """engine.HostStepper (pinned host buffers, copies overlapped on 3 streams) delivers exactly what FusedUsvEnv.step produces."""
+    from omniisaacgymenvs_loop_b200.engine import HostStepper
+    cfg = UsvEnvConfig(max_episode_length=6).full_dr()
+    n, K = 50000 + 3, 9
+    a, b = FusedUsvEnv(cfg, n, DEV), FusedUsvEnv(cfg, n, DEV)
+    hs = HostStepper(b, depth=2)
+    g = torch.Generator().manual_seed(2)
+    acts = [(torch.rand((n, 2), generator=g) * 2 - 1).pin_memory() for _ in range(K)]
+    outs = [(torch.empty((n, 13)).pin_memory(), torch.empty(n).pin_memory(), torch.empty(n, dtype=torch.uint8).pin_memory()) for _ in range(K)]
+    tickets = [hs.submit(acts[k], *outs[k]) for k in range(K)]
+    hs.wait(tickets[-1])
+    hs.synchronize()
+    for k in range(K):
+        obs, rew, done = a.step(acts[k].to(DEV))
+        assert torch.equal(outs[k][0], obs.cpu()) and torch.equal(outs[k][1], rew.cpu()) and torch.equal(outs[k][2], done.cpu().to(torch.uint8)), k
+    assert torch.equal(a.state, b.state)
