@@ -113,7 +113,7 @@ __device__ __forceinline__ void post_classic(EnvState& e, const EnvConst& k, con
 }
 
 // one full control step for one env, state in registers
-template <bool kDisturb, bool kLutGlobal>
+template <int kDisturb, bool kLutGlobal>
 __device__ __forceinline__ void control_step(EnvState& e, EnvConst& k, const UsvStepParams& p, bool do_reset,
                                              float2 act, uint64_t gid, int64_t lid, uint64_t step, bool first_call,
                                              const float* __restrict__ s_lutL, const float* __restrict__ s_lutR,
@@ -167,7 +167,7 @@ __device__ __forceinline__ void write_obs_tile(float* s_obs, const StepOut& o, b
   __syncwarp();
 }
 
-template <bool kDisturb, bool kStats>
+template <int kDisturb, bool kStats>
 __global__ void __launch_bounds__(kBlock, USV_MINB) step_fused_kernel(UsvEnvBuffers b, const float2* __restrict__ actions,
                                                             float* __restrict__ obs, float* __restrict__ rew,
                                                             int64_t n, const __grid_constant__ UsvStepParams p) {
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(kBlock, USV_MINB) step_fused_kernel(UsvEnvBuff
 }
 
 // T control steps per launch, state in registers between steps.
-template <bool kDisturb, bool kStats>
+template <int kDisturb, bool kStats>
 __global__ void __launch_bounds__(kBlock) rollout_fused_kernel(UsvEnvBuffers b, const float2* __restrict__ actions,
                                                                float* __restrict__ obs, float* __restrict__ rew,
                                                                int64_t* __restrict__ done, int T, int64_t n,
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(kBlock) rollout_fused_kernel(UsvEnvBuffers b, 
   }
 }
 
-template <bool kDisturb>
+template <int kDisturb>
 __global__ void __launch_bounds__(kBlock) planar_forces_kernel(UsvEnvBuffers b, float* __restrict__ out, int64_t n,
                                                                const __grid_constant__ UsvStepParams p) {
   const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
@@ -335,10 +335,12 @@ int usv_step_fused_f32(const UsvEnvBuffers* b, const float* actions, float* obs,
     ensure_smem(step_fused_kernel<D, S>, smem);                                                            \
     step_fused_kernel<D, S><<<grid, kBlock, smem, s>>>(*b, (const float2*)actions, obs, rew, n, *p);       \
   } while (0)
-  if (dis && st) USV_LAUNCH_STEP(true, true);
-  else if (dis) USV_LAUNCH_STEP(true, false);
-  else if (st) USV_LAUNCH_STEP(false, true);
-  else USV_LAUNCH_STEP(false, false);
+  const bool all4 = p->use_const_force && p->use_sin_force && p->use_const_torque && p->use_sin_torque;
+  if (dis && all4 && !st) USV_LAUNCH_STEP(2, false);
+  else if (dis && st) USV_LAUNCH_STEP(1, true);
+  else if (dis) USV_LAUNCH_STEP(1, false);
+  else if (st) USV_LAUNCH_STEP(0, true);
+  else USV_LAUNCH_STEP(0, false);
 #undef USV_LAUNCH_STEP
   return finish_launch();
 }

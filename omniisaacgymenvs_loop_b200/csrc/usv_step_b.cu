@@ -295,7 +295,7 @@ __device__ __forceinline__ void write_obs_tile_b(float* s_obs, float* __restrict
   __syncwarp();
 }
 
-template <bool kDisturb, bool kStats>
+template <int kDisturb, bool kStats>
 __global__ void __launch_bounds__(kBlock, 3) step_live_kernel(UsvEnvBuffers b, UsvLiveBuffers lb, const float2* __restrict__ actions,
                                                               float* __restrict__ obs, float* __restrict__ rew, int64_t n,
                                                               const __grid_constant__ UsvStepParams p,
@@ -459,7 +459,7 @@ __device__ __forceinline__ void post_task(EnvState& e, const EnvConst& k, const 
   o.finite = (fmaf(o.rew, 0.0f, o.chk) == 0.0f);
 }
 
-template <int kTask, bool kDisturb>
+template <int kTask, int kDisturb>
 __global__ void __launch_bounds__(kBlock, 3) step_task_kernel(UsvEnvBuffers b, UsvLiveBuffers lb, const float2* __restrict__ actions,
                                                               float* __restrict__ obs, float* __restrict__ rew, int64_t n,
                                                               const __grid_constant__ UsvStepParams p,

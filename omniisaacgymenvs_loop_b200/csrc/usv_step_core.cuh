@@ -82,7 +82,7 @@ __device__ __forceinline__ void store_state(float* __restrict__ s0, int64_t /*ca
   s[USV_S_PROGRESS * stride + i] = __int_as_float(e.progress);
 }
 
-template <bool kDisturb>
+template <int kDisturb>
 __device__ __forceinline__ void load_consts(const float* __restrict__ c0, int64_t /*cap*/, int64_t i0, EnvConst& k) {
   const float* __restrict__ c = c0 + tile_base(i0, USV_C_COUNT);
   constexpr int i = 0;
@@ -116,7 +116,7 @@ __device__ __forceinline__ void load_consts(const float* __restrict__ c0, int64_
   }
 }
 
-template <bool kDisturb>
+template <int kDisturb>
 __device__ __forceinline__ void store_consts(float* __restrict__ c0, int64_t /*cap*/, int64_t i0, const EnvConst& k) {
   float* __restrict__ c = c0 + tile_base(i0, USV_C_COUNT);
   constexpr int i = 0;
@@ -232,7 +232,7 @@ __device__ __forceinline__ void spawn_xy(const UsvStepParams& p, const Uniform4&
 }
 
 // reset_idx for one env  [ref: SNAP/USV_Virtual.py:750-817 ; OIGE/tasks/USV_Virtual.py:1502-1618]
-template <bool kDisturb>
+template <int kDisturb>
 __device__ __forceinline__ void reset_env(EnvState& e, EnvConst& k, const UsvStepParams& p, uint64_t gid, uint64_t step) {
   const Uniform4 r0 = philox_uniform4(p.seed, gid, step, RS_RESET_0);
   const Uniform4 r1 = philox_uniform4(p.seed, gid, step, RS_RESET_1);
@@ -339,7 +339,7 @@ __device__ __forceinline__ void reset_env(EnvState& e, EnvConst& k, const UsvSte
 }
 
 // planar force model for one physics sub-step; returns body wrench and world acceleration
-template <bool kDisturb>
+template <int kDisturb>
 __device__ __forceinline__ void planar_wrench(const EnvState& e, const EnvConst& k, const UsvStepParams& p, float ox,
                                               float oy, float inv_m, float inv_iz, float s, float c, float& du, float& dv,
                                               float& dr, float& Fx, float& Fy, float& Tz, float& ax, float& ay,
@@ -363,13 +363,16 @@ __device__ __forceinline__ void planar_wrench(const EnvState& e, const EnvConst&
   // [ref USV_disturbances.py:386-410,510-530 ; SNAP/USV_Virtual.py:621-650]
   float fdx = 0.0f, fdy = 0.0f, td = 0.0f;
   if (kDisturb) {
-    if (p.use_const_force) { fdx = k.fcx; fdy = k.fcy; }
-    if (p.use_sin_force) {
+    // kDisturb == 2: all four disturbance kinds are on (the full-DR configuration): no per-sub-step flag tests
+    const bool cf = kDisturb == 2 || p.use_const_force, sf = kDisturb == 2 || p.use_sin_force;
+    const bool ct = kDisturb == 2 || p.use_const_torque, stq = kDisturb == 2 || p.use_sin_torque;
+    if (cf) { fdx = k.fcx; fdy = k.fcy; }
+    if (sf) {
       fdx = k.fcx + fsin_sfu((e.x + ox) * k.fxf + k.fxs) * k.famp;
       fdy = k.fcy + fsin_sfu((e.y + oy) * k.fyf + k.fys) * k.famp;
     }
-    if (p.use_const_torque) td = k.tc;
-    if (p.use_sin_torque) td = k.tc + fsin_sfu(((e.x + ox) + (e.y + oy)) * k.tf + k.ts) * k.tamp;
+    if (ct) td = k.tc;
+    if (stq) td = k.tc + fsin_sfu(((e.x + ox) + (e.y + oy)) * k.tf + k.ts) * k.tamp;
   }
   // net wrench at the base link; thrusters push along body x at (thr_x, thr_y_*)  (heron.urdf:167,242)
   Fx = fdx + du + e.thrL + e.thrR;
@@ -390,7 +393,7 @@ struct DynOut {
 };
 
 // pre_physics_step + the physics sub-steps + update_state of one control step for one env, state in registers
-template <bool kDisturb, bool kLutGlobal>
+template <int kDisturb, bool kLutGlobal>
 __device__ __forceinline__ void step_dynamics(EnvState& e, EnvConst& k, const UsvStepParams& p, bool do_reset,
                                              float2 act, uint64_t gid, int64_t lid, uint64_t step,
                                              const float* __restrict__ s_lutL, const float* __restrict__ s_lutR,
