@@ -23,6 +23,9 @@ constexpr uint32_t kSpinLimit = 1u << 24;   // ~seconds; on expiry the kernel fl
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void st_relaxed_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -53,15 +56,21 @@ __global__ void __launch_bounds__(kPeerThreads, 1) peer_allreduce_kernel(PpoPeer
   for (int64_t i = (n4 << 2) + gtid; i < count; i += gstride) mine[i] = src[i];
   __threadfence_system();
   __syncthreads();
-  // 2. last CTA of this rank announces
+  // 2. the last CTA of this rank to arrive announces: one fence, then `world` threads store to the `world` pads in parallel
+  //    (a chain of release stores issued by one thread cost ~2 us per peer on the 8-GPU box)
+  __shared__ int s_last;
   if (threadIdx.x == 0) {
     const uint32_t old = atomicAdd(mypad + 32, 1u);
-    if (old == gridDim.x - 1) {
+    s_last = (old == gridDim.x - 1) ? 1 : 0;
+    if (s_last) {
       mypad[32] = 0;
       *seq_dev = seq;
-      __threadfence_system();
-      for (int r = 0; r < c.world; ++r) st_release_sys(reinterpret_cast<uint32_t*>(c.windows[r] + 2 * c.cap) + c.rank, seq);
     }
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x < c.world) {
+    __threadfence_system();
+    st_relaxed_sys(reinterpret_cast<uint32_t*>(c.windows[threadIdx.x] + 2 * c.cap) + c.rank, seq);
   }
   // 3. wait for every peer's announcement (local memory, written remotely)
   if (threadIdx.x < c.world) {
