@@ -503,8 +503,22 @@ def main():
         e1.record()
         torch.cuda.synchronize(device)
         rms = e0.elapsed_time(e1)
+        # the same launch-per-step kernel replayed from a CUDA graph of 256 control steps (device-side Philox step offset)
+        gact = torch.rand((256, 4096, 2), device=device, generator=g) * 2 - 1
+        replay = small.capture_steps(gact)
+        for _ in range(3):
+            replay()
+        torch.cuda.synchronize(device)
+        e0.record()
+        for _ in range(16):
+            replay()
+        e1.record()
+        torch.cuda.synchronize(device)
+        gms = e0.elapsed_time(e1)
+        small.check_finite()
         line["c2_4096"] = {"envs_per_gpu": 4096, "step_kernel_env_steps_per_s": world * 4096 * max(args.steps, 2000) / (sms * 1e-3),
                            "us_per_step": sms * 1e3 / max(args.steps, 2000),
+                           "graph_replay_env_steps_per_s": world * 4096 * 256 * 16 / (gms * 1e-3), "graph_replay_us_per_step": gms * 1e3 / (256 * 16),
                            "rollout_kernel_env_steps_per_s": world * 4096 * T * 4 / (rms * 1e-3),
                            "note": "one launch per control step vs one launch per 512 control steps (state in registers); "
                                    "latency-bound, working set L2-resident -> no HBM roofline claimed"}

@@ -164,6 +164,35 @@ class FusedUsvEnv:
         self.step_counter += steps
         self._step_offset_host += steps
 
+    def capture_steps(self, actions: torch.Tensor, obs: Optional[torch.Tensor] = None, rew: Optional[torch.Tensor] = None,
+                      done: Optional[torch.Tensor] = None):
+        """Captures K = actions.shape[0] control steps (actions (K,N,2) read in place at every replay; optional outputs (K,N,13),
+        (K,N), (K,N) long) into ONE CUDA graph and returns a `replay()` callable.  The Philox step index advances by K per replay
+        through the device-side step offset, so replays continue the same random sequence the eager path would produce.  For
+        small batches (BASELINE config[1]: 4096 envs) this removes the per-step launch / Python cost."""
+        if self._buffers.step_offset in (None, 0):
+            raise NotImplementedError("graph capture of control steps needs the device-side step offset (classic engine)")
+        K = int(actions.shape[0])
+        if self.first_call:
+            raise RuntimeError("take at least one eager step before capturing (the first-call flag is baked into the graph)")
+        saved = self.step_counter
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for k in range(K):
+                self.step(actions[k], None if obs is None else obs[k], None if rew is None else rew[k])
+                if done is not None:
+                    done[k].copy_(self.reset_buf)
+            self.advance_step_offset(K)
+        self.step_counter = saved                        # the capture ran the host code without executing anything
+
+        def replay():
+            graph.replay()
+            self.note_graph_replay(K)
+
+        replay.graph = graph
+        return replay
+
     # ---- the hot path ------------------------------------------------------------------
     def step(self, actions: torch.Tensor, obs: Optional[torch.Tensor] = None, rew: Optional[torch.Tensor] = None):
         """One control step of every env (== VecEnvRLGames.step).  Returns (obs (N,13), rew (N,), reset_buf (N,) long);

@@ -434,3 +434,24 @@ def test_host_stepper_equals_plain_steps():
         obs, rew, done = a.step(acts[k].to(DEV))
         assert torch.equal(outs[k][0], obs.cpu()) and torch.equal(outs[k][1], rew.cpu()) and torch.equal(outs[k][2], done.cpu().to(torch.uint8)), k
     assert torch.equal(a.state, b.state)
+
+
+def test_captured_steps_equal_eager_steps():
+    """FusedUsvEnv.capture_steps: K control steps replayed from one CUDA graph continue the eager Philox sequence bit for bit."""
+    cfg = UsvEnvConfig(max_episode_length=7).full_dr()
+    n, K = 4096, 12
+    a, b = FusedUsvEnv(cfg, n, DEV), FusedUsvEnv(cfg, n, DEV)
+    g = torch.Generator().manual_seed(5)
+    warm = (torch.rand((n, 2), generator=g) * 2 - 1).to(DEV)
+    a.step(warm); b.step(warm)
+    acts = (torch.rand((K, n, 2), generator=g) * 2 - 1).to(DEV)
+    obs, rew, done = torch.empty((K, n, 13), device=DEV), torch.empty((K, n), device=DEV), torch.empty((K, n), dtype=torch.long, device=DEV)
+    replay = b.capture_steps(acts, obs, rew, done)
+    for rep in range(3):
+        replay()
+        for k in range(K):
+            o, r, d = a.step(acts[k])
+            assert torch.equal(o, obs[k]) and torch.equal(r, rew[k]) and torch.equal(d, done[k]), (rep, k)
+    assert a.step_counter == b.step_counter and torch.equal(a.state, b.state)
+    o1, o2 = a.step(warm)[0].clone(), b.step(warm)[0].clone()       # eager steps after replays stay in sequence
+    assert torch.equal(o1, o2)
