@@ -22,15 +22,18 @@ __device__ __forceinline__ void post_classic(EnvState& e, const EnvConst& k, con
   // get_state_observations  [ref SNAP/USV_capture_xy.py:80-97]
   const float ex = k.tx - pxn, ey = k.ty - pyn;
   const float theta = wrap_pi(yawn);  // == atan2(sin, cos) up to rounding, same (-pi,pi] branch
-  const float beta = atan2f(ey, ex);
+  const float beta = fast_atan2(ey, ex);
   // torch.fmod(x, 2pi) has C semantics (sign of the dividend).  beta, theta in [-pi, pi] -> x in [-pi, 3pi]:
   // fmod only acts for x >= 2pi, where x - 2pi is exact; negative x stays unwrapped (reference quirk).
   const float xa = beta - theta + USV_PI_F;
   const float alpha = ((xa >= USV_2PI_F) ? xa - USV_2PI_F : xa) - USV_PI_F;
   const float herr = fabsf(alpha);
-  float sa, ca;
-  fsincos(alpha, &sa, &ca);
   const float d = sqrtf(ex * ex + ey * ey);
+  // (cos, sin)(alpha) = (cos, sin)(beta - theta) from the unit vectors e/|e| and (hc, hs): no trigonometric call
+  // (shifts by 2pi leave them unchanged); beta = atan2(0, 0) = 0 for a zero error vector
+  const float inv_d = (d > 0.0f) ? __fdividef(1.0f, d) : 0.0f;
+  const float cb = (d > 0.0f) ? ex * inv_d : 1.0f, sb = ey * inv_d;
+  const float ca = cb * hc + sb * hs, sa = sb * hc - cb * hs;
   // Core.update_observation_tensor, "local" frame  [ref SNAP/USV_core.py:41-54]
   o.obs[0] = hc * vxn + hs * vyn;
   o.obs[1] = -hs * vxn + hc * vyn;
