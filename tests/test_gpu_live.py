@@ -285,3 +285,55 @@ def test_live_priv_tail_vs_reference_golden(golden):
             env.set_field(name, T(np.ascontiguousarray(v)))
         obs, _, _ = env.step(torch.zeros((n, 2), device=DEV), rebuild_scene=False)
         assert_close(obs[:, 25:33], G[f"priv_{mode}"], 1e-6, 1e-7, f"priv tail ({mode})")
+
+
+def test_scene_replay_npz_vs_oracle(tmp_path):
+    """(f)3: the reference's NPZ scene format drives resets (goal, <= 16 obstacles with a count, start pose / velocity); the oracle
+    applies the same scenes the way CaptureXYTask.apply_scene / _scene_replay_apply do."""
+    from omniisaacgymenvs_loop_b200.scene_replay import SceneReplay
+    S, n = 7, 20
+    g = torch.Generator().manual_seed(17)
+    goal = torch.rand((S, 2), generator=g) * 2 - 1
+    ang = torch.rand(S, generator=g) * 6.28
+    start = goal + torch.stack([torch.cos(ang), torch.sin(ang)], 1) * (9 + 3 * torch.rand((S, 1), generator=g))
+    obst = torch.cat([goal.unsqueeze(1) + torch.rand((S, 10, 2), generator=g) * 24 - 12, torch.full((S, 10, 1), 2.0)], dim=-1)   # (S,k,3): z ignored
+    count = torch.randint(3, 11, (S,), generator=g)
+    path = str(tmp_path / "scenes.npz")
+    np.savez(path, obstacles_xy=obst.numpy(), obstacles_count=count.numpy(), start_pos=start.numpy(), start_yaw=(torch.rand(S, generator=g) * 6 - 3).numpy(),
+             start_vel=(torch.rand((S, 2), generator=g) - 0.5).numpy(), goal_pos=goal.numpy())
+    cfg = dataclasses.replace(LIVE_CFG, max_episode_length=4, reset_pose_external=True, retarget_on_reset=False)
+    live = UsvLiveConfig()
+    env = FusedUsvLiveEnv(cfg, live, n, DEV)
+    rp = SceneReplay(env, path, cycle=True)
+    orc = B.LiveEnvOracle(oracle_cfg(cfg), oracle_task(cfg), oracle_live(live), n)
+    # oracle-side scene application (the oracle's own reset_idx must not place obstacles: it is bypassed for the scene part)
+    base_reset = B.ClassicEnvOracle.reset_idx
+    nxt = torch.zeros(n, dtype=torch.long)
+
+    def reset_with_scene(self, ids, step):
+        if ids.numel() == 0:
+            return
+        idx = nxt[ids] % S
+        nxt[ids] += 1
+        pos, yaw, vel, gl, ob = rp.scenes(idx)
+        self.outcome_at_reset = {}
+        self.S.reset(ids)
+        gids = self.env_ids[ids.numpy()]
+        rc = torch.from_numpy(B.philox.uniform4(self.cfg.seed, gids, step, B.philox.RS_RESET_COM))
+        self.com[ids] = torch.tensor(self.priv.com_base) + (rc[:, 0:3] * 2 - 1) * torch.tensor(self.priv.com_disp)
+        self.target[ids], self.obstacles[ids] = gl, ob
+        self.field[ids] = B.build_field(ob, gl)[0]
+        base_reset(self, ids, step)                                    # dynamics DR + bookkeeping (pose is external)
+        self.pos[ids], self.psi[ids], self.vel[ids], self.r[ids] = pos, yaw, vel, 0.0
+
+    orc.reset_idx = reset_with_scene.__get__(orc)
+    for k in range(11):
+        act = torch.rand((n, 2), generator=g) * 2 - 1
+        o_obs, o_rew, o_done = orc.step(act)
+        obs, rew, done = rp.step(act.to(DEV))
+        assert torch.equal(env.obstacles.cpu(), orc.obstacles), k
+        assert_close(env.potential, orc.field, 1e-6, 1e-6, f"fields step {k}")
+        assert_close(obs, o_obs, 1e-4, 2e-3, f"obs step {k}")
+        assert_close(rew, o_rew, 1e-4, 5e-3, f"reward step {k}")
+        assert torch.equal(done.cpu(), o_done), k
+    assert int(rp.next_scene_idx.min()) >= 3 and torch.equal(rp.last_scene_idx, (nxt - 1) % S)
