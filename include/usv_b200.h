@@ -411,7 +411,8 @@ int ppo_policy_forward_f32(const float* params, const float* obs /*[M,D]*/, int3
                            float* mus /*[M,2]*/, float* sigmas /*[M,2]*/, int64_t M, void* stream);
 
 /* the same contract on the tcgen05 tensor cores (TF32 operands, fp32 accumulation in TMEM, tanh.approx): ~1e-3 relative
- * of the fp32 entry point above; requires obs_dim <= 15 (one padded K column carries the first-layer bias) */
+ * of the fp32 entry point above; obs_dim <= 47: the first GEMM runs with K = 16 (obs_dim <= 15, classic task) or K = 48 (live task, 33),
+ * one padded K column carries the first-layer bias */
 int64_t ppo_packed_weight_floats(void);
 /* params -> weight operand tiles pre-arranged in the kernels' shared-memory order (staged by TMA bulk copies); call after
  * every parameter update.  `packed`: ppo_packed_weight_floats() floats, 16 B aligned */
@@ -447,7 +448,7 @@ int ppo_minibatch_grad_f32(const float* params, const float* obs /*[M,D]*/, int3
                            int64_t M, void* stream);
 
 /* the same minibatch step with every GEMM (forward, dH, and the weight gradients, which accumulate in TMEM across the
- * CTA's tiles) on the tcgen05 tensor cores in TF32; obs_dim <= 15 */
+ * CTA's tiles) on the tcgen05 tensor cores in TF32; obs_dim <= 47 */
 int ppo_minibatch_grad_tc(const float* params, const float* packed, const float* obs, int32_t obs_dim, const float* obs_mean, const float* obs_var,
                           const float* actions, const float* old_neglogp, const float* advantages, const float* old_values,
                           const float* returns, float* old_mu, float* old_sigma, const PpoLossParams* lp, float* grads,

@@ -103,7 +103,7 @@ class PolicyMLP:
         self.counter_offset = torch.zeros(1, dtype=torch.int64, device=self.device)
         self._counter_offset_host = 0
         # tcgen05/TMEM kernels (TF32) when the obs fit their padded K tile; the fp32 SIMT kernels are the numerics reference
-        self.tensor_cores = bool(tensor_cores) and self.D <= 15
+        self.tensor_cores = bool(tensor_cores) and self.D <= 47     # padded K of the first GEMM: 16 (D <= 15) or 48 (D <= 47)
         self._ws = None
         self.packed = torch.zeros(int(self.lib.ppo_packed_weight_floats()), **f32) if self.tensor_cores else None
         self._packed_dirty = True

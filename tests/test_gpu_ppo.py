@@ -141,11 +141,14 @@ def test_tensor_core_forward_vs_fp32(golden):
     assert_close(out["values"], G["inf_values"], 5e-3, 1e-2, "tc values vs reference")
 
 
-def test_tensor_core_minibatch_grad_vs_fp32():
-    """tcgen05 training kernel (all GEMMs incl. the TMEM-resident weight-gradient accumulators) vs the fp32 SIMT kernel."""
+@pytest.mark.parametrize("D", [13, 33])
+def test_tensor_core_minibatch_grad_vs_fp32(D):
+    """tcgen05 training kernel (all GEMMs incl. the TMEM-resident weight-gradient accumulators) vs the fp32 SIMT kernel, for the
+    classic (13 -> K = 16) and the live (33 -> K = 48, X / W1 tiles aliased with W2^T) observation widths."""
     torch.manual_seed(11)
-    for M in (200, 8192, 8192 * 3 + 5):      # ragged single tile / the reference minibatch / several tiles per CTA
+    for M in (200, 8192, 8192 * 3 + 5, 128 * 200):      # ragged single tile / the reference minibatch / several tiles per CTA
         tc, ref = PolicyMLP(D, DEV, seed=5, tensor_cores=True), PolicyMLP(D, DEV, seed=5, tensor_cores=False)
+        assert tc.tensor_cores
         delta = 0.02 * torch.randn(tc.P, device=DEV)
         tc.params.add_(delta); ref.params.add_(delta)
         obs = torch.randn((M, D), device=DEV) * 2
@@ -254,3 +257,33 @@ def test_fused_minibatch_step_equals_unfused():
     g.replay(); g.replay()
     torch.cuda.synchronize()
     assert int(b.step) == 6 and not torch.equal(before, b.params) and torch.isfinite(b.params).all()
+
+
+def test_tensor_core_paths_at_live_obs_width():
+    """D = 33 (the live task's observation): forward and the fused minibatch step on the K = 48 tensor-core kernels vs fp32."""
+    Dw = 33
+    torch.manual_seed(4)
+    tc, ref = PolicyMLP(Dw, DEV, seed=9, tensor_cores=True), PolicyMLP(Dw, DEV, seed=9, tensor_cores=False)
+    assert tc.tensor_cores and tc.P == 21253
+    for M in (77, 16384, 128 * 300 + 5):
+        obs = torch.randn((M, Dw), device=DEV) * 2
+        for p in (tc, ref):
+            p.obs_rms.update(obs[: min(M, 500)])
+        a, b = tc.act(obs), ref.act(obs)
+        assert_close(a["mus"], b["mus"], 5e-3, 5e-3, f"mus M={M}")
+        assert_close(a["values"], b["values"], 5e-3, 1e-2, f"values M={M}")
+        assert_close(a["actions"] - a["mus"], b["actions"] - b["mus"], 1e-6, 1e-6, "same noise")
+    M = 8192
+    obs = torch.randn((M, Dw), device=DEV) * 2
+    inf = ref.act(obs)
+    args = [obs, inf["actions"].contiguous(), (inf["neglogpacs"] + 0.1 * torch.randn(M, device=DEV)).contiguous(), torch.randn(M, device=DEV),
+            torch.randn(M, device=DEV) * 0.3, torch.randn(M, device=DEV) * 0.5]
+    for it in range(3):
+        tc.minibatch_step(*args, inf["mus"].clone(), inf["sigmas"].clone())
+        ref.minibatch_grad(*args, inf["mus"].clone(), inf["sigmas"].clone())
+        ref.optimizer_step()
+        sa, sb = tc.stats(), ref.stats()
+        for k in ("a_loss", "c_loss", "b_loss", "kl", "loss"):
+            assert abs(sa[k] - sb[k]) <= 1e-2 * abs(sb[k]) + 5e-4, (it, k, sa[k], sb[k])
+        # each Adam step moves a weight by <= lr (sign flips of near-zero gradients: <= 2 lr apart), lr grows x1.5 per step at low KL
+        assert float((tc.params - ref.params).abs().max()) < (it + 1) * 4e-4
