@@ -464,7 +464,7 @@ def main():
     peak, peak_src = measured_peak()
     achieved = BYTES_PER_ENV_STEP * n / (ms_per_step * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "kernel": "usv::step_fused_kernel<true,false>", "peak_source": peak_src,
+                "kernel": "usv::step_fused_kernel<2,false> (kDisturb = 2: all disturbance kinds on, stats off)", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": BYTES_PER_ENV_STEP * n}
     tr = os.path.join(ROOT, "profiles", "traffic.json")      # dram bytes/launch from the committed ncu --set full capture
     if os.path.exists(tr):
