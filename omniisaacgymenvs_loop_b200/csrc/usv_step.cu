@@ -112,7 +112,8 @@ __device__ __forceinline__ void post_classic(EnvState& e, const EnvConst& k, con
   o.finite = (chk == 0.0f);
   // _process_data: clamp obs to +-clipObservations  [ref vec_env_rlgames.py:82-95]
 #pragma unroll
-  for (int j = 0; j < kObs; ++j) o.obs[j] = fminf(fmaxf(o.obs[j], -p.clip_obs), p.clip_obs);
+  for (int j = 0; j < kObs; ++j)
+    if (j != 8 && j != 11 && j != 12) o.obs[j] = fminf(fmaxf(o.obs[j], -p.clip_obs), p.clip_obs);   // 8, 11, 12 are constant zeros
 }
 
 // one full control step for one env, state in registers
@@ -285,7 +286,7 @@ __global__ void __launch_bounds__(kBlock) planar_forces_kernel(UsvEnvBuffers b, 
   }
   float du, dv, dr, Fx, Fy, Tz, ax, ay, rdot, hsn, hcs;
   fsincos(e.psi, &hsn, &hcs);
-  planar_wrench<kDisturb>(e, k, p, ox, oy, 1.0f / k.mass, 1.0f / (p.izz * k.kiz), hsn, hcs, du, dv, dr, Fx, Fy, Tz, ax, ay, rdot);
+  planar_wrench<kDisturb>(e, k, p, make_damp(k, p), ox, oy, 1.0f / k.mass, 1.0f / (p.izz * k.kiz), hsn, hcs, du, dv, dr, Fx, Fy, Tz, ax, ay, rdot);
   float* o = out + i * 8;
   o[0] = du; o[1] = dv; o[2] = dr; o[3] = Fx; o[4] = Fy; o[5] = Tz; o[6] = ax; o[7] = ay;
 }
