@@ -26,7 +26,8 @@ constexpr int kRowIters = (kG + 31) / 32;  // 5
 constexpr int kColIters = (kG + 31) / 32;  // 5
 constexpr int kMaxSweeps = (int)(kG * 1.5);  // 225  (d_multi_gemini.py:160)
 constexpr float kObstR = 0.5f;
-constexpr int kChunks = 5, kBands = 6, kBandRows = 25, kTiles = kChunks * kBands;  // wavefront tiles: 32 columns x 25 rows
+constexpr int kChunks = 5, kBandRows = 8, kBands = (kG + kBandRows - 1) / kBandRows, kTiles = kChunks * kBands;  // wavefront tiles: 32 columns x 8 rows (95)
+constexpr int kActStride = 96;       // tile-active flags per sweep parity
 constexpr float kReach = 1.7f + 1e-3f;  // an obstacle matters to a cell only within 0.5 (radius) + 0.5 + 0.7 (influence) of its centre
 
 // counters (uint32[8]) in the workspace
@@ -164,8 +165,9 @@ __global__ void __launch_bounds__(kSceneThreads, 1) scene_cost_kernel(SceneIO io
   float* bufB = smem + kGP * kGP;
   float* s_sc = bufB + kGP * kGP;     // 34 floats
   float* s_red = s_sc + 64;           // 32 floats
-  int* s_act = reinterpret_cast<int*>(s_red + 32);        // [2][32] tile-active flags of the current / next sweep
-  uint32_t* s_rowmask = reinterpret_cast<uint32_t*>(s_act + 64);  // [150] obstacles that can matter on a grid row
+  int* s_act = reinterpret_cast<int*>(s_red + 32);        // [2][96] tile-active flags of the current / next sweep
+  uint32_t* s_rowmask = reinterpret_cast<uint32_t*>(s_act + 2 * kActStride);  // [150] obstacles that can matter on a grid row
+  unsigned char* s_free = reinterpret_cast<unsigned char*>(s_rowmask + 160);  // [95][32] free bits of a lane's 8 cells of a tile
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t total = scene_count(io);
   for (int64_t j = blockIdx.x; j < total; j += gridDim.x) {
@@ -191,7 +193,7 @@ __global__ void __launch_bounds__(kSceneThreads, 1) scene_cost_kernel(SceneIO io
     }
     // both buffers +inf (halo included)
     for (int q = threadIdx.x; q < kGP * kGP; q += kSceneThreads) { bufA[q] = CUDART_INF_F; bufB[q] = CUDART_INF_F; }
-    if (threadIdx.x < 64) s_act[threadIdx.x] = 0;
+    if (threadIdx.x < 2 * kActStride) s_act[threadIdx.x] = 0;
     __syncthreads();
     if (threadIdx.x < kG) s_rowmask[threadIdx.x] = row_obstacle_mask(io.lin[threadIdx.x], s_sc + 16);
     if (threadIdx.x == 0) {
@@ -207,54 +209,65 @@ __global__ void __launch_bounds__(kSceneThreads, 1) scene_cost_kernel(SceneIO io
           if (tc + dc >= 0 && tc + dc < kChunks && tb + db >= 0 && tb + db < kBands) s_act[(tb + db) * kChunks + tc + dc] = 1;
     }
     __syncthreads();
-    // warp w < 30 owns the tile (chunk = w % 5: 32 columns, band = w / 5: 25 rows); a lane walks down its column with a rolling
-    // 3x3 window in registers: 3 shared loads + 1 store per cell instead of 9 + 1 (the r01 kernel ran the shared-memory pipe
-    // at 84 % of peak: profiles/r01_live_kernels.md)
-    const bool has_tile = warp < kTiles;
-    const int chunk = warp % kChunks, band = warp / kChunks;
-    const int x = chunk * 32 + lane, y0 = band * kBandRows;
-    const bool xin = has_tile && x < kG;
-    const int xc = min(x, kG - 1);
-    uint32_t freemask = 0;   // bit i: cell (y0 + i, x) is free
-    if (xin) {
+    // Tiles of 32 columns x 8 rows (95 per grid), dealt round-robin to the 32 warps so that the ring of tiles the wavefront is
+    // crossing is spread over all of them (one 32 x 25 tile per warp left most warps waiting at the sweep barrier: 7 barrier
+    // stalls per issue in the r01 capture).  A lane walks down its column of the tile with a rolling 3x3 window in registers:
+    // 3 shared loads + 1 store per cell instead of 9 + 1.  The per-cell "free" bits of a tile live in shared memory.
+    for (int t = warp; t < kTiles; t += 32) {
+      const int chunk = t % kChunks, band = t / kChunks;
+      const int x = chunk * 32 + lane, y0 = band * kBandRows;
+      uint32_t fm = 0;
+      if (x < kG) {
 #pragma unroll 1
-      for (int i = 0; i < kBandRows; ++i) {
-        const int y = y0 + i;
-        const bool border = (y == 0) || (y == kG - 1) || (x == 0) || (x == kG - 1);
-        const float sdf = cell_sdf_masked(io.lin[x], io.lin[y], s_sc, s_sc + 16, s_rowmask[y]);
-        if (!border && !(sdf <= 0.0f)) freemask |= 1u << i;
+        for (int i = 0; i < kBandRows && y0 + i < kG; ++i) {
+          const int y = y0 + i;
+          const bool border = (y == 0) || (y == kG - 1) || (x == 0) || (x == kG - 1);
+          const float sdf = cell_sdf_masked(io.lin[x], io.lin[y], s_sc, s_sc + 16, s_rowmask[y]);
+          if (!border && !(sdf <= 0.0f)) fm |= 1u << i;
+        }
       }
+      s_free[t * 32 + lane] = (unsigned char)fm;
     }
+    __syncthreads();
     float* cur = bufA;
     float* nxt = bufB;
     for (int sweep = 0; sweep < kMaxSweeps; ++sweep) {
-      int* act_cur = s_act + (sweep & 1) * 32;
-      int* act_nxt = s_act + ((sweep + 1) & 1) * 32;
+      int* act_cur = s_act + (sweep & 1) * kActStride;
+      int* act_nxt = s_act + ((sweep + 1) & 1) * kActStride;
       int any_change = 0;
-      if (has_tile && act_cur[warp]) {
+      for (int t = warp; t < kTiles; t += 32) {
+        if (!act_cur[t]) continue;                 // warp-uniform
         __syncwarp();
-        if (lane == 0) act_cur[warp] = 0;  // consumed; writers of this sweep only touch act_nxt
+        if (lane == 0) act_cur[t] = 0;             // consumed; writers of this sweep only touch act_nxt
+        const int chunk = t % kChunks, band = t / kChunks;
+        const int x = chunk * 32 + lane, y0 = band * kBandRows;
+        const int rows = min(kBandRows, kG - y0);
+        const bool xin = x < kG;
+        const int xc = min(x, kG - 1);
+        const uint32_t freemask = s_free[t * 32 + lane];
         const float* c0 = cur + y0 * kGP + xc + 1;  // (row y0 - 1, column x) in padded coordinates
         float* n0 = nxt + (y0 + 1) * kGP + xc + 1;
         float ul = c0[-1], uc = c0[0], ur = c0[1];
         float ml = c0[kGP - 1], mc = c0[kGP], mr = c0[kGP + 1];
         uint32_t chg = 0;
-#pragma unroll 5
+#pragma unroll
         for (int i = 0; i < kBandRows; ++i) {
-          const float* d = c0 + (i + 2) * kGP;
-          const float dl = d[-1], dc = d[0], dr = d[1];
-          float best = CUDART_INF_F;
-          if ((freemask >> i) & 1u) {
-            const float a = fminf(fminf(ml, mr), fminf(uc, dc)) + 1.0f;
-            const float b = fminf(fminf(ul, ur), fminf(dl, dr)) + 1.414f;
-            best = fminf(mc, fminf(a, b));
+          if (i < rows) {
+            const float* d = c0 + (i + 2) * kGP;
+            const float dl = d[-1], dc = d[0], dr = d[1];
+            float best = CUDART_INF_F;
+            if ((freemask >> i) & 1u) {
+              const float a = fminf(fminf(ml, mr), fminf(uc, dc)) + 1.0f;
+              const float b = fminf(fminf(ul, ur), fminf(dl, dr)) + 1.414f;
+              best = fminf(mc, fminf(a, b));
+            }
+            if (xin) {
+              n0[i * kGP] = best;
+              chg |= (best != mc) ? (1u << i) : 0u;
+            }
+            ul = ml; uc = mc; ur = mr;
+            ml = dl; mc = dc; mr = dr;
           }
-          if (xin) {
-            n0[i * kGP] = best;
-            chg |= (best != mc) ? (1u << i) : 0u;
-          }
-          ul = ml; uc = mc; ur = mr;
-          ml = dl; mc = dc; mr = dr;
         }
         // activate for the next sweep exactly the tiles whose inputs changed: this one, and a neighbour only when a cell on the
         // shared edge changed
@@ -262,7 +275,7 @@ __global__ void __launch_bounds__(kSceneThreads, 1) scene_cost_kernel(SceneIO io
         if (any_b) {
           any_change = 1;
           const bool left = any_b & 1u, right = (any_b >> 31) & 1u;
-          const bool up = __any_sync(0xffffffffu, chg & 1u), down = __any_sync(0xffffffffu, (chg >> (kBandRows - 1)) & 1u);
+          const bool up = __any_sync(0xffffffffu, chg & 1u), down = __any_sync(0xffffffffu, (chg >> (rows - 1)) & 1u);
           if (lane < 9) {
             const int dc = lane % 3 - 1, db = lane / 3 - 1;
             const bool need = (dc == 0 || (dc < 0 ? left : right)) && (db == 0 || (db < 0 ? up : down));
@@ -272,7 +285,7 @@ __global__ void __launch_bounds__(kSceneThreads, 1) scene_cost_kernel(SceneIO io
         }
       }
       const int any = __syncthreads_or(any_change);
-      float* t = cur; cur = nxt; nxt = t;
+      float* tsw = cur; cur = nxt; nxt = tsw;
       if (!any) break;
     }
     // raw cost -> field[env] (and the optional dense cost output); max finite cost of the whole batch
@@ -432,7 +445,7 @@ __global__ void compact_resets_kernel(const int64_t* __restrict__ reset_buf, int
   }
 }
 
-static size_t cost_smem_bytes() { return (size_t)(2 * kGP * kGP + 64 + 32 + 64 + 160) * sizeof(float); }
+static size_t cost_smem_bytes() { return (size_t)(2 * kGP * kGP + 64 + 32 + 2 * kActStride + 160) * sizeof(float) + (size_t)kTiles * 32; }
 
 static int scene_grid() {
   static int sms = 0;
