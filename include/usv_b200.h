@@ -503,6 +503,83 @@ int ppo_peer_allreduce_f32(const PpoPeerComm* c, const float* src, float* dst, i
 int ppo_rms_update_f64(const float* x /*[M,D]*/, int64_t M, int32_t D, double* mean /*[D]*/, double* var /*[D]*/, double* count /*[1]*/,
                        float* mean32 /*[D]*/, float* var32 /*[D]*/, void* stream);
 
+/* ------------------------------------------------------------------------- */
+/* L  the loopz PPO learner: what OIGE/scripts/rlgames_train_loopz.py trains with                       */
+/*   actor and critic are separate MLPEncode networks over obs = [speed | task | mass(Md)]:                                  */
+/*     mass -> Linear(Md,64)+LeakyReLU -> Linear(64,16)+LeakyReLU -> Linear(16,8)+LeakyReLU = latent                         */
+/*     cat(speed, task, latent) -> Linear(D-Md+8,128)+LeakyReLU -> Linear(128,128)+LeakyReLU -> Linear(128,OUT) [+tanh]      */
+/*   actor OUT = 2 (+ tanh when tanh_out), critic OUT = 1; actions ~ tanh(Normal(mean, std)) * action_scale, std a free      */
+/*   parameter (NOT a log-std).      [ref: OIGE/algo/ppo/module.py:54-115,184-361,517-659 ; rlgames_train_loopz.py:784-842]  */
+/* ONE flat fp32 parameter vector in the order of PPO's optimiser ([*actor.parameters(), *critic.parameters()], ppo.py:60): */
+/*   actor: mass_encoder.{0,2,4}.{weight,bias} | action_mlp.{0,2,4}.{weight,bias} | std[2] | critic: the same twelve tensors  */
+#define PPO_LOOPZ_ENC1 64
+#define PPO_LOOPZ_ENC2 16
+#define PPO_LOOPZ_LATENT 8
+#define PPO_LOOPZ_MAX_MASS 8
+typedef struct {
+  int32_t obs_dim;      /* D (33 for the live task)                                   */
+  int32_t mass_dim;     /* Md: privileged tail width, 4 or 8 (cfg.yaml environment.mass_dim) */
+  int32_t tanh_out;     /* architecture.activation == 'tanh': tanh on the actor output */
+  float action_scale;   /* task.env.clipActions                                       */
+  float eps;            /* 1e-6                                                       */
+} PpoLoopzNet;
+typedef struct {
+  float clip_param;         /* 0.2 */
+  float value_loss_coef;    /* 0.5 */
+  float entropy_coef;       /* 0.0 ("entropy" is -log_prob of the stored action, module.py:632-637) */
+  int32_t use_clipped_value_loss;
+} PpoLoopzLossParams;
+typedef struct {
+  float beta1, beta2, eps;  /* torch.optim.Adam defaults 0.9, 0.999, 1e-8 */
+  float max_grad_norm;      /* 0.5 */
+} PpoLoopzAdamParams;
+enum { PPO_LOOPZ_STAT_SURROGATE = 0, PPO_LOOPZ_STAT_VALUE_LOSS, PPO_LOOPZ_STAT_LOG_PROB, PPO_LOOPZ_STAT_LOSS, PPO_LOOPZ_STAT_GRAD_NORM,
+       PPO_LOOPZ_STAT_SKIPPED, PPO_LOOPZ_STAT_COUNT };
+
+int64_t ppo_loopz_param_count(const PpoLoopzNet* net);          /* P; < 0: unsupported shape */
+int64_t ppo_loopz_actor_param_count(const PpoLoopzNet* net);    /* std lives at [PA, PA+2), the critic starts at PA+2 */
+int64_t ppo_loopz_train_scratch_floats(const PpoLoopzNet* net);
+int64_t ppo_loopz_returns_scratch_bytes(void);
+
+/* PPO.observe / PPO.step: actor.sample(actor_obs) -> (actions, log_prob) and critic.predict(critic_obs) -> values.            */
+/* The actor runs when actions, means or eval_actions is given, the critic when values is given (one launch, blockIdx.y =      */
+/* network).  With eval_actions ([M,2]) nothing is sampled: log_prob receives the log-probability of those actions              */
+/* (Actor.evaluate, module.py:72-74,586-637).                                                                                   */
+/*   [ref: OIGE/algo/ppo/ppo.py:97-148 ; module.py:67-70,104-105,568-583]                                                     */
+int ppo_loopz_act_f32(const float* params, const PpoLoopzNet* net, const float* actor_obs /*[M,D]*/, const float* critic_obs /*[M,D]*/,
+                      uint64_t seed, uint64_t counter, const uint64_t* counter_offset /*device addend or NULL*/, int64_t row_offset,
+                      const float* eval_actions /*[M,2] or NULL*/, float* actions /*[M,2]*/, float* log_prob /*[M]*/,
+                      float* means /*[M,2] noiseless action*/, float* values /*[M]*/,
+                      int64_t M, void* stream);
+
+/* RolloutStorage.compute_returns: GAE with the done flag of the SAME step, returns = A + V, advantages = returns - values      */
+/* standardised over the whole batch ((x - mean) / (unbiased std + 1e-8)), non-finite inputs / outputs zeroed.                  */
+/*   [ref: OIGE/algo/ppo/storage.py:92-124]                                                                                     */
+int ppo_loopz_returns_f32(const float* rewards /*[T,n]*/, const float* values /*[T,n]*/, const uint8_t* dones /*[T,n]*/,
+                          const float* last_values /*[n]*/, float gamma, float lam, float* returns /*[T,n]*/, float* advantages /*[T,n]*/,
+                          void* scratch /*ppo_loopz_returns_scratch_bytes()*/, int32_t T, int64_t n, void* stream);
+
+/* one minibatch of PPO._train_step: clipped surrogate on the actor, (clipped) value loss on the critic, full backward.         */
+/* index (optional): row ids of the minibatch inside the [T*n] storage (mini_batch_generator_shuffle); NULL = rows [0, M) of     */
+/* the pointers given (mini_batch_generator_inorder: pass pointers offset to the minibatch).                                     */
+/* grads[P + PPO_LOOPZ_STAT_COUNT]: gradient of mean(surrogate + value_loss_coef*value_loss - entropy_coef*entropy) + SUMS of    */
+/* the per-sample statistics (ppo_loopz_adam_step_f32 turns them into means).   [ref: OIGE/algo/ppo/ppo.py:232-284]              */
+int ppo_loopz_minibatch_grad_f32(const float* params, const PpoLoopzNet* net, const float* actor_obs, const float* critic_obs,
+                                 const float* actions /*[.,2]*/, const float* old_log_prob, const float* advantages,
+                                 const float* target_values, const float* returns, const int64_t* index /*[M] or NULL*/,
+                                 const PpoLoopzLossParams* lp, float* grads, float* scratch, int64_t M, void* stream);
+
+/* clip_grad_norm_(max_grad_norm) + Adam on the whole flat vector; skipped (parameters, moments and step count untouched) when   */
+/* the loss is not finite.  step: device int32[2], the current count is step[parity] and the new one is written to               */
+/* step[1-parity] (the caller alternates parity: no CTA can observe another CTA's update); lr: device float (the host owns the   */
+/* schedule); accum: device float[3] += (value loss, surrogate, 1) of the valid updates or NULL.   [ref: ppo.py:286-318]         */
+int ppo_loopz_adam_step_f32(float* params, float* grads, float* exp_avg, float* exp_avg_sq, const float* lr, int32_t* step,
+                            int32_t parity, float* accum, int64_t P, int64_t M, const PpoLoopzLossParams* lp,
+                            const PpoLoopzAdamParams* ap, void* stream);
+
+/* SquashedGaussianDiagonalCovariance.enforce_minimum_std   [ref: module.py:649-659] */
+int ppo_loopz_enforce_min_std_f32(float* std, const float* min_std, int32_t dim, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

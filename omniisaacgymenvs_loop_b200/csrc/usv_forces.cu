@@ -204,6 +204,9 @@ int64_t usv_b200_sizeof(const char* name) {
   USV_SZ(PpoLossParams);
   USV_SZ(PpoAdamParams);
   USV_SZ(PpoPeerComm);
+  USV_SZ(PpoLoopzNet);
+  USV_SZ(PpoLoopzLossParams);
+  USV_SZ(PpoLoopzAdamParams);
 #undef USV_SZ
   return -1;
 }

@@ -640,6 +640,124 @@ def classic_curriculum():
     print("classic_curriculum.npz")
 
 
+def loopz():
+    """The loopz PPO learner: MLPEncode actor / critic, squashed Gaussian, RolloutStorage.compute_returns and PPO._train_step of the
+    UNMODIFIED reference (OIGE/algo/ppo/{module,storage,ppo}.py) in the configuration rlgames_train_loopz.py:784-842 builds."""
+    import tempfile
+
+    import torch.nn as nn
+    from torch.distributions import Normal
+
+    ref_shim.install()
+    import omniisaacgymenvs.algo.ppo.module as M
+    import omniisaacgymenvs.algo.ppo.ppo as P
+
+    D, MD, T, N = 33, 8, 8, 48
+    torch.manual_seed(11)
+    g = gen()
+
+    def build(n_epochs, n_mb, lr, max_norm, state=None, sampling="in_order"):
+        actor = M.Actor(M.MLPEncode_wrap([128, 128], nn.LeakyReLU, D, 2, nn.Tanh, False, speed_dim=3, mass_dim=MD, mass_latent_dim=8,
+                                         mass_encoder_shape=[64, 16]),
+                        M.SquashedGaussianDiagonalCovariance(2, 0.3, action_scale=1.0), "cpu")
+        critic = M.Critic(M.MLPEncode_wrap([128, 128], nn.LeakyReLU, D, 1, speed_dim=3, mass_dim=MD, mass_latent_dim=8,
+                                           mass_encoder_shape=[64, 16]), "cpu")
+        with ref_shim.quiet():
+            ppo_ = P.PPO(actor=actor, critic=critic, num_envs=N, num_transitions_per_env=T, num_learning_epochs=n_epochs, gamma=0.997,
+                         lam=0.95, num_mini_batches=n_mb, device="cpu", log_dir=tempfile.mkdtemp(), mini_batch_sampling=sampling,
+                         learning_rate=lr, max_grad_norm=max_norm)
+        if state is not None:
+            with torch.no_grad():
+                for p_, s_ in zip([*actor.parameters(), *critic.parameters()], state):
+                    p_.copy_(s_)
+        return actor, critic, ppo_
+
+    actor, critic, ppo_ = build(4, 4, 5e-4, 0.5)
+    with torch.no_grad():
+        for prm in [*actor.parameters(), *critic.parameters()]:
+            prm.add_(0.05 * torch.randn(prm.shape, generator=g))
+        actor.distribution.std.copy_(torch.tensor([0.3, 0.45]))
+    plist = [*actor.parameters(), *critic.parameters()]
+    state0 = [p_.detach().clone() for p_ in plist]
+    out = {"param_names": np.array([n for n, _ in actor.architecture.named_parameters()] + ["distribution.std"] +
+                                   [n for n, _ in critic.architecture.named_parameters()]),
+           "param_sizes": np.array([p_.numel() for p_ in plist]), "params0": torch.cat([p_.reshape(-1) for p_ in state0])}
+
+    # ---- inference: means / values / log-prob of a sample with known noise / evaluate() of given actions -------------------
+    Mrows = 200
+    obs = torch.randn((Mrows, D), generator=g) * torch.linspace(0.3, 2.0, D)
+    obs[:, -MD:] = torch.rand((Mrows, MD), generator=g) * 2 - 1
+    with torch.no_grad():
+        means = actor.architecture.architecture(obs)
+        values = critic.predict(obs)
+        std = actor.distribution.std.reshape(2)
+        noise = torch.randn((Mrows, 2), generator=g)
+        u = means + std * noise
+        logp_u = actor.distribution._log_prob_from_u(Normal(means, std), u)
+        acts = torch.tanh(u) * actor.distribution.action_scale
+        eval_actions = torch.rand((Mrows, 2), generator=g) * 2 - 1
+        eval_actions[0] = torch.tensor([1.0, -1.0])            # the atanh clamp
+        eval_actions[1] = torch.tensor([0.999999, 0.0])
+        (logp_eval, ent_eval), mean_eval = actor.evaluate(obs, eval_actions)
+    out.update(inf_obs=obs, inf_means=means, inf_values=values, inf_noise=noise, inf_u=u, inf_logp_u=logp_u, inf_actions=acts,
+               eval_actions=eval_actions, eval_logp=logp_eval, eval_entropy=ent_eval, eval_means=mean_eval)
+
+    # ---- a rollout in the storage + compute_returns ------------------------------------------------------------------------
+    st = ppo_.storage
+    roll_obs = torch.randn((T + 1, N, D), generator=g) * torch.linspace(0.3, 2.0, D)
+    roll_obs[:, :, -MD:] = torch.rand((T + 1, N, MD), generator=g) * 2 - 1
+    rewards = torch.randn((T, N), generator=g) * 0.05
+    rewards[2, 5] = float("nan")                                # sanitised to 0 by add_transitions
+    dones = (torch.rand((T, N), generator=g) < 0.12)
+    for t in range(T):
+        with torch.no_grad():
+            m_ = actor.architecture.architecture(roll_obs[t])
+            nz = torch.randn((N, 2), generator=g)
+            u_ = m_ + std * nz
+            a_ = torch.tanh(u_) * actor.distribution.action_scale
+            lp_ = actor.distribution._log_prob_from_u(Normal(m_, std), u_)
+            v_ = critic.predict(roll_obs[t])
+        st.add_transitions(roll_obs[t].numpy(), roll_obs[t].numpy(), a_, rewards[t].numpy(), dones[t].numpy(), v_, lp_)
+    with torch.no_grad():
+        last_values = critic.predict(roll_obs[T])
+    st.compute_returns(last_values, ppo_.gamma, ppo_.lam)
+    out.update(roll_obs=roll_obs, roll_rewards=rewards, roll_dones=dones.to(torch.uint8), roll_actions=st.actions.clone(),
+               roll_log_prob=st.actions_log_prob.clone(), roll_values=st.values.clone(), roll_last_values=last_values,
+               roll_returns=st.returns.clone(), roll_advantages=st.advantages.clone(), gamma=np.float32(0.997), lam=np.float32(0.95))
+    fields = ["actor_obs", "critic_obs", "rewards", "actions", "dones", "actions_log_prob", "values", "returns", "advantages"]
+    filled = {k: getattr(st, k).clone() for k in fields}
+
+    def fill(p2):
+        for k in fields:
+            setattr(p2.storage, k, filled[k].clone())
+        p2.storage.step = T
+
+    # ---- raw gradient of ONE minibatch (lr = 0, no clipping) over rows [0, 96) and over the full batch ----------------------
+    for tag, n_mb in (("full", 1), ("quarter", 4)):
+        a2, c2, p2 = build(1, n_mb, 0.0, 1e9, state0)
+        fill(p2)
+        if n_mb == 4:       # only the FIRST minibatch: stop after one step
+            orig = p2.batch_sampler
+            p2.batch_sampler = lambda k, _o=orig: (b for i, b in enumerate(_o(k)) if i == 0)
+        with ref_shim.quiet():
+            vl, sl, _ = p2._train_step()
+        out[f"grad_{tag}"] = torch.cat([p_.grad.reshape(-1) for p_ in [*a2.parameters(), *c2.parameters()]])
+        out[f"grad_{tag}_value_loss"] = np.float32(vl)
+        out[f"grad_{tag}_surrogate"] = np.float32(sl)
+
+    # ---- one full update as the live script configures it: 4 epochs x 4 in-order minibatches, lr 5e-4, clip 0.5 ---------------
+    a3, c3, p3 = build(4, 4, 5e-4, 0.5, state0)
+    fill(p3)
+    with ref_shim.quiet():
+        vl, sl, _ = p3._train_step()
+    out.update(update_params_after=torch.cat([p_.detach().reshape(-1) for p_ in [*a3.parameters(), *c3.parameters()]]),
+               update_value_loss=np.float32(vl), update_surrogate=np.float32(sl))
+    a3.distribution.enforce_minimum_std(torch.tensor([0.05, 0.5]))
+    out["min_std_after"] = a3.distribution.std.detach().clone()
+    np.savez_compressed(os.path.join(OUT, "loopz_ppo.npz"), **t2n(out))
+    print("loopz_ppo.npz")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)
@@ -652,6 +770,7 @@ def main():
     live_virtual()
     tier3()
     classic_curriculum()
+    loopz()
 
 
 if __name__ == "__main__":

@@ -1,0 +1,231 @@
+"""GPU parity of the loopz PPO kernels (csrc/ppo_loopz.cu, through the C ABI) against goldens produced by the reference's own
+OIGE/algo/ppo classes and against the CPU oracle on other seeds / sizes / the 4-wide privileged tail."""
+import dataclasses
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from omniisaacgymenvs_loop_b200.algo.ppo import PPO, module as M  # noqa: E402
+from oracle import loopz_oracle as Z  # noqa: E402
+
+DEV = "cuda:0"
+T = torch.from_numpy
+
+
+def build(D=33, md=8, n=48, horizon=8, sampling="in_order", graph=False, seed=0, **kw):
+    arch = dict(speed_dim=3, mass_dim=md, mass_latent_dim=8, mass_encoder_shape=[64, 16])
+    actor = M.Actor(M.MLPEncode_wrap([128, 128], "LeakyReLU", D, 2, "Tanh", False, **arch),
+                    M.SquashedGaussianDiagonalCovariance(2, 0.3, action_scale=1.0), DEV, seed=seed)
+    critic = M.Critic(M.MLPEncode_wrap([128, 128], "LeakyReLU", D, 1, **arch), DEV)
+    args = dict(num_learning_epochs=4, gamma=0.997, lam=0.95, num_mini_batches=4, learning_rate=5e-4)
+    args.update(kw)
+    ppo = PPO(actor=actor, critic=critic, num_envs=n, num_transitions_per_env=horizon, device=DEV, mini_batch_sampling=sampling,
+              use_cuda_graph=graph, **args)
+    return actor, critic, ppo
+
+
+def fill_from_golden(ppo, G):
+    st = ppo.storage
+    obs = T(G["roll_obs"]).to(DEV)
+    st.actor_obs.copy_(obs[:-1]); st.critic_obs.copy_(obs[:-1])
+    st.actions.copy_(T(G["roll_actions"])); st.actions_log_prob.copy_(T(G["roll_log_prob"])); st.values.copy_(T(G["roll_values"]))
+    st.rewards.copy_(T(G["roll_rewards"]).unsqueeze(-1)); st.dones.copy_(T(G["roll_dones"]).unsqueeze(-1))
+    st.step = st.num_transitions_per_env
+
+
+def test_inference_and_evaluate_vs_reference(golden):
+    G = golden("loopz_ppo")
+    actor, critic, ppo = build()
+    ppo.params.copy_(T(G["params0"]))
+    obs = T(G["inf_obs"]).to(DEV)
+    means = actor.noiseless_action(obs)
+    values = critic.predict(obs)
+    # fp32 forward of a 5-layer net vs torch CPU: 1e-5 relative (north_star), atol for outputs near zero
+    assert torch.allclose(means.cpu(), T(G["inf_means"]), rtol=1e-5, atol=2e-6)
+    assert torch.allclose(values.cpu(), T(G["inf_values"]), rtol=1e-5, atol=2e-6)
+    (lp, ent), m2 = actor.evaluate(obs, T(G["eval_actions"]).to(DEV))
+    assert torch.equal(m2, means)
+    assert torch.allclose(lp.cpu(), T(G["eval_logp"]), rtol=1e-5, atol=2e-5) and torch.equal(ent, -lp)
+    # state_dict uses the reference's key names and round-trips
+    sd = actor.architecture.state_dict()
+    assert list(sd)[0] == "architecture.mass_encoder.0.weight" and sd["architecture.action_mlp.4.weight"].shape == (2, 128)
+    a2, c2, p2 = build(seed=5)
+    p2.load_state_dict(ppo.state_dict(update=7))
+    assert torch.equal(p2.params, ppo.params)
+
+
+def test_sampling_is_a_squashed_gaussian(golden):
+    G = golden("loopz_ppo")
+    actor, critic, ppo = build()
+    ppo.params.copy_(T(G["params0"]))
+    obs = T(G["inf_obs"]).to(DEV).repeat(200, 1)                 # 40 000 rows
+    acts, logp = actor.sample(obs)
+    acts2, _ = actor.sample(obs)
+    assert not torch.equal(acts, acts2)                          # the Philox counter advances
+    assert float(acts.abs().max()) <= 1.0
+    means = actor.noiseless_action(obs)
+    std = actor.distribution.std
+    u = torch.atanh(acts.double().clamp(-1 + 1e-12, 1 - 1e-12)).float()
+    z = (u - means) / std
+    ok = acts.abs().max(dim=1).values < 0.999                    # atanh is ill-conditioned at saturation
+    assert abs(float(z[ok].mean())) < 0.02 and abs(float(z[ok].std()) - 1.0) < 0.02
+    # log-prob of the sample == evaluate() of the squashed action (same formula through atanh)
+    (lp, _), _ = actor.evaluate(obs, acts)
+    assert torch.allclose(lp[ok], logp[ok], rtol=1e-3, atol=2e-3)
+    # and == the oracle's log-prob for the recovered pre-squash sample
+    want = Z.log_prob_from_u(means.cpu(), std.cpu(), u.cpu(), Z.LoopzCfg())
+    assert torch.allclose(logp.cpu()[ok.cpu()], want[ok.cpu()], rtol=1e-3, atol=2e-3)
+
+
+def test_returns_vs_reference(golden):
+    G = golden("loopz_ppo")
+    _, _, ppo = build()
+    fill_from_golden(ppo, G)
+    ppo.storage.compute_returns(T(G["roll_last_values"]).to(DEV), float(G["gamma"]), float(G["lam"]))
+    assert torch.equal(ppo.storage.returns.cpu(), T(G["roll_returns"]))                       # op-by-op like torch: bit-exact
+    assert torch.allclose(ppo.storage.advantages.cpu(), T(G["roll_advantages"]), rtol=1e-5, atol=1e-6)
+    assert torch.isfinite(ppo.storage.returns).all()
+
+
+def test_returns_large_vs_oracle():
+    g = torch.Generator().manual_seed(5)
+    Tn, n = 16, 5003
+    _, _, ppo = build(n=n, horizon=Tn)
+    st = ppo.storage
+    rew, val = torch.randn((Tn, n, 1), generator=g), torch.randn((Tn, n, 1), generator=g)
+    rew[3, 7] = float("inf"); val[5, 9] = float("nan")
+    dn = (torch.rand((Tn, n, 1), generator=g) < 0.1).to(torch.uint8)
+    lv = torch.randn((n, 1), generator=g)
+    st.rewards.copy_(rew); st.values.copy_(val); st.dones.copy_(dn)
+    st.compute_returns(lv.to(DEV), 0.997, 0.95)
+    ret, adv = Z.compute_returns(rew, val, dn, lv, 0.997, 0.95)
+    assert torch.equal(st.returns.cpu(), ret)
+    assert torch.allclose(st.advantages.cpu(), adv, rtol=1e-5, atol=1e-5)
+
+
+def test_minibatch_gradient_vs_reference(golden):
+    G = golden("loopz_ppo")
+    _, _, ppo = build(max_grad_norm=1e9, learning_rate=0.0)
+    ppo.params.copy_(T(G["params0"]))
+    fill_from_golden(ppo, G)
+    ppo.storage.returns.copy_(T(G["roll_returns"])); ppo.storage.advantages.copy_(T(G["roll_advantages"]))
+    for tag, hi in (("full", 384), ("quarter", 96)):
+        ppo._minibatch(0, hi)
+        g = ppo.grads[:ppo.P].cpu()
+        want = T(G[f"grad_{tag}"])
+        # fp32 sums over <= 384 samples in a different order than autograd: 1e-4 relative + 1e-5 of the largest entry
+        assert torch.allclose(g, want, rtol=1e-4, atol=1e-5 * float(want.abs().max())), float((g - want).abs().max())
+        st = ppo.minibatch_statistics()
+        assert abs(st["value_loss"] - float(G[f"grad_{tag}_value_loss"])) < 1e-5
+        assert abs(st["surrogate"] - float(G[f"grad_{tag}_surrogate"])) < 1e-5
+        assert st["skipped"] == 0.0 and st["grad_norm"] == pytest.approx(float(want.norm()), rel=1e-4)
+    assert torch.equal(ppo.params.cpu(), T(G["params0"]))          # lr = 0
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_full_update_vs_reference(golden, graph):
+    """PPO.update semantics: 4 epochs x 4 in-order minibatches, clip 0.5, Adam 5e-4 -- parameters after 16 optimiser steps."""
+    G = golden("loopz_ppo")
+    actor, _, ppo = build(graph=graph)
+    ppo.params.copy_(T(G["params0"]))
+    fill_from_golden(ppo, G)
+    ppo.storage.compute_returns(T(G["roll_last_values"]).to(DEV), float(G["gamma"]), float(G["lam"]))
+    vl, sl, info = ppo._train_step()
+    want = T(G["update_params_after"])
+    err = float((ppo.params.cpu() - want).abs().max())
+    assert err < 2e-5, err                                          # 16 Adam steps of 5e-4 each; the reference moved by > 1e-3
+    assert abs(vl - float(G["update_value_loss"])) < 1e-4 and abs(sl - float(G["update_surrogate"])) < 1e-4
+    assert info["num_valid_updates"] == 16 and int(ppo.adam_step[ppo._parity]) == 16
+    actor.distribution.enforce_minimum_std(torch.tensor([0.05, 0.5]))
+    assert torch.allclose(actor.distribution.std.cpu(), T(G["min_std_after"]), atol=2e-5)
+
+
+@pytest.mark.parametrize("md,D", [(4, 29), (8, 33), (8, 40)])
+def test_gradient_vs_oracle_other_shapes(md, D):
+    """Other privileged-tail widths / obs sizes, 1500 rows (ragged last tile), saturated actions, shuffled index path."""
+    g = torch.Generator().manual_seed(md * 100 + D)
+    n, Tn = 375, 4
+    _, _, ppo = build(D=D, md=md, n=n, horizon=Tn, max_grad_norm=1e9, learning_rate=0.0)
+    cfg = dataclasses.replace(Z.LoopzCfg(), obs_dim=D, mass_dim=md)
+    flat = ppo.params.cpu().clone()
+    flat += 0.03 * torch.randn(flat.shape, generator=g)
+    ppo.params.copy_(flat)
+    st = ppo.storage
+    B = n * Tn
+    obs = torch.randn((Tn, n, D), generator=g)
+    act = torch.tanh(torch.randn((Tn, n, 2), generator=g) * 1.5)
+    act[0, 0] = torch.tensor([1.0, -1.0])
+    cols = {"actor_obs": obs, "critic_obs": obs * 0.5 + 0.1, "actions": act, "values": torch.randn((Tn, n, 1), generator=g),
+            "advantages": torch.randn((Tn, n, 1), generator=g), "returns": torch.randn((Tn, n, 1), generator=g),
+            "actions_log_prob": torch.randn((Tn, n, 1), generator=g) * 0.3 - 1.0}
+    for k, v in cols.items():
+        getattr(st, k).copy_(v)
+    rows = [cols[k].reshape(B, -1) for k in ("actor_obs", "critic_obs", "actions", "values", "advantages", "returns", "actions_log_prob")]
+    want, loss, surr, vloss = Z.minibatch_grad(flat, cfg, *rows)
+    ppo._minibatch(0, B)
+    got = ppo.grads[:ppo.P].cpu()
+    assert torch.allclose(got, want, rtol=2e-4, atol=2e-5 * float(want.abs().max())), float((got - want).abs().max())
+    s = ppo.minibatch_statistics()
+    assert s["loss"] == pytest.approx(loss, rel=1e-4, abs=1e-5) and s["value_loss"] == pytest.approx(vloss, rel=1e-4)
+    # shuffled minibatch: an index list into the storage
+    idx = torch.randperm(B, generator=g)[:701]
+    want_i, *_ = Z.minibatch_grad(flat, cfg, *[r[idx] for r in rows])
+    ppo._minibatch(0, 0, idx.to(DEV))
+    got_i = ppo.grads[:ppo.P].cpu()
+    assert torch.allclose(got_i, want_i, rtol=2e-4, atol=2e-5 * float(want_i.abs().max()))
+
+
+def test_nonfinite_loss_skips_the_step():
+    _, _, ppo = build(n=64, horizon=4)
+    g = torch.Generator().manual_seed(1)
+    st = ppo.storage
+    st.actor_obs.copy_(torch.randn(st.actor_obs.shape, generator=g)); st.critic_obs.copy_(st.actor_obs)
+    st.actions.copy_(torch.rand(st.actions.shape, generator=g) - 0.5)
+    st.advantages.fill_(float("nan"))
+    p0, m0 = ppo.params.clone(), ppo.exp_avg.clone()
+    ppo._minibatch(0, 256)
+    assert ppo.minibatch_statistics()["skipped"] == 1.0
+    assert torch.equal(ppo.params, p0) and torch.equal(ppo.exp_avg, m0) and int(ppo.adam_step[ppo._parity]) == 0
+    st.advantages.normal_(generator=None)
+    ppo._minibatch(0, 256)
+    assert ppo.minibatch_statistics()["skipped"] == 0.0 and not torch.equal(ppo.params, p0) and int(ppo.adam_step[ppo._parity]) == 1
+
+
+def test_shuffle_mode_runs_and_covers_batch():
+    _, _, ppo = build(n=100, horizon=8, sampling="shuffle")
+    parts = ppo.storage.shuffled_indices(4, ppo._gen)
+    assert len(parts) == 4 and sorted(torch.cat(parts).tolist()) == list(range(800))
+    g = torch.Generator().manual_seed(2)
+    st = ppo.storage
+    st.actor_obs.copy_(torch.randn(st.actor_obs.shape, generator=g)); st.critic_obs.copy_(st.actor_obs)
+    st.actions.copy_(torch.rand(st.actions.shape, generator=g) - 0.5)
+    st.rewards.copy_(torch.randn(st.rewards.shape, generator=g) * 0.1)
+    st.compute_returns(torch.zeros(100, 1, device=DEV), 0.997, 0.95)
+    p0 = ppo.params.clone()
+    vl, sl, info = ppo._train_step()
+    assert info["num_valid_updates"] == 16 and math.isfinite(vl) and math.isfinite(sl) and not torch.equal(p0, ppo.params)
+
+
+def test_training_loop_on_the_live_task_learns():
+    """The loopz loop (scripts/train_loopz.py) on the live CaptureXY task: finite throughout, graph replay == eager, return improves."""
+    from omniisaacgymenvs_loop_b200.config import live_default_config, live_task_cfg
+    from scripts.train_loopz import build_learner, make_env, train
+
+    def run(graph, updates):
+        torch.manual_seed(3)                    # network initialisation draws from torch's global generator, like the reference
+        env = make_env(live_task_cfg(live_default_config(num_envs=1024, max_episode_length=300)), DEV, seed=3)
+        ppo = build_learner(env, DEV, 16, seed=3, use_cuda_graph=graph)
+        hist = train(env, ppo, updates, 16, log_every=5, quiet=True)
+        return ppo, hist
+
+    pe, _ = run(False, 3)
+    pg, _ = run(True, 3)
+    assert torch.equal(pe.params, pg.params)                       # the captured update is the eager update
+    ppo, hist = run(True, 120)
+    assert torch.isfinite(ppo.params).all() and float(ppo.actor.distribution.std.min()) >= 0.05
+    rets = [h[1] for h in hist if h[1] == h[1]]
+    assert len(rets) >= 6 and np.mean(rets[-3:]) > np.mean(rets[:3]), rets
