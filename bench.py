@@ -329,6 +329,47 @@ def bench_gae_mlp(device):
     return out
 
 
+def bench_loopz(device, envs=16384, updates=10):
+    """the loopz learner (MLPEncode actor / critic, squashed Gaussian) on the live CaptureXY task, 16 384 envs, horizon 16,
+    4 epochs x 4 in-order minibatches of 65 536 rows: frames/s of the whole loop, the update phase alone, and the kernels."""
+    from omniisaacgymenvs_loop_b200.config import live_default_config, live_task_cfg
+    from scripts.train_loopz import build_learner, make_env, train
+
+    torch.manual_seed(1234)
+    env = make_env(live_task_cfg(live_default_config(num_envs=envs)), str(device), seed=1234)
+    ppo = build_learner(env, str(device), 16, seed=1234)
+    train(env, ppo, 3, 16, log_every=0, quiet=True)                      # warm-up: kernels, graph capture
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    train(env, ppo, updates, 16, log_every=0, quiet=True)
+    e1.record()
+    torch.cuda.synchronize(device)
+    ms = e0.elapsed_time(e1) / updates
+    # update phase alone on the last rollout (storage contents are still there; advantages recomputed)
+    obs = env.observe(as_numpy=False)
+    ppo.storage.step = 16
+    e0.record()
+    for _ in range(5):
+        ppo.storage.compute_returns(ppo.critic.predict(obs), ppo.gamma, ppo.lam)
+        ppo._train_step()
+    e1.record()
+    torch.cuda.synchronize(device)
+    ums = e0.elapsed_time(e1) / 5
+    M = envs * 16 // 4
+    e0.record()
+    for _ in range(4):
+        ppo._minibatch(0, M)
+    e1.record()
+    torch.cuda.synchronize(device)
+    mms = e0.elapsed_time(e1) / 4
+    flops = 3 * 2.0 * (22874 + 22745) * M                                 # fwd + 2x bwd, both networks, algorithmic
+    return {"metric": "PPO frames/sec (loopz learner)", "value": envs * 16 / (ms * 1e-3), "unit": "frames/s", "envs_per_gpu": envs, "horizon": 16,
+            "ms_per_update": ms, "update_phase_ms": ums, "minibatch_rows": M, "minibatch_step_ms": mms,
+            "minibatch_algorithmic_tflops": flops / (mms * 1e-3) / 1e12, "update_in_cuda_graph": ppo._graph is not None,
+            "kernels": "loopz::train_kernel + reduce + adam (fp32 SIMT, csrc/ppo_loopz.cu)", "params": ppo.P}
+
+
 def bench_variant_b(device, envs=16384, steps=400, warmup=50):
     """SURVEY rows B1-B6 (live CaptureXY, 16 obstacles, potential field): the fused live step alone, the steady state with the
     scene rebuilds of the envs that reset (episodes of <= 200 steps), and the scene builder on a dense batch; the CPU oracle's
@@ -423,6 +464,7 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the 4096-env and e2e legs (profiling runs)")
     ap.add_argument("--no-ppo", action="store_true", help="skip the PPO frames/s leg")
     ap.add_argument("--no-variant-b", action="store_true", help="skip the live-task (Variant B) leg")
+    ap.add_argument("--no-loopz", action="store_true", help="skip the loopz-learner leg")
     ap.add_argument("--ppo-envs", type=int, default=16384, help="envs per GPU of the PPO leg (BASELINE config[2])")
     ap.add_argument("--ppo-epochs", type=int, default=10)
     args = ap.parse_args()
@@ -528,6 +570,8 @@ def main():
         line["secondary_kernels"] = bench_gae_mlp(device)
     if not args.no_extra and not args.no_variant_b and rank == 0:
         line["variant_b"] = bench_variant_b(device)
+    if not args.no_extra and not args.no_loopz and rank == 0:
+        line["loopz_ppo"] = bench_loopz(device)
     if dist_on:
         dist.barrier()
     if rank == 0 and not args.no_cpu_baseline and world == 1:

@@ -136,22 +136,64 @@ __device__ inline void load_obs_tile(const Smem& s, const float* __restrict__ ob
   }
 }
 
-template <int KU>
+// C[4 rows][8 cols] += A[rows ty*4..][0..K) * B[0..K)[cols].  A thread's 8 columns are tx*4..+3 and 64+tx*4..+3, so the 16 threads
+// of a half-warp read two contiguous 256 B runs of a B row: conflict-free LDS.128 (8 consecutive columns per thread cost 2 wavefronts
+// more per load; the first capture of this kernel ran the shared-memory pipe at 76 % with 35 % of the wavefronts bank conflicts).
+__device__ __forceinline__ int tile_col(int tx, int c) { return (c < 4) ? tx * 4 + c : 64 + tx * 4 + (c - 4); }
+template <int KU, bool A4>
 __device__ inline void gemm_4x8(const float* __restrict__ Asm, int lda, const float* __restrict__ Bsm, int ldb, int K, int ty, int tx,
                                 float (&acc)[4][8]) {
   const float* a0 = Asm + (ty * 4) * lda;
-  const float* b0 = Bsm + tx * 8;
+  const float* b0 = Bsm + tx * 4;
+  if constexpr (A4) {   // lda and K multiples of 4, A rows 16 B aligned
 #pragma unroll KU
-  for (int k = 0; k < K; ++k) {
-    const float4 bl = *reinterpret_cast<const float4*>(b0 + k * ldb);
-    const float4 bh = *reinterpret_cast<const float4*>(b0 + k * ldb + 4);
-    const float b[8] = {bl.x, bl.y, bl.z, bl.w, bh.x, bh.y, bh.z, bh.w};
+    for (int k = 0; k < K; k += 4) {
+      float4 av[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float a = a0[j * lda + k];
+      for (int j = 0; j < 4; ++j) av[j] = *reinterpret_cast<const float4*>(a0 + j * lda + k);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) acc[j][c] = fmaf(a, b[c], acc[j][c]);
+      for (int kk = 0; kk < 4; ++kk) {
+        const float4 bl = *reinterpret_cast<const float4*>(b0 + (k + kk) * ldb);
+        const float4 bh = *reinterpret_cast<const float4*>(b0 + (k + kk) * ldb + 64);
+        const float b[8] = {bl.x, bl.y, bl.z, bl.w, bh.x, bh.y, bh.z, bh.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float a = kk == 0 ? av[j].x : (kk == 1 ? av[j].y : (kk == 2 ? av[j].z : av[j].w));
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[j][c] = fmaf(a, b[c], acc[j][c]);
+        }
+      }
     }
+  } else {
+#pragma unroll KU
+    for (int k = 0; k < K; ++k) {
+      const float4 bl = *reinterpret_cast<const float4*>(b0 + k * ldb);
+      const float4 bh = *reinterpret_cast<const float4*>(b0 + k * ldb + 64);
+      const float b[8] = {bl.x, bl.y, bl.z, bl.w, bh.x, bh.y, bh.z, bh.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float a = a0[j * lda + k];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[j][c] = fmaf(a, b[c], acc[j][c]);
+      }
+    }
+  }
+}
+// bias -> accumulators, accumulators -> LeakyReLU -> activation tile (two float4 per row)
+__device__ __forceinline__ void acc_init(float (&acc)[4][8], const float* __restrict__ bias, int tx) {
+  const float4 bl = *reinterpret_cast<const float4*>(bias + tx * 4), bh = *reinterpret_cast<const float4*>(bias + 64 + tx * 4);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    acc[j][0] = bl.x; acc[j][1] = bl.y; acc[j][2] = bl.z; acc[j][3] = bl.w;
+    acc[j][4] = bh.x; acc[j][5] = bh.y; acc[j][6] = bh.z; acc[j][7] = bh.w;
+  }
+}
+__device__ __forceinline__ void acc_store_lrelu(const float (&acc)[4][8], float* __restrict__ h, int ty, int tx) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float* row = h + (ty * 4 + j) * HS;
+    *reinterpret_cast<float4*>(row + tx * 4) = make_float4(lrelu(acc[j][0]), lrelu(acc[j][1]), lrelu(acc[j][2]), lrelu(acc[j][3]));
+    *reinterpret_cast<float4*>(row + 64 + tx * 4) = make_float4(lrelu(acc[j][4]), lrelu(acc[j][5]), lrelu(acc[j][6]), lrelu(acc[j][7]));
   }
 }
 
@@ -186,25 +228,13 @@ __device__ inline void net_forward(const Smem& s, const NetLayout& L) {
   __syncthreads();
   const int ty = t >> 4, tx = t & 15;
   float acc[4][8];
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-#pragma unroll
-    for (int c = 0; c < 8; ++c) acc[j][c] = s.b1[tx * 8 + c];
-  gemm_4x8<1>(s.xs, s.xstride, s.w1t, H, L.IN, ty, tx, acc);
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-#pragma unroll
-    for (int c = 0; c < 8; ++c) s.h1[(ty * 4 + j) * HS + tx * 8 + c] = lrelu(acc[j][c]);
+  acc_init(acc, s.b1, tx);
+  gemm_4x8<1, false>(s.xs, s.xstride, s.w1t, H, L.IN, ty, tx, acc);
+  acc_store_lrelu(acc, s.h1, ty, tx);
   __syncthreads();
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-#pragma unroll
-    for (int c = 0; c < 8; ++c) acc[j][c] = s.b2[tx * 8 + c];
-  gemm_4x8<4>(s.h1, HS, s.w2t, HS, H, ty, tx, acc);
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-#pragma unroll
-    for (int c = 0; c < 8; ++c) s.h2[(ty * 4 + j) * HS + tx * 8 + c] = lrelu(acc[j][c]);
+  acc_init(acc, s.b2, tx);
+  gemm_4x8<2, true>(s.h1, HS, s.w2t, HS, H, ty, tx, acc);
+  acc_store_lrelu(acc, s.h2, ty, tx);
   __syncthreads();
 }
 
@@ -415,26 +445,35 @@ __global__ void __launch_bounds__(NT, 1) train_kernel(const float* __restrict__ 
     }
     __syncthreads();
     // ---- dz2 = (dz3 . W3) * lrelu'(h2), in place over h2 --------------------------------------------------
+    {
+      float4 wa[2], wb[2];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int r = ty * 4 + j;
-      const float g0 = s.dz3[r * 4], g1 = s.dz3[r * 4 + 1];
+      for (int hh = 0; hh < 2; ++hh) {
+        wa[hh] = *reinterpret_cast<const float4*>(s.w3 + hh * 64 + tx * 4);
+        wb[hh] = *reinterpret_cast<const float4*>(s.w3 + H + hh * 64 + tx * 4);
+      }
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const int k = tx * 8 + c;
-        const float h = s.h2[r * HS + k];
-        s.h2[r * HS + k] = (g0 * s.w3[k] + g1 * s.w3[H + k]) * lrelu_grad(h);
+      for (int j = 0; j < 4; ++j) {
+        const int r = ty * 4 + j;
+        const float g0 = s.dz3[r * 4], g1 = s.dz3[r * 4 + 1];
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          float4* hp = reinterpret_cast<float4*>(s.h2 + r * HS + hh * 64 + tx * 4);
+          const float4 h = *hp;
+          *hp = make_float4((g0 * wa[hh].x + g1 * wb[hh].x) * lrelu_grad(h.x), (g0 * wa[hh].y + g1 * wb[hh].y) * lrelu_grad(h.y),
+                            (g0 * wa[hh].z + g1 * wb[hh].z) * lrelu_grad(h.z), (g0 * wa[hh].w + g1 * wb[hh].w) * lrelu_grad(h.w));
+        }
       }
     }
     __syncthreads();
     // ---- gW2[o][i] += sum_r dz2[r][o]*h1[r][i]  (8x8 block per thread, registers) ; db2 --------------------
     {
       const float* za = s.h2 + ty * 8;
-      const float* hb = s.h1 + tx * 8;
+      const float* hb = s.h1 + tx * 4;   // i columns tx*4..+3 and 64+tx*4..+3 (conflict-free float4)
 #pragma unroll 4
       for (int r = 0; r < TM; ++r) {
         const float4 al = *reinterpret_cast<const float4*>(za + r * HS), ah = *reinterpret_cast<const float4*>(za + r * HS + 4);
-        const float4 bl = *reinterpret_cast<const float4*>(hb + r * HS), bh = *reinterpret_cast<const float4*>(hb + r * HS + 4);
+        const float4 bl = *reinterpret_cast<const float4*>(hb + r * HS), bh = *reinterpret_cast<const float4*>(hb + r * HS + 64);
         const float av[8] = {al.x, al.y, al.z, al.w, ah.x, ah.y, ah.z, ah.w};
         const float bv[8] = {bl.x, bl.y, bl.z, bl.w, bh.x, bh.y, bh.z, bh.w};
 #pragma unroll
@@ -484,20 +523,40 @@ __global__ void __launch_bounds__(NT, 1) train_kernel(const float* __restrict__ 
     }
     __syncthreads();
     // ---- gw1[o][d] += sum_r dz1[r][o]*zin[r][d] ; db1 ; d(latent) -----------------------------------------
-    for (int e = t; e < H * L.IN; e += NT) {
-      const int d = e >> 7, o = e & (H - 1);
-      float acc = 0.f;
-#pragma unroll 8
-      for (int r = 0; r < TM; ++r) acc = fmaf(s.h1[r * HS + o], s.xs[r * s.xstride + d], acc);
-      s.gw1[o * L.IN + d] += acc;
+    {   // 4 outputs x <= 8 input columns per thread: one LDS.128 of dz1 + one broadcast word of zin feed 4 FMAs each
+      const int o4 = (t & 31) * 4, dg = t >> 5;
+      float g1a[8][4];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { g1a[q][0] = 0.f; g1a[q][1] = 0.f; g1a[q][2] = 0.f; g1a[q][3] = 0.f; }
+#pragma unroll 2
+      for (int r = 0; r < TM; ++r) {
+        const float4 dz = *reinterpret_cast<const float4*>(s.h1 + r * HS + o4);
+        const float* xr = s.xs + r * s.xstride + dg;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (dg + 8 * q < L.IN) {
+            const float x = xr[8 * q];
+            g1a[q][0] = fmaf(dz.x, x, g1a[q][0]); g1a[q][1] = fmaf(dz.y, x, g1a[q][1]);
+            g1a[q][2] = fmaf(dz.z, x, g1a[q][2]); g1a[q][3] = fmaf(dz.w, x, g1a[q][3]);
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int d = dg + 8 * q;
+        if (d < L.IN) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) s.gw1[(o4 + i) * L.IN + d] += g1a[q][i];
+        }
+      }
     }
     if (t < H) {
       float acc = 0.f;
       for (int r = 0; r < TM; ++r) acc += s.h1[r * HS + t];
       s.gb[t] += acc;
     }
-    for (int e = t; e < TM * E3; e += NT) {       // dlat_pre[r][j] = (dz1[r] . W1[:, m0c+j]) * lrelu'(lat[r][j])
-      const int r = e / E3, j = e - r * E3;
+    for (int e = t; e < TM * E3; e += NT) {       // dlat_pre[r][j] = (dz1[r] . W1[:, m0c+j]) * lrelu'(lat[r][j]); a warp = 32 rows, one j
+      const int j = e / TM, r = e - j * TM;
       const float* dz = s.h1 + r * HS;
       const float* w = s.w1t + (m0c + j) * H;
       float acc = 0.f;
@@ -584,7 +643,7 @@ __global__ void __launch_bounds__(NT, 1) train_kernel(const float* __restrict__ 
 #pragma unroll
   for (int a = 0; a < 8; ++a)
 #pragma unroll
-    for (int b = 0; b < 8; ++b) out[L.w2 + (ty * 8 + a) * H + tx * 8 + b] = gW2[a][b];
+    for (int b = 0; b < 8; ++b) out[L.w2 + (ty * 8 + a) * H + tile_col(tx, b)] = gW2[a][b];
   __shared__ float red[4][NT / 32];
   float vals[4] = {st_loss, st_lp, g_sd0, g_sd1};
 #pragma unroll
