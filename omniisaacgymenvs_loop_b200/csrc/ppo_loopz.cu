@@ -210,12 +210,19 @@ __device__ inline void net_forward(const Smem& s, const NetLayout& L) {
     s.e1[r * E1S + o] = lrelu(acc);
   }
   __syncthreads();
-  for (int e = t; e < TM * E2; e += NT) {
-    const int r = e / E2, o = e - r * E2;
-    float acc = s.be2[o];
+  {   // thread = (row, 4 outputs): one broadcast word of e1 + one LDS.128 of W_e2^T feed 4 FMAs
+    static_assert(TM * E2 == NT * 4, "e2 tiling");
+    const int r = t >> 2, o4 = (t & 3) * 4;
+    float4 acc = *reinterpret_cast<const float4*>(s.be2 + o4);
+    const float* er = s.e1 + r * E1S;
 #pragma unroll 8
-    for (int k = 0; k < E1; ++k) acc = fmaf(s.e1[r * E1S + k], s.we2t[k * E2 + o], acc);
-    s.e2[r * E2S + o] = lrelu(acc);
+    for (int k = 0; k < E1; ++k) {
+      const float a = er[k];
+      const float4 w = *reinterpret_cast<const float4*>(s.we2t + k * E2 + o4);
+      acc.x = fmaf(a, w.x, acc.x); acc.y = fmaf(a, w.y, acc.y); acc.z = fmaf(a, w.z, acc.z); acc.w = fmaf(a, w.w, acc.w);
+    }
+    float* out = s.e2 + r * E2S + o4;
+    out[0] = lrelu(acc.x); out[1] = lrelu(acc.y); out[2] = lrelu(acc.z); out[3] = lrelu(acc.w);
   }
   __syncthreads();
   for (int e = t; e < TM * E3; e += NT) {
@@ -591,12 +598,17 @@ __global__ void __launch_bounds__(NT, 1) train_kernel(const float* __restrict__ 
     }
     __syncthreads();
     // ---- encoder layer 2: gwe2[o][k] += sum_r de2[r][o]*e1[r][k] ; de1 in place ------------------------------
-    for (int e = t; e < E2 * E1; e += NT) {
-      const int o = e / E1, k = e - o * E1;
-      float acc = 0.f;
+    {   // thread = (k, 4 outputs o): one word of e1 + 4 broadcast words of de2 feed 4 FMAs
+      static_assert(E2 * E1 == NT * 4, "gwe2 tiling");
+      const int k = t & (E1 - 1), og = (t >> 6) * 4;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll 8
-      for (int r = 0; r < TM; ++r) acc = fmaf(s.e2[r * E2S + o], s.e1[r * E1S + k], acc);
-      s.gwe2[e] += acc;
+      for (int r = 0; r < TM; ++r) {
+        const float x = s.e1[r * E1S + k];
+        const float* d = s.e2 + r * E2S + og;
+        a0 = fmaf(d[0], x, a0); a1 = fmaf(d[1], x, a1); a2 = fmaf(d[2], x, a2); a3 = fmaf(d[3], x, a3);
+      }
+      s.gwe2[(og + 0) * E1 + k] += a0; s.gwe2[(og + 1) * E1 + k] += a1; s.gwe2[(og + 2) * E1 + k] += a2; s.gwe2[(og + 3) * E1 + k] += a3;
     }
     if (t < E2) {
       float acc = 0.f;
@@ -604,12 +616,25 @@ __global__ void __launch_bounds__(NT, 1) train_kernel(const float* __restrict__ 
       s.gbe2[t] += acc;
     }
     __syncthreads();
-    for (int e = t; e < TM * E1; e += NT) {
-      const int r = e / E1, k = e - r * E1;
-      float acc = 0.f;
+    {   // thread = (row, 16 columns k): the row's de2 in registers, W_e2^T rows by LDS.128 (a per-output loop reads W_e2^T with a
+        // 16-way bank conflict: stride 16 words)
+      static_assert(TM * 4 == NT, "de1 tiling");
+      const int r = t >> 2, kb = (t & 3) * 16;
+      float d[E2];
 #pragma unroll
-      for (int o = 0; o < E2; ++o) acc = fmaf(s.e2[r * E2S + o], s.we2t[k * E2 + o], acc);
-      s.e1[r * E1S + k] = acc * lrelu_grad(s.e1[r * E1S + k]);
+      for (int o = 0; o < E2; ++o) d[o] = s.e2[r * E2S + o];
+#pragma unroll 4
+      for (int kk = 0; kk < 16; ++kk) {
+        const float* w = s.we2t + (kb + kk) * E2;
+        float acc = 0.f;
+#pragma unroll
+        for (int o = 0; o < E2; o += 4) {
+          const float4 wv = *reinterpret_cast<const float4*>(w + o);
+          acc = fmaf(d[o], wv.x, acc); acc = fmaf(d[o + 1], wv.y, acc); acc = fmaf(d[o + 2], wv.z, acc); acc = fmaf(d[o + 3], wv.w, acc);
+        }
+        float* ep = s.e1 + r * E1S + kb + kk;
+        *ep = acc * lrelu_grad(*ep);
+      }
     }
     __syncthreads();
     // ---- encoder layer 1: gwe1[o][k] += sum_r de1[r][o]*mass[r][k] -------------------------------------------
