@@ -192,6 +192,18 @@ class _Store:
         self.flat = torch.zeros(self.P, dtype=torch.float32, device=device)
         self.seed = 0
         self.counter = 0
+        # device-side part of the sampling counter: a captured rollout graph adds to it at the end of each replay, the kernels see
+        # (counter - _offset_host) + *counter_offset == counter at every launch (same scheme as FusedUsvEnv.step_offset)
+        self.counter_offset = torch.zeros(1, dtype=torch.int64, device=device)
+        self._offset_host = 0
+
+    def advance_counter_offset(self, calls: int) -> None:
+        """Inside a CUDA-graph capture containing `calls` sampling launches: the next replay draws fresh Philox samples."""
+        self.counter_offset += calls
+
+    def note_graph_replay(self, calls: int) -> None:
+        self.counter += calls
+        self._offset_host += calls
 
 
 def _as_dev(x, device) -> torch.Tensor:
@@ -217,7 +229,8 @@ def _act(store: _Store, actor_obs, critic_obs, eval_actions, actions, log_prob, 
     if sample:
         store.counter += 1
     rc = L.ppo_loopz_act_f32(_lib.ptr(store.flat), ctypes.byref(store.net), _lib.ptr(actor_obs), _lib.ptr(critic_obs),
-                             ctypes.c_uint64(store.seed), ctypes.c_uint64(store.counter), ctypes.c_void_p(0), ctypes.c_int64(0),
+                             ctypes.c_uint64(store.seed), ctypes.c_uint64(store.counter - store._offset_host), _lib.ptr(store.counter_offset),
+                             ctypes.c_int64(0),
                              _lib.ptr(eval_actions), _lib.ptr(actions), _lib.ptr(log_prob), _lib.ptr(means), _lib.ptr(values),
                              ctypes.c_int64(M), _lib.stream())
     _lib.check(rc, "ppo_loopz_act_f32")

@@ -42,7 +42,7 @@ class PPO:
         # one flat parameter vector for both networks: [actor | std | critic] = the reference optimiser's parameter order (ppo.py:60)
         net = actor._store.net
         store = _Store(net, self.device)
-        store.seed, store.counter = actor._store.seed, actor._store.counter
+        store.seed, store.counter = actor._store.seed, actor._store.counter - actor._store._offset_host
         store.flat[:store.PA + 2].copy_(actor._store.flat[:store.PA + 2])
         store.flat[store.PA + 2:].copy_(critic._store.flat[store.PA + 2:])
         actor._bind(store)

@@ -124,15 +124,15 @@ __device__ __forceinline__ int64_t load_scene(const SceneIO& io, int64_t j, floa
 }
 
 // get_spawns obstacle placement for one env by warp 0 (lanes 0..15 = obstacles)  [ref :970-1047]
-__device__ __forceinline__ void place_obstacles(const UsvStepParams& p, uint64_t gid, float tx, float ty, float& ox, float& oy) {
+__device__ __forceinline__ void place_obstacles(const UsvStepParams& p, uint64_t step, uint64_t gid, float tx, float ty, float& ox, float& oy) {
   const int j = threadIdx.x & 31;
-  const Uniform4 r0 = philox_uniform4(p.seed, gid, p.step_counter, RS_RESET_0);
+  const Uniform4 r0 = philox_uniform4(p.seed, gid, step, RS_RESET_0);
   float sx, sy;
   spawn_xy(p, r0, tx, ty, sx, sy);  // the same draw reset_env() of the step kernel will use for the pose
   const float mnx = tx - 12.0f, mny = ty - 12.0f;
   const float spx = (tx + 12.0f) - mnx, spy = (ty + 12.0f) - mny;
   auto draw = [&](int round) {
-    const Uniform4 u = philox_uniform4(p.seed, gid, p.step_counter, RS_OBST + (uint32_t)round * 8u + (uint32_t)((j & 15) >> 1));
+    const Uniform4 u = philox_uniform4(p.seed, gid, step, RS_OBST + (uint32_t)round * 8u + (uint32_t)((j & 15) >> 1));
     ox = __fadd_rn(__fmul_rn((j & 1) ? u.c : u.a, spx), mnx);  // rand * (max - min) + min: two roundings, as torch
     oy = __fadd_rn(__fmul_rn((j & 1) ? u.d : u.b, spy), mny);
   };
@@ -159,7 +159,9 @@ __device__ __forceinline__ void place_obstacles(const UsvStepParams& p, uint64_t
 }
 
 __global__ void __launch_bounds__(kSceneThreads, 1) scene_cost_kernel(SceneIO io, uint32_t* __restrict__ counters, int place,
-                                                                      const __grid_constant__ UsvStepParams p) {
+                                                                      const __grid_constant__ UsvStepParams p,
+                                                                      const uint64_t* __restrict__ step_offset) {
+  const uint64_t step = p.step_counter + (step_offset ? *step_offset : 0ull);   // device-side addend: CUDA-graph replays
   extern __shared__ __align__(16) float smem[];
   float* bufA = smem;
   float* bufB = smem + kGP * kGP;
@@ -178,7 +180,7 @@ __global__ void __launch_bounds__(kSceneThreads, 1) scene_cost_kernel(SceneIO io
         const float* c = io.consts + tile_base(env, USV_C_COUNT);
         const float tx = c[USV_C_TX * kTile], ty = c[USV_C_TY * kTile];
         float ox = 0.0f, oy = 0.0f;
-        place_obstacles(p, (uint64_t)(p.env_id_offset + env), tx, ty, ox, oy);
+        place_obstacles(p, step, (uint64_t)(p.env_id_offset + env), tx, ty, ox, oy);
         if (lane < USV_B_OBSTACLES) {
           float* bc = io.bconsts + tile_base(env, USV_BC_COUNT);
           bc[(USV_BC_OBST + 2 * lane) * kTile] = ox;
@@ -457,14 +459,15 @@ static int scene_grid() {
   return sms;
 }
 
-static int launch_scene(const SceneIO& io, uint32_t* counters, int place, const UsvStepParams* p, cudaStream_t s) {
+static int launch_scene(const SceneIO& io, uint32_t* counters, int place, const UsvStepParams* p, const uint64_t* step_offset,
+                        cudaStream_t s) {
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(scene_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cost_smem_bytes());
     attr = true;
   }
   const int grid = scene_grid();
-  scene_cost_kernel<<<grid, kSceneThreads, cost_smem_bytes(), s>>>(io, counters, place, *p);
+  scene_cost_kernel<<<grid, kSceneThreads, cost_smem_bytes(), s>>>(io, counters, place, *p, step_offset);
   scene_jmax_kernel<<<grid, kSceneThreads, 0, s>>>(io, counters);
   scene_field_kernel<<<grid, kSceneThreads, 0, s>>>(io, counters);
   return finish_launch(3);
@@ -500,7 +503,7 @@ int usv_live_reset_scene_f32(const UsvEnvBuffers* b, const UsvLiveBuffers* lb, c
   io.consts = b->consts;
   io.field = lb->field;
   io.lin = cell_centres;
-  return launch_scene(io, counters, 1, p, s);
+  return launch_scene(io, counters, 1, p, b->step_offset, s);
 }
 
 int usv_live_build_fields_f32(const float* obstacles, const float* targets, const float* cell_centres, float* field,
@@ -520,7 +523,7 @@ int usv_live_build_fields_f32(const float* obstacles, const float* targets, cons
   io.cost_out = cost_out;
   io.lin = cell_centres;
   UsvStepParams p{};
-  return launch_scene(io, counters, 0, &p, s);
+  return launch_scene(io, counters, 0, &p, nullptr, s);
 }
 
 }  // extern "C"

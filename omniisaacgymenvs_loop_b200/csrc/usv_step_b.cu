@@ -304,7 +304,8 @@ __global__ void __launch_bounds__(kBlock, 3) step_live_kernel(UsvEnvBuffers b, U
   const int64_t block_start = (int64_t)blockIdx.x * kBlock;
   const int64_t i = block_start + threadIdx.x;
   const bool active = i < n;
-  const bool any_reset = (lb.reset_epoch[p.step_counter & 1] == p.step_counter);
+  const uint64_t step = p.step_counter + (b.step_offset ? *b.step_offset : 0ull);   // device-side addend: CUDA-graph replays
+  const bool any_reset = (lb.reset_epoch[step & 1] == step);
   LiveOut o;
   o.sw = smem + (threadIdx.x >> 5) * (32 * kObsB) + (threadIdx.x & 31) * kObsB;
   o.chk = 0.0f;
@@ -324,13 +325,13 @@ __global__ void __launch_bounds__(kBlock, 3) step_live_kernel(UsvEnvBuffers b, U
     const float2 act = actions[i];
     const uint64_t gid = (uint64_t)(p.env_id_offset + i);
     if (do_reset && lp.com_rand) {  // MDD._randomize_com  [ref USV_disturbances.py:100-106]
-      const Uniform4 rc = philox_uniform4(p.seed, gid, p.step_counter, RS_RESET_COM);
+      const Uniform4 rc = philox_uniform4(p.seed, gid, step, RS_RESET_COM);
       bc[USV_BC_COM_X * kTile] = lp.com_base[0] + (rc.a * 2.0f - 1.0f) * lp.com_disp[0];
       bc[USV_BC_COM_Y * kTile] = lp.com_base[1] + (rc.b * 2.0f - 1.0f) * lp.com_disp[1];
       bc[USV_BC_COM_Z * kTile] = lp.com_base[2] + (rc.c * 2.0f - 1.0f) * lp.com_disp[2];
     }
     DynOut s;
-    step_dynamics<kDisturb, true>(e, k, p, do_reset, act, gid, i, p.step_counter, b.lut_left, b.lut_right, s);
+    step_dynamics<kDisturb, true>(e, k, p, do_reset, act, gid, i, step, b.lut_left, b.lut_right, s);
     post_live<kStats>(e, k, ls, bc, lb.field + i * (int64_t)(kGridB * kGridB), p, lp, do_reset, any_reset, p.first_call != 0, s, o);
     store_state(b.state, b.state_stride, i, e);
     if (do_reset) store_consts<kDisturb>(b.consts, b.consts_stride, i, k);
@@ -344,7 +345,7 @@ __global__ void __launch_bounds__(kBlock, 3) step_live_kernel(UsvEnvBuffers b, U
     }
     rew[i] = o.rew;
     b.reset_buf[i] = (int64_t)o.done;
-    if (o.done) lb.reset_epoch[(p.step_counter + 1) & 1] = p.step_counter + 1;  // every writer stores the same value
+    if (o.done) lb.reset_epoch[(step + 1) & 1] = step + 1;  // every writer stores the same value
     if (b.nonfinite_flag) {
       if (!o.finite) atomicOr(b.nonfinite_flag, 1u);
       if (!isfinite(act.x) || !isfinite(act.y)) atomicOr(b.nonfinite_flag, 2u);
@@ -468,6 +469,7 @@ __global__ void __launch_bounds__(kBlock, 3) step_task_kernel(UsvEnvBuffers b, U
   const int64_t block_start = (int64_t)blockIdx.x * kBlock;
   const int64_t i = block_start + threadIdx.x;
   const bool active = i < n;
+  const uint64_t step = p.step_counter + (b.step_offset ? *b.step_offset : 0ull);   // device-side addend: CUDA-graph replays
   LiveOut o;
   o.sw = smem + (threadIdx.x >> 5) * (32 * kObsB) + (threadIdx.x & 31) * kObsB;
   o.chk = 0.0f;
@@ -482,7 +484,7 @@ __global__ void __launch_bounds__(kBlock, 3) step_task_kernel(UsvEnvBuffers b, U
     const float2 act = actions[i];
     const uint64_t gid = (uint64_t)(p.env_id_offset + i);
     if (do_reset) {
-      const Uniform4 rc = philox_uniform4(p.seed, gid, p.step_counter, RS_RESET_COM);
+      const Uniform4 rc = philox_uniform4(p.seed, gid, step, RS_RESET_COM);
       if (lp.com_rand) {
         bc[USV_BC_COM_X * kTile] = lp.com_base[0] + (rc.a * 2.0f - 1.0f) * lp.com_disp[0];
         bc[USV_BC_COM_Y * kTile] = lp.com_base[1] + (rc.b * 2.0f - 1.0f) * lp.com_disp[1];
@@ -492,14 +494,14 @@ __global__ void __launch_bounds__(kBlock, 3) step_task_kernel(UsvEnvBuffers b, U
         // task.get_goals at the end of reset_idx  [ref USV_go_to_pose.py:244-246 ; USV_track_xy_velocity.py:141-146]
         if (kTask == USV_TASK_GO_TO_POSE) bc[USV_BC_TARGET_HEADING * kTile] = rc.d * USV_PI_F * 2.0f;
         if (kTask == USV_TASK_TRACK_XY_VELOCITY) {
-          const Uniform4 rt = philox_uniform4(p.seed, gid, p.step_counter, RS_RESET_TASK);
+          const Uniform4 rt = philox_uniform4(p.seed, gid, step, RS_RESET_TASK);
           bc[USV_BC_TARGET_VX * kTile] = rt.a * lp.goal_random_velocity * 2.0f - lp.goal_random_velocity;
           bc[USV_BC_TARGET_VY * kTile] = rt.b * lp.goal_random_velocity * 2.0f - lp.goal_random_velocity;
         }
       }
     }
     DynOut s;
-    step_dynamics<kDisturb, true>(e, k, p, do_reset, act, gid, i, p.step_counter, b.lut_left, b.lut_right, s);
+    step_dynamics<kDisturb, true>(e, k, p, do_reset, act, gid, i, step, b.lut_left, b.lut_right, s);
     post_task<kTask>(e, k, bc, p, lp, do_reset, p.first_call != 0, s, o);
     store_state(b.state, b.state_stride, i, e);
     if (do_reset) store_consts<kDisturb>(b.consts, b.consts_stride, i, k);

@@ -155,6 +155,15 @@ class FusedUsvEnv:
             p.kill_dist = self.cfg.curriculum(self.curriculum_step + 1.0 / self.cfg.horizon_length)[2]
         return p
 
+    def graph_key(self, steps: int):
+        """Host-side parameters that a captured graph of the next `steps` control steps would bake in (None: the window straddles a
+        change and must run eagerly).  The only such parameter is the live task's initial action bias, which is switched off by the
+        host after `action_bias_steps` control steps  [ref: OIGE/tasks/USV_Virtual.py:1070-1077]."""
+        lim = self.cfg.action_bias_steps
+        if self.cfg.action_bias == 0.0 or self.step_counter >= lim:
+            return "steady"
+        return "bias" if self.step_counter + steps <= lim else None
+
     def advance_step_offset(self, steps: int) -> None:
         """Inside a CUDA-graph capture of `steps` control steps: make the next replay continue the Philox step sequence."""
         self.step_offset += steps
@@ -246,7 +255,6 @@ class FusedUsvLiveEnv(FusedUsvEnv):
                  env_id_offset: int = 0, collect_stats: bool = False):
         super().__init__(cfg, num_envs, device, env_id_offset, collect_stats=False)
         self.live = live if live is not None else UsvLiveConfig()
-        self._buffers.step_offset = None          # the live kernels take the step index from UsvStepParams only
         n, nt = self.num_envs, self.stride // 32
         f32 = dict(dtype=torch.float32, device=self.device)
         self.bstate = torch.zeros((nt, E["USV_BS_COUNT"], 32), **f32)

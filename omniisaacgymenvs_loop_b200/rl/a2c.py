@@ -111,7 +111,7 @@ class A2CAgent:
         # "nccl" = dist.all_reduce launched eagerly (NCCL inside a captured graph deadlocked on the 2-GPU box, r01 notes in DESIGN.md)
         self.collective = collective if world_size > 1 else "none"
         self.use_cuda_graph, self._graph = (use_cuda_graph and (world_size == 1 or collective == "peer")), None
-        self._graph_play, self._probe_after_replay = None, False
+        self._graph_play, self._probe_after_replay, self._graph_play_key = None, False, None
         self.graph_launches = {"play": 0, "update": 0}
         self.fused_step = True      # single rank + tensor cores: use PolicyMLP.minibatch_step (fused reduce / Adam / re-pack tail)
         info = vec_env.get_env_info()
@@ -239,12 +239,12 @@ class A2CAgent:
                 pol.optimizer_step()
 
     def _rollout_graph_ok(self) -> bool:
-        """The rollout is captured when the env is the classic fused engine (its kernels take a device-side step offset) and the
-        NaN probe can be deferred to one flag read per epoch."""
+        """The rollout is captured when the env is a fused engine (classic or live: their kernels take a device-side step offset) and
+        the NaN probe can be deferred to one flag read per epoch."""
         task = getattr(getattr(self.vec_env, "env", None), "_task", None)
         eng = getattr(task, "engine", None)
         return (self.use_cuda_graph and eng is not None and getattr(eng, "_buffers", None) is not None
-                and bool(eng._buffers.step_offset) and not getattr(task, "_live", False) and not eng.cfg.spawn_curriculum)
+                and bool(eng._buffers.step_offset) and not eng.cfg.spawn_curriculum)
 
     def _play(self):
         if not self._rollout_graph_ok() or self.epoch_num < 2:
@@ -252,6 +252,12 @@ class A2CAgent:
             return
         task = self.vec_env.env._task
         eng, pol, T = task.engine, self.policy, self.T
+        key = eng.graph_key(T)               # host-side step parameters the capture bakes in (live task: the initial action bias)
+        if key is None:
+            self.play_steps()                                            # the window straddles a parameter change
+            return
+        if key != self._graph_play_key:
+            self._graph_play, self._graph_play_key = None, key
         if self._graph_play is None:
             probe, task._nan_probe = task._nan_probe, False              # no host sync inside the capture: checked after replay
             saved = (eng.step_counter, eng.first_call, pol.sample_counter, task.step, task._calls)

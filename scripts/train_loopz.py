@@ -6,7 +6,6 @@ import argparse
 import os
 import sys
 import time
-from collections import deque
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -35,36 +34,97 @@ def build_learner(env, device, horizon, seed, mass_dim=8, sampling="in_order", u
                lam=0.95, num_mini_batches=4, device=device, mini_batch_sampling=sampling, learning_rate=5e-4, use_cuda_graph=use_cuda_graph)
 
 
-def train(env, ppo, updates, horizon=16, reward_scale=0.01, log_every=10, quiet=False):
-    """-> list of (update, mean episode return over the last 100 finished episodes, frames/s)."""
-    dev = ppo.device
-    ep_ret = torch.zeros(env.num_envs, device=dev)
-    window = deque(maxlen=100)
-    hist = []
-    min_std = torch.full((env.num_acts,), 0.05, device=dev)
-    env.reset()
-    for update in range(updates):
-        t0 = time.time()
-        for _ in range(horizon):
-            obs = env.observe(as_numpy=False)
+class LoopzRunner:
+    """The rollout / update cycle of the loopz script.  The rollout phase (horizon x {observe, env.step, ppo.step, episode-return
+    bookkeeping}) only touches static buffers and device-side counters, so after two eager cycles it is captured into a CUDA graph and
+    replayed (the env kernels and the sampling kernel take device-side step / counter offsets); graphs are keyed by the host-side
+    parameters they bake in (`FusedUsvEnv.graph_key`), a window that straddles a change runs eagerly."""
+
+    def __init__(self, env, ppo, horizon=16, reward_scale=0.01, use_cuda_graph=True):
+        self.env, self.ppo, self.T, self.reward_scale = env, ppo, int(horizon), float(reward_scale)
+        dev = ppo.device
+        self.task = env._task
+        self.engine = getattr(self.task, "engine", None)
+        self.use_cuda_graph = bool(use_cuda_graph) and os.environ.get("USV_NO_GRAPH") != "1" and self.engine is not None
+        self.ep_ret = torch.zeros(env.num_envs, device=dev)
+        self.fin = torch.zeros(2, dtype=torch.float64, device=dev)        # sum of finished-episode returns, their count
+        self.min_std = torch.full((env.num_acts,), 0.05, device=dev)
+        env.reset()
+        self.obs = env.observe(as_numpy=False).clone()                     # static: graph replays read / write it in place
+        self.cycles = 0
+        self._graph, self._graph_key = None, None
+
+    def _rollout(self):
+        env, ppo = self.env, self.ppo
+        obs = self.obs
+        for _ in range(self.T):
             action = ppo.observe(obs)
             reward, dones = env.step(action)
-            ep_ret += reward
-            ppo.step(value_obs=obs, rews=reward * reward_scale, dones=dones, infos=[])
-            if log_every and update % log_every == 0:          # episode-return monitor (host read only on logging updates)
-                d = dones.bool()
-                if bool(d.any()):
-                    window.extend(ep_ret[d].tolist())
-            ep_ret.masked_fill_(dones.bool(), 0.0)
-        ppo.update(actor_obs=env.observe(as_numpy=False), value_obs=env.observe(as_numpy=False), log_this_iteration=False, update=update)
-        ppo.actor.distribution.enforce_minimum_std(min_std)
-        if log_every and update % log_every == 0:
-            torch.cuda.synchronize(dev)
-            fps = horizon * env.num_envs / (time.time() - t0)
-            mean_ret = sum(window) / len(window) if window else float("nan")
+            ppo.step(value_obs=obs, rews=reward * self.reward_scale, dones=dones, infos=[])
+            d = dones.to(torch.float32)
+            self.ep_ret += reward
+            self.fin += torch.stack([(self.ep_ret * d).sum(), d.sum()]).double()
+            self.ep_ret *= 1.0 - d
+            obs = env.observe(as_numpy=False)
+        self.obs.copy_(obs)
+
+    def rollout(self):
+        eng, task, ppo, T = self.engine, self.task, self.ppo, self.T
+        key = eng.graph_key(T) if self.use_cuda_graph else None
+        if key is None or self.cycles < 2 or eng.cfg.spawn_curriculum:
+            self._rollout()
+            return
+        if key != self._graph_key:
+            self._graph, self._graph_key = None, key
+        if self._graph is None:
+            task._nan_probe = False                                         # no host sync inside the capture: check_finite() at log time
+            saved = (eng.step_counter, eng.first_call, task.step, task._calls, ppo._store.counter, ppo.storage.step)
+            torch.cuda.synchronize(ppo.device)
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._rollout()
+                eng.advance_step_offset(T)
+                ppo._store.advance_counter_offset(T)
+            # the capture ran the host code once without executing anything: rewind the host-side counters
+            eng.step_counter, eng.first_call, task.step, task._calls, ppo._store.counter, ppo.storage.step = saved
+        self._graph.replay()
+        eng.note_graph_replay(T)
+        ppo._store.note_graph_replay(T)
+        task.step += T / task.cfg.horizon_length
+        task._calls += T
+        ppo.storage.step = T
+
+    def cycle(self, update: int = 0):
+        self.rollout()
+        self.ppo.update(actor_obs=self.obs, value_obs=self.obs, log_this_iteration=False, update=update)
+        self.ppo.actor.distribution.enforce_minimum_std(self.min_std)       # rlgames_train_loopz.py:1380-1384
+        self.cycles += 1
+
+    def pop_episode_stats(self):
+        """(mean return, count) of the episodes that finished since the last call (one host read)."""
+        s, c = self.fin.tolist()
+        self.fin.zero_()
+        return (s / c if c > 0 else float("nan")), int(c)
+
+
+def train(env, ppo, updates, horizon=16, reward_scale=0.01, log_every=10, quiet=False, use_cuda_graph=True, runner=None):
+    """-> list of (update, mean return of the episodes finished since the previous log line, frames/s)."""
+    run = runner if runner is not None else LoopzRunner(env, ppo, horizon, reward_scale, use_cuda_graph)
+    hist = []
+    t0, n0 = time.time(), 0
+    for update in range(updates):
+        run.cycle(update)
+        if log_every and (update % log_every == 0 or update == updates - 1):
+            torch.cuda.synchronize(ppo.device)
+            if run.engine is not None:
+                run.engine.check_finite()
+            dt = time.time() - t0
+            fps = horizon * env.num_envs * (update + 1 - n0) / max(dt, 1e-9)
+            t0, n0 = time.time(), update + 1
+            mean_ret, n_ep = run.pop_episode_stats()
             hist.append((update, mean_ret, fps))
             if not quiet:
-                print(f"update {update:5d}  return(100) {mean_ret:9.3f}  std {ppo.actor.distribution.std.tolist()}  "
+                print(f"update {update:5d}  return {mean_ret:9.3f} ({n_ep} episodes)  std {ppo.actor.distribution.std.tolist()}  "
                       f"v_loss {ppo.last_stats['mean_value_loss']:.4f}  fps {fps:,.0f}", flush=True)
     return hist
 

@@ -171,6 +171,33 @@ def test_graphed_rollout_and_update_equal_eager():
     assert torch.equal(oa[0]["obs"]["state"], ob[0]["obs"]["state"]) and torch.equal(oa[1], ob[1])
 
 
+def test_graphed_live_rollout_equals_eager():
+    """The LIVE task's rollout (scene rebuilds + fused live step, device-side step offset) replayed as a CUDA graph reproduces the eager
+    loop bit for bit, across the boundary where the host switches the initial action bias off (graphs are keyed by that parameter;
+    the straddling rollout runs eagerly)."""
+    import dataclasses
+    from omniisaacgymenvs_loop_b200.config import live_default_config, live_task_cfg
+
+    def build(graph):
+        cfg = dataclasses.replace(live_default_config(num_envs=512, max_episode_length=30), action_bias_steps=72)
+        env = make_env(live_task_cfg(cfg), DEV, seed=5, collect_stats=False)
+        return A2CAgent(env, PPOConfig(seed=5, minibatch_size=4096), DEV, use_cuda_graph=graph)
+    a, b = build(False), build(True)
+    keys = []
+    for ep in range(8):
+        a.train_epoch()
+        b.train_epoch()
+        keys.append(b._graph_play_key)
+        for k in ("obses", "actions", "rewards", "dones", "values"):
+            assert torch.equal(a.buf[k], b.buf[k]), (ep, k)
+        ea, eb = a.vec_env.env._task.engine, b.vec_env.env._task.engine
+        assert ea.step_counter == eb.step_counter == 16 * (ep + 1) + 1        # + the reset step
+        assert torch.equal(ea.state, eb.state) and torch.equal(ea.bstate, eb.bstate) and torch.equal(ea.bconsts, eb.bconsts)
+        assert torch.equal(ea.potential, eb.potential) and torch.equal(ea.reset_epoch, eb.reset_epoch)
+        assert torch.equal(a.policy.params, b.policy.params), ep
+    assert "bias" in keys and keys[-1] == "steady" and b._graph_play is not None and a._graph_play is None
+
+
 def test_vecenv_curriculum_free_running_vs_oracle():
     """The task-level `step` (control steps / horizon_length) drives the spawn / kill curriculum through USVVirtual."""
     cfg = UsvEnvConfig(num_envs=512, max_episode_length=6, seed=9, spawn_curriculum=True, spawn_curriculum_min_dist=0.2,

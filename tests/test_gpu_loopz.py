@@ -219,12 +219,13 @@ def test_training_loop_on_the_live_task_learns():
         torch.manual_seed(3)                    # network initialisation draws from torch's global generator, like the reference
         env = make_env(live_task_cfg(live_default_config(num_envs=1024, max_episode_length=300)), DEV, seed=3)
         ppo = build_learner(env, DEV, 16, seed=3, use_cuda_graph=graph)
-        hist = train(env, ppo, updates, 16, log_every=5, quiet=True)
+        hist = train(env, ppo, updates, 16, log_every=5, quiet=True, use_cuda_graph=graph)
         return ppo, hist
 
-    pe, _ = run(False, 3)
-    pg, _ = run(True, 3)
-    assert torch.equal(pe.params, pg.params)                       # the captured update is the eager update
+    pe, _ = run(False, 5)
+    pg, _ = run(True, 5)                                             # cycles 0-1 eager, 2 captured, 3-4 replayed
+    assert torch.equal(pe.params, pg.params)                       # the captured rollout + update is the eager loop, bit for bit
+    assert torch.equal(pe.storage.actor_obs, pg.storage.actor_obs) and torch.equal(pe.storage.actions, pg.storage.actions)
     ppo, hist = run(True, 120)
     assert torch.isfinite(ppo.params).all() and float(ppo.actor.distribution.std.min()) >= 0.05
     rets = [h[1] for h in hist if h[1] == h[1]]
