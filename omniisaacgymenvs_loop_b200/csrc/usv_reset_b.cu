@@ -3,9 +3,9 @@
 // [ref: OIGE/tasks/USV/d_multi_gemini.py:66-104 occupancy + SDF, :135-192 cost-to-go wavefront, :194-271 potential field].
 //
 // The reference runs 225 Jacobi sweeps of an 8-neighbour min-plus relaxation as ~30 torch ops per sweep over the whole
-// (B,150,150) batch in HBM.  Here ONE CTA owns one env: both 150x150 cost buffers live in shared memory (2 x 92 KB with an
-// +inf halo), a sweep is one pass over smem, and the CTA stops as soon as a sweep changes nothing (Jacobi iterates are then
-// fixed, so the result is bit-identical to running all 225 sweeps).  The reference's BATCH-GLOBAL maxima (max finite cost,
+// (B,150,150) batch in HBM.  Here ONE CTA owns one env: the 150x150 cost buffer lives in shared memory (92 KB with an +inf halo,
+// two scenes per SM) and is relaxed in place until nothing changes -- the same fixed point, bit for bit, as the reference's Jacobi
+// sweeps (see the comment at scene_cost_kernel).  The reference's BATCH-GLOBAL maxima (max finite cost,
 // max repulsion: quirk 9 of SURVEY appendix C) need two grid-wide reductions, hence three kernels:
 //   scene_cost_kernel  : obstacles (warp 0) -> free mask -> wavefront -> raw cost into field[env], atomicMax(max cost)
 //   scene_jmax_kernel  : repulsion J per cell with the global max cost -> atomicMax(max J), any-inside flag
@@ -158,14 +158,76 @@ __device__ __forceinline__ void place_obstacles(const UsvStepParams& p, uint64_t
   if (invalid()) { ox = 999.0f; oy = 999.0f; }  // leftovers go to limbo
 }
 
-__global__ void __launch_bounds__(kSceneThreads, 1) scene_cost_kernel(SceneIO io, uint32_t* __restrict__ counters, int place,
-                                                                      const __grid_constant__ UsvStepParams p,
-                                                                      const uint64_t* __restrict__ step_offset) {
+// ---- cost-to-go -------------------------------------------------------------------------------------------------------------
+// The reference's 225 Jacobi sweeps converge to the greatest fixed point of  d(c) = min(d(c), min_nb fl(d(nb) + w))  with d = 0 at the
+// target; fl(d + w) is monotone in d, so ANY fair asynchronous (chaotic) iteration from +inf reaches the same fixed point bit for
+// bit.  That licenses an in-place relaxation: ONE 150x150 buffer per scene (92 KB instead of 185 KB: two scenes per SM, which removes
+// the second wave of the typical ~150 resets per control step on 148 SMs), values move a whole tile column per sweep (Gauss-Seidel
+// along the walking direction, which alternates down / up), tiles whose inputs did not change are skipped, and the scene ends at the
+// first sweep without a change.  The 225th Jacobi iterate IS the fixed point whenever every shortest path has <= 225 hops; a hop
+// costs >= 1, so "max finite cost < 224" proves it.  Otherwise (or when the target cell is not free: its 0 is overwritten after one
+// Jacobi sweep, which an asynchronous order does not reproduce) the scene is redone by literal Jacobi sweeps through a global scratch
+// (the env's own field slot) -- never seen with the task's obstacle placement, covered by a dense-batch test.
+constexpr int kCostThreads = 512, kCostWarps = kCostThreads / 32;
+constexpr int kAsyncSweepCap = 4 * kMaxSweeps;
+constexpr int kInner = 32;            // passes of a warp over its tile per outer sweep (one tile width)
+constexpr float kJacobiSafeCost = 224.0f;
+
+__device__ __forceinline__ float block_reduce_max_cost(float v, float* s_red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) s_red[warp] = v;
+  __syncthreads();
+  v = (lane < kCostWarps) ? s_red[lane] : -CUDART_INF_F;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ bool cell_free(const unsigned char* s_free, int x, int y) {
+  return (s_free[((y / kBandRows) * kChunks + (x >> 5)) * 32 + (x & 31)] >> (y % kBandRows)) & 1u;
+}
+
+// literal Jacobi sweeps (d_multi_gemini.py:160-190): cur = buf (shared), nxt = tmp (global), early exit at the first unchanged sweep
+__device__ void jacobi_exact(float* buf, float* __restrict__ tmp, const unsigned char* s_free, int txi, int tyi) {
+  for (int q = threadIdx.x; q < kGP * kGP; q += kCostThreads) buf[q] = CUDART_INF_F;
+  __syncthreads();
+  if (threadIdx.x == 0) buf[(tyi + 1) * kGP + txi + 1] = 0.0f;
+  __syncthreads();
+  for (int sweep = 0; sweep < kMaxSweeps; ++sweep) {
+    int chg = 0;
+    for (int cell = threadIdx.x; cell < kCells; cell += kCostThreads) {
+      const int y = cell / kG, x = cell - y * kG;
+      const float* c = buf + (y + 1) * kGP + x + 1;
+      const float mc = c[0];
+      float best = CUDART_INF_F;
+      if (cell_free(s_free, x, y)) {
+        const float a = fminf(fminf(c[-1], c[1]), fminf(c[-kGP], c[kGP])) + 1.0f;
+        const float b = fminf(fminf(c[-kGP - 1], c[-kGP + 1]), fminf(c[kGP - 1], c[kGP + 1])) + 1.414f;
+        best = fminf(mc, fminf(a, b));
+      }
+      tmp[cell] = best;
+      chg |= (best != mc) ? 1 : 0;
+    }
+    const int any = __syncthreads_or(chg);
+    for (int cell = threadIdx.x; cell < kCells; cell += kCostThreads) {
+      const int y = cell / kG, x = cell - y * kG;
+      buf[(y + 1) * kGP + x + 1] = tmp[cell];
+    }
+    __syncthreads();
+    if (!any) break;
+  }
+}
+
+__global__ void __launch_bounds__(kCostThreads, 2) scene_cost_kernel(SceneIO io, uint32_t* __restrict__ counters, int place,
+                                                                     const __grid_constant__ UsvStepParams p,
+                                                                     const uint64_t* __restrict__ step_offset) {
   const uint64_t step = p.step_counter + (step_offset ? *step_offset : 0ull);   // device-side addend: CUDA-graph replays
   extern __shared__ __align__(16) float smem[];
-  float* bufA = smem;
-  float* bufB = smem + kGP * kGP;
-  float* s_sc = bufB + kGP * kGP;     // 34 floats
+  float* buf = smem;                  // padded 152 x 152, +inf halo
+  float* s_sc = buf + kGP * kGP;      // 34 floats
   float* s_red = s_sc + 64;           // 32 floats
   int* s_act = reinterpret_cast<int*>(s_red + 32);        // [2][96] tile-active flags of the current / next sweep
   uint32_t* s_rowmask = reinterpret_cast<uint32_t*>(s_act + 2 * kActStride);  // [150] obstacles that can matter on a grid row
@@ -193,29 +255,24 @@ __global__ void __launch_bounds__(kSceneThreads, 1) scene_cost_kernel(SceneIO io
     } else {
       env = load_scene(io, j, s_sc);
     }
-    // both buffers +inf (halo included)
-    for (int q = threadIdx.x; q < kGP * kGP; q += kSceneThreads) { bufA[q] = CUDART_INF_F; bufB[q] = CUDART_INF_F; }
+    for (int q = threadIdx.x; q < kGP * kGP; q += kCostThreads) buf[q] = CUDART_INF_F;   // halo included
     if (threadIdx.x < 2 * kActStride) s_act[threadIdx.x] = 0;
     __syncthreads();
     if (threadIdx.x < kG) s_rowmask[threadIdx.x] = row_obstacle_mask(io.lin[threadIdx.x], s_sc + 16);
+    // target cell: ((pos + map/2) / cell).long().clamp(0, 149)   (d_multi_gemini.py:148-155)
+    const int txi = min(max((int)__fdiv_rn(s_sc[32] + 15.0f, 0.2f), 0), kG - 1);
+    const int tyi = min(max((int)__fdiv_rn(s_sc[33] + 15.0f, 0.2f), 0), kG - 1);
     if (threadIdx.x == 0) {
-      // target cell: ((pos + map/2) / cell).long().clamp(0, 149)   (d_multi_gemini.py:148-155).  It is written into BOTH buffers:
-      // the tile-skipping below relies on "a tile that is not swept holds the same values in both buffers"
-      const int txi = min(max((int)__fdiv_rn(s_sc[32] + 15.0f, 0.2f), 0), kG - 1);
-      const int tyi = min(max((int)__fdiv_rn(s_sc[33] + 15.0f, 0.2f), 0), kG - 1);
-      bufA[(tyi + 1) * kGP + txi + 1] = 0.0f;
-      bufB[(tyi + 1) * kGP + txi + 1] = 0.0f;
+      buf[(tyi + 1) * kGP + txi + 1] = 0.0f;
       const int tc = txi >> 5, tb = tyi / kBandRows;
       for (int db = -1; db <= 1; ++db)
         for (int dc = -1; dc <= 1; ++dc)
           if (tc + dc >= 0 && tc + dc < kChunks && tb + db >= 0 && tb + db < kBands) s_act[(tb + db) * kChunks + tc + dc] = 1;
     }
     __syncthreads();
-    // Tiles of 32 columns x 8 rows (95 per grid), dealt round-robin to the 32 warps so that the ring of tiles the wavefront is
-    // crossing is spread over all of them (one 32 x 25 tile per warp left most warps waiting at the sweep barrier: 7 barrier
-    // stalls per issue in the r01 capture).  A lane walks down its column of the tile with a rolling 3x3 window in registers:
-    // 3 shared loads + 1 store per cell instead of 9 + 1.  The per-cell "free" bits of a tile live in shared memory.
-    for (int t = warp; t < kTiles; t += 32) {
+    // free bits of the 95 tiles of 32 columns x 8 rows (dealt round-robin to the warps, so that the ring of tiles the wavefront is
+    // crossing is spread over all of them)
+    for (int t = warp; t < kTiles; t += kCostWarps) {
       const int chunk = t % kChunks, band = t / kChunks;
       const int x = chunk * 32 + lane, y0 = band * kBandRows;
       uint32_t fm = 0;
@@ -231,85 +288,102 @@ __global__ void __launch_bounds__(kSceneThreads, 1) scene_cost_kernel(SceneIO io
       s_free[t * 32 + lane] = (unsigned char)fm;
     }
     __syncthreads();
-    float* cur = bufA;
-    float* nxt = bufB;
-    for (int sweep = 0; sweep < kMaxSweeps; ++sweep) {
-      int* act_cur = s_act + (sweep & 1) * kActStride;
-      int* act_nxt = s_act + ((sweep + 1) & 1) * kActStride;
-      int any_change = 0;
-      for (int t = warp; t < kTiles; t += 32) {
-        if (!act_cur[t]) continue;                 // warp-uniform
-        __syncwarp();
-        if (lane == 0) act_cur[t] = 0;             // consumed; writers of this sweep only touch act_nxt
-        const int chunk = t % kChunks, band = t / kChunks;
-        const int x = chunk * 32 + lane, y0 = band * kBandRows;
-        const int rows = min(kBandRows, kG - y0);
-        const bool xin = x < kG;
-        const int xc = min(x, kG - 1);
-        const uint32_t freemask = s_free[t * 32 + lane];
-        const float* c0 = cur + y0 * kGP + xc + 1;  // (row y0 - 1, column x) in padded coordinates
-        float* n0 = nxt + (y0 + 1) * kGP + xc + 1;
-        float ul = c0[-1], uc = c0[0], ur = c0[1];
-        float ml = c0[kGP - 1], mc = c0[kGP], mr = c0[kGP + 1];
-        uint32_t chg = 0;
+    bool exact = cell_free(s_free, txi, tyi);      // CTA-uniform
+    if (exact) {
+      int sweep = 0;
+      for (; sweep < kAsyncSweepCap; ++sweep) {
+        int* act_cur = s_act + (sweep & 1) * kActStride;
+        int* act_nxt = s_act + ((sweep + 1) & 1) * kActStride;
+        int any_change = 0;
+        for (int t = warp; t < kTiles; t += kCostWarps) {
+          if (!act_cur[t]) continue;                 // warp-uniform
+          __syncwarp();
+          if (lane == 0) act_cur[t] = 0;             // consumed; writers of this sweep only touch act_nxt
+          const int chunk = t % kChunks, band = t / kChunks;
+          const int x = chunk * 32 + lane, y0 = band * kBandRows;
+          const int rows = min(kBandRows, kG - y0);
+          const bool xin = x < kG;
+          const int xc = min(x, kG - 1);
+          const uint32_t freemask = s_free[t * 32 + lane];
+          // Temporal blocking: the warp relaxes ITS tile up to kInner times (until it stops changing) before the CTA-wide barrier, so a
+          // value crosses a whole 32 x 8 tile per outer sweep instead of one cell (legal: any fair asynchronous order reaches the same
+          // fixed point).
+          bool e_left = false, e_right = false, e_up = false, e_dn = false, changed = false, more = true;
+          for (int inner = 0; inner < kInner && more; ++inner) {
+            // one block-Jacobi pass over the tile: all 10 x 3 window values are loaded first (independent loads), then the 8 cells of
+            // the lane's column are relaxed from those registers -- no loop-carried dependency, so the rows pipeline (a Gauss-Seidel
+            // walk that feeds each relaxed row into the next one serialises them: ~4x the latency per pass in the r01 capture)
+            const float* rp = buf + y0 * kGP + xc + 1;    // padded row y0 == grid row y0 - 1
+            float w[kBandRows + 2][3];
 #pragma unroll
-        for (int i = 0; i < kBandRows; ++i) {
-          if (i < rows) {
-            const float* d = c0 + (i + 2) * kGP;
-            const float dl = d[-1], dc = d[0], dr = d[1];
-            float best = CUDART_INF_F;
-            if ((freemask >> i) & 1u) {
-              const float a = fminf(fminf(ml, mr), fminf(uc, dc)) + 1.0f;
-              const float b = fminf(fminf(ul, ur), fminf(dl, dr)) + 1.414f;
-              best = fminf(mc, fminf(a, b));
+            for (int r = 0; r < kBandRows + 2; ++r) {
+              if (r < rows + 2) { w[r][0] = rp[r * kGP - 1]; w[r][1] = rp[r * kGP]; w[r][2] = rp[r * kGP + 1]; }
+              else { w[r][0] = CUDART_INF_F; w[r][1] = CUDART_INF_F; w[r][2] = CUDART_INF_F; }
             }
-            if (xin) {
-              n0[i * kGP] = best;
-              chg |= (best != mc) ? (1u << i) : 0u;
+            uint32_t chg = 0;
+#pragma unroll
+            for (int i = 0; i < kBandRows; ++i) {
+              if (i < rows && ((freemask >> i) & 1u)) {
+                const float mc = w[i + 1][1];
+                const float a = fminf(fminf(w[i + 1][0], w[i + 1][2]), fminf(w[i][1], w[i + 2][1])) + 1.0f;
+                const float b = fminf(fminf(w[i][0], w[i][2]), fminf(w[i + 2][0], w[i + 2][2])) + 1.414f;
+                const float best = fminf(mc, fminf(a, b));
+                if (xin && best != mc) {
+                  buf[(y0 + i + 1) * kGP + xc + 1] = best;
+                  chg |= 1u << i;
+                }
+              }
             }
-            ul = ml; uc = mc; ur = mr;
-            ml = dl; mc = dc; mr = dr;
+            const uint32_t any_b = __ballot_sync(0xffffffffu, chg != 0u);
+            more = any_b != 0u;
+            if (more) {
+              changed = true;
+              e_left |= (any_b & 1u) != 0u;
+              e_right |= ((any_b >> 31) & 1u) != 0u;
+              e_up |= __any_sync(0xffffffffu, chg & 1u) != 0;
+              e_dn |= __any_sync(0xffffffffu, (chg >> (rows - 1)) & 1u) != 0;
+            }
+            __syncwarp();
+          }
+          // activate for the next outer sweep exactly the tiles whose inputs changed: a neighbour when a cell on the shared edge
+          // changed, this tile only if it ran out of passes while still changing
+          if (changed) {
+            any_change = 1;
+            if (lane < 9) {
+              const int dc = lane % 3 - 1, db = lane / 3 - 1;
+              const bool self = dc == 0 && db == 0;
+              const bool need = self ? more : ((dc == 0 || (dc < 0 ? e_left : e_right)) && (db == 0 || (db < 0 ? e_up : e_dn)));
+              const int c2 = chunk + dc, b2 = band + db;
+              if (need && c2 >= 0 && c2 < kChunks && b2 >= 0 && b2 < kBands) act_nxt[b2 * kChunks + c2] = 1;
+            }
           }
         }
-        // activate for the next sweep exactly the tiles whose inputs changed: this one, and a neighbour only when a cell on the
-        // shared edge changed
-        const uint32_t any_b = __ballot_sync(0xffffffffu, chg != 0u);
-        if (any_b) {
-          any_change = 1;
-          const bool left = any_b & 1u, right = (any_b >> 31) & 1u;
-          const bool up = __any_sync(0xffffffffu, chg & 1u), down = __any_sync(0xffffffffu, (chg >> (rows - 1)) & 1u);
-          if (lane < 9) {
-            const int dc = lane % 3 - 1, db = lane / 3 - 1;
-            const bool need = (dc == 0 || (dc < 0 ? left : right)) && (db == 0 || (db < 0 ? up : down));
-            const int c2 = chunk + dc, b2 = band + db;
-            if (need && c2 >= 0 && c2 < kChunks && b2 >= 0 && b2 < kBands) act_nxt[b2 * kChunks + c2] = 1;
-          }
-        }
+        if (!__syncthreads_or(any_change)) break;
       }
-      const int any = __syncthreads_or(any_change);
-      float* tsw = cur; cur = nxt; nxt = tsw;
-      if (!any) break;
+      exact = sweep < kAsyncSweepCap;
     }
-    // raw cost -> field[env] (and the optional dense cost output); max finite cost of the whole batch
-    float mx = -1.0f;
     float* out = io.field + env * (int64_t)kCells;
+    float mx = -1.0f;
+    for (int pass = 0; pass < 2; ++pass) {
+      if (pass == 1 || !exact) jacobi_exact(buf, out, s_free, txi, tyi);
+      // raw cost -> field[env] (and the optional dense cost output); max finite cost
+      mx = -1.0f;
 #pragma unroll 1
-    for (int ri = 0; ri < kRowIters; ++ri) {
-      const int y = warp + 32 * ri;
-      if (y < kG) {
+      for (int y = warp; y < kG; y += kCostWarps) {
 #pragma unroll
         for (int ci = 0; ci < kColIters; ++ci) {
           const int x = lane + 32 * ci;
           if (x < kG) {
-            const float c = cur[(y + 1) * kGP + x + 1];
+            const float c = buf[(y + 1) * kGP + x + 1];
             out[y * kG + x] = c;
             if (io.cost_out) io.cost_out[j * (int64_t)kCells + y * kG + x] = c;
             if (c < CUDART_INF_F) mx = fmaxf(mx, c);
           }
         }
       }
+      mx = block_reduce_max_cost(mx, s_red);
+      if (pass == 1 || !exact || mx < kJacobiSafeCost) break;   // the fixed point is the 225th Jacobi iterate
     }
-    mx = block_reduce_max(mx, s_red);
     if (threadIdx.x == 0 && mx >= 0.0f) {  // non-negative floats order like their bit patterns
       atomicMax(counters + CW_MAXCOST, __float_as_uint(mx));
       atomicOr(counters + CW_HAVE, 1u);
@@ -447,7 +521,7 @@ __global__ void compact_resets_kernel(const int64_t* __restrict__ reset_buf, int
   }
 }
 
-static size_t cost_smem_bytes() { return (size_t)(2 * kGP * kGP + 64 + 32 + 2 * kActStride + 160) * sizeof(float) + (size_t)kTiles * 32; }
+static size_t cost_smem_bytes() { return (size_t)(kGP * kGP + 64 + 32 + 2 * kActStride + 160) * sizeof(float) + (size_t)kTiles * 32; }
 
 static int scene_grid() {
   static int sms = 0;
@@ -467,7 +541,7 @@ static int launch_scene(const SceneIO& io, uint32_t* counters, int place, const 
     attr = true;
   }
   const int grid = scene_grid();
-  scene_cost_kernel<<<grid, kSceneThreads, cost_smem_bytes(), s>>>(io, counters, place, *p, step_offset);
+  scene_cost_kernel<<<2 * grid, kCostThreads, cost_smem_bytes(), s>>>(io, counters, place, *p, step_offset);   // two scenes per SM
   scene_jmax_kernel<<<grid, kSceneThreads, 0, s>>>(io, counters);
   scene_field_kernel<<<grid, kSceneThreads, 0, s>>>(io, counters);
   return finish_launch(3);

@@ -20,11 +20,11 @@ t0 = time.perf_counter()
 for _ in range(a.epochs):
     torch.cuda.synchronize(); t1 = time.perf_counter()
     with torch.no_grad():
-        agent.play_steps()
+        agent._play()                          # rollout graph replay when captured (live kernels take a device-side step offset)
     torch.cuda.synchronize(); t2 = time.perf_counter()
     agent._graph.replay() if agent._graph is not None else agent.update()
     torch.cuda.synchronize(); t3 = time.perf_counter()
     play += t2 - t1; upd += t3 - t2
 tot = time.perf_counter() - t0
-print(f"live PPO envs={a.envs} obs_dim={agent.obs_dim} tensor_cores={agent.policy.tensor_cores}: {tot/a.epochs*1e3:.2f} ms/epoch "
+print(f"live PPO envs={a.envs} obs_dim={agent.obs_dim} tensor_cores={agent.policy.tensor_cores} rollout_graph={agent._graph_play is not None}: {tot/a.epochs*1e3:.2f} ms/epoch "
       f"(rollout {play/a.epochs*1e3:.2f}, update {upd/a.epochs*1e3:.2f}) = {a.envs*16/(tot/a.epochs):.3e} frames/s; reward {agent.episode_stats()}")

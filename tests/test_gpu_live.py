@@ -60,6 +60,29 @@ def test_potential_field_builder_vs_reference_golden(golden):
     assert_close(f1, want, 1e-6, 1e-6, "potential field (batch of one)")
 
 
+def test_cost_to_go_in_place_relaxation_equals_jacobi_on_odd_scenes():
+    """The in-place asynchronous relaxation reaches the Jacobi fixed point bit for bit; scenes where the 225th Jacobi iterate is NOT
+    the fixed point of an asynchronous order (target cell occupied / on the border wall) take the literal-Jacobi path."""
+    g = torch.Generator().manual_seed(31)
+    m = 12
+    obst = (torch.rand((m, 16, 2), generator=g) * 24 - 12)
+    target = torch.rand((m, 2), generator=g) * 20 - 10
+    obst[0, 0] = target[0]                                   # target inside an obstacle
+    target[1] = torch.tensor([14.95, -14.95])                # target in the corner cell (border wall: occupied)
+    target[2] = torch.tensor([-14.7, -14.7])                 # target next to a corner: longest paths (~209 < 224)
+    target[3] = torch.tensor([40.0, 3.0])                    # outside the map: clamped onto the border
+    obst[4, :8, 0] = torch.linspace(-3.5, 3.5, 8); obst[4, :8, 1] = 2.0      # a wall of touching discs across the map centre
+    target[4] = torch.tensor([0.0, 6.0])
+    obst[5] = 999.0                                          # all obstacles in limbo
+    env = FusedUsvLiveEnv(LIVE_CFG, UsvLiveConfig(), 16, DEV)
+    field, cost = env.build_fields(obst, target, want_cost=True)
+    occ, sdf = B.occupancy_and_sdf(obst)
+    want = B.cost_to_go(occ, target)
+    assert torch.equal(cost.cpu(), want)
+    assert float(want[2][torch.isfinite(want[2])].max()) > 200.0
+    assert_close(field, B.potential_field(want, sdf), 1e-6, 1e-6, "potential field (odd scenes)")
+
+
 def test_live_task_vs_reference_golden(golden):
     """B1-B4 on the states the reference task was driven with (n_substeps=0: the kernel's physics is a no-op, the host writes
     pose / velocity every step = the reference's scene-replay mode): obs(33), reward, kills, outcome latches."""
