@@ -126,9 +126,12 @@ def cpu_port(budget_s: float, steps: int | None = None, warmup: int = 1, envs: i
         t = time.perf_counter()
         probe.step(act)
         rate = 16384 / (time.perf_counter() - t)
+        auto_steps = steps is None
         steps = steps or 8
         envs = envs or int(min(1 << 20, max(4096, rate * budget_s / (steps + warmup))))
         envs = 1 << (envs.bit_length() - 1)
+        if auto_steps:          # the env count is capped at the workload's: spend the rest of the budget on more control steps
+            steps = int(max(8, min(64, rate * budget_s / envs - warmup)))
     env = mk(envs)
     g = torch.Generator().manual_seed(0)
     acts = [torch.rand((envs, 2), generator=g) * 2 - 1 for _ in range(4)]
