@@ -98,3 +98,35 @@ def test_host_surface_without_gpu():
         M.Actor(w, dist, "cpu")
     with pytest.raises(_lib.UsvLibraryError):
         M.Critic(M.MLPEncode_wrap([128, 128], "LeakyReLU", 33, 1, speed_dim=3, mass_dim=8), "cpu")
+
+
+def test_loopz_abi_argument_checks_without_gpu():
+    """The loopz entry points validate their arguments before touching the device: sizes, NULL pointers, unsupported shapes."""
+    import ctypes
+    from omniisaacgymenvs_loop_b200 import _lib
+
+    L = _lib.lib()
+    E = _lib.ENUMS
+    Net = _lib.STRUCTS["PpoLoopzNet"]
+    for f in ("ppo_loopz_param_count", "ppo_loopz_actor_param_count", "ppo_loopz_train_scratch_floats", "ppo_loopz_returns_scratch_bytes"):
+        getattr(L, f).restype = ctypes.c_int64
+    net = Net(33, 8, 1, 1.0, 1e-6)
+    assert L.ppo_loopz_param_count(ctypes.byref(net)) == 45621 and L.ppo_loopz_actor_param_count(ctypes.byref(net)) == 22874
+    assert L.ppo_loopz_param_count(ctypes.byref(Net(29, 4, 1, 1.0, 1e-6))) == 2 * (64 * 4 + 64 + 1040 + 136 + 33 * 128 + 128 + 16512) + 258 + 129 + 2
+    assert L.ppo_loopz_param_count(ctypes.byref(Net(33, 9, 1, 1.0, 1e-6))) == -1          # mass_dim > 8
+    assert L.ppo_loopz_param_count(ctypes.byref(Net(8, 8, 1, 1.0, 1e-6))) == -1           # no task columns left
+    assert L.ppo_loopz_train_scratch_floats(ctypes.byref(net)) > 2 * 45621 and L.ppo_loopz_returns_scratch_bytes() > 0
+    null, one = ctypes.c_void_p(0), ctypes.c_void_p(16)
+    i64, i32, f32 = ctypes.c_int64, ctypes.c_int32, ctypes.c_float
+    act = lambda M, params, obs, actions: L.ppo_loopz_act_f32(params, ctypes.byref(net), obs, null, ctypes.c_uint64(0), ctypes.c_uint64(0), null,
+                                                              i64(0), null, actions, null, null, null, i64(M), null)
+    assert act(0, null, null, null) == E["USV_OK"]                                         # empty batch: nothing to do
+    assert act(-1, one, one, one) == E["USV_E_SIZE"]
+    assert act(8, null, one, one) == E["USV_E_NULL"] and act(8, one, null, one) == E["USV_E_NULL"] and act(8, one, one, null) == E["USV_E_NULL"]
+    ret = lambda T, n, p: L.ppo_loopz_returns_f32(p, p, p, p, f32(0.99), f32(0.95), p, p, p, i32(T), i64(n), null)
+    assert ret(0, 5, null) == E["USV_OK"] and ret(16, 0, null) == E["USV_OK"] and ret(-1, 5, one) == E["USV_E_SIZE"] and ret(16, 5, null) == E["USV_E_NULL"]
+    lp = _lib.STRUCTS["PpoLoopzLossParams"](0.2, 0.5, 0.0, 1)
+    grad = lambda M, p: L.ppo_loopz_minibatch_grad_f32(p, ctypes.byref(net), p, p, p, p, p, p, p, null, ctypes.byref(lp), p, p, i64(M), null)
+    assert grad(0, one) == E["USV_E_SIZE"] and grad(64, null) == E["USV_E_NULL"]
+    assert L.ppo_loopz_enforce_min_std_f32(null, null, i32(2), null) == E["USV_E_NULL"]
+    assert L.ppo_loopz_enforce_min_std_f32(one, one, i32(0), null) == E["USV_E_SIZE"]
