@@ -569,6 +569,15 @@ int ppo_loopz_minibatch_grad_f32(const float* params, const PpoLoopzNet* net, co
                                  const float* target_values, const float* returns, const int64_t* index /*[M] or NULL*/,
                                  const PpoLoopzLossParams* lp, float* grads, float* scratch, int64_t M, void* stream);
 
+/* the same minibatch gradient with the two 128-wide layers of each network on the tcgen05 tensor cores (TF32 operands, fp32        */
+/* accumulation in TMEM; ~1e-3 relative of the fp32 entry point above, which stays the numerics reference).  In-order minibatches  */
+/* only (no index list); obs_dim - mass_dim + 8 <= 47.  workspace: ppo_loopz_tc_workspace_floats(net, M) floats, 16 B aligned.    */
+int64_t ppo_loopz_tc_workspace_floats(const PpoLoopzNet* net, int64_t M);
+int ppo_loopz_minibatch_grad_tc(const float* params, const PpoLoopzNet* net, const float* actor_obs, const float* critic_obs,
+                                const float* actions, const float* old_log_prob, const float* advantages, const float* target_values,
+                                const float* returns, const PpoLoopzLossParams* lp, float* grads, float* workspace, int64_t M,
+                                void* stream);
+
 /* clip_grad_norm_(max_grad_norm) + Adam on the whole flat vector; skipped (parameters, moments and step count untouched) when   */
 /* the loss is not finite.  step: device int32[2], the current count is step[parity] and the new one is written to               */
 /* step[1-parity] (the caller alternates parity: no CTA can observe another CTA's update); lr: device float (the host owns the   */

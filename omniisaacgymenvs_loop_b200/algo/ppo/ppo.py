@@ -29,7 +29,7 @@ class PPO:
     def __init__(self, actor: Actor, critic: Critic, num_envs, num_transitions_per_env, num_learning_epochs, num_mini_batches,
                  clip_param=0.2, gamma=0.998, lam=0.95, value_loss_coef=0.5, entropy_coef=0.0, learning_rate=5e-4, max_grad_norm=0.5,
                  use_clipped_value_loss=True, log_dir="run", device="cuda:0", mini_batch_sampling="shuffle", log_intervals=10,
-                 flat_expert=None, use_cuda_graph=True):
+                 flat_expert=None, use_cuda_graph=True, tensor_cores=False):
         if flat_expert is not None:
             raise NotImplementedError("flat_expert (imitation term) is not part of the USV pipeline (rlgames_train_loopz.py:93)")
         if mini_batch_sampling not in ("shuffle", "in_order"):
@@ -81,6 +81,9 @@ class PPO:
         self.log_intervals = log_intervals
         self.actions = self.actions_log_prob = self.actor_obs = None
         self.flat_expert = None
+        # tcgen05 path of the minibatch gradient (TF32 operands; in-order minibatches only); the fp32 SIMT kernels are the numerics reference
+        self.tensor_cores = bool(tensor_cores) and mini_batch_sampling == "in_order"
+        self._tc_ws = None
         self.use_cuda_graph = bool(use_cuda_graph) and mini_batch_sampling == "in_order" and os.environ.get("USV_NO_GRAPH") != "1"
         self._graph = None
         self._gen = torch.Generator(device=self.device)
@@ -144,10 +147,22 @@ class PPO:
             args, M, idx = [ao[lo:hi], co[lo:hi], ac[lo:hi], lp[lo:hi], ad[lo:hi], va[lo:hi], re[lo:hi]], hi - lo, None
         else:
             args, M, idx = [ao, co, ac, lp, ad, va, re], int(index.numel()), index
-        rc = self.lib.ppo_loopz_minibatch_grad_f32(_lib.ptr(self.params), ctypes.byref(self._store.net), *[_lib.ptr(a) for a in args],
-                                                   _lib.ptr(idx), ctypes.byref(self.loss_params), _lib.ptr(self.grads), _lib.ptr(self.scratch),
-                                                   ctypes.c_int64(M), _lib.stream())
-        _lib.check(rc, "ppo_loopz_minibatch_grad_f32")
+        if self.tensor_cores and idx is None:
+            if self._tc_ws is None or self._tc_ws[0] < M:
+                self.lib.ppo_loopz_tc_workspace_floats.restype = ctypes.c_int64
+                nws = int(self.lib.ppo_loopz_tc_workspace_floats(ctypes.byref(self._store.net), ctypes.c_int64(M)))
+                if nws < 0:
+                    raise NotImplementedError("tensor-core loopz path: obs_dim - mass_dim + 8 must be <= 47")
+                self._tc_ws = (M, torch.zeros(nws, dtype=torch.float32, device=self.device))
+            rc = self.lib.ppo_loopz_minibatch_grad_tc(_lib.ptr(self.params), ctypes.byref(self._store.net), *[_lib.ptr(a) for a in args],
+                                                      ctypes.byref(self.loss_params), _lib.ptr(self.grads), _lib.ptr(self._tc_ws[1]),
+                                                      ctypes.c_int64(M), _lib.stream())
+            _lib.check(rc, "ppo_loopz_minibatch_grad_tc")
+        else:
+            rc = self.lib.ppo_loopz_minibatch_grad_f32(_lib.ptr(self.params), ctypes.byref(self._store.net), *[_lib.ptr(a) for a in args],
+                                                       _lib.ptr(idx), ctypes.byref(self.loss_params), _lib.ptr(self.grads),
+                                                       _lib.ptr(self.scratch), ctypes.c_int64(M), _lib.stream())
+            _lib.check(rc, "ppo_loopz_minibatch_grad_f32")
         rc = self.lib.ppo_loopz_adam_step_f32(_lib.ptr(self.params), _lib.ptr(self.grads), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
                                               _lib.ptr(self.lr), _lib.ptr(self.adam_step), ctypes.c_int32(self._parity), _lib.ptr(self._accum),
                                               ctypes.c_int64(self.P), ctypes.c_int64(M), ctypes.byref(self.loss_params),

@@ -179,6 +179,89 @@ def test_gradient_vs_oracle_other_shapes(md, D):
     assert torch.allclose(got_i, want_i, rtol=2e-4, atol=2e-5 * float(want_i.abs().max()))
 
 
+def _fill_random(ppo, g, n, Tn, D):
+    obs = torch.randn((Tn, n, D), generator=g)
+    act = torch.tanh(torch.randn((Tn, n, 2), generator=g) * 1.2)
+    cols = {"actor_obs": obs, "critic_obs": obs, "actions": act, "values": torch.randn((Tn, n, 1), generator=g),
+            "advantages": torch.randn((Tn, n, 1), generator=g), "returns": torch.randn((Tn, n, 1), generator=g),
+            "actions_log_prob": torch.randn((Tn, n, 1), generator=g) * 0.3 - 1.0}
+    for k, v in cols.items():
+        getattr(ppo.storage, k).copy_(v)
+
+
+@pytest.mark.parametrize("n,Tn", [(48, 8), (1500, 4), (4096, 16)])
+def test_tensor_core_gradient_vs_fp32_kernels(n, Tn):
+    """tcgen05 (TF32) minibatch gradient vs the fp32 SIMT kernels on the same minibatch: every parameter block within 40 % of its largest
+    entry (the large blocks also at cosine > 0.98), the whole gradient at cosine > 0.998, statistics at 5e-3.  The bound is not the TF32 rounding itself
+    (~1e-3) but the kinks of LeakyReLU: a pre-activation within that noise of zero flips its derivative between 1 and 0.01, which
+    for ~0.1 % of the (sample, unit) pairs changes a whole gradient term (the same happens to any TF32 training of a ReLU-family net)."""
+    g = torch.Generator().manual_seed(n)
+    _, _, ref = build(n=n, horizon=Tn, max_grad_norm=1e9, learning_rate=0.0)
+    _, _, tc = build(n=n, horizon=Tn, max_grad_norm=1e9, learning_rate=0.0, tensor_cores=True)
+    flat = ref.params.cpu() + 0.03 * torch.randn(ref.P, generator=g)
+    ref.params.copy_(flat); tc.params.copy_(flat)
+    _fill_random(ref, g, n, Tn, 33)
+    # a rollout-like minibatch: old log-probs / values are the current networks' own outputs plus a little drift, so that ratios and
+    # value deltas sit inside the clip ranges (far-off random values put ~0.1 % of the samples within TF32 noise of a clip boundary,
+    # where the surrogate's gradient is discontinuous: the comparison would measure branch flips, not arithmetic)
+    st = ref.storage
+    flat_obs = st.actor_obs.view(-1, 33)
+    (lp0, _), _ = ref.actor.evaluate(flat_obs, st.actions.view(-1, 2))
+    st.actions_log_prob.copy_((lp0 + 0.03 * torch.randn(lp0.shape, generator=g).to(DEV)).view(Tn, n, 1))
+    v0 = ref.critic.predict(flat_obs)
+    st.values.copy_((v0 + 0.03 * torch.randn(v0.shape, generator=g).to(DEV)).view(Tn, n, 1))
+    st.returns.copy_(st.values + 0.5 * torch.randn(st.values.shape, generator=g).to(DEV))
+    for k in ("actor_obs", "critic_obs", "actions", "values", "advantages", "returns", "actions_log_prob"):
+        getattr(tc.storage, k).copy_(getattr(ref.storage, k))
+    B = n * Tn
+    for lo, hi in ((0, B), (B // 4, B // 2)):
+        ref._minibatch(lo, hi); tc._minibatch(lo, hi)
+        a, b = ref.grads[:ref.P].cpu(), tc.grads[:tc.P].cpu()
+        assert torch.isfinite(b).all()
+        cos = float(torch.dot(a, b) / (a.norm() * b.norm()))
+        assert cos > 0.998, cos
+        off = 0
+        sizes = [int(x) for out in (2, 1) for x in [int(np.prod(s)) for s in Z.net_shapes(Z.LoopzCfg(), out)]]
+        sizes = sizes[:12] + [2] + sizes[12:]
+        for i, sz in enumerate(sizes):
+            ea, eb = a[off:off + sz], b[off:off + sz]
+            if sz < 8:                 # std / head biases: sums of strongly cancelling per-sample terms; covered by the overall cosine
+                off += sz
+                continue
+            scale = float(ea.abs().max()) + 1e-12
+            # TF32 products (10-bit mantissas) summed over the samples with cancellation: a few % of the block's largest entry
+            assert float((ea - eb).abs().max()) <= 0.4 * scale + 1e-7, (i, sz, float((ea - eb).abs().max()), scale)
+            if sz >= 1024:
+                assert float(torch.dot(ea, eb) / (ea.norm() * eb.norm() + 1e-20)) > 0.98, i
+            off += sz
+        sa, sb = ref.minibatch_statistics(), tc.minibatch_statistics()
+        for k in ("surrogate", "value_loss", "log_prob", "loss"):
+            assert sb[k] == pytest.approx(sa[k], rel=5e-3, abs=5e-3), (k, sa[k], sb[k])
+
+
+def test_tensor_core_update_tracks_fp32_update(golden):
+    """A full 16-step update on the tensor-core path stays close to the fp32 one (reference golden), eager == graph replay."""
+    G = golden("loopz_ppo")
+    out = []
+    for graph in (False, True):
+        _, _, ppo = build(graph=graph, tensor_cores=True)
+        ppo.params.copy_(T(G["params0"]))
+        fill_from_golden(ppo, G)
+        ppo.storage.compute_returns(T(G["roll_last_values"]).to(DEV), float(G["gamma"]), float(G["lam"]))
+        vl, sl, info = ppo._train_step()
+        assert info["num_valid_updates"] == 16
+        assert abs(vl - float(G["update_value_loss"])) < 5e-3 and abs(sl - float(G["update_surrogate"])) < 5e-3
+        want = T(G["update_params_after"])
+        # Adam normalises every step, so a parameter whose gradient is at the TF32 noise level can move by +-lr per step either way:
+        # compare the MOVEMENT of the whole vector (direction and length), not the worst single parameter
+        d_ref, d_tc = want - T(G["params0"]), ppo.params.cpu() - T(G["params0"])
+        cos = float(torch.dot(d_ref, d_tc) / (d_ref.norm() * d_tc.norm()))
+        rel = float((d_tc - d_ref).norm() / d_ref.norm())
+        assert cos > 0.98 and rel < 0.2, (cos, rel)
+        out.append(ppo.params.clone())
+    assert torch.equal(out[0], out[1])
+
+
 def test_nonfinite_loss_skips_the_step():
     _, _, ppo = build(n=64, horizon=4)
     g = torch.Generator().manual_seed(1)
