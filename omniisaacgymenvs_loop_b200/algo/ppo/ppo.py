@@ -188,8 +188,9 @@ class PPO:
             if self._graph is None:
                 # warm the kernels (cudaFuncSetAttribute etc.) outside capture on a throw-away copy of the optimiser state
                 keep = [t.clone() for t in (self.params, self.exp_avg, self.exp_avg_sq, self.adam_step, self._accum)]
-                self._minibatch(0, self.num_envs)
-                self._minibatch(0, self.num_envs)
+                mb = self.num_envs * self.num_transitions_per_env // self.num_mini_batches
+                self._minibatch(0, mb)          # the real minibatch size: every workspace is allocated before the capture
+                self._minibatch(0, mb)
                 for t, k in zip((self.params, self.exp_avg, self.exp_avg_sq, self.adam_step, self._accum), keep):
                     t.copy_(k)
                 torch.cuda.synchronize(self.device)
