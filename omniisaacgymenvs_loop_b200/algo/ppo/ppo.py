@@ -80,6 +80,7 @@ class PPO:
         self.ep_infos = []
         self.log_intervals = log_intervals
         self.actions = self.actions_log_prob = self.actor_obs = None
+        self.fuse_value, self._fused_obs = True, None
         self.flat_expert = None
         # tcgen05 path of the minibatch gradient (TF32 operands; in-order minibatches only); the fp32 SIMT kernels are the numerics reference
         self.tensor_cores = bool(tensor_cores) and mini_batch_sampling == "in_order"
@@ -103,7 +104,12 @@ class PPO:
         obs_t = _as_dev(actor_obs, self.device)
         s = st.step
         st.actor_obs[s].copy_(obs_t)
-        _act(self._store, st.actor_obs[s], None, None, st.actions[s], st.actions_log_prob[s].view(-1), None, None, self.num_envs, True)
+        # the USV loop hands the SAME observation to step(value_obs=...) (rlgames_train_loopz.py:1038,1184): evaluate the critic on it in
+        # the same launch (grid y = network); step() recognises the object and skips its own critic launch
+        fuse = self.fuse_value and not as_numpy and st.critic_obs.shape[2:] == st.actor_obs.shape[2:]
+        self._fused_obs = actor_obs if fuse else None
+        _act(self._store, st.actor_obs[s], st.actor_obs[s] if fuse else None, None, st.actions[s], st.actions_log_prob[s].view(-1), None,
+             st.values[s].view(-1) if fuse else None, self.num_envs, True)
         self.actor_obs = st.actor_obs[s]
         self.actions, self.actions_log_prob = st.actions[s], st.actions_log_prob[s].view(-1)
         return self.actions.cpu().numpy() if as_numpy else self.actions
@@ -113,8 +119,12 @@ class PPO:
         s = st.step
         if s >= st.num_transitions_per_env:
             raise AssertionError("Rollout buffer overflow")
-        st.critic_obs[s].copy_(_as_dev(value_obs, self.device))
-        _act(self._store, None, st.critic_obs[s], None, None, None, None, st.values[s].view(-1), self.num_envs, False)
+        if value_obs is not None and value_obs is self._fused_obs:
+            st.critic_obs[s].copy_(st.actor_obs[s])                # values[s] was written by observe()
+        else:
+            st.critic_obs[s].copy_(_as_dev(value_obs, self.device))
+            _act(self._store, None, st.critic_obs[s], None, None, None, None, st.values[s].view(-1), self.num_envs, False)
+        self._fused_obs = None
         if isinstance(rews, np.ndarray):
             rews = torch.from_numpy(rews)
         if isinstance(dones, np.ndarray):
