@@ -191,8 +191,8 @@ def _fill_random(ppo, g, n, Tn, D):
 
 @pytest.mark.parametrize("n,Tn", [(48, 8), (1500, 4), (4096, 16)])
 def test_tensor_core_gradient_vs_fp32_kernels(n, Tn):
-    """tcgen05 (TF32) minibatch gradient vs the fp32 SIMT kernels on the same minibatch: every parameter block within 40 % of its largest
-    entry (the large blocks also at cosine > 0.98), the whole gradient at cosine > 0.998, statistics at 5e-3.  The bound is not the TF32 rounding itself
+    """tcgen05 (TF32) minibatch gradient vs the fp32 SIMT kernels on the same minibatch: every weight matrix at cosine > 0.98 and
+    relative L2 error < 0.2, the whole gradient at cosine > 0.998, statistics at 5e-3.  The bound is not the TF32 rounding itself
     (~1e-3) but the kinks of LeakyReLU: a pre-activation within that noise of zero flips its derivative between 1 and 0.01, which
     for ~0.1 % of the (sample, unit) pairs changes a whole gradient term (the same happens to any TF32 training of a ReLU-family net)."""
     g = torch.Generator().manual_seed(n)
@@ -225,14 +225,9 @@ def test_tensor_core_gradient_vs_fp32_kernels(n, Tn):
         sizes = sizes[:12] + [2] + sizes[12:]
         for i, sz in enumerate(sizes):
             ea, eb = a[off:off + sz], b[off:off + sz]
-            if sz < 128:               # std / biases of the narrow layers: sums of strongly cancelling terms; covered by the overall cosine
-                off += sz
-                continue
-            scale = float(ea.abs().max()) + 1e-12
-            # TF32 products (10-bit mantissas) summed over the samples with cancellation: a few % of the block's largest entry
-            assert float((ea - eb).abs().max()) <= 0.4 * scale + 1e-7, (i, sz, float((ea - eb).abs().max()), scale)
-            if sz >= 1024:
+            if sz >= 1024:             # the weight matrices; biases / std are sums of strongly cancelling terms, covered by the overall cosine
                 assert float(torch.dot(ea, eb) / (ea.norm() * eb.norm() + 1e-20)) > 0.98, i
+                assert float((ea - eb).norm() / (ea.norm() + 1e-20)) < 0.2, i
             off += sz
         sa, sb = ref.minibatch_statistics(), tc.minibatch_statistics()
         for k in ("surrogate", "value_loss", "log_prob", "loss"):
