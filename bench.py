@@ -367,10 +367,27 @@ def bench_loopz(device, envs=16384, updates=10):
     torch.cuda.synchronize(device)
     mms = e0.elapsed_time(e1) / 4
     flops = 3 * 2.0 * (22874 + 22745) * M                                 # fwd + 2x bwd, both networks, algorithmic
+    # the same minibatch step by the CPU oracle (plain torch + autograd, the reference's algorithm) on a bounded sample
+    from oracle import loopz_oracle as Z
+    cm = 8192
+    g = torch.Generator().manual_seed(0)
+    rows = [torch.randn((cm, 33), generator=g), None, torch.tanh(torch.randn((cm, 2), generator=g)), torch.randn((cm, 1), generator=g),
+            torch.randn((cm, 1), generator=g), torch.randn((cm, 1), generator=g), torch.randn((cm, 1), generator=g) - 1.0]
+    rows[1] = rows[0]
+    flat = ppo.params.detach().cpu().clone()
+    opt = Z.Adam(flat.numel(), 5e-4)
+    Z.minibatch_grad(flat, Z.LoopzCfg(), *rows)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        gr, *_ = Z.minibatch_grad(flat, Z.LoopzCfg(), *rows)
+        opt.step(flat, gr, 0.5)
+    cpu_s = (time.perf_counter() - t0) / 3
     return {"metric": "PPO frames/sec (loopz learner)", "value": envs * 16 / (ms * 1e-3), "unit": "frames/s", "envs_per_gpu": envs, "horizon": 16,
             "ms_per_update": ms, "update_phase_ms": ums, "minibatch_rows": M, "minibatch_step_ms": mms,
             "minibatch_algorithmic_tflops": flops / (mms * 1e-3) / 1e12, "update_in_cuda_graph": ppo._graph is not None,
-            "kernels": "loopz::train_kernel + reduce + adam (fp32 SIMT, csrc/ppo_loopz.cu)", "params": ppo.P}
+            "kernels": "loopz::train_kernel + reduce + adam (fp32 SIMT, csrc/ppo_loopz.cu)", "params": ppo.P,
+            "cpu_oracle": {"minibatch_rows": cm, "minibatch_step_ms": cpu_s * 1e3, "rows_per_s": cm / cpu_s, "threads": torch.get_num_threads(),
+                           "kind": "port", "gpu_rows_per_s": M / (mms * 1e-3)}}
 
 
 def bench_variant_b(device, envs=16384, steps=400, warmup=50):
