@@ -198,6 +198,27 @@ def time_steps(env, acts, steps, warmup, dist_on, device):
     return ms
 
 
+def gpu_local_cpus(device):
+    """CPUs on the NUMA node of `device`'s PCIe slot (sysfs local_cpulist), or None."""
+    try:
+        pr = torch.cuda.get_device_properties(device)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/local_cpulist") as f:
+            txt = f.read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        return cpus or None
+    except Exception:
+        return None
+
+
 def time_e2e(env, steps, warmup, dist_on, device):
     """The same metric through the public host-buffer call (engine.HostStepper.submit): per step the actions come from pinned host
     memory and obs + reward + done go back to pinned host memory; every copy is inside the timed region, the copies of neighbouring
@@ -206,6 +227,15 @@ def time_e2e(env, steps, warmup, dist_on, device):
     from omniisaacgymenvs_loop_b200.engine import HostStepper
 
     n = env.num_envs
+    # multi-rank: allocate (first-touch) the pinned staging buffers from the CPUs next to this rank's GPU, otherwise every rank's
+    # copies cross the socket interconnect and share one memory controller (8 ranks: 1.55e9 env-steps/s whatever the rank count)
+    saved_aff = None
+    if dist_on:
+        cpus = gpu_local_cpus(device)
+        if cpus:
+            saved_aff = os.sched_getaffinity(0)
+            os.sched_setaffinity(0, cpus)
+            log(f"  e2e: rank pinned to {len(cpus)} CPUs local to {device}")
     g = torch.Generator().manual_seed(1)
     h_act = [(torch.rand((n, 2), generator=g) * 2 - 1).pin_memory() for _ in range(2)]
     h_obs = [torch.empty((n, 13), dtype=torch.float32).pin_memory() for _ in range(2)]
@@ -234,6 +264,8 @@ def time_e2e(env, steps, warmup, dist_on, device):
         ms = float(t.item())
     h2d = n * 2 * 4
     d2h = n * 13 * 4 + n * 4 + n * 1
+    if saved_aff is not None:
+        os.sched_setaffinity(0, saved_aff)
     return ms, h2d, d2h, float(h_rew[0].mean())
 
 
