@@ -23,7 +23,7 @@
 namespace loopztc {
 
 constexpr int E1 = PPO_LOOPZ_ENC1, E2 = PPO_LOOPZ_ENC2, E3 = PPO_LOOPZ_LATENT;
-constexpr int ETM = 64, ENT = 256, E1S = E1 + 1, E2S = E2 + 1, MS = PPO_LOOPZ_MAX_MASS + 1, DZS = H + 4;
+constexpr int ETM = 64, ENT = 256, E1S = E1 + 1, E2S = E2 + 1, MS = PPO_LOOPZ_MAX_MASS + 1;
 constexpr float kSlope = 0.01f;
 constexpr int kEncSlots = 320;          // partial-gradient slots of the encoder backward kernel (>= its grid)
 __device__ __forceinline__ float lrelu(float x) { return x > 0.f ? x : kSlope * x; }
