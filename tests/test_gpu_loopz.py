@@ -294,6 +294,31 @@ def test_shuffle_mode_runs_and_covers_batch():
     assert info["num_valid_updates"] == 16 and math.isfinite(vl) and math.isfinite(sl) and not torch.equal(p0, ppo.params)
 
 
+def test_rollout_storage_surface():
+    """RolloutStorage keeps the reference's surface: add_transitions from numpy or tensors, overflow assertion, both generators."""
+    from omniisaacgymenvs_loop_b200.algo.ppo import RolloutStorage
+    st = RolloutStorage(10, 3, [33], [33], [2], DEV)
+    g = torch.Generator().manual_seed(0)
+    for k in range(3):
+        obs = torch.randn((10, 33), generator=g)
+        args = (obs.numpy(), obs.numpy(), torch.rand((10, 2), generator=g), torch.randn(10, generator=g).numpy(),
+                (torch.rand(10, generator=g) < 0.3).numpy(), torch.randn((10, 1), generator=g), torch.randn(10, generator=g))
+        if k == 1:                                  # CUDA tensors are accepted as well
+            args = tuple(torch.as_tensor(a).to(DEV) for a in args)
+        st.add_transitions(*args)
+    assert st.step == 3 and st.dones.dtype == torch.uint8 and st.actor_obs.shape == (3, 10, 33)
+    with pytest.raises(AssertionError, match="overflow"):
+        st.add_transitions(*args)
+    st.compute_returns(torch.zeros((10, 1)), 0.99, 0.95)
+    assert torch.isfinite(st.returns).all() and abs(float(st.advantages.mean())) < 1e-5
+    ordered = list(st.mini_batch_generator_inorder(3))
+    assert len(ordered) == 3 and ordered[0][0].shape == (10, 33) and torch.equal(ordered[1][0], st.actor_obs[1])   # time-major row blocks
+    shuffled = list(st.mini_batch_generator_shuffle(3))
+    assert len(shuffled) == 3 and all(b[2].shape == (10, 2) for b in shuffled)
+    st.clear()
+    assert st.step == 0
+
+
 def test_numpy_boundary_and_fused_value_path():
     """The reference's host contract (numpy observations in, numpy actions out, numpy rewards / dones into step) and the device fast
     path (CUDA tensors, critic evaluated in observe()'s launch) fill the storage identically."""
