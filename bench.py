@@ -399,6 +399,17 @@ def bench_loopz(device, envs=16384, updates=10):
     torch.cuda.synchronize(device)
     mms = e0.elapsed_time(e1) / 4
     flops = 3 * 2.0 * (22874 + 22745) * M                                 # fwd + 2x bwd, both networks, algorithmic
+    # the optional tcgen05 path of the same minibatch step (TF32 trunk, off by default)
+    ppo.tensor_cores = True
+    for _ in range(2):
+        ppo._minibatch(0, M)
+    e0.record()
+    for _ in range(4):
+        ppo._minibatch(0, M)
+    e1.record()
+    torch.cuda.synchronize(device)
+    tms = e0.elapsed_time(e1) / 4
+    ppo.tensor_cores = False
     # the same minibatch step by the CPU oracle (plain torch + autograd, the reference's algorithm) on a bounded sample
     from oracle import loopz_oracle as Z
     cm = 8192
@@ -416,7 +427,8 @@ def bench_loopz(device, envs=16384, updates=10):
     cpu_s = (time.perf_counter() - t0) / 3
     return {"metric": "PPO frames/sec (loopz learner)", "value": envs * 16 / (ms * 1e-3), "unit": "frames/s", "envs_per_gpu": envs, "horizon": 16,
             "ms_per_update": ms, "update_phase_ms": ums, "minibatch_rows": M, "minibatch_step_ms": mms,
-            "minibatch_algorithmic_tflops": flops / (mms * 1e-3) / 1e12, "update_in_cuda_graph": ppo._graph is not None,
+            "minibatch_algorithmic_tflops": flops / (mms * 1e-3) / 1e12, "minibatch_step_ms_tcgen05_tf32": tms,
+            "update_in_cuda_graph": ppo._graph is not None,
             "kernels": "loopz::train_kernel + reduce + adam (fp32 SIMT, csrc/ppo_loopz.cu)", "params": ppo.P,
             "cpu_oracle": {"minibatch_rows": cm, "minibatch_step_ms": cpu_s * 1e3, "rows_per_s": cm / cpu_s, "threads": torch.get_num_threads(),
                            "kind": "port", "gpu_rows_per_s": M / (mms * 1e-3)}}
