@@ -385,6 +385,15 @@ int ppo_gae_f32(const float* rewards /*[T,n]*/, const float* values /*[T,n]*/,
                 float* advantages /*[T,n]*/, float* returns /*[T,n] or NULL*/,
                 int32_t T, int64_t n, void* stream);
 
+/* P6  play_steps bookkeeping of one control step, fused: rewards_out = rew*scale (DefaultRewardsShaper), dones_out = uint8(dones),   */
+/*   current_rewards += rew, current_lengths += 1, sums over the finished envs into episode_acc (fp64: return, length, count) and    */
+/*   into the two windowed AverageMeters (mean, current_size), then the finished envs' running values are zeroed.                    */
+/*     [ref: RLG/common/a2c_common.py:708-747 ; RLG/algos_torch/torch_ext.py:281-307]                                                */
+int ppo_rollout_bookkeep_f32(const float* rew /*[n]*/, const int64_t* dones /*[n]*/, float scale, float* rewards_out /*[n]*/,
+                             uint8_t* dones_out /*[n]*/, float* cur_rew /*[n]*/, float* cur_len /*[n]*/, double* episode_acc /*[3]*/,
+                             float* meter_r, float* meter_r_size, float* meter_l, float* meter_l_size, float max_size, int64_t n,
+                             void* stream);
+
 /* ------------------------------------------------------------------------- */
 /* P4/P5  USV_PPOcontinuous_MLP: shared-trunk actor-critic                     */
 /*   obs(D) -> RunningMeanStd norm (clamp +-5) -> Linear(D,128)+tanh -> Linear(128,128)+tanh -> {mu: Linear(128,2),  */

@@ -65,9 +65,77 @@ __global__ void __launch_bounds__(256) gae_kernel(const float* __restrict__ rewa
   }
 }
 
+// play_steps bookkeeping of one control step, fused (the eager loop spends ~40 tiny elementwise / reduction launches on it per step,
+// more than the env step and the policy inference together): reward shaping, uint8 dones, per-env running return / length, the sums
+// over the envs that finished, the fp64 epoch accumulators and the two windowed AverageMeters.  One CTA, fixed-order tree reduction:
+// deterministic.   [ref: RLG/common/a2c_common.py:708-747 ; RLG/algos_torch/torch_ext.py:281-307]
+constexpr int kBookThreads = 1024;
+__device__ __forceinline__ void meter_update(float* mean, float* size, float max_size, float value_sum, float count) {
+  if (count > 0.0f) {   // size = clip(count, 0, max); old = min(max - size, current); mean = (mean*old + new_mean*size) / (old + size)
+    const float new_mean = value_sum / fmaxf(count, 1.0f);
+    const float sz = fminf(fmaxf(count, 0.0f), max_size);
+    const float old = fminf(max_size - sz, *size);
+    const float tot = old + sz;
+    *mean = (*mean * old + new_mean * sz) / fmaxf(tot, 1.0f);
+    *size = tot;
+  }
+}
+__global__ void __launch_bounds__(kBookThreads) rollout_bookkeep_kernel(const float* __restrict__ rew, const int64_t* __restrict__ dones,
+                                                                        float scale, float* __restrict__ rewards_out,
+                                                                        uint8_t* __restrict__ dones_out, float* __restrict__ cur_rew,
+                                                                        float* __restrict__ cur_len, double* __restrict__ episode_acc,
+                                                                        float* __restrict__ meter_r, float* __restrict__ meter_r_size,
+                                                                        float* __restrict__ meter_l, float* __restrict__ meter_l_size,
+                                                                        float max_size, int64_t n) {
+  __shared__ float sh[3][kBookThreads / 32];
+  float rs = 0.f, ls = 0.f, cnt = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += kBookThreads) {
+    const float r = rew[i];
+    const float d = dones[i] != 0 ? 1.0f : 0.0f;
+    rewards_out[i] = r * scale;                  // DefaultRewardsShaper
+    dones_out[i] = (uint8_t)(d != 0.0f);
+    const float cr = cur_rew[i] + r, cl = cur_len[i] + 1.0f;
+    rs += cr * d; ls += cl * d; cnt += d;
+    cur_rew[i] = cr * (1.0f - d);
+    cur_len[i] = cl * (1.0f - d);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    rs += __shfl_xor_sync(0xffffffffu, rs, o); ls += __shfl_xor_sync(0xffffffffu, ls, o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = rs; sh[1][threadIdx.x >> 5] = ls; sh[2][threadIdx.x >> 5] = cnt; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    rs = sh[0][threadIdx.x]; ls = sh[1][threadIdx.x]; cnt = sh[2][threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      rs += __shfl_xor_sync(0xffffffffu, rs, o); ls += __shfl_xor_sync(0xffffffffu, ls, o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if (threadIdx.x == 0) {
+      episode_acc[0] += (double)rs; episode_acc[1] += (double)ls; episode_acc[2] += (double)cnt;
+      meter_update(meter_r, meter_r_size, max_size, rs, cnt);
+      meter_update(meter_l, meter_l_size, max_size, ls, cnt);
+    }
+  }
+}
+
 }  // namespace usv
 
 using namespace usv;
+
+extern "C" int ppo_rollout_bookkeep_f32(const float* rew, const int64_t* dones, float scale, float* rewards_out, uint8_t* dones_out,
+                                        float* cur_rew, float* cur_len, double* episode_acc, float* meter_r, float* meter_r_size,
+                                        float* meter_l, float* meter_l_size, float max_size, int64_t n, void* stream) {
+  if (n < 0) return USV_E_SIZE;
+  if (n == 0) return USV_OK;
+  if (!rew || !dones || !rewards_out || !dones_out || !cur_rew || !cur_len || !episode_acc || !meter_r || !meter_r_size || !meter_l ||
+      !meter_l_size)
+    return USV_E_NULL;
+  rollout_bookkeep_kernel<<<1, kBookThreads, 0, (cudaStream_t)stream>>>(rew, dones, scale, rewards_out, dones_out, cur_rew, cur_len,
+                                                                         episode_acc, meter_r, meter_r_size, meter_l, meter_l_size,
+                                                                         max_size, n);
+  return finish_launch();
+}
 
 extern "C" int ppo_gae_f32(const float* rewards, const float* values, const uint8_t* dones, const float* last_values,
                            const uint8_t* last_dones, float gamma, float tau, float* advantages, float* returns,

@@ -142,6 +142,7 @@ class A2CAgent:
         self.returns = torch.zeros((T, N), **f32)
         self.last_values = torch.zeros((N, 1), **f32)
         self.dones = torch.ones(N, dtype=torch.uint8, device=self.device)   # [ref: a2c_common.py:454]
+        self._dones_next = torch.zeros((2, N), dtype=torch.uint8, device=self.device)   # double buffer: step n's flags are read at step n+1
         self.current_rewards = torch.zeros(N, **f32)
         self.current_lengths = torch.zeros(N, **f32)
         # finished-episode accumulators: [sum of returns, sum of lengths, count] (all-reduced once per epoch)
@@ -172,16 +173,16 @@ class A2CAgent:
             # preprocess_actions: clamp to [-1, 1]  [ref: a2c_common.py:1134-1144] (the stored action stays unclamped)
             obs_dict, rew, dones, infos = self.vec_env.step(torch.clamp(b["actions"][n], -1.0, 1.0))
             obs = obs_dict["obs"]["state"]
-            b["rewards"][n] = rew * self.cfg.reward_scale                    # DefaultRewardsShaper [ref: tr_helpers.py:33-42]
-            dones_u8 = dones.to(torch.uint8)
-            # episode bookkeeping without host syncs  [ref: a2c_common.py:720-747]
-            self.current_rewards += rew
-            self.current_lengths += 1
-            d = dones.to(torch.float32)
-            rs, ls, cnt = (self.current_rewards * d).sum(), (self.current_lengths * d).sum(), d.sum()
-            self.episode_acc += torch.stack([rs, ls, cnt]).double()
-            self.game_rewards.update(rs, cnt)
-            self.game_lengths.update(ls, cnt)
+            # reward shaping (DefaultRewardsShaper [ref: tr_helpers.py:33-42]), uint8 dones and the episode bookkeeping [ref:
+            # a2c_common.py:720-747] in ONE launch, no host sync: ~40 tiny elementwise / reduction launches per control step otherwise
+            dones_u8 = self._dones_next[n & 1]
+            rew_c, dones_c = rew.contiguous(), dones.contiguous()
+            _lib.check(_lib.lib().ppo_rollout_bookkeep_f32(
+                _lib.ptr(rew_c, torch.float32), _lib.ptr(dones_c, torch.int64), ctypes.c_float(self.cfg.reward_scale), _lib.ptr(b["rewards"][n]),
+                _lib.ptr(dones_u8), _lib.ptr(self.current_rewards), _lib.ptr(self.current_lengths), _lib.ptr(self.episode_acc),
+                ctypes.c_void_p(self.game_rewards.mean.data_ptr()), ctypes.c_void_p(self.game_rewards.current_size.data_ptr()),
+                ctypes.c_void_p(self.game_lengths.mean.data_ptr()), ctypes.c_void_p(self.game_lengths.current_size.data_ptr()),
+                ctypes.c_float(self.game_rewards.max_size), ctypes.c_int64(self.num_actors), _lib.stream()), "ppo_rollout_bookkeep_f32")
             ep = infos.get("episode") if isinstance(infos, dict) else None
             if ep:                                                       # observer.process_infos
                 for k, v in ep.items():
@@ -189,8 +190,6 @@ class A2CAgent:
                         self.ep_info_sum[k] = torch.zeros((), dtype=torch.float32, device=self.device)
                     self.ep_info_sum[k] += v
                 self.ep_info_n += 1
-            self.current_rewards *= 1.0 - d
-            self.current_lengths *= 1.0 - d
         self.obs.copy_(obs)
         self.dones.copy_(dones_u8)
         pol.values(self.obs, self.last_values)
