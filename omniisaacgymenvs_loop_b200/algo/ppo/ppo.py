@@ -114,7 +114,9 @@ class PPO:
         self.actions, self.actions_log_prob = st.actions[s], st.actions_log_prob[s].view(-1)
         return self.actions.cpu().numpy() if as_numpy else self.actions
 
-    def step(self, value_obs, rews, dones, infos):
+    def step(self, value_obs, rews, dones, infos, prewritten: bool = False):
+        """`prewritten`: storage.rewards[step] / storage.dones[step] were already filled on the device (the fused bookkeeping kernel of
+        scripts/train_loopz.py writes them), rews / dones are ignored."""
         st = self.storage
         s = st.step
         if s >= st.num_transitions_per_env:
@@ -125,12 +127,13 @@ class PPO:
             st.critic_obs[s].copy_(_as_dev(value_obs, self.device))
             _act(self._store, None, st.critic_obs[s], None, None, None, None, st.values[s].view(-1), self.num_envs, False)
         self._fused_obs = None
-        if isinstance(rews, np.ndarray):
-            rews = torch.from_numpy(rews)
-        if isinstance(dones, np.ndarray):
-            dones = torch.from_numpy(dones)
-        st.rewards[s].copy_(rews.to(self.device, torch.float32).view(-1, 1))
-        st.dones[s].copy_(dones.to(self.device).view(-1, 1))
+        if not prewritten:
+            if isinstance(rews, np.ndarray):
+                rews = torch.from_numpy(rews)
+            if isinstance(dones, np.ndarray):
+                dones = torch.from_numpy(dones)
+            st.rewards[s].copy_(rews.to(self.device, torch.float32).view(-1, 1))
+            st.dones[s].copy_(dones.to(self.device).view(-1, 1))
         st.step += 1
         for info in infos:
             ep_info = info.get("episode")

@@ -8,8 +8,11 @@ import sys
 import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ctypes
+
 import torch
 
+from omniisaacgymenvs_loop_b200 import _lib
 from omniisaacgymenvs_loop_b200.algo.ppo import PPO, module as ppo_module
 from omniisaacgymenvs_loop_b200.config import live_default_config, live_task_cfg, load_task_yaml
 from omniisaacgymenvs_loop_b200.envs.usv_raisim_vecenv import USVRaisimVecEnv
@@ -47,7 +50,9 @@ class LoopzRunner:
         self.engine = getattr(self.task, "engine", None)
         self.use_cuda_graph = bool(use_cuda_graph) and os.environ.get("USV_NO_GRAPH") != "1" and self.engine is not None
         self.ep_ret = torch.zeros(env.num_envs, device=dev)
-        self.fin = torch.zeros(2, dtype=torch.float64, device=dev)        # sum of finished-episode returns, their count
+        self.ep_len = torch.zeros(env.num_envs, device=dev)
+        self.fin = torch.zeros(3, dtype=torch.float64, device=dev)        # finished episodes: sum of returns, sum of lengths, count
+        self.meter = torch.zeros(4, device=dev)                           # windowed (100) mean return / size, mean length / size
         self.min_std = torch.full((env.num_acts,), 0.05, device=dev)
         env.reset()
         self.obs = env.observe(as_numpy=False).clone()                     # static: graph replays read / write it in place
@@ -60,11 +65,15 @@ class LoopzRunner:
         for _ in range(self.T):
             action = ppo.observe(obs)
             reward, dones = env.step(action)
-            ppo.step(value_obs=obs, rews=reward * self.reward_scale, dones=dones, infos=[])
-            d = dones.to(torch.float32)
-            self.ep_ret += reward
-            self.fin += torch.stack([(self.ep_ret * d).sum(), d.sum()]).double()
-            self.ep_ret *= 1.0 - d
+            # reward scaling into the storage, uint8 dones, running returns / lengths and the finished-episode sums: one launch
+            st, m = ppo.storage, self.meter
+            _lib.check(_lib.lib().ppo_rollout_bookkeep_f32(
+                _lib.ptr(reward.contiguous(), torch.float32), _lib.ptr(dones.contiguous(), torch.int64), ctypes.c_float(self.reward_scale),
+                _lib.ptr(st.rewards[st.step]), _lib.ptr(st.dones[st.step]), _lib.ptr(self.ep_ret), _lib.ptr(self.ep_len), _lib.ptr(self.fin),
+                ctypes.c_void_p(m.data_ptr()), ctypes.c_void_p(m.data_ptr() + 4), ctypes.c_void_p(m.data_ptr() + 8),
+                ctypes.c_void_p(m.data_ptr() + 12), ctypes.c_float(100.0), ctypes.c_int64(env.num_envs), _lib.stream()),
+                "ppo_rollout_bookkeep_f32")
+            ppo.step(value_obs=obs, rews=None, dones=None, infos=[], prewritten=True)
             obs = env.observe(as_numpy=False)
         self.obs.copy_(obs)
 
@@ -102,7 +111,7 @@ class LoopzRunner:
 
     def pop_episode_stats(self):
         """(mean return, count) of the episodes that finished since the last call (one host read)."""
-        s, c = self.fin.tolist()
+        s, _, c = self.fin.tolist()
         self.fin.zero_()
         return (s / c if c > 0 else float("nan")), int(c)
 

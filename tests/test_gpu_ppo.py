@@ -287,3 +287,39 @@ def test_tensor_core_paths_at_live_obs_width():
             assert abs(sa[k] - sb[k]) <= 1e-2 * abs(sb[k]) + 5e-4, (it, k, sa[k], sb[k])
         # each Adam step moves a weight by <= lr (sign flips of near-zero gradients: <= 2 lr apart), lr grows x1.5 per step at low KL
         assert float((tc.params - ref.params).abs().max()) < (it + 1) * 4e-4
+
+
+def test_rollout_bookkeeping_kernel_vs_torch_ops():
+    """ppo_rollout_bookkeep_f32 == the eager bookkeeping of play_steps (reward shaping, uint8 dones, running returns / lengths, epoch
+    accumulators) and AverageMeter.update (the windowed mean pinned against rl_games' in test_ppo_oracle_cpu.py), over several steps."""
+    import ctypes
+    from omniisaacgymenvs_loop_b200 import _lib
+    from omniisaacgymenvs_loop_b200.rl.a2c import AverageMeter
+    n = 5003
+    g = torch.Generator().manual_seed(3)
+    cur_r, cur_l = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    acc = torch.zeros(3, dtype=torch.float64, device=DEV)
+    mr, ml = AverageMeter(100, DEV), AverageMeter(100, DEV)
+    t_r, t_l, t_acc = cur_r.clone(), cur_l.clone(), acc.clone()
+    t_mr, t_ml = AverageMeter(100, DEV), AverageMeter(100, DEV)
+    out_r, out_d = torch.empty(n, device=DEV), torch.empty(n, dtype=torch.uint8, device=DEV)
+    for k in range(12):
+        rew = torch.randn(n, generator=g).to(DEV)
+        dones = (torch.rand(n, generator=g) < (0.0 if k == 0 else 0.02 * k)).long().to(DEV)      # first step: nothing finishes
+        _lib.check(_lib.lib().ppo_rollout_bookkeep_f32(
+            _lib.ptr(rew), _lib.ptr(dones), ctypes.c_float(0.01), _lib.ptr(out_r), _lib.ptr(out_d), _lib.ptr(cur_r), _lib.ptr(cur_l), _lib.ptr(acc),
+            ctypes.c_void_p(mr.mean.data_ptr()), ctypes.c_void_p(mr.current_size.data_ptr()), ctypes.c_void_p(ml.mean.data_ptr()),
+            ctypes.c_void_p(ml.current_size.data_ptr()), ctypes.c_float(100.0), ctypes.c_int64(n), _lib.stream()))
+        # the eager formulation
+        t_r += rew; t_l += 1
+        d = dones.float()
+        rs, ls, cnt = (t_r * d).sum(), (t_l * d).sum(), d.sum()
+        t_acc += torch.stack([rs, ls, cnt]).double()
+        t_mr.update(rs, cnt); t_ml.update(ls, cnt)
+        t_r *= 1.0 - d; t_l *= 1.0 - d
+        assert torch.equal(out_r, rew * 0.01) and torch.equal(out_d, dones.to(torch.uint8))
+        assert torch.equal(cur_r, t_r) and torch.equal(cur_l, t_l)
+        assert torch.allclose(acc, t_acc, rtol=1e-6, atol=1e-4) and float(acc[2]) == float(t_acc[2])
+        assert float(mr.mean) == pytest.approx(float(t_mr.mean), rel=1e-5, abs=1e-5) and float(mr.current_size) == float(t_mr.current_size)
+        assert float(ml.mean) == pytest.approx(float(t_ml.mean), rel=1e-5, abs=1e-5) and float(ml.current_size) == float(t_ml.current_size)
+    assert float(mr.current_size) == 100.0 and float(acc[2]) > 500
