@@ -184,6 +184,9 @@ class FusedUsvEnv:
         K = int(actions.shape[0])
         if self.first_call:
             raise RuntimeError("take at least one eager step before capturing (the first-call flag is baked into the graph)")
+        if self.graph_key(K) is None:
+            raise RuntimeError("the next K control steps straddle the end of the initial action bias (a host-side parameter the graph "
+                               "would bake in): step eagerly past it, then capture")
         saved = self.step_counter
         torch.cuda.synchronize(self.device)
         graph = torch.cuda.CUDAGraph()

@@ -360,3 +360,24 @@ def test_scene_replay_npz_vs_oracle(tmp_path):
         assert_close(rew, o_rew, 1e-4, 5e-3, f"reward step {k}")
         assert torch.equal(done.cpu(), o_done), k
     assert int(rp.next_scene_idx.min()) >= 3 and torch.equal(rp.last_scene_idx, (nxt - 1) % S)
+
+
+def test_live_capture_steps_equals_eager():
+    """K live control steps (scene rebuilds included) replayed from one CUDA graph == the eager steps, bit for bit, over several replays."""
+    n, K = 300, 6
+    cfg = dataclasses.replace(LIVE_CFG, max_episode_length=9, action_bias_steps=0)
+    g = torch.Generator().manual_seed(4)
+    acts = (torch.rand((3 * K + 1, n, 2), generator=g) * 2 - 1).to(DEV)
+    a, b = FusedUsvLiveEnv(cfg, UsvLiveConfig(), n, DEV), FusedUsvLiveEnv(cfg, UsvLiveConfig(), n, DEV)
+    a.step(acts[0]); b.step(acts[0])
+    slot = torch.zeros((K, n, 2), device=DEV)
+    obs, rew, done = torch.zeros((K, n, 33), device=DEV), torch.zeros((K, n), device=DEV), torch.zeros((K, n), dtype=torch.long, device=DEV)
+    replay = b.capture_steps(slot, obs, rew, done)
+    for r in range(3):
+        slot.copy_(acts[1 + r * K:1 + (r + 1) * K])
+        replay()
+        for k in range(K):
+            o, w, d = a.step(acts[1 + r * K + k])
+            assert torch.equal(o, obs[k]) and torch.equal(w, rew[k]) and torch.equal(d, done[k]), (r, k)
+        assert a.step_counter == b.step_counter and torch.equal(a.state, b.state) and torch.equal(a.potential, b.potential)
+    assert int(done.sum()) > 0
