@@ -368,16 +368,17 @@ def bench_loopz(device, envs=16384, updates=10):
     """the loopz learner (MLPEncode actor / critic, squashed Gaussian) on the live CaptureXY task, 16 384 envs, horizon 16,
     4 epochs x 4 in-order minibatches of 65 536 rows: frames/s of the whole loop, the update phase alone, and the kernels."""
     from omniisaacgymenvs_loop_b200.config import live_default_config, live_task_cfg
-    from scripts.train_loopz import build_learner, make_env, train
+    from scripts.train_loopz import LoopzRunner, build_learner, make_env, train
 
     torch.manual_seed(1234)
     env = make_env(live_task_cfg(live_default_config(num_envs=envs)), str(device), seed=1234)
     ppo = build_learner(env, str(device), 16, seed=1234)
-    train(env, ppo, 3, 16, log_every=0, quiet=True)                      # warm-up: kernels, graph capture
+    run = LoopzRunner(env, ppo, 16)
+    train(env, ppo, 4, 16, log_every=0, quiet=True, runner=run)          # warm-up: kernels, rollout / update graph capture
     torch.cuda.synchronize(device)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    train(env, ppo, updates, 16, log_every=0, quiet=True)
+    train(env, ppo, updates, 16, log_every=0, quiet=True, runner=run)
     e1.record()
     torch.cuda.synchronize(device)
     ms = e0.elapsed_time(e1) / updates
@@ -428,7 +429,7 @@ def bench_loopz(device, envs=16384, updates=10):
     return {"metric": "PPO frames/sec (loopz learner)", "value": envs * 16 / (ms * 1e-3), "unit": "frames/s", "envs_per_gpu": envs, "horizon": 16,
             "ms_per_update": ms, "update_phase_ms": ums, "minibatch_rows": M, "minibatch_step_ms": mms,
             "minibatch_algorithmic_tflops": flops / (mms * 1e-3) / 1e12, "minibatch_step_ms_tcgen05_tf32": tms,
-            "update_in_cuda_graph": ppo._graph is not None,
+            "update_in_cuda_graph": ppo._graph is not None, "rollout_in_cuda_graph": run._graph is not None,
             "kernels": "loopz::train_kernel + reduce + adam (fp32 SIMT, csrc/ppo_loopz.cu)", "params": ppo.P,
             "cpu_oracle": {"minibatch_rows": cm, "minibatch_step_ms": cpu_s * 1e3, "rows_per_s": cm / cpu_s, "threads": torch.get_num_threads(),
                            "kind": "port", "gpu_rows_per_s": M / (mms * 1e-3)}}
