@@ -758,6 +758,57 @@ def loopz():
     print("loopz_ppo.npz")
 
 
+def loopz_md4():
+    """The 4-wide privileged tail (cfg.yaml mass_dim: 4, obs 29): forward, evaluate and one raw minibatch gradient of the reference."""
+    import tempfile
+
+    import torch.nn as nn
+
+    ref_shim.install()
+    import omniisaacgymenvs.algo.ppo.module as M
+    import omniisaacgymenvs.algo.ppo.ppo as P
+
+    D, MD, T, N = 29, 4, 4, 40
+    torch.manual_seed(12)
+    g = gen()
+    arch = dict(speed_dim=3, mass_dim=MD, mass_latent_dim=8, mass_encoder_shape=[64, 16])
+    actor = M.Actor(M.MLPEncode_wrap([128, 128], nn.LeakyReLU, D, 2, nn.Tanh, False, **arch),
+                    M.SquashedGaussianDiagonalCovariance(2, 0.3, action_scale=1.0), "cpu")
+    critic = M.Critic(M.MLPEncode_wrap([128, 128], nn.LeakyReLU, D, 1, **arch), "cpu")
+    with ref_shim.quiet():
+        ppo_ = P.PPO(actor=actor, critic=critic, num_envs=N, num_transitions_per_env=T, num_learning_epochs=1, gamma=0.997, lam=0.95,
+                     num_mini_batches=1, device="cpu", log_dir=tempfile.mkdtemp(), mini_batch_sampling="in_order", learning_rate=0.0,
+                     max_grad_norm=1e9)
+    with torch.no_grad():
+        for prm in [*actor.parameters(), *critic.parameters()]:
+            prm.add_(0.05 * torch.randn(prm.shape, generator=g))
+        actor.distribution.std.copy_(torch.tensor([0.25, 0.4]))
+    plist = [*actor.parameters(), *critic.parameters()]
+    out = {"params0": torch.cat([p_.detach().reshape(-1) for p_ in plist]), "param_sizes": np.array([p_.numel() for p_ in plist])}
+    obs = torch.randn((T, N, D), generator=g)
+    flat = obs.reshape(-1, D)
+    with torch.no_grad():
+        means = actor.architecture.architecture(flat)
+        values = critic.predict(flat)
+    actions = torch.tanh(torch.randn((T * N, 2), generator=g) * 1.2)
+    with torch.no_grad():
+        (logp, _), _ = actor.evaluate(flat, actions)
+    st = ppo_.storage
+    st.actor_obs.copy_(obs); st.critic_obs.copy_(obs); st.actions.copy_(actions.view(T, N, 2))
+    st.actions_log_prob.copy_((logp + 0.05 * torch.randn(logp.shape, generator=g)).view(T, N, 1))
+    st.values.copy_((values + 0.05 * torch.randn(values.shape, generator=g)).view(T, N, 1))
+    st.returns.copy_(st.values + 0.5 * torch.randn(st.values.shape, generator=g))
+    st.advantages.copy_(torch.randn(st.advantages.shape, generator=g))
+    st.step = T
+    cols = {k: getattr(st, k).clone() for k in ("actor_obs", "actions", "actions_log_prob", "values", "returns", "advantages")}
+    with ref_shim.quiet():
+        vl, sl, _ = ppo_._train_step()
+    out.update(means=means, values=values, eval_logp=logp, grad=torch.cat([p_.grad.reshape(-1) for p_ in plist]),
+               value_loss=np.float32(vl), surrogate=np.float32(sl), **{"st_" + k: v for k, v in cols.items()})
+    np.savez_compressed(os.path.join(OUT, "loopz_ppo_md4.npz"), **t2n(out))
+    print("loopz_ppo_md4.npz")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)
@@ -771,6 +822,7 @@ def main():
     tier3()
     classic_curriculum()
     loopz()
+    loopz_md4()
 
 
 if __name__ == "__main__":

@@ -58,6 +58,29 @@ def test_inference_and_evaluate_vs_reference(golden):
     assert torch.equal(p2.params, ppo.params)
 
 
+def test_four_wide_privileged_tail_vs_reference(golden):
+    """mass_dim = 4 / obs 29: kernels vs the reference's own forward, evaluate and raw minibatch gradient (IN = 33 > obs_dim: the
+    latent spills past the observation width in the staged tile)."""
+    G = golden("loopz_ppo_md4")
+    actor, critic, ppo = build(D=29, md=4, n=40, horizon=4, max_grad_norm=1e9, learning_rate=0.0, num_learning_epochs=1, num_mini_batches=1)
+    ppo.params.copy_(T(G["params0"]))
+    obs = T(G["st_actor_obs"]).to(DEV)
+    flat = obs.view(-1, 29)
+    assert torch.allclose(actor.noiseless_action(flat).cpu(), T(G["means"]), rtol=1e-5, atol=2e-6)
+    assert torch.allclose(critic.predict(flat).cpu(), T(G["values"]), rtol=1e-5, atol=2e-6)
+    (lp, _), _ = actor.evaluate(flat, T(G["st_actions"]).to(DEV).view(-1, 2))
+    assert torch.allclose(lp.cpu(), T(G["eval_logp"]), rtol=1e-5, atol=2e-5)
+    st = ppo.storage
+    st.actor_obs.copy_(obs); st.critic_obs.copy_(obs)
+    for k in ("actions", "actions_log_prob", "values", "returns", "advantages"):
+        getattr(st, k).copy_(T(G["st_" + k]))
+    ppo._minibatch(0, 160)
+    g, want = ppo.grads[:ppo.P].cpu(), T(G["grad"])
+    assert torch.allclose(g, want, rtol=1e-4, atol=1e-5 * float(want.abs().max())), float((g - want).abs().max())
+    s_ = ppo.minibatch_statistics()
+    assert abs(s_["value_loss"] - float(G["value_loss"])) < 1e-5 and abs(s_["surrogate"] - float(G["surrogate"])) < 1e-5
+
+
 def test_sampling_is_a_squashed_gaussian(golden):
     G = golden("loopz_ppo")
     actor, critic, ppo = build()

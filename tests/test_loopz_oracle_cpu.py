@@ -130,3 +130,23 @@ def test_loopz_abi_argument_checks_without_gpu():
     assert grad(0, one) == E["USV_E_SIZE"] and grad(64, null) == E["USV_E_NULL"]
     assert L.ppo_loopz_enforce_min_std_f32(null, null, i32(2), null) == E["USV_E_NULL"]
     assert L.ppo_loopz_enforce_min_std_f32(one, one, i32(0), null) == E["USV_E_SIZE"]
+
+
+def test_four_wide_privileged_tail_vs_reference(golden):
+    """mass_dim = 4 / obs 29 (environment.mass_dim of the older configs): oracle forward, evaluate and minibatch gradient vs the reference."""
+    import dataclasses
+    G = golden("loopz_ppo_md4")
+    cfg = dataclasses.replace(Z.LoopzCfg(), obs_dim=29, mass_dim=4)
+    flat = T(G["params0"])
+    assert flat.numel() == 2 * (64 * 4 + 64 + 1040 + 136 + 33 * 128 + 128 + 16512) + 258 + 129 + 2
+    pa, std, pc = Z.split(flat, cfg)
+    obs = T(G["st_actor_obs"]).reshape(-1, 29)
+    assert torch.allclose(Z.mlp_encode(pa, obs, cfg, True), T(G["means"]), rtol=1e-6, atol=1e-6)
+    assert torch.allclose(Z.mlp_encode(pc, obs, cfg, False), T(G["values"]), rtol=1e-6, atol=1e-6)
+    lp, _ = Z.evaluate(T(G["means"]), std, T(G["st_actions"]).reshape(-1, 2), cfg)
+    assert torch.allclose(lp, T(G["eval_logp"]), rtol=1e-6, atol=1e-6)
+    rows = [T(G["st_" + k]).reshape(obs.shape[0], -1) for k in ("actor_obs", "actor_obs", "actions", "values", "advantages", "returns", "actions_log_prob")]
+    g, loss, surr, vloss = Z.minibatch_grad(flat, cfg, *rows)
+    want = T(G["grad"])
+    assert torch.allclose(g, want, rtol=1e-4, atol=1e-7), float((g - want).abs().max())
+    assert abs(vloss - float(G["value_loss"])) < 1e-6 and abs(surr - float(G["surrogate"])) < 1e-6
