@@ -480,7 +480,8 @@ int ppo_adam_step_f32(float* params, float* grads /*[P+PPO_STAT_COUNT], scaled i
                       int32_t* step /*device int32[2]: [0] Adam step count (incremented), [1] scratch*/,
                       int64_t P, const PpoAdamParams* ap, void* stream);
 /* one whole minibatch step on a single rank: ppo_minibatch_grad_tc + ppo_adam_step_f32 + ppo_pack_weights_tc with the second-stage
- * reduction, clip, Adam, adaptive lr and re-pack fused into ONE cooperative launch (3 launches per minibatch instead of 7) */
+ * reduction, clip, Adam, adaptive lr and the refresh of the packed operand tiles fused into ONE cooperative launch (+ a one-thread
+ * lr / step roll: 4 launches per minibatch instead of 7) */
 int ppo_minibatch_step_tc(float* params, float* packed, const float* obs, int32_t obs_dim, const float* obs_mean, const float* obs_var,
                           const float* actions, const float* old_neglogp, const float* advantages, const float* old_values,
                           const float* returns, float* old_mu, float* old_sigma, const PpoLossParams* lp, float* grads, float* scratch,

@@ -228,7 +228,7 @@ class A2CAgent:
                 args = (ds["obs"][s], ds["actions"][s], ds["old_logp_actions"][s], ds["advantages"][s], ds["old_values"][s],
                         ds["returns"][s], ds["mu"][s], ds["sigma"][s])
                 if not self.multi_gpu and pol.tensor_cores and self.fused_step:
-                    pol.minibatch_step(*args)                            # gradient + clip + Adam + lr + re-pack: 3 launches
+                    pol.minibatch_step(*args)                            # gradient + clip + Adam + lr + operand-tile refresh: 4 launches
                     continue
                 pol.minibatch_grad(*args)
                 if self.peer is not None:
