@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(256) reduce_kernel(RedIn in, PpoLoopzNet cfg, 
       const Layout L(packed_dims(sp.IN, cfg.mass_dim, net == 0 ? 2 : 1));
       if (loc < encn) { src = in.enc[net]; cnt = in.g3[net]; stride = encn; c0 = loc; }
       else if (loc >= L.b3) { src = in.t1[net]; cnt = in.g1[net]; stride = 16; c0 = 7 + (loc - L.b3); }
-      else { src = in.t2[net]; cnt = in.g2[net]; stride = L.P; c0 = loc; }
+      else { src = in.t2[net]; cnt = in.g2[net]; stride = slot_stride(L); c0 = slot_pad(L) + loc; }
     }
   }
   float acc = 0.f;
@@ -324,7 +324,8 @@ int64_t ppo_loopz_tc_workspace_floats(const PpoLoopzNet* net, int64_t M) {
   const int64_t slabs = (4 * (int64_t)H + DP + 16) * ld;
   const int64_t zin = 2 * M * sp.IN + 8;
   const int64_t packed = 2 * (int64_t)PK_TOTAL;
-  const int64_t slots = 2 * (160 * 16 + (int64_t)kWgradCtas * sp.PA + kEncSlots * (int64_t)enc_floats(net->mass_dim));
+  const int64_t slots = 2 * (160 * 16 + (int64_t)kWgradCtas * slot_stride(Layout(packed_dims(sp.IN, net->mass_dim, 2))) +
+                             kEncSlots * (int64_t)enc_floats(net->mass_dim));
   return slabs + zin + packed + slots + 64;
 }
 
@@ -351,7 +352,7 @@ int ppo_loopz_minibatch_grad_tc(const float* params, const PpoLoopzNet* net, con
   float* pk[2]; pk[0] = p; p += PK_TOTAL; pk[1] = p; p += PK_TOTAL;
   float* t1s[2]; float* t2s[2]; float* encs[2];
   for (int k = 0; k < 2; ++k) { t1s[k] = p; p += 160 * 16; }
-  for (int k = 0; k < 2; ++k) { t2s[k] = p; p += (size_t)kWgradCtas * sp.PA; }
+  for (int k = 0; k < 2; ++k) { t2s[k] = p; p += (size_t)kWgradCtas * slot_stride(Layout(packed_dims(sp.IN, md, 2))); }
   for (int k = 0; k < 2; ++k) { encs[k] = p; p += (size_t)kEncSlots * encn; }
   const int sms = num_sms();
   const int64_t ntiles = ld / TM, nchunks = ld / WK, etiles = (M + ETM - 1) / ETM;
