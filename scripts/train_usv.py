@@ -36,6 +36,8 @@ def main():
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--checkpoint", default=None)
     ap.add_argument("--save", default=None)
+    ap.add_argument("--play", action="store_true", help="the reference's test=True path: evaluate --checkpoint with PpoPlayerContinuous")
+    ap.add_argument("--games", type=int, default=2000, help="--play: episodes to finish (player.games_num)")
     args = ap.parse_args()
     world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
     device = f"cuda:{local}"
@@ -50,6 +52,13 @@ def main():
         cfg = UsvEnvConfig(num_envs=args.num_envs)
         task_cfg = (cfg.full_dr() if args.full_dr else cfg).to_task_cfg()
     env = make_env(task_cfg, device, args.seed, env_id_offset=rank * args.num_envs)
+    if args.play:                                   # [ref: OIGE/scripts/rlgames_train111.py test=True -> runner.run({'play': True})]
+        from omniisaacgymenvs_loop_b200.rl.players import PpoPlayerContinuous
+        player = PpoPlayerContinuous(env, {"games_num": args.games, "deterministic": True}, device, seed=args.seed)
+        if args.checkpoint:
+            player.restore(args.checkpoint)
+        player.run()
+        return
     agent = A2CAgent(env, PPOConfig(seed=args.seed), device, rank, world)
     if args.checkpoint:
         agent.restore(args.checkpoint)

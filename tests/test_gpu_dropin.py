@@ -101,6 +101,38 @@ def test_reference_trained_policy_captures_in_fused_env():
         assert 30.0 < r["mean_return"] < 48.0, r            # checkpoint: rew_38.55 at save time
 
 
+def test_player_restores_checkpoint_and_plays_reference_policy(tmp_path, capsys):
+    """rl_games' test=True path [ref: RLG/algos_torch/players.py:116-219, RLG/common/player.py:319-422]: PpoPlayerContinuous restores the
+    reference's .pth schema, get_action(deterministic) is the clamped mu, and run() over the reference's own trained classic policy
+    reports the reward the checkpoint was saved at (file name: rew_38.55)."""
+    import numpy as np
+    from omniisaacgymenvs_loop_b200.rl.players import PpoPlayerContinuous
+    n = 1024
+    env = make_env(UsvEnvConfig(num_envs=n).to_task_cfg(), DEV, seed=5)
+    G = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "classic_policy.npz")))
+    player = PpoPlayerContinuous(env, {"games_num": 3000, "deterministic": True, "print_stats": False}, DEV, tensor_cores=False)
+    player.set_weights({"model": G})
+    # checkpoint round trip through the reference schema: a trainer with these weights saves, a fresh player restores
+    agent = A2CAgent(env, PPOConfig(seed=1), DEV)
+    agent.policy.load_state_dict(player.get_weights()["model"])
+    agent.save(str(tmp_path / "ck.pth"))
+    other = PpoPlayerContinuous(env, {"games_num": 10}, DEV, tensor_cores=False)
+    other.restore(str(tmp_path / "ck.pth"))
+    a, b = player.get_weights()["model"], other.get_weights()["model"]
+    assert set(a) == set(b) and all(torch.equal(a[k], b[k]) for k in a)
+    obs = env.reset()["obs"]
+    det = player.get_action(obs, is_deterministic=True)
+    ref = player.model.act(obs["state"])
+    assert torch.equal(det, torch.clamp(ref["mus"], -1.0, 1.0)) and det.shape == (n, 2)
+    sto = player.get_action(obs, is_deterministic=False)
+    assert float(sto.abs().max()) <= 1.0 and not torch.equal(sto, det)
+    av_reward, av_steps, games = player.run()
+    out = capsys.readouterr().out
+    assert "av reward:" in out and "av steps:" in out
+    assert 3000 <= games < 3000 + n
+    assert 25.0 < av_reward < 50.0 and 20.0 < av_steps < 400.0, (av_reward, av_steps)   # first-finished episodes are biased short
+
+
 def test_live_vecenv_matches_oracle_and_contract():
     """The live USVVirtual (Variant B: 33-dim obs, obstacles, potential field) behind VecEnvRLGames, from the live YAML tree."""
     from omniisaacgymenvs_loop_b200.config import UsvLiveConfig, live_default_config, live_task_cfg
