@@ -46,6 +46,18 @@ def test_product_fails_loudly_without_cuda_tensors():
     from omniisaacgymenvs_loop_b200.envs.USV.Hydrostatics import HydrostaticsObject
     with pytest.raises(_lib.UsvLibraryError):
         HydrostaticsObject(4, "cpu", 1000, -9.81, 0.5, 0.65, 275, 1.0, 0.0, 1.0, 0.3, -10.0)
+    # the evaluation player has no torch-module fallback either: its policy is the CUDA kernel
+    import numpy as np
+    from omniisaacgymenvs_loop_b200.rl.players import PpoPlayerContinuous, rescale_actions
+    from omniisaacgymenvs_loop_b200.utils.spaces import Box, Dict
+
+    class _Env:
+        def get_env_info(self):
+            return {"action_space": Box(-1.0, 1.0, (2,)), "observation_space": Dict({"state": Box(-np.inf, np.inf, (13,))})}
+    with pytest.raises(_lib.UsvLibraryError):
+        PpoPlayerContinuous(_Env(), {"games_num": 1}, device="cpu")
+    lo, hi = torch.tensor([-2.0, 0.0]), torch.tensor([2.0, 1.0])
+    assert torch.equal(rescale_actions(lo, hi, torch.tensor([[1.0, -1.0], [0.0, 0.0]])), torch.tensor([[2.0, 0.0], [0.0, 0.5]]))
 
 
 def test_params_roundtrip():
