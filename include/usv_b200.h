@@ -340,6 +340,10 @@ typedef struct {
   int32_t heading_reward_mode;  /* GoToPoseReward.heading_reward_mode (USV_REWARD_*)                  */
   float heading_exponential_reward_coeff, heading_scale, sig_gain;
   float goal_random_velocity, lin_vel_tolerance;   /* TrackXYVelocityParameters                       */
+  /* mass.masscom_obs_source == "base" (evaluation ablation, USV_Virtual.py:840-880; USV_disturbances.py:196-250): the tail shows
+   * every env the BASE mass / CoM encodings and the encodings of priv_neutral[] (minmax: mid-range, else 1.0) instead of the
+   * simulated values; the dynamics stay randomised                                                   */
+  int32_t masscom_obs_base; float priv_neutral[4];
 } UsvLiveParams;
 
 typedef struct {

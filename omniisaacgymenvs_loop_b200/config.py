@@ -423,6 +423,7 @@ class UsvLiveConfig:
     collision_threshold: float = 1.2
     map_size: float = 30.0
     fixed_horizon_eval: bool = False
+    masscom_obs_base: bool = False           # mass.masscom_obs_source == "base": the tail shows base / neutral values (evaluation ablation)
     # Tier-3 tasks behind the same live step: 0 CaptureXY+obstacles, 1 GoToPose, 2 KeepXY, 3 TrackXYVelocity
     # [ref: OIGE/tasks/USV/USV_task_rewards.py:170-325 ; USV_task_parameters.py:95-177]
     task: int = 0
@@ -446,6 +447,11 @@ class UsvLiveConfig:
         for j in range(4):
             lp.priv_a[j], lp.priv_b[j], lp.priv_active[j] = float(self.priv_a[j]), float(self.priv_b[j]), int(self.priv_active[j])
         lp.com_rand = int(self.com_rand)
+        lp.masscom_obs_base = int(self.masscom_obs_base)
+        for j in range(4):
+            # minmax: `0.5 * (min + max)` in Python floats, then an fp32 tensor; raw / centered: ones  [ref: USV_Virtual.py:859-880]
+            lp.priv_neutral[j] = float(np.float32(0.5 * (float(self.priv_a[j]) + (float(self.priv_a[j]) + float(self.priv_b[j]))))) \
+                if int(self.priv_mode) == 2 else 1.0
         lp.collision_threshold, lp.map_size, lp.fixed_horizon_eval = self.collision_threshold, self.map_size, int(self.fixed_horizon_eval)
         return lp
 
@@ -476,8 +482,9 @@ class UsvLiveConfig:
             pb = [hi - lo for lo, hi in rng]
             active = [act and (hi - lo) > 1e-6 for act, (lo, hi) in zip(active, rng)]   # degenerate range -> neutral 0
             pb = [b if b > 1e-6 else 1.0 for b in pb]
-        if str(m.get("masscom_obs_source", "sim")) != "sim":
-            raise NotImplementedError("masscom_obs_source='base' (ablation mode) is not built into the fused live step")
+        source = str(m.get("masscom_obs_source", "sim"))
+        if source not in ("sim", "base"):
+            raise ValueError(f"mass.masscom_obs_source must be 'sim' or 'base', got {source}")      # [ref: USV_Virtual.py:469-472]
         disp = m.get("com_displacement_xyz", None)
         if disp is None and float(m.get("CoM_max_displacement", 0.0) or 0.0) > 0.0:
             raise NotImplementedError("legacy disc-shaped CoM randomisation is not built into the fused live step")
@@ -488,7 +495,7 @@ class UsvLiveConfig:
                    com_rand=bool(m.get("add_mass_disturbances", False)) and disp is not None,
                    com_base=tuple(float(x) for x in m.get("base_com", [0.0, 0.0, 0.0])),
                    com_disp=tuple(float(x) for x in (disp or [0.0, 0.0, 0.0])),
-                   fixed_horizon_eval=bool(env.get("fixed_horizon_eval", False)))
+                   fixed_horizon_eval=bool(env.get("fixed_horizon_eval", False)), masscom_obs_base=source == "base")
 
 
 def live_env_config(task_cfg: dict, **overrides) -> "UsvEnvConfig":

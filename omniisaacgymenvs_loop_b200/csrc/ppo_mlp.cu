@@ -467,7 +467,8 @@ __global__ void __launch_bounds__(256) reduce_kernel(const float* __restrict__ p
     for (int c = grp; c < nparts; c += 4) acc += partial[(size_t)c * n + e];
   sm[grp][col] = acc;
   __syncthreads();
-  if (grp == 0 && e < n) {
+  // the total-loss slot belongs to block 0 (below): the column sum of that slot is 0 and, written from another block, raced with it
+  if (grp == 0 && e < n && e != P + PPO_STAT_LOSS) {
     float v = (sm[0][col] + sm[1][col]) + (sm[2][col] + sm[3][col]);
     grads[e] = v;
   }

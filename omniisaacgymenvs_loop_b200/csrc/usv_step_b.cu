@@ -84,17 +84,19 @@ __device__ __forceinline__ void obs_tail(LiveOut& o, const DynOut& s, const EnvC
   // prev_thrust_cmds: the raw policy command of THIS control step, zero for an env reset in it (USV_Virtual.py:1063-1066)
   o.put(23, do_reset ? 0.0f : s.raw0);
   o.put(24, do_reset ? 0.0f : s.raw1);
-  // privileged tail  (USV_Virtual.py:837-984)
-  o.put(25, lp.mass_obs_relative ? __fdiv_rn(k.mass - p.mass_base, fmaxf(fabsf(p.mass_base), 1e-6f)) : k.mass);
+  // privileged tail  (USV_Virtual.py:837-984); `base`: the ablation source shows base / neutral values (:840-880)
+  const bool base = lp.masscom_obs_base != 0;
+  const float m = base ? p.mass_base : k.mass;
+  o.put(25, lp.mass_obs_relative ? (base ? 0.0f : __fdiv_rn(m - p.mass_base, fmaxf(fabsf(p.mass_base), 1e-6f))) : m);
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
-    const float c = bc[(USV_BC_COM_X + j) * kTile];
+    const float c = base ? lp.com_base[j] : bc[(USV_BC_COM_X + j) * kTile];
     o.put(26 + j, lp.com_obs_scaled ? __fdiv_rn(c, lp.com_scale_eps[j]) : c);
   }
-  o.put(29, priv_encode(lp, 0, k.kdrag));
-  o.put(30, priv_encode(lp, 1, k.mL));
-  o.put(31, priv_encode(lp, 2, k.mR));
-  o.put(32, priv_encode(lp, 3, k.kiz));
+  o.put(29, priv_encode(lp, 0, base ? lp.priv_neutral[0] : k.kdrag));
+  o.put(30, priv_encode(lp, 1, base ? lp.priv_neutral[1] : k.mL));
+  o.put(31, priv_encode(lp, 2, base ? lp.priv_neutral[2] : k.mR));
+  o.put(32, priv_encode(lp, 3, base ? lp.priv_neutral[3] : k.kiz));
 }
 
 // Variant B task part of a control step.  `any_reset`: some env of the batch was reset on entry to this control step

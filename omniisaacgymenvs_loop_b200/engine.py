@@ -158,11 +158,13 @@ class FusedUsvEnv:
     def graph_key(self, steps: int):
         """Host-side parameters that a captured graph of the next `steps` control steps would bake in (None: the window straddles a
         change and must run eagerly).  The only such parameter is the live task's initial action bias, which is switched off by the
-        host after `action_bias_steps` control steps  [ref: OIGE/tasks/USV_Virtual.py:1070-1077]."""
+        host after `action_bias_steps` control steps  [ref: OIGE/tasks/USV_Virtual.py:1070-1077]; the live task's evaluation switch
+        of the privileged tail's source (`masscom_obs_base`) is part of the key too."""
         lim = self.cfg.action_bias_steps
+        src = "/base" if getattr(getattr(self, "live", None), "masscom_obs_base", False) else ""
         if self.cfg.action_bias == 0.0 or self.step_counter >= lim:
-            return "steady"
-        return "bias" if self.step_counter + steps <= lim else None
+            return "steady" + src
+        return "bias" + src if self.step_counter + steps <= lim else None
 
     def advance_step_offset(self, steps: int) -> None:
         """Inside a CUDA-graph capture of `steps` control steps: make the next replay continue the Philox step sequence."""

@@ -124,6 +124,25 @@ class USVVirtual:
     def progress_buf(self) -> torch.Tensor:
         return self.engine.progress_buf
 
+    # the evaluation scripts switch the observation source of the privileged tail at run time
+    # [ref: OIGE/tasks/USV_Virtual.py:468-472,840-880 ; OIGE/scripts/rlgames_play_loopz.py:1100-1110 (_set_obs_source)]
+    @property
+    def _masscom_obs_source(self) -> str:
+        return "base" if (self._live and self.live_cfg.masscom_obs_base) else "sim"
+
+    @_masscom_obs_source.setter
+    def _masscom_obs_source(self, mode: str) -> None:
+        if mode not in ("sim", "base"):
+            raise ValueError(f"mass.masscom_obs_source must be 'sim' or 'base', got {mode}")
+        if not self._live:
+            if mode == "base":
+                raise NotImplementedError("the classic 13-dim observation has no privileged tail")
+            return
+        import dataclasses
+        self.live_cfg = dataclasses.replace(self.live_cfg, masscom_obs_base=(mode == "base"))
+        self.engine.live = self.live_cfg
+        self.engine._live_params = self.live_cfg.to_params()
+
     def _stat_names(self):
         on = lambda k: k not in _PENALTY_FLAGS or getattr(self.cfg, _PENALTY_FLAGS[k]).form != 0
         return [k for k in (_LIVE_STAT_KEYS if self._live else _STAT_KEYS) if on(k)]

@@ -524,6 +524,12 @@ def live_virtual():
         with ref_shim.quiet():
             V.USVVirtual.get_observations(me)
         out.update({f"priv_{mode}": captured["priv"]})
+        # the ablation source: base mass / CoM encodings and neutral dynamics parameters for every env  (USV_Virtual.py:840-880)
+        me._masscom_obs_source = "base"
+        with ref_shim.quiet():
+            V.USVVirtual.get_observations(me)
+        out.update({f"priv_base_{mode}": captured["priv"]})
+        me._masscom_obs_source = "sim"
         if mode == "minmax":
             out.update(cpl_mass=me.MDD.platforms_mass[:, 0].clone(), cpl_com=me.MDD.platforms_CoM.clone(), cpl_kdrag=me.hydrodynamics.drag_scale[:, 0].clone(),
                        cpl_thr=me.thrusters_dynamics.thruster_multiplier[:, 0].clone(), cpl_kiz=me.k_Iz[:, 0].clone(),
@@ -826,4 +832,10 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1:                 # python oracle/make_golden.py live_virtual tier3 ...
+        os.makedirs(OUT, exist_ok=True)
+        torch.set_num_threads(1)
+        for name in sys.argv[1:]:
+            globals()[name]()
+    else:
+        main()

@@ -289,6 +289,7 @@ class LivePrivConfig:
     com_disp: tuple = (0.15, 0.05, 0.02)
     collision_threshold: float = COLLISION_TH
     fixed_horizon_eval: bool = False
+    masscom_obs_base: bool = False           # mass.masscom_obs_source == 'base'  [OIGE/tasks/USV_Virtual.py:840-880]
 
 
 def priv_encode(pc: LivePrivConfig, j: int, x: torch.Tensor) -> torch.Tensor:
@@ -378,6 +379,17 @@ class LiveEnvOracle(ClassicEnvOracle):
 
     def priv_tail(self):
         c, pc = self.cfg, self.priv
+        if pc.masscom_obs_base:
+            # ablation source: base mass / CoM encodings (USV_disturbances.py:196-250) and neutral dynamics parameters -- the mid-range
+            # in minmax mode, 1.0 otherwise (USV_Virtual.py:859-880) -- for every env, then the same encoders
+            n = self.mass.shape[0]
+            mass = torch.zeros(n, dtype=F32) if pc.mass_obs_relative else torch.full((n,), float(c.mass_base), dtype=F32)
+            com = torch.tensor(pc.com_base, dtype=F32).unsqueeze(0).repeat(n, 1)
+            if pc.com_obs_scaled:
+                com = com / (torch.tensor(pc.com_scale, dtype=F32) + 1e-6)
+            neutral = [0.5 * (float(a) + (float(a) + float(b))) if pc.priv_mode == 2 else 1.0 for a, b in zip(pc.priv_a, pc.priv_b)]
+            cols = [mass.unsqueeze(1), com] + [priv_encode(pc, j, torch.ones(n, dtype=F32) * x).unsqueeze(1) for j, x in enumerate(neutral)]
+            return torch.cat(cols, dim=1)
         mass = (self.mass - c.mass_base) / max(abs(c.mass_base), 1e-6) if pc.mass_obs_relative else self.mass
         com = self.com / (torch.tensor(pc.com_scale, dtype=F32) + 1e-6) if pc.com_obs_scaled else self.com
         cols = [mass.unsqueeze(1), com] + [priv_encode(pc, j, x).unsqueeze(1) for j, x in

@@ -42,6 +42,8 @@ def main():
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--checkpoint", default=None)
     ap.add_argument("--csv", default=None)
+    ap.add_argument("--obs-source", default="sim", choices=["sim", "base", "both"],
+                    help="privileged-tail source (mass.masscom_obs_source); both = the reference's two-mode comparison (eval.modes)")
     args = ap.parse_args()
     device = "cuda:0"
     task_cfg = load_task_yaml(args.task_yaml, num_envs=args.num_envs) if args.task_yaml else live_task_cfg(live_default_config(num_envs=args.num_envs))
@@ -49,13 +51,18 @@ def main():
     ppo = build_learner(env, device, 16, args.seed, use_cuda_graph=False)
     if args.checkpoint:
         ppo.load_state_dict(torch.load(args.checkpoint, map_location=device, weights_only=False))
-    rec = play(env, ppo.actor, args.episodes, run_id="play", ckpt=str(args.checkpoint), seed=args.seed)
+    rows = []
+    for mode in (["sim", "base"] if args.obs_source == "both" else [args.obs_source]):
+        env._task._masscom_obs_source = mode                    # rlgames_play_loopz.py:1100-1110 (_set_obs_source)
+        rec = play(env, ppo.actor, args.episodes, run_id="play", ckpt=str(args.checkpoint), seed=args.seed, obs_source=mode)
+        print(f"[loopz-play][EVAL] mode={mode}")
+        rec.summarize(seed=args.seed)
+        rows += rec.rows
     if args.csv:
         os.makedirs(os.path.dirname(os.path.abspath(args.csv)), exist_ok=True)
+        rec.rows = rows
         rec.write_csv(args.csv)
-        print(f"[loopz-play][EVAL] wrote {len(rec.rows)} rows to {args.csv}")
-    rec.summarize(seed=args.seed)
-
+        print(f"[loopz-play][EVAL] wrote {len(rows)} rows to {args.csv}")
 
 if __name__ == "__main__":
     main()

@@ -308,6 +308,11 @@ def test_live_priv_tail_vs_reference_golden(golden):
             env.set_field(name, T(np.ascontiguousarray(v)))
         obs, _, _ = env.step(torch.zeros((n, 2), device=DEV), rebuild_scene=False)
         assert_close(obs[:, 25:33], G[f"priv_{mode}"], 1e-6, 1e-7, f"priv tail ({mode})")
+        # mass.masscom_obs_source == "base": same envs, the tail shows base / neutral values  [ref: USV_Virtual.py:840-880]
+        env.live = dataclasses.replace(env.live, masscom_obs_base=True)
+        env._live_params = env.live.to_params()
+        obs, _, _ = env.step(torch.zeros((n, 2), device=DEV), rebuild_scene=False)
+        assert torch.equal(obs[:, 25:33].cpu(), T(G[f"priv_base_{mode}"])), mode
 
 
 def test_scene_replay_npz_vs_oracle(tmp_path):

@@ -80,6 +80,18 @@ def test_play_loopz_rows_match_scalar_loop(tmp_path):
         assert math.isfinite(r["return_raw"]) and r["path_length"] >= 0 and r["straight_line_dist"] >= 0
         assert r["min_obs_dist_start"] > 1.2 and r["control_dt"] == pytest.approx(0.2)
         assert r["collision"] == int(r["done_reason"] == "collision")
+    # the play script's obs-source switch (_set_obs_source): in "base" mode every env sees the same (base / neutral) privileged tail
+    task = env._task
+    assert task._masscom_obs_source == "sim"
+    tail = env.observe(as_numpy=False)[:, 25:33]
+    assert float(tail.std(dim=0).max()) > 0.01
+    task._masscom_obs_source = "base"
+    env.step(torch.zeros((n, 2), device=DEV))
+    tail = env.observe(as_numpy=False)[:, 25:33]
+    assert torch.equal(tail, torch.zeros_like(tail)) and task._masscom_obs_source == "base"      # minmax + relative / scaled: all neutral = 0
+    task._masscom_obs_source = "sim"
+    with pytest.raises(ValueError):
+        task._masscom_obs_source = "other"
     path = tmp_path / "play.csv"
     rec.write_csv(str(path))
     back = list(csv.DictReader(open(path)))

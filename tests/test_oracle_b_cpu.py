@@ -110,3 +110,11 @@ def test_mass_coupling_and_priv_tail_vs_reference(golden):
         orc.mass, orc.com = T(G["cpl_mass"]).clone(), T(G["cpl_com"]).clone()
         orc.drag_scale[:, 0], orc.thr_mult_left, orc.thr_mult_right, orc.k_iz = kd, sthr.clone(), sthr.clone(), kiz
         assert torch.allclose(orc.priv_tail(), T(G[f"priv_{mode}"]), rtol=1e-6, atol=1e-7), mode
+        # mass.masscom_obs_source == "base": base encodings / neutral parameters for every env  [ref: USV_Virtual.py:840-880]
+        orc.priv = B.LivePrivConfig(priv_mode=code, priv_a=a, priv_b=b, com_scale=scale, masscom_obs_base=True)
+        assert torch.equal(orc.priv_tail(), T(G[f"priv_base_{mode}"])), mode
+    # a non-zero base CoM and raw encodings: the tail is the constants themselves
+    orc.priv = B.LivePrivConfig(priv_mode=2, priv_a=(1.0, 0.5, 0.5, 1.0), priv_b=(0.5, 0.5, 0.5, 0.5), mass_obs_relative=False, com_obs_scaled=False,
+                                com_base=(0.1, -0.02, 0.03), masscom_obs_base=True)
+    want = torch.tensor([cfg.mass_base, 0.1, -0.02, 0.03, 0.0, 0.0, 0.0, 0.0]).repeat(n, 1)
+    assert torch.equal(orc.priv_tail(), want)
