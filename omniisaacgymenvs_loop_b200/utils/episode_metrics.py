@@ -85,6 +85,34 @@ def infer_done_reason(collision: bool, out_of_bounds: bool, in_goal_tolerance: b
     return "other"
 
 
+def apply_mass_mode_to_obs(obs: torch.Tensor, mode: str, rng: np.random.Generator) -> torch.Tensor:
+    """The play script's control-side intervention on the LAST 4 observation columns (`LOOPZ_PLAY_MASS_MODE` with
+    `LOOPZ_PLAY_MASS_APPLY=control`): normal -> unchanged, zero -> 0, shuffle -> a fresh permutation across envs every step (drawn from
+    the same numpy generator call as the reference, so the same seed gives the same permutation), swap -> env pairs (0<->1, 2<->3, ...)
+    exchanged; shuffle / swap with one env fall back to zero, unknown modes to normal  [ref: rlgames_play_loopz.py:560-621].
+    Works on the device tensor the policy reads (no host round trip); returns a new tensor unless the mode is normal."""
+    mode_l = (mode or "normal").strip().lower()
+    if obs.dim() != 2 or obs.shape[0] < 1 or mode_l in ("normal", "none", "off", ""):
+        return obs
+    n = int(obs.shape[0])
+    if mode_l in ("shuffle", "swap") and n < 2:
+        mode_l = "zero"
+    if mode_l not in ("zero", "shuffle", "swap"):
+        return obs
+    out = obs.clone()
+    if mode_l == "zero":
+        out[:, -4:] = 0.0
+    elif mode_l == "shuffle":
+        perm = torch.as_tensor(rng.permutation(n), dtype=torch.long, device=obs.device)
+        out[:, -4:] = obs[:, -4:][perm]
+    else:
+        idx = torch.arange(n, device=obs.device)
+        pair = idx ^ 1
+        pair = torch.where(pair < n, pair, idx)          # an odd env count leaves the last env alone
+        out[:, -4:] = obs[:, -4:][pair]
+    return out
+
+
 class EpisodeRecorder:
     """Call `record(actions, rewards, dones)` after every `engine.step(actions)`; finished episodes append to `rows`.
 

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """TEST INFRASTRUCTURE (not product code).  Freezes known answers of the reference play script's pure helper functions
-(`_quantize_xy`, `_hash_obstacles_xy`, `_bootstrap_mean_ci`, `_infer_done_reason`; OIGE/scripts/rlgames_play_loopz.py:135-171,493-533)
-into tests/golden/play_metrics.json.  The script itself imports hydra / Isaac Sim at module level, so the four function definitions are
+(`_quantize_xy`, `_hash_obstacles_xy`, `_bootstrap_mean_ci`, `_infer_done_reason`, `_apply_mass_mode_to_obs`;
+OIGE/scripts/rlgames_play_loopz.py:135-171,493-533,560-621)
+into tests/golden/play_metrics.json.  The script itself imports hydra / Isaac Sim at module level, so the function definitions are
 taken out of its syntax tree and executed unmodified.  Run in the build container (needs /root/reference):  python oracle/make_golden_play.py"""
 import ast
 import hashlib
@@ -13,7 +14,7 @@ from typing import Any, Dict, Optional, Tuple
 import numpy as np
 
 REF = "/root/reference/omniisaacgymenvs/scripts/rlgames_play_loopz.py"
-WANT = {"_quantize_xy", "_hash_obstacles_xy", "_bootstrap_mean_ci", "_infer_done_reason"}
+WANT = {"_quantize_xy", "_hash_obstacles_xy", "_bootstrap_mean_ci", "_infer_done_reason", "_apply_mass_mode_to_obs"}
 
 
 def load():
@@ -53,8 +54,14 @@ def main():
             for g in (0.0, 1.0):
                 reasons.append({"collision": c, "out_of_bounds": o, "in_goal_tolerance": g,
                                 "reason": ns["_infer_done_reason"]({"collision": c, "out_of_bounds": o, "in_goal_tolerance": g})})
+    mass_modes = []
+    for n in (1, 2, 7, 12):
+        obs = rng.normal(size=(n, 9)).astype(np.float32)
+        for mode in ("normal", "zero", "shuffle", "swap", "Swap ", "bogus"):
+            mass_modes.append({"obs": obs.tolist(), "mode": mode, "seed": 5,
+                               "out": ns["_apply_mass_mode_to_obs"](obs, mode=mode, rng=np.random.default_rng(5), warn_once={}).tolist()})
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "play_metrics.json")
-    json.dump({"layouts": layouts, "bootstrap": boots, "reasons": reasons}, open(out, "w"))
+    json.dump({"layouts": layouts, "bootstrap": boots, "reasons": reasons, "mass_modes": mass_modes}, open(out, "w"))
     print("wrote", os.path.normpath(out))
 
 

@@ -11,12 +11,16 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
 from omniisaacgymenvs_loop_b200.config import live_default_config, live_task_cfg, load_task_yaml
-from omniisaacgymenvs_loop_b200.utils.episode_metrics import EpisodeRecorder
+import numpy as np
+
+from omniisaacgymenvs_loop_b200.utils.episode_metrics import EpisodeRecorder, apply_mass_mode_to_obs
 from scripts.train_loopz import build_learner, make_env
 
 
-def play(env, actor, episodes: int, reward_scale: float = 0.01, max_steps: int = 1_000_000, **meta) -> EpisodeRecorder:
-    """Runs until `episodes` episodes have finished (all envs in parallel; the last step may overshoot); returns the recorder."""
+def play(env, actor, episodes: int, reward_scale: float = 0.01, max_steps: int = 1_000_000, mass_mode: str = "normal", **meta) -> EpisodeRecorder:
+    """Runs until `episodes` episodes have finished (all envs in parallel; the last step may overshoot); returns the recorder.
+    `mass_mode`: the control-side intervention on the mass / CoM columns the policy sees (LOOPZ_PLAY_MASS_MODE, :1212-1218)."""
+    rng = np.random.default_rng(int(meta.get("seed", 0)))
     rec = EpisodeRecorder(env._task.engine, reward_scale=reward_scale, action_scale=float(actor.distribution.action_scale.reshape(-1)[0]), **meta)
     # reset() flags every env and runs the zero-action reset step (VecEnvRLGames.reset): feed it to the recorder as the start snapshot
     env.reset()
@@ -27,7 +31,7 @@ def play(env, actor, episodes: int, reward_scale: float = 0.01, max_steps: int =
     for _ in range(max_steps):
         if len(rec.rows) >= episodes:
             break
-        obs = env.observe(as_numpy=False)
+        obs = apply_mass_mode_to_obs(env.observe(as_numpy=False), mass_mode, rng)
         action = torch.tanh(actor.noiseless_action(obs)) * scale
         reward, dones = env.step(action)
         rec.record(action, reward, dones)
@@ -42,6 +46,7 @@ def main():
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--checkpoint", default=None)
     ap.add_argument("--csv", default=None)
+    ap.add_argument("--mass-mode", default=os.getenv("LOOPZ_PLAY_MASS_MODE", "normal"), help="normal | zero | shuffle | swap (policy-side only)")
     ap.add_argument("--obs-source", default="sim", choices=["sim", "base", "both"],
                     help="privileged-tail source (mass.masscom_obs_source); both = the reference's two-mode comparison (eval.modes)")
     args = ap.parse_args()
@@ -54,7 +59,7 @@ def main():
     rows = []
     for mode in (["sim", "base"] if args.obs_source == "both" else [args.obs_source]):
         env._task._masscom_obs_source = mode                    # rlgames_play_loopz.py:1100-1110 (_set_obs_source)
-        rec = play(env, ppo.actor, args.episodes, run_id="play", ckpt=str(args.checkpoint), seed=args.seed, obs_source=mode)
+        rec = play(env, ppo.actor, args.episodes, run_id="play", ckpt=str(args.checkpoint), seed=args.seed, obs_source=mode, mass_mode=args.mass_mode)
         print(f"[loopz-play][EVAL] mode={mode}")
         rec.summarize(seed=args.seed)
         rows += rec.rows

@@ -36,6 +36,15 @@ def test_done_reason_priority_matches_reference():
         assert EM.infer_done_reason(r["collision"] > 0.5, r["out_of_bounds"] > 0.5, r["in_goal_tolerance"] > 0.5) == r["reason"]
 
 
+def test_mass_mode_intervention_matches_reference():
+    for c in G["mass_modes"]:
+        obs = torch.tensor(c["obs"], dtype=torch.float32)
+        keep = obs.clone()
+        got = EM.apply_mass_mode_to_obs(obs, c["mode"], np.random.default_rng(c["seed"]))
+        assert torch.equal(got, torch.tensor(c["out"], dtype=torch.float32)), (c["mode"], obs.shape)
+        assert torch.equal(obs, keep)                                            # the input is never modified
+
+
 class FakeEngine:
     """Just the attributes EpisodeRecorder reads from FusedUsvLiveEnv, with scripted trajectories."""
 
