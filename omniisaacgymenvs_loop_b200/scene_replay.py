@@ -93,3 +93,79 @@ class SceneReplay:
         ids = env.reset_buf.nonzero(as_tuple=False).squeeze(-1)       # host sync, as `reset_buf.nonzero()` in the reference
         self.apply(ids)
         return env.step(actions, rebuild_scene=False)
+
+
+# ---- writing scene files: the reference's scene builder  [ref: OIGE/scripts/build_usv_scenes.py:560-740] -------------------------------
+def snapshot_scenes(engine, seed: int = 0, max_obstacles: Optional[int] = None) -> dict:
+    """The scene of EVERY env of a live engine right after `env.reset()` (flag + one zero-action step), in the arrays of the reference's
+    scene file.  The reference builder resets a vec-env N times and snapshots env 0 each time (:580-640); here one reset of an N-env
+    engine yields N scenes.  Obstacles keep their slots, limbo ones included (the reference stores `xunlian_pos` as it is and sets
+    `obstacles_count` to the number of slots, :598-611)."""
+    n = int(engine.num_envs)
+    f = lambda name: engine.field(name).detach().float().cpu().numpy().astype(np.float32)
+    obst = engine.obstacles.detach().float().cpu().numpy().astype(np.float32)
+    k = int(obst.shape[1]) if max_obstacles is None else min(int(obst.shape[1]), int(max_obstacles))
+    return {
+        "num_episodes": n,
+        "episode_idx": np.arange(n, dtype=np.int32),
+        "seed": (int(seed) + np.arange(n)).astype(np.int64),
+        "max_obstacles": k,
+        "obstacles_xy": np.ascontiguousarray(obst[:, :k, :2]),
+        "obstacles_count": np.full((n,), k, dtype=np.int32),
+        "start_pos": np.stack([f("USV_S_X"), f("USV_S_Y")], axis=1),
+        "start_yaw": f("USV_S_PSI"),
+        "start_vel": np.stack([f("USV_S_VX"), f("USV_S_VY")], axis=1),
+        "goal_pos": np.stack([f("USV_C_TX"), f("USV_C_TY")], axis=1),
+    }
+
+
+def save_scenes(out_dir: str, scenes: dict, task_name: str = "USV", generator_cfg: Optional[dict] = None) -> str:
+    """Writes `<task>__scenes__N<N>__seed<seed>.npz` (compressed, via a temporary file) and its `.sha1` side-car, with the keys of the
+    reference builder (:704-737); returns the path of the npz."""
+    import datetime
+    import hashlib
+    import json
+    import re
+
+    missing = [k for k in REQUIRED if k not in scenes]
+    if missing:
+        raise KeyError(f"scene dict misses keys={missing}")
+    n = int(np.asarray(scenes["start_pos"]).shape[0])
+    seed0 = int(np.asarray(scenes.get("seed", [0])).reshape(-1)[0])
+    safe = re.sub(r"[^A-Za-z0-9_.-]+", "_", str(task_name)).strip("_") or "task"
+    os.makedirs(out_dir, exist_ok=True)
+    final_path = os.path.join(out_dir, f"{safe}__scenes__N{n}__seed{seed0}.npz")
+    tmp_path = final_path + ".tmp.npz"
+    cfg = {"task_name": str(task_name), "num_episodes": n, "seed": seed0, "max_obstacles": int(scenes.get("max_obstacles", np.asarray(scenes["obstacles_xy"]).shape[1]))}
+    cfg.update(generator_cfg or {})
+    data = {k: scenes[k] for k in ("episode_idx", "seed", *REQUIRED) if k in scenes}
+    data.update(num_episodes=n, max_obstacles=cfg["max_obstacles"], generator_cfg=json.dumps(cfg), created_at=datetime.datetime.now().isoformat())
+    np.savez_compressed(tmp_path, **data)
+    sha1 = hashlib.sha1()
+    with open(tmp_path, "rb") as fp:
+        for chunk in iter(lambda: fp.read(8192), b""):
+            sha1.update(chunk)
+    os.replace(tmp_path, final_path)
+    with open(final_path + ".sha1", "w") as fp:
+        fp.write(sha1.hexdigest())
+    return final_path
+
+
+def load_scenes(npz_path: str, verify_sha1: bool = False) -> dict:
+    """The arrays `SceneReplay` consumes (same key check as `_scene_replay_load_npz`, USV_Virtual.py:1329-1370); `verify_sha1` compares
+    the file with its `.sha1` side-car when one exists."""
+    import hashlib
+
+    path = os.path.abspath(npz_path)
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"scene_replay.npz_path not found: {path}")
+    if verify_sha1 and os.path.exists(path + ".sha1"):
+        want = open(path + ".sha1").read().strip()
+        got = hashlib.sha1(open(path, "rb").read()).hexdigest()
+        if want != got:
+            raise ValueError(f"scene file {path} does not match its .sha1 side-car ({got} != {want})")
+    with np.load(path, allow_pickle=True) as npz:
+        missing = [k for k in REQUIRED if k not in npz.files]
+        if missing:
+            raise KeyError(f"scene_replay npz missing keys={missing}; found={list(npz.files)}")
+        return {k: np.array(npz[k]) for k in npz.files}

@@ -145,3 +145,31 @@ def test_recorder_equals_per_env_scalar_loop(tmp_path):
     lines = []
     summ = rec.summarize(log=lines.append)
     assert set(summ) == set(EM.SUMMARY_METRICS) and 0.0 <= summ["success"][0] <= 1.0 and len(lines) == 1 + len(EM.SUMMARY_METRICS)
+
+
+def test_scene_file_writer_round_trip(tmp_path):
+    """The scene builder's file format [ref: OIGE/scripts/build_usv_scenes.py:704-737]: keys, dtypes, name, .sha1 side-car; what
+    SceneReplay reads back is what the engine held."""
+    import json
+
+    from omniisaacgymenvs_loop_b200 import scene_replay as SR
+    eng = FakeEngine(10, 2)
+    eng.step(torch.zeros((10, 2)))                                   # env.reset(): flag + one zero-action step
+    sc = SR.snapshot_scenes(eng, seed=40)
+    assert sc["obstacles_xy"].shape == (10, 16, 2) and sc["obstacles_xy"].dtype == np.float32 and sc["obstacles_count"].tolist() == [16] * 10
+    assert np.array_equal(sc["start_pos"][:, 0], eng.f["USV_S_X"].numpy()) and np.array_equal(sc["goal_pos"][:, 1], eng.f["USV_C_TY"].numpy())
+    assert np.array_equal(sc["obstacles_xy"], eng.obstacles.numpy()) and sc["seed"].tolist() == list(range(40, 50))
+    path = SR.save_scenes(str(tmp_path), sc, task_name="USV Virtual/CaptureXY", generator_cfg={"goal_random_position": 4.0})
+    assert os.path.basename(path) == "USV_Virtual_CaptureXY__scenes__N10__seed40.npz" and os.path.exists(path + ".sha1")
+    back = SR.load_scenes(path, verify_sha1=True)
+    assert set(SR.REQUIRED) | {"num_episodes", "episode_idx", "seed", "max_obstacles", "generator_cfg", "created_at"} <= set(back)
+    for k in SR.REQUIRED:
+        assert np.array_equal(back[k], sc[k]) and back[k].dtype == sc[k].dtype, k
+    assert json.loads(str(back["generator_cfg"]))["goal_random_position"] == 4.0 and int(back["num_episodes"]) == 10
+    with open(path, "ab") as fp:                                    # a corrupted file is caught by the side-car
+        fp.write(b"x")
+    import pytest
+    with pytest.raises(ValueError):
+        SR.load_scenes(path, verify_sha1=True)
+    with pytest.raises(KeyError):
+        SR.save_scenes(str(tmp_path), {"start_pos": sc["start_pos"]})
