@@ -555,7 +555,8 @@ def live_task_cfg(cfg: Optional["UsvEnvConfig"] = None, live: Optional["UsvLiveC
     dist["coupling"] = {"mass_driven": {"enabled": cfg.mass_coupling, "targets": ["drag_scale", "thruster", "yaw_inertia"]}}
     dist["mass"].update(com_displacement_xyz=list(live.com_disp) if live.com_rand else None, base_com=list(live.com_base),
                         apply_com_to_sim=True, mass_obs_mode="relative" if live.mass_obs_relative else "raw",
-                        com_obs_mode="scaled" if live.com_obs_scaled else "raw", masscom_obs_source="sim")
+                        com_obs_mode="scaled" if live.com_obs_scaled else "raw",
+                        masscom_obs_source="base" if live.masscom_obs_base else "sim")
     dist["drag"]["use_drag_scale_randomization"] = cfg.kdrag_rand
     dist["thruster"]["thruster_rand"] = cfg.couple_thr_a if cfg.mass_coupling else cfg.thr_rand_frac
     dist["inertia"] = {"use_yaw_inertia_randomization": False, "k_Iz_min": cfg.couple_kiz_min, "k_Iz_max": cfg.couple_kiz_max,

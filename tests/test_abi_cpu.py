@@ -103,6 +103,16 @@ def test_live_task_cfg_round_trip():
     assert UsvLiveConfig.from_task_cfg(t) == live
     lp = live.to_params()
     assert lp.priv_mode == 2 and list(lp.priv_a) == [1.0, 0.5, 0.5, 1.0] and list(lp.priv_active) == [1, 1, 1, 1]
+    # mass.masscom_obs_source: base  [ref: OIGE/tasks/USV_Virtual.py:468-472,859-880]: round trip + the neutral parameters of each encoding
+    base = dataclasses.replace(live, masscom_obs_base=True)
+    tb = live_task_cfg(cfg, base)
+    assert tb["env"]["disturbances"]["mass"]["masscom_obs_source"] == "base" and UsvLiveConfig.from_task_cfg(tb) == base
+    lpb = base.to_params()
+    assert lpb.masscom_obs_base == 1 and lp.masscom_obs_base == 0 and list(lpb.priv_neutral) == [1.25, 0.75, 0.75, 1.25]   # minmax: mid-range
+    assert list(dataclasses.replace(base, priv_mode=1).to_params().priv_neutral) == [1.0] * 4                              # centered / raw: 1.0
+    tb["env"]["disturbances"]["mass"]["masscom_obs_source"] = "other"
+    with pytest.raises(ValueError):
+        UsvLiveConfig.from_task_cfg(tb)
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference YAMLs only exist in the build container")
