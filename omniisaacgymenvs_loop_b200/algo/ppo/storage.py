@@ -87,3 +87,47 @@ class RolloutStorage:
         mb = batch_size // num_mini_batches
         for b in range(num_mini_batches):
             yield tuple(t[b * mb:(b + 1) * mb] for t in self._flat())
+
+
+class ObsStorage:
+    """Supervised (observation, expert target) buffer of the DAgger / SysID trainers  [ref: omniisaacgymenvs/algo/ppo/storage.py:4-42]:
+    `[T, N, ...]` tensors on `device`, time-major flattening, in-order minibatches = contiguous row blocks (views, no copy),
+    shuffled minibatches from one `torch.randperm` (the reference draws them with `BatchSampler(SubsetRandomSampler(...))`,
+    `drop_last=True`).  `add_obs` takes numpy (the reference's contract) or tensors already on the device.  A plain tensor container:
+    no kernel behind it, so any device is accepted."""
+
+    def __init__(self, num_envs, num_transitions_per_env, obs_shape, action_shape, device):
+        self.device = torch.device(device)
+        self.obs = torch.zeros(num_transitions_per_env, num_envs, *obs_shape, dtype=torch.float32, device=self.device)
+        self.expert = torch.zeros(num_transitions_per_env, num_envs, *action_shape, dtype=torch.float32, device=self.device)
+        self.num_envs = int(num_envs)
+        self.num_transitions_per_env = int(num_transitions_per_env)
+        self.step = 0
+
+    def add_obs(self, obs, expert_action):
+        if self.step >= self.num_transitions_per_env:
+            raise AssertionError("Rollout buffer overflow")
+        self.obs[self.step].copy_(_dev(obs, self.device))
+        self.expert[self.step].copy_(_dev(expert_action, self.device))
+        self.step += 1
+
+    def clear(self):
+        self.step = 0
+
+    def _flat(self):
+        return self.obs.view(-1, *self.obs.size()[2:]), self.expert.view(-1, *self.expert.size()[2:])
+
+    def mini_batch_generator_inorder(self, num_mini_batches):
+        obs, expert = self._flat()
+        mb = (self.num_envs * self.num_transitions_per_env) // num_mini_batches
+        for b in range(num_mini_batches):
+            yield obs[b * mb:(b + 1) * mb], expert[b * mb:(b + 1) * mb]
+
+    def mini_batch_generator_shuffle(self, num_mini_batches, generator=None):
+        obs, expert = self._flat()
+        batch = self.num_envs * self.num_transitions_per_env
+        mb = batch // num_mini_batches
+        perm = torch.randperm(batch, generator=generator).to(self.device)
+        for b in range(batch // mb):                                  # drop_last=True
+            idx = perm[b * mb:(b + 1) * mb]
+            yield obs[idx], expert[idx]

@@ -83,3 +83,35 @@ def test_history_matches_reference_class(fill):
         assert np.array_equal(ours.observe_sysid_obs(), ref.observe_sysid_obs())
         assert np.array_equal(ours.observe_history(), ref.observe_history()) and np.array_equal(ours.observe_nonpriv(), ref.observe_nonpriv())
         assert torch.equal(ours.get_priv_tail(), ref.get_priv_tail())
+
+
+def test_obs_storage_surface_and_generators():
+    """ObsStorage [ref: omniisaacgymenvs/algo/ppo/storage.py:4-42]: time-major flattening, in-order blocks, overflow, shuffle = a partition."""
+    from omniisaacgymenvs_loop_b200.algo.ppo import ObsStorage
+    T, n, hd, lat = 3, 4, 5, 2
+    st = ObsStorage(n, T, [hd], [lat], "cpu")
+    g = torch.Generator().manual_seed(0)
+    obs = torch.randn((T, n, hd), generator=g)
+    tgt = torch.randn((T, n, lat), generator=g)
+    for t in range(T):
+        st.add_obs(obs[t].numpy() if t % 2 else obs[t], tgt[t])                  # numpy or tensor
+    with pytest.raises(AssertionError):
+        st.add_obs(obs[0], tgt[0])
+    got = list(st.mini_batch_generator_inorder(4))
+    assert len(got) == 4
+    for b, (o, e) in enumerate(got):
+        assert torch.equal(o, obs.reshape(-1, hd)[3 * b:3 * b + 3]) and torch.equal(e, tgt.reshape(-1, lat)[3 * b:3 * b + 3])
+    rows = torch.cat([o for o, _ in st.mini_batch_generator_shuffle(4, generator=torch.Generator().manual_seed(1))])
+    assert rows.shape == (12, hd) and torch.equal(rows.sort(dim=0).values, obs.reshape(-1, hd).sort(dim=0).values)
+    assert len(list(st.mini_batch_generator_shuffle(5))) == 6                    # 12 // 5 = 2 rows per batch, drop_last
+    st.clear()
+    assert st.step == 0
+    if os.path.isdir("/root/reference"):
+        from oracle import ref_shim
+        ref_shim.install()
+        import omniisaacgymenvs.algo.ppo.storage as RS
+        ref = RS.ObsStorage(n, T, [hd], [lat], "cpu")
+        for t in range(T):
+            st.add_obs(obs[t], tgt[t]); ref.add_obs(obs[t].numpy(), tgt[t])
+        for (a, b), (c, d) in zip(st.mini_batch_generator_inorder(2), ref.mini_batch_generator_inorder(2)):
+            assert torch.equal(a, c) and torch.equal(b, d)
