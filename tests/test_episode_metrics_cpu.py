@@ -173,3 +173,33 @@ def test_scene_file_writer_round_trip(tmp_path):
         SR.load_scenes(path, verify_sha1=True)
     with pytest.raises(KeyError):
         SR.save_scenes(str(tmp_path), {"start_pos": sc["start_pos"]})
+
+
+def test_scene_file_built_on_b200_feeds_scene_replay_host_logic():
+    """tests/golden/scenes_b200_N64_seed3.npz was written by scripts/build_usv_scenes.py on a B200 (64 envs, one reset).  The file obeys
+    the spawn rules of the live task [ref: USV_capture_xy_static_obs.py:936-1047] and SceneReplay's host side (per-env scene counters,
+    16-slot normalisation) consumes it; the device side of the replay is tests/test_gpu_live.py::test_scene_replay_npz_vs_oracle."""
+    from omniisaacgymenvs_loop_b200 import scene_replay as SR
+    path = os.path.join(os.path.dirname(__file__), "golden", "scenes_b200_N64_seed3.npz")
+    d = SR.load_scenes(path, verify_sha1=True)
+    ob, sp = d["obstacles_xy"], d["start_pos"]
+    assert ob.shape == (64, 16, 2) and d["obstacles_count"].tolist() == [16] * 64
+    real = ob[..., 0] < 900
+    dist = np.linalg.norm(ob - sp[:, None, :], axis=2)
+    assert dist[real].min() > 3.0 - 0.35                                  # 3 m from the start, minus one zero-action step of drift
+    assert np.linalg.norm(ob - d["goal_pos"][:, None, :], axis=2)[real].min() >= 3.0 - 1e-4          # 3 m from the target
+    for i in range(64):                                                   # 2.5 m between any two placed obstacles
+        p = ob[i][real[i]]
+        dd = np.linalg.norm(p[:, None] - p[None], axis=2) + np.eye(len(p)) * 99
+        assert dd.min() >= 2.5 - 1e-4
+    r = np.linalg.norm(sp, axis=1)
+    assert 9.0 - 0.35 <= r.min() and r.max() <= 12.0 + 0.35 and 0.0 <= d["start_yaw"].min() and d["start_yaw"].max() < np.pi + 0.1
+    rp = object.__new__(SR.SceneReplay)                                   # host logic only: no engine behind it
+    rp.data, rp.num_scenes, rp.cycle = {k: d[k] for k in SR.REQUIRED}, 64, True
+    rp.next_scene_idx, rp.last_scene_idx = torch.zeros(8, dtype=torch.long), torch.full((8,), -1, dtype=torch.long)
+    rp.next_scene_idx[3] = 63
+    idx = rp.take_scene_indices(torch.tensor([1, 3]))
+    assert idx.tolist() == [0, 63] and rp.take_scene_indices(torch.tensor([3])).tolist() == [0]      # cycles past the end
+    pos, yaw, vel, goal, obst = rp.scenes(idx)
+    assert obst.shape == (2, 16, 2) and torch.equal(obst, torch.from_numpy(ob[[0, 63]])) and torch.equal(pos, torch.from_numpy(sp[[0, 63]]))
+    assert yaw.shape == (2,) and vel.shape == (2, 2) and goal.shape == (2, 2)
