@@ -512,6 +512,20 @@ int ppo_peer_window_close(void* window, int32_t owned);
 int ppo_peer_allreduce_f32(const PpoPeerComm* c, const float* src, float* dst, int64_t count, uint32_t* seq_dev,
                            uint32_t* err_flag, void* stream);
 
+/* ppo_minibatch_step_tc on `world` ranks: the gradient all-reduce of trancate_gradients_and_step [ref: RLG/common/a2c_common.py:308-323]
+ * runs INSIDE the cooperative tail kernel -- every 64-entry block of the span [gradient | loss statistics | KL] is pushed to the peers
+ * as 8-byte {value, sequence} packets (P2P stores over NVLink, payload and flag in one word), summed in rank order as the packets
+ * arrive, then clipped / Adam-stepped / re-packed by the same CTA: T1 + T2 + tail + roll = 4 launches per minibatch at any world size.
+ * comm: windows from ppo_peer_window_alloc/open with cap >= world * ppo_minibatch_step_peer_entries(obs_dim) * 2 floats;
+ * seq_dev as in ppo_peer_allreduce_f32 (its own counter); err_flag: set when a peer does not arrive within 10 s -- the parameters
+ * are then left untouched by this and every later step until the host clears the flag.                                          */
+int64_t ppo_minibatch_step_peer_entries(int32_t obs_dim);
+int ppo_minibatch_step_peer_tc(float* params, float* packed, const float* obs, int32_t obs_dim, const float* obs_mean, const float* obs_var,
+                               const float* actions, const float* old_neglogp, const float* advantages, const float* old_values,
+                               const float* returns, float* old_mu, float* old_sigma, const PpoLossParams* lp, float* grads, float* scratch,
+                               float* workspace, float* exp_avg, float* exp_avg_sq, float* lr, int32_t* step, const PpoAdamParams* ap,
+                               const PpoPeerComm* comm, uint32_t* seq_dev, uint32_t* err_flag, int64_t M, void* stream);
+
 /* RunningMeanStd training-mode update, fused: batch moments of x[M,D] + Chan merge into the fp64 running state + fp32 copies
  *   [ref: RLG/algos_torch/running_mean_std.py:69-89] */
 int ppo_rms_update_f64(const float* x /*[M,D]*/, int64_t M, int32_t D, double* mean /*[D]*/, double* var /*[D]*/, double* count /*[1]*/,

@@ -18,6 +18,7 @@
 // which remain the numerics reference.
 #include <cooperative_groups.h>
 #include <math_constants.h>
+#include <string.h>
 #include "philox.cuh"
 #include "usv_common.cuh"
 
@@ -71,5 +72,23 @@ extern "C" int ppo_minibatch_step_tc(float* params, float* packed, const float* 
                                      float* exp_avg_sq, float* lr, int32_t* step, const PpoAdamParams* ap, int64_t M, void* stream) {
   PPOTC_DISPATCH(obs_dim, host_minibatch_step(params, packed, obs, obs_dim, obs_mean, obs_var, actions, old_neglogp, advantages, old_values,
                                               returns, old_mu, old_sigma, lp, grads, scratch, workspace, exp_avg, exp_avg_sq, lr, step, ap,
-                                              M, stream));
+                                              nullptr, nullptr, nullptr, M, stream));
+}
+
+extern "C" int64_t ppo_minibatch_step_peer_entries(int32_t obs_dim) {
+  if (obs_dim >= 1 && obs_dim < 16) return ppotc16::tail_entries(obs_dim);
+  if (obs_dim >= 16 && obs_dim < 48) return ppotc48::tail_entries(obs_dim);
+  return -1;
+}
+
+extern "C" int ppo_minibatch_step_peer_tc(float* params, float* packed, const float* obs, int32_t obs_dim, const float* obs_mean,
+                                          const float* obs_var, const float* actions, const float* old_neglogp, const float* advantages,
+                                          const float* old_values, const float* returns, float* old_mu, float* old_sigma,
+                                          const PpoLossParams* lp, float* grads, float* scratch, float* workspace, float* exp_avg,
+                                          float* exp_avg_sq, float* lr, int32_t* step, const PpoAdamParams* ap, const PpoPeerComm* comm,
+                                          uint32_t* seq_dev, uint32_t* err_flag, int64_t M, void* stream) {
+  if (!comm) return USV_E_NULL;
+  PPOTC_DISPATCH(obs_dim, host_minibatch_step(params, packed, obs, obs_dim, obs_mean, obs_var, actions, old_neglogp, advantages, old_values,
+                                              returns, old_mu, old_sigma, lp, grads, scratch, workspace, exp_avg, exp_avg_sq, lr, step, ap,
+                                              comm, seq_dev, err_flag, M, stream));
 }

@@ -127,12 +127,14 @@ class A2CAgent:
                                 clip_value=cfg.clip_value, grad_norm=cfg.grad_norm if cfg.truncate_grads else 0.0,
                                 kl_threshold=cfg.kl_threshold, adaptive_lr=cfg.lr_schedule == "adaptive", world_size=world_size)
         self.policy.seed = cfg.seed + rank                                  # [ref: RLG/torch_runner.py:74-75]
-        self.peer = None
+        self.peer, self.peer_step = None, None
         if self.multi_gpu:                                                  # [ref: a2c_common.py:1350-1355]
             dist.broadcast(self.policy.params, 0)
             if self.collective == "peer":
-                from .peer import PeerAllReduce
+                from .peer import PeerAllReduce, PeerStepExchange
                 self.peer = PeerAllReduce(self.policy.grads.numel(), self.device, rank, world_size)
+                if self.policy.tensor_cores:      # the all-reduce fused into the cooperative minibatch tail (4 launches per minibatch)
+                    self.peer_step = PeerStepExchange(self.obs_dim, self.device, rank, world_size)
         N, T, D = self.num_actors, self.T, self.obs_dim
         f32 = dict(dtype=torch.float32, device=self.device)
         self.buf = dict(obses=torch.zeros((T, N, D), **f32), rewards=torch.zeros((T, N), **f32), values=torch.zeros((T, N, 1), **f32),
@@ -227,8 +229,9 @@ class A2CAgent:
                     pol.obs_rms.update(ds["obs"][s])                    # train-mode forward updates the normaliser first
                 args = (ds["obs"][s], ds["actions"][s], ds["old_logp_actions"][s], ds["advantages"][s], ds["old_values"][s],
                         ds["returns"][s], ds["mu"][s], ds["sigma"][s])
-                if not self.multi_gpu and pol.tensor_cores and self.fused_step:
-                    pol.minibatch_step(*args)                            # gradient + clip + Adam + lr + operand-tile refresh: 4 launches
+                if pol.tensor_cores and self.fused_step and (not self.multi_gpu or self.peer_step is not None):
+                    # gradient (+ all-reduce over NVLink inside the tail kernel) + clip + Adam + lr + operand-tile refresh: 4 launches
+                    pol.minibatch_step(*args, peer=self.peer_step)
                     continue
                 pol.minibatch_grad(*args)
                 if self.peer is not None:
@@ -303,6 +306,25 @@ class A2CAgent:
         self.frame += self.batch_size * self.world
         return t1 - t0, time.perf_counter() - t1
 
+    def check_peers(self) -> None:
+        """Raises when a gradient exchange timed out on this rank (one host read per window; the kernels leave the parameters
+        untouched from the failing step on, so ranks cannot silently diverge)."""
+        for p in (self.peer, self.peer_step):
+            if p is not None:
+                p.check()
+
+    def ranks_identical(self) -> bool:
+        """True when every rank holds bit-identical parameters, Adam moments and learning rate (all-gather of an exact checksum)."""
+        if not self.multi_gpu:
+            return True
+        P = self.policy
+        words = torch.cat([P.params, P.exp_avg, P.exp_avg_sq, P.lr]).view(torch.int32).to(torch.int64)
+        idx = torch.arange(1, words.numel() + 1, device=self.device, dtype=torch.int64)
+        sig = torch.stack([words.sum(), (words * idx).sum(), P.step.to(torch.int64).sum()])
+        sigs = [torch.empty_like(sig) for _ in range(self.world)]
+        dist.all_gather(sigs, sig)
+        return all(torch.equal(s, sigs[0]) for s in sigs)
+
     def episode_stats(self):
         """Mean return / length of the episodes finished since the last call, reduced over ranks (one small all-reduce)."""
         acc = self.episode_acc.clone()
@@ -327,6 +349,7 @@ class A2CAgent:
             play, update = self.train_epoch()
             if self.epoch_num % log_every == 0:
                 torch.cuda.synchronize(self.device)
+                self.check_peers()
                 rew, length, cnt = self.episode_stats()
                 if cnt:
                     self.mean_reward = rew

@@ -60,6 +60,9 @@ class PeerAllReduce:
         if int(self.err.item()) != 0:
             raise RuntimeError("PeerAllReduce: a peer rank did not reach the all-reduce (spin bound expired)")
 
+    def clear_error(self) -> None:
+        self.err.zero_()
+
     def close(self) -> None:
         for p in self._opened:
             self.lib.ppo_peer_window_close(p, ctypes.c_int32(0))
@@ -67,3 +70,40 @@ class PeerAllReduce:
         if self._own is not None:
             self.lib.ppo_peer_window_close(self._own, ctypes.c_int32(1))
             self._own = None
+
+
+class PeerStepExchange(PeerAllReduce):
+    """The windows of the all-reduce that runs INSIDE the fused minibatch tail kernel (ppo_minibatch_step_peer_tc): per rank
+    [2 parities][world][entries] packets of 8 bytes {value, sequence}.  Same IPC plumbing as PeerAllReduce; its own sequence counter."""
+
+    def __init__(self, obs_dim: int, device, rank: int = 0, world_size: int = 1, group=None):
+        entries = int(_lib.lib().ppo_minibatch_step_peer_entries(ctypes.c_int32(int(obs_dim))))
+        if entries <= 0:
+            raise ValueError(f"no tensor-core minibatch step for obs_dim {obs_dim}")
+        self.entries = entries
+        super().__init__(int(world_size) * entries * 2, device, rank, world_size, group)
+
+
+class InProcessStepExchange:
+    """`world` ranks of the fused exchange living in ONE process on ONE device (each rank drives its own stream): the windows are plain
+    device allocations instead of IPC mappings, the kernel and its packet protocol are the same.  Used to exercise the multi-rank
+    data path where only one GPU is visible (tests/test_gpu_ppo.py); `ranks[r]` quacks like a PeerStepExchange."""
+
+    class _Rank:
+        pass
+
+    def __init__(self, obs_dim: int, device, world_size: int):
+        entries = int(_lib.lib().ppo_minibatch_step_peer_entries(ctypes.c_int32(int(obs_dim))))
+        cap = int(world_size) * entries * 2
+        self.windows = [torch.zeros(2 * cap + 64, dtype=torch.float32, device=device) for _ in range(world_size)]
+        self.ranks = []
+        for r in range(world_size):
+            k = self._Rank()
+            k.world, k.rank = int(world_size), r
+            k.comm = _lib.PpoPeerComm()
+            k.comm.cap, k.comm.world, k.comm.rank = cap, int(world_size), r
+            for q in range(world_size):
+                k.comm.windows[q] = self.windows[q].data_ptr()
+            k.seq = torch.zeros(1, dtype=torch.int32, device=device)
+            k.err = torch.zeros(1, dtype=torch.int32, device=device)
+            self.ranks.append(k)

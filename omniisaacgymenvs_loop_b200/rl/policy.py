@@ -219,21 +219,26 @@ class PolicyMLP:
         _lib.check(rc, "ppo_minibatch_grad_f32")
         return self.grads
 
-    def minibatch_step(self, obs, actions, old_neglogp, advantages, old_values, returns, mu, sigma) -> None:
-        """minibatch_grad + optimizer_step + pack for a single rank on the tensor-core path: 3 launches (T1, T2 and one
-        cooperative kernel that reduces, clips, applies Adam / the adaptive lr and re-packs the operand tiles)."""
+    def minibatch_step(self, obs, actions, old_neglogp, advantages, old_values, returns, mu, sigma, peer=None) -> None:
+        """minibatch_grad + (gradient all-reduce) + optimizer_step + pack on the tensor-core path: T1, T2 and ONE cooperative kernel that
+        reduces the partial gradients, exchanges them with the peer ranks over NVLink (`peer`: a rl.peer.PeerStepExchange), clips,
+        applies Adam / the adaptive lr and re-packs the operand tiles  [ref: RLG/common/a2c_common.py:308-330]."""
         M = obs.shape[0]
         need = int(self.lib.ppo_train_tc_workspace_floats(ctypes.c_int64(M)))
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.float32, device=self.device)
         if self._packed_dirty:
             self.pack()
-        rc = self.lib.ppo_minibatch_step_tc(
-            _lib.ptr(self.params), _lib.ptr(self.packed), _lib.ptr(obs, torch.float32), ctypes.c_int32(self.D), _lib.ptr(self.obs_rms.mean32),
-            _lib.ptr(self.obs_rms.var32), _lib.ptr(actions), _lib.ptr(old_neglogp), _lib.ptr(advantages), _lib.ptr(old_values),
-            _lib.ptr(returns), _lib.ptr(mu), _lib.ptr(sigma), ctypes.byref(self.loss_params), _lib.ptr(self.grads), _lib.ptr(self.scratch),
-            _lib.ptr(self._ws), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq), _lib.ptr(self._lr2), _lib.ptr(self._step2),
-            ctypes.byref(self.adam_params), ctypes.c_int64(M), _lib.stream())
+        args = (_lib.ptr(self.params), _lib.ptr(self.packed), _lib.ptr(obs, torch.float32), ctypes.c_int32(self.D), _lib.ptr(self.obs_rms.mean32),
+                _lib.ptr(self.obs_rms.var32), _lib.ptr(actions), _lib.ptr(old_neglogp), _lib.ptr(advantages), _lib.ptr(old_values),
+                _lib.ptr(returns), _lib.ptr(mu), _lib.ptr(sigma), ctypes.byref(self.loss_params), _lib.ptr(self.grads), _lib.ptr(self.scratch),
+                _lib.ptr(self._ws), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq), _lib.ptr(self._lr2), _lib.ptr(self._step2),
+                ctypes.byref(self.adam_params))
+        if peer is not None and peer.world > 1:
+            rc = self.lib.ppo_minibatch_step_peer_tc(*args, ctypes.byref(peer.comm), _lib.ptr(peer.seq), _lib.ptr(peer.err),
+                                                     ctypes.c_int64(M), _lib.stream())
+        else:
+            rc = self.lib.ppo_minibatch_step_tc(*args, ctypes.c_int64(M), _lib.stream())
         _lib.check(rc, "ppo_minibatch_step_tc")
         self._packed_dirty = False          # the fused tail re-packed the tiles from the updated parameters
 

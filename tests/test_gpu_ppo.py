@@ -243,11 +243,16 @@ def test_fused_minibatch_step_equals_unfused():
             b.minibatch_step(obs, act, old_nlp, adv, old_v, ret, mu_b, sg_b)
             # identical T1/T2 kernels; only the summation order of the gradient norm differs (clip coefficient ~1e-7 relative)
             assert_close(b.params, a.params, 1e-6, 1e-8, f"params M={M} it={it}")
-            assert_close(b.exp_avg, a.exp_avg, 1e-5, 1e-10, "exp_avg"); assert_close(b.exp_avg_sq, a.exp_avg_sq, 1e-5, 1e-14, "exp_avg_sq")
+            # after the first step the parameters differ in their last bits, and a last-bit difference that straddles a TF32 rounding
+            # boundary of an operand is a 2^-11 relative change of that operand: gradients agree to ~1e-4 of their scale from then on
+            gs = float(a.exp_avg.abs().max())
+            assert_close(b.exp_avg, a.exp_avg, 1e-5 if it == 0 else 2e-4, 1e-10 if it == 0 else 2e-4 * gs, "exp_avg")
+            assert_close(b.exp_avg_sq, a.exp_avg_sq, 1e-5 if it == 0 else 4e-4, 1e-14 if it == 0 else 4e-4 * gs * gs, "exp_avg_sq")
             assert_close(b.packed, a.packed, 1e-6, 1e-8, "packed tiles")
             sa, sb = a.stats(), b.stats()
             assert all(abs(sa[k] - sb[k]) <= 1e-5 * abs(sa[k]) + 1e-7 for k in sa), (sa, sb)
-            assert int(a.step) == int(b.step) == it + 1 and torch.equal(mu_a, mu_b)
+            assert int(a.step) == int(b.step) == it + 1
+            assert_close(mu_b, mu_a, 1e-5, 1e-6, "mu write-back")     # the fused tail sums the five scalar gradients in another order
     # capturable (cooperative launch inside a graph)
     g = torch.cuda.CUDAGraph()
     before = b.params.clone()
@@ -257,6 +262,65 @@ def test_fused_minibatch_step_equals_unfused():
     g.replay(); g.replay()
     torch.cuda.synchronize()
     assert int(b.step) == 6 and not torch.equal(before, b.params) and torch.isfinite(b.params).all()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_fused_peer_minibatch_step_packet_protocol(world):
+    """The multi-rank minibatch step (gradient all-reduce INSIDE the cooperative tail kernel, 8-byte {value, sequence} packets) on ONE
+    GPU: the packets of the peer ranks are placed into rank 0's window beforehand (a cooperative kernel does not share the device
+    with a second one, so in-process ranks cannot spin on each other), rank 0 runs its fused step and must (i) land on the unfused
+    sequence  sum_r minibatch_grad_r -> Adam with 1/world  [ref: RLG/common/a2c_common.py:308-330], (ii) have stored its own packets,
+    sequence-stamped, into every peer's window, (iii) alternate the slot parity and advance the sequence counter.  The concurrent
+    NVLink run of the same kernel, with bit-identity across ranks: scripts/check_peer_allreduce.py (torchrun, >= 2 GPUs)."""
+    from omniisaacgymenvs_loop_b200.rl.peer import InProcessStepExchange
+    torch.manual_seed(11)
+    M = 2048
+    ex = InProcessStepExchange(D, DEV, world)
+    ecap = int(ex.ranks[0].comm.cap) // (2 * world)
+    pol = PolicyMLP(D, DEV, seed=5, tensor_cores=True, world_size=world)
+    ref = PolicyMLP(D, DEV, seed=5, tensor_cores=True, world_size=world)
+    P = pol.P
+    data = []
+    for r in range(world):
+        obs = torch.randn((M, D), device=DEV) * 2
+        inf = ref.act(obs)
+        data.append(dict(obs=obs, act=(inf["actions"] + 0.2 * torch.randn((M, 2), device=DEV)).contiguous(),
+                         nlp=(inf["neglogpacs"] + 0.1 * torch.randn(M, device=DEV)).contiguous(), adv=torch.randn(M, device=DEV),
+                         old_v=torch.randn(M, device=DEV) * 0.3, ret=torch.randn(M, device=DEV) * 0.5,
+                         mu=inf["mus"].clone(), sg=inf["sigmas"].clone(), mu_ref=inf["mus"].clone(), sg_ref=inf["sigmas"].clone()))
+    step = lambda p, d, mu, sg, **kw: p(d["obs"], d["act"], d["nlp"], d["adv"], d["old_v"], d["ret"], d[mu], d[sg], **kw)
+    win = [w.view(torch.int32) for w in ex.windows]
+    for it in range(5):
+        seq, par = it + 1, (it + 1) & 1
+        local = [step(ref.minibatch_grad, data[r], "mu_ref", "sg_ref").clone() for r in range(world)]   # span a rank sends: grads + sums
+        for r in range(1, world):                          # the peers' packets, as their tail kernels would have stored them
+            base = (par * world + r) * ecap * 2
+            win[0][base:base + 2 * (P + 5):2] = local[r][:P + 5].view(torch.int32)
+            win[0][base + 1:base + 2 * (P + 5):2] = seq
+        step(pol.minibatch_step, data[0], "mu", "sg", peer=ex.ranks[0])
+        torch.cuda.synchronize()
+        assert int(ex.ranks[0].err.item()) == 0 and int(ex.ranks[0].seq.item()) == seq
+        for r in range(1, world):                          # rank 0's packets in the peers' windows, slot [parity][0]
+            base = (par * world + 0) * ecap * 2
+            got_v = win[r][base:base + 2 * (P + 5):2].view(torch.float32)
+            got_s = win[r][base + 1:base + 2 * (P + 5):2]
+            assert bool((got_s == seq).all()), "sequence stamp"
+            if it == 0:       # same parameters as `ref`: the matrix entries (w1 .. value weights) are the same sums in the same order
+                assert torch.equal(got_v[2:P - 260], local[0][2:P - 260]), "matrix gradient entries travel bit-exact"
+            gsc = float(local[0][:P].abs().max())
+            assert_close(got_v, local[0][:P + 5], 1e-5 if it == 0 else 2e-4, 1e-7 if it == 0 else 2e-4 * gsc, "packets of rank 0")
+            other = ((1 - par) * world + 0) * ecap * 2
+            assert bool((win[r][other + 1:other + 2 * (P + 5):2] == (seq - 1 if seq > 1 else 0)).all()), "the other parity is untouched"
+        ref.grads.copy_(torch.stack(local).sum(0))
+        ref.optimizer_step()
+        assert_close(pol.params, ref.params, 1e-6, 1e-8, f"params it={it}")
+        gs = float(ref.exp_avg.abs().max())
+        assert_close(pol.exp_avg, ref.exp_avg, 1e-5 if it == 0 else 2e-4, 1e-10 if it == 0 else 2e-4 * gs, "exp_avg")
+        assert_close(pol.packed, ref.packed, 1e-6, 1e-8, "packed tiles")
+        sa, sb = ref.stats(), pol.stats()
+        assert all(abs(sa[k] - sb[k]) <= 1e-5 * abs(sa[k]) + 1e-7 for k in sa), (sa, sb)
+        assert float(pol.lr) == float(ref.lr) and int(pol.step) == int(ref.step) == seq
+        assert_close(data[0]["mu"], data[0]["mu_ref"], 1e-5, 1e-6, "mu write-back")
 
 
 def test_tensor_core_paths_at_live_obs_width():
