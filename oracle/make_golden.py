@@ -345,6 +345,105 @@ def ppo():
     print("ppo.npz")
 
 
+def ppo_epoch():
+    """Two whole PPO epochs of the reference's own loop on fixed rollouts: ContinuousA2CBase.train_epoch -> prepare_dataset ->
+    PPODataset -> calc_gradients / trancate_gradients_and_step / legacy adaptive-KL schedule, executed UNMODIFIED on a bare
+    a2c_continuous.A2CAgent instance whose play_steps() hands over a recorded rollout (the env / experience buffer / writers of
+    __init__ are Isaac Sim + config plumbing)  [RLG/common/a2c_common.py:1152-1320, common/datasets.py:25-77,
+    algos_torch/a2c_continuous.py:78-196].  T=16, 64 actors, 2 minibatches of 512, 2 mini-epochs."""
+    rl = ref_shim.load_rl_games()
+    A2C, base = rl.a2c_continuous.A2CAgent, rl.a2c_common
+    torch.manual_seed(11)
+    D, T, NA, MB, ME = 13, 16, 64, 512, 2
+    with ref_shim.quiet():
+        net = rl.model_builder.ModelBuilder().load({
+            "model": {"name": "continuous_a2c_logstd"},
+            "network": {"name": "actor_critic_mlp_dict", "separate": False,
+                        "space": {"continuous": {"mu_activation": "None", "sigma_activation": "None", "mu_init": {"name": "default"},
+                                                 "sigma_init": {"name": "const_initializer", "val": 0}, "fixed_sigma": True}},
+                        "mlp": {"units": [128, 128], "activation": "tanh", "d2rl": False, "initializer": {"name": "default"},
+                                "regularizer": {"name": "None"}}}})
+        model = net.build({"actions_num": 2, "input_shape": {"state": (D,)}, "num_seqs": 1, "value_size": 1,
+                           "normalize_value": True, "normalize_input": True, "normalize_input_keys": ["state"]})
+    g = gen()
+    with torch.no_grad():
+        for prm in model.parameters():
+            prm.add_(0.03 * torch.randn(prm.shape, generator=g))
+        model.a2c_network.sigma.copy_(torch.tensor([-0.2, 0.1]))
+    rms = model.running_mean_std.running_mean_std["state"]
+    vms = model.value_mean_std
+    model.train()
+    rms(torch.randn((256, D), generator=g) * torch.linspace(0.5, 4.0, D) + torch.linspace(-1, 1, D))
+    vms(torch.randn((256, 1), generator=g) * 1.5 + 0.3)
+    model.eval()
+    ag = object.__new__(A2C)
+    ag.__dict__.update(
+        model=model, value_mean_std=vms, normalize_value=True, normalize_input=True, normalize_advantage=True, normalize_rms_advantage=False,
+        is_rnn=False, has_central_value=False, has_value_loss=True, multi_gpu=False, mixed_precision=False, ppo=True, ppo_device="cpu",
+        device="cpu", e_clip=0.2, clip_value=True, bound_loss_type="bound", bounds_loss_coef=1e-4, critic_coef=0.5, entropy_coef=0.0,
+        truncate_grads=True, grad_norm=1.0, schedule_type="legacy", scheduler=rl.schedulers.AdaptiveScheduler(0.016), last_lr=1e-4,
+        epoch_num=0, frame=0, mini_epochs_num=ME, gamma=0.99, tau=0.95, horizon_length=T, batch_size=T * NA, seq_len=4, zero_rnn_on_done=False,
+        actor_loss_func=rl.common_losses.actor_loss, diagnostics=base.DefaultDiagnostics(),
+        algo_observer=types.SimpleNamespace(after_steps=lambda: None), vec_env=types.SimpleNamespace(set_train_info=lambda *a: None),
+        scaler=torch.cuda.amp.GradScaler(enabled=False),
+        dataset=rl.datasets.PPODataset(T * NA, MB, False, False, "cpu", 4))
+    ag.optimizer = torch.optim.Adam(model.parameters(), 1e-4, eps=1e-08, weight_decay=0.0)
+    flat = lambda: torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    moments = lambda key: torch.cat([ag.optimizer.state[p][key].reshape(-1) for p in model.parameters()])
+    out = dict(params0=flat(), obs_mean0=rms.running_mean.clone(), obs_var0=rms.running_var.clone(), obs_count0=rms.count.clone(),
+               val_mean0=vms.running_mean.clone(), val_var0=vms.running_var.clone(), val_count0=vms.count.clone(),
+               shape=np.array([D, T, NA, MB, ME]), lr0=np.float32(1e-4))
+    for ep in range(2):
+        # a rollout as play_steps leaves it in the experience buffer: (T, N, ...) tensors  [a2c_common.py:670-760]
+        obses = torch.randn((T, NA, D), generator=g) * torch.linspace(0.5, 4.0, D) * (1.0 + 0.3 * ep) + torch.linspace(-1, 1, D)
+        with torch.no_grad():
+            r = model({"is_train": False, "prev_actions": None, "obs": {"state": obses.reshape(T * NA, D).clone()}, "rnn_states": None})
+        actions, neglogpacs = r["actions"].reshape(T, NA, 2), r["neglogpacs"].reshape(T, NA)
+        values, mus, sigmas = r["values"].reshape(T, NA, 1), r["mus"].reshape(T, NA, 2), r["sigmas"].reshape(T, NA, 2)
+        rewards = (torch.randn((T, NA, 1), generator=g) * 0.05 + 0.02)
+        dones = (torch.rand((T, NA), generator=g) < 0.08).to(torch.uint8)
+        last_values = torch.randn((NA, 1), generator=g) * 0.5 + 0.3
+        last_dones = (torch.rand(NA, generator=g) < 0.08).to(torch.uint8)
+        advs = A2C.discount_values(ag, last_dones.float(), last_values, dones.float(), values, rewards)
+        returns = advs + values
+        fl = base.swap_and_flatten01
+        batch = dict(obses={"state": fl(obses)}, returns=fl(returns), dones=fl(dones), values=fl(values), actions=fl(actions),
+                     neglogpacs=fl(neglogpacs), mus=fl(mus).clone(), sigmas=fl(sigmas).clone(), played_frames=T * NA, step_time=0.0)
+        ag.play_steps = lambda b=batch: dict(b)
+        out.update({f"ep{ep}_obses": obses, f"ep{ep}_actions": actions, f"ep{ep}_neglogpacs": neglogpacs, f"ep{ep}_values": values,
+                    f"ep{ep}_mus": mus.clone(), f"ep{ep}_sigmas": sigmas.clone(), f"ep{ep}_rewards": rewards, f"ep{ep}_dones": dones,
+                    f"ep{ep}_last_values": last_values, f"ep{ep}_last_dones": last_dones, f"ep{ep}_returns": returns})
+        # record what every minibatch step saw and left behind
+        trace = []
+        orig = A2C.train_actor_critic
+
+        def traced(self, input_dict, _t=trace):
+            lr_used = self.optimizer.param_groups[0]["lr"]
+            res = orig(self, input_dict)
+            _t.append(dict(a_loss=res[0].detach().clone(), c_loss=res[1].detach().clone(), kl=res[3].detach().clone(), lr=torch.tensor(lr_used),
+                           mu=res[6].clone(), sigma=res[7].clone(), params=flat(), obs_mean=rms.running_mean.clone(),
+                           obs_count=rms.count.clone()))
+            return res
+
+        ag.train_actor_critic = types.MethodType(traced, ag)
+        with ref_shim.quiet():
+            res = A2C.train_epoch(ag)
+        ds = ag.dataset.values_dict
+        out.update({f"ep{ep}_ds_old_values": ds["old_values"], f"ep{ep}_ds_returns": ds["returns"], f"ep{ep}_ds_advantages": ds["advantages"],
+                    f"ep{ep}_ds_obs": ds["obs"]["state"], f"ep{ep}_ds_actions": ds["actions"], f"ep{ep}_ds_old_logp_actions": ds["old_logp_actions"],
+                    f"ep{ep}_ds_mu_final": ds["mu"], f"ep{ep}_ds_sigma_final": ds["sigma"],
+                    f"ep{ep}_params": flat(), f"ep{ep}_exp_avg": moments("exp_avg"), f"ep{ep}_exp_avg_sq": moments("exp_avg_sq"),
+                    f"ep{ep}_last_lr": torch.tensor(ag.last_lr), f"ep{ep}_obs_mean": rms.running_mean.clone(), f"ep{ep}_obs_var": rms.running_var.clone(),
+                    f"ep{ep}_obs_count": rms.count.clone(), f"ep{ep}_val_mean": vms.running_mean.clone(), f"ep{ep}_val_var": vms.running_var.clone(),
+                    f"ep{ep}_val_count": vms.count.clone(), f"ep{ep}_obs_rms_training_after": torch.tensor(int(model.running_mean_std.training))})
+        for k in trace[0]:
+            if k != "params" or ep == 0:          # per-minibatch parameter snapshots for the first epoch only (fixture size)
+                out[f"ep{ep}_mb_{k}"] = torch.stack([t[k] for t in trace])
+        ag.epoch_num += 1
+    np.savez(os.path.join(OUT, "ppo_epoch.npz"), **t2n(out))
+    print("ppo_epoch.npz", {k: tuple(v.shape) for k, v in out.items() if k.startswith("ep1_mb")})
+
+
 def variant_b():
     """Live CaptureXY with static obstacles (Variant B): spawn + potential-field build + K steps of obs / reward / kills,
     with a reset batch in the middle  [OIGE/tasks/USV/USV_capture_xy_static_obs.py, d_multi_gemini.py]."""
@@ -823,6 +922,7 @@ def main():
     classic_task()
     gae()
     ppo()
+    ppo_epoch()
     variant_b()
     live_virtual()
     tier3()

@@ -170,3 +170,54 @@ def discount_values(fdones, last_values, mb_fdones, mb_values, mb_rewards, gamma
         delta = mb_rewards[t] + gamma * nv * nnt - mb_values[t]
         adv[t] = last = delta + gamma * tau * nnt * last
     return adv
+
+
+def swap_and_flatten01(x):                                               # [RLG/common/a2c_common.py:30-37]
+    return x.transpose(0, 1).reshape(x.shape[0] * x.shape[1], *x.shape[2:])
+
+
+def prepare_dataset(roll: dict, returns, val_rms: RunningMeanStd, *, normalize_value=True, normalize_advantage=True) -> dict:
+    """play_steps' hand-over + A2CBase.prepare_dataset  [RLG/common/a2c_common.py:760-774,1257-1320]: (T,N,..) rollout tensors ->
+    env-major flat dataset; the value normaliser is updated with the values and applied to them, THEN updated with the returns and
+    applied to those (two training-mode forwards); advantages come from the un-normalised pair and are standardised with the
+    unbiased std over the whole batch."""
+    fl = swap_and_flatten01
+    values, rets = fl(roll["values"]), fl(returns)
+    adv = rets - values
+    if normalize_value:
+        val_rms.update(values)
+        values = val_rms.normalize(values)
+        val_rms.update(rets)
+        rets = val_rms.normalize(rets)
+    adv = adv.sum(dim=1)
+    if normalize_advantage:
+        adv = (adv - adv.mean()) / (adv.std() + 1e-8)
+    return dict(old_values=values, old_logp_actions=fl(roll["neglogpacs"]), advantages=adv, returns=rets, actions=fl(roll["actions"]),
+                obs=fl(roll["obses"]), mu=fl(roll["mus"]).clone(), sigma=fl(roll["sigmas"]).clone())
+
+
+def train_epoch(params, m, v, step, lr, ds: dict, D, obs_rms: RunningMeanStd, *, minibatch_size, mini_epochs, normalize_input=True,
+                kl_threshold=0.016, grad_norm=1.0, trace=None, **loss_kw):
+    """The update half of ContinuousA2CBase.train_epoch  [RLG/common/a2c_common.py:1197-1245 ; common/datasets.py:25-77]: in-order
+    contiguous minibatches (no shuffling), the obs normaliser updated by the minibatches of mini-epoch 0 only (training-mode forward,
+    then .eval()), mu / sigma of every minibatch written back into the dataset, 'legacy' adaptive-KL lr after every minibatch.
+    Returns (params, m, v, step, lr)."""
+    n_mb = ds["obs"].shape[0] // minibatch_size
+    for mini_ep in range(mini_epochs):
+        for i in range(n_mb):
+            sl = slice(i * minibatch_size, (i + 1) * minibatch_size)
+            batch = {k: t[sl] for k, t in ds.items()}
+            batch["old_values"], batch["returns"] = batch["old_values"].reshape(-1, 1), batch["returns"].reshape(-1, 1)
+            if normalize_input and mini_ep == 0:
+                obs_rms.update(batch["obs"])
+            prm = params.clone().requires_grad_(True)
+            loss, st = minibatch_loss(prm, batch, D, obs_rms, **loss_kw)
+            loss.backward()
+            step += 1
+            params, m, v, norm = adam_step(params, prm.grad, m, v, step, lr, grad_norm=grad_norm)
+            ds["mu"][sl], ds["sigma"][sl] = st["mu"], st["sigma"]                   # dataset.update_mu_sigma
+            if trace is not None:
+                trace.append(dict(a_loss=st["a_loss"].detach(), c_loss=st["c_loss"].detach(), kl=st["kl"], lr=lr, mu=st["mu"], sigma=st["sigma"],
+                                  params=params.clone(), obs_mean=obs_rms.mean.clone(), obs_count=obs_rms.count.clone()))
+            lr = adaptive_lr(lr, float(st["kl"]), kl_threshold)
+    return params, m, v, step, lr

@@ -387,3 +387,97 @@ def test_rollout_bookkeeping_kernel_vs_torch_ops():
         assert float(mr.mean) == pytest.approx(float(t_mr.mean), rel=1e-5, abs=1e-5) and float(mr.current_size) == float(t_mr.current_size)
         assert float(ml.mean) == pytest.approx(float(t_ml.mean), rel=1e-5, abs=1e-5) and float(ml.current_size) == float(t_ml.current_size)
     assert float(mr.current_size) == 100.0 and float(acc[2]) > 500
+
+
+class _StubVecEnv:
+    """The two things A2CAgent.__init__ asks of an IVecEnv; update() never steps it."""
+
+    def __init__(self, obs_dim, num_envs):
+        import types
+        self.env = types.SimpleNamespace(num_envs=num_envs)
+        self._info = {"observation_space": {"state": types.SimpleNamespace(shape=(obs_dim,))}}
+
+    def get_env_info(self):
+        return self._info
+
+
+@pytest.mark.parametrize("path", ["fp32", "fp32-graph", "tf32", "tf32-fused"])
+def test_update_phase_vs_reference_train_epoch(golden, path):
+    """Rows P2 / P3 / P5 end to end: A2CAgent.update() -- env-major dataset, value-normaliser schedule (values, then returns),
+    advantage standardisation, obs normaliser updated in mini-epoch 0 only, in-order minibatches, mu / sigma write-back, per-minibatch
+    adaptive-KL lr, Adam -- against two whole epochs of the reference's own ContinuousA2CBase.train_epoch / prepare_dataset / PPODataset
+    on the same recorded rollouts (tests/golden/ppo_epoch.npz, oracle/make_golden.py:ppo_epoch)
+    [ref: RLG/common/a2c_common.py:1197-1320, common/datasets.py:25-77].  fp32 kernels: 1e-5; the tcgen05 TF32 kernels at their own bar."""
+    from omniisaacgymenvs_loop_b200.rl.a2c import A2CAgent, PPOConfig, gae
+    G = golden("ppo_epoch")
+    Dd, Th, NA, MB, ME = (int(x) for x in G["shape"])
+    tf32 = path.startswith("tf32")
+    agent = A2CAgent(_StubVecEnv(Dd, NA), PPOConfig(horizon_length=Th, minibatch_size=MB, mini_epochs=ME, learning_rate=1e-4), DEV,
+                     use_cuda_graph=False)
+    pol = agent.policy
+    pol.tensor_cores = pol.tensor_cores and tf32
+    agent.fused_step = path == "tf32-fused"
+    pol.params.copy_(cu(G["params0"])); pol._packed_dirty = True
+    pol.obs_rms.load(G["obs_mean0"], G["obs_var0"], G["obs_count0"])
+    pol.val_rms.load(G["val_mean0"], G["val_var0"], G["val_count0"])
+    rt, at = (1e-5, 1e-6) if not tf32 else (2e-2, 2e-3)
+    graph = None
+    for ep in range(2):
+        b = agent.buf
+        for k, name in (("obses", "obses"), ("actions", "actions"), ("neglogpacs", "neglogpacs"), ("values", "values"), ("mus", "mus"),
+                        ("sigmas", "sigmas"), ("dones", "dones")):
+            b[k].copy_(cu(G[f"ep{ep}_{name}"]))
+        b["rewards"].copy_(cu(G[f"ep{ep}_rewards"])[..., 0])
+        # returns through the GAE kernel from the recorded rewards / values / dones: bit-exact vs the reference's discount_values
+        gae(b["rewards"], b["values"].view(Th, -1), b["dones"], cu(G[f"ep{ep}_last_values"]).view(-1), cu(G[f"ep{ep}_last_dones"]),
+            0.99, 0.95, agent.advs, agent.returns)
+        assert torch.equal(agent.returns.cpu(), T(G[f"ep{ep}_returns"])[..., 0])
+        if path == "fp32-graph":            # the whole update phase as one CUDA graph, as train_epoch replays it
+            if graph is None:
+                graph = torch.cuda.CUDAGraph()
+                torch.cuda.synchronize()
+                snap = (pol.params.clone(), pol.exp_avg.clone(), pol.exp_avg_sq.clone(), pol._lr2.clone(), pol._step2.clone(),
+                        [x.clone() for r in (pol.obs_rms, pol.val_rms) for x in (r.mean, r.var, r.count, r.mean32, r.var32)])
+                agent.update()              # warm-up (allocations), then rewind and capture
+                for dst, src in zip((pol.params, pol.exp_avg, pol.exp_avg_sq, pol._lr2, pol._step2), snap[:5]):
+                    dst.copy_(src)
+                for dst, src in zip([x for r in (pol.obs_rms, pol.val_rms) for x in (r.mean, r.var, r.count, r.mean32, r.var32)], snap[5]):
+                    dst.copy_(src)
+                for k in ("mus", "sigmas"):
+                    b[k].copy_(cu(G[f"ep{ep}_{k}"]))
+                with torch.cuda.graph(graph):
+                    agent.update()
+            graph.replay()
+        else:
+            agent.update()
+        torch.cuda.synchronize()
+        ds = agent.ds
+        for k in ("obs", "actions", "old_logp_actions"):
+            assert torch.equal(ds[k].cpu(), T(G[f"ep{ep}_ds_{k}"])), k                     # env-major flatten: bit-exact
+        assert_close(ds["old_values"], G[f"ep{ep}_ds_old_values"][:, 0], 1e-5, 1e-6, "normalised old values")
+        assert_close(ds["returns"], G[f"ep{ep}_ds_returns"][:, 0], 1e-5, 1e-6, "normalised returns")
+        assert_close(ds["advantages"], G[f"ep{ep}_ds_advantages"], 1e-5, 2e-6, "standardised advantages")
+        assert_close(pol.val_rms.mean, G[f"ep{ep}_val_mean"], 1e-6, 1e-7); assert_close(pol.val_rms.var, G[f"ep{ep}_val_var"], 1e-6, 1e-7)
+        assert float(pol.val_rms.count) == float(G[f"ep{ep}_val_count"])
+        assert_close(pol.obs_rms.mean, G[f"ep{ep}_obs_mean"], 1e-6, 1e-7); assert_close(pol.obs_rms.var, G[f"ep{ep}_obs_var"], 1e-6, 1e-7)
+        assert float(pol.obs_rms.count) == float(G[f"ep{ep}_obs_count"])                     # + one minibatch per minibatch of mini-epoch 0
+        assert int(pol.step) == (ep + 1) * ME * (Th * NA // MB)
+        assert abs(float(pol.lr) - float(G[f"ep{ep}_last_lr"])) <= 1e-6 * float(pol.lr), "adaptive-KL schedule"
+        if not tf32:
+            assert_close(pol.params, G[f"ep{ep}_params"], rt, at, f"parameters after epoch {ep}")
+        else:
+            # Adam's m / sqrt(v) is sign-like where a gradient is small against its TF32 rounding noise, so single parameters may move
+            # by up to lr per step the other way; the bar: the parameter UPDATE of the epoch points the reference's way (cosine), 99.5 %
+            # of the parameters within 2 % / 2e-4, and nothing further off than the steps taken allow
+            want, got, prev = T(G[f"ep{ep}_params"]).double(), pol.params.cpu().double(), T(G["params0" if ep == 0 else "ep0_params"]).double()
+            dw, dg = want - prev, got - (prev if ep == 0 else prev0_got)
+            cos = float((dw * dg).sum() / (dw.norm() * dg.norm()))
+            assert cos > 0.98, f"update direction, epoch {ep}: cosine {cos}"
+            bad = (got - want).abs() > 2e-4 + 2e-2 * want.abs()
+            assert float(bad.double().mean()) < 5e-3, f"{int(bad.sum())} parameters outside 2e-2 / 2e-4"
+            assert float((got - want).abs().max()) < (ep + 1) * ME * (Th * NA // MB) * 2.5e-4, "further than the Adam steps allow"
+        prev0_got = pol.params.cpu().double()
+        assert_close(ds["mu"], G[f"ep{ep}_ds_mu_final"], rt, 1e-5 if not tf32 else 5e-3, "mu write-back")
+        assert_close(ds["sigma"], G[f"ep{ep}_ds_sigma_final"], rt, at, "sigma write-back")
+        if not tf32:
+            assert_close(pol.exp_avg, G[f"ep{ep}_exp_avg"], 1e-4, 1e-7, "exp_avg"); assert_close(pol.exp_avg_sq, G[f"ep{ep}_exp_avg_sq"], 1e-4, 1e-10)

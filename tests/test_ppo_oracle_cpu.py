@@ -101,3 +101,50 @@ def test_average_meter_matches_reference_rule():
         assert abs(meter.get_mean() - float(mean)) < 1e-5 and len(meter) == cur
     meter.clear()
     assert len(meter) == 0 and meter.get_mean() == 0.0
+
+
+def epoch_golden_state(G):
+    o = P.RunningMeanStd((D,)); o.mean, o.var, o.count = T(G["obs_mean0"]), T(G["obs_var0"]), T(G["obs_count0"])
+    v = P.RunningMeanStd((1,)); v.mean, v.var, v.count = T(G["val_mean0"]), T(G["val_var0"]), T(G["val_count0"])
+    return o, v
+
+
+def test_epoch_prepare_dataset_and_train_epoch_vs_reference(golden):
+    """Rows P2 / P3: the oracle's prepare_dataset + train_epoch against two whole epochs of the reference's own
+    ContinuousA2CBase.train_epoch / PPODataset / calc_gradients (oracle/make_golden.py:ppo_epoch)."""
+    G = golden("ppo_epoch")
+    Dd, Th, NA, MB, ME = (int(x) for x in G["shape"])
+    assert Dd == D
+    o, vr = epoch_golden_state(G)
+    params = T(G["params0"]).clone()
+    m, v, step, lr = torch.zeros_like(params), torch.zeros_like(params), 0, 1e-4       # G["lr0"], stored as fp32
+    for ep in range(2):
+        roll = {k: T(G[f"ep{ep}_{k}"]) for k in ("obses", "actions", "neglogpacs", "values", "mus", "sigmas", "rewards", "dones")}
+        adv = P.discount_values(T(G[f"ep{ep}_last_dones"]).float(), T(G[f"ep{ep}_last_values"])[:, 0], roll["dones"].float(),
+                                roll["values"][..., 0], roll["rewards"][..., 0])
+        assert torch.equal((adv + roll["values"][..., 0]).unsqueeze(-1), T(G[f"ep{ep}_returns"]))
+        ds = P.prepare_dataset(roll, T(G[f"ep{ep}_returns"]), vr)
+        for k in ("obs", "actions", "old_logp_actions"):
+            assert torch.equal(ds[k], T(G[f"ep{ep}_ds_{k}"])), k                                   # env-major flatten, bit-exact
+        for k in ("old_values", "returns", "advantages"):
+            assert torch.allclose(ds[k], T(G[f"ep{ep}_ds_{k}"]), rtol=1e-6, atol=1e-6), k
+        assert torch.allclose(vr.mean, T(G[f"ep{ep}_val_mean"]), rtol=1e-12) and torch.allclose(vr.var, T(G[f"ep{ep}_val_var"]), rtol=1e-12)
+        assert float(vr.count) == float(G[f"ep{ep}_val_count"])
+        trace = []
+        params, m, v, step, lr = P.train_epoch(params, m, v, step, lr, ds, D, o, minibatch_size=MB, mini_epochs=ME, trace=trace)
+        assert len(trace) == ME * (Th * NA // MB)
+        for i, t in enumerate(trace):
+            assert abs(t["lr"] - float(G[f"ep{ep}_mb_lr"][i])) <= 1e-6 * t["lr"], (ep, i)         # the adaptive schedule, step by step
+            for k in ("a_loss", "c_loss", "kl"):
+                assert torch.allclose(t[k], torch.tensor(G[f"ep{ep}_mb_{k}"][i]), rtol=2e-5, atol=1e-6), (ep, i, k)
+            assert torch.allclose(t["mu"], T(G[f"ep{ep}_mb_mu"][i]), rtol=1e-5, atol=1e-5), (ep, i)
+            assert torch.allclose(t["obs_mean"], T(G[f"ep{ep}_mb_obs_mean"][i]), rtol=1e-12) and float(t["obs_count"]) == float(G[f"ep{ep}_mb_obs_count"][i])
+            if ep == 0:
+                assert torch.allclose(t["params"], T(G["ep0_mb_params"][i]), rtol=1e-5, atol=1e-6), i
+        # the obs normaliser only moved during mini-epoch 0 (count: + one minibatch per minibatch of that mini-epoch)
+        assert float(o.count) == float(G[f"ep{ep}_obs_count"]) and torch.allclose(o.var, T(G[f"ep{ep}_obs_var"]), rtol=1e-12)
+        assert torch.allclose(params, T(G[f"ep{ep}_params"]), rtol=1e-5, atol=1e-6)
+        assert torch.allclose(m, T(G[f"ep{ep}_exp_avg"]), rtol=1e-4, atol=1e-7) and torch.allclose(v, T(G[f"ep{ep}_exp_avg_sq"]), rtol=1e-4, atol=1e-10)
+        assert abs(lr - float(G[f"ep{ep}_last_lr"])) <= 1e-6 * lr
+        assert torch.allclose(ds["mu"], T(G[f"ep{ep}_ds_mu_final"]), rtol=1e-5, atol=1e-5)           # update_mu_sigma write-back
+        assert torch.equal(ds["sigma"], T(G[f"ep{ep}_ds_sigma_final"]))
