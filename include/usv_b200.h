@@ -262,6 +262,39 @@ int usv_step_fused_f32(const UsvEnvBuffers* b, const float* actions /*[n,2]*/,
                        float* obs /*[n,13]*/, float* rew /*[n]*/,
                        int64_t n, const UsvStepParams* p, void* stream);
 
+/* A9/A16-A18 stand-alone: the classic CaptureXYTask's get_state_observations / compute_reward / update_kills and
+ * Penalties.compute_penalty on the CALLER's state tensors -- the same device code as the task part of usv_step_fused_f32, so the
+ * reference's task classes can be fed identical state tensors and compared output by output.
+ *   [ref: SNAP/USV_capture_xy.py:80-97 (obs), :101-227 (reward), :231-275 (kills) ; SNAP/USV_task_rewards.py:40-76,422-506 ;
+ *         SNAP/USV_core.py:31-54 (observation tensor, "local" frame)]
+ * `what` selects the calls; like the reference, compute_reward advances the goal counter and prev_position_dist, compute_penalty
+ * advances prev_state / prev_actions, the other two are pure.  All tensors row-major fp32 unless noted; optional ones may be NULL. */
+enum { USV_CXY_OBS = 1, USV_CXY_REWARD = 2, USV_CXY_PENALTY = 4, USV_CXY_KILLS = 8, USV_CXY_ALL = 15 };
+typedef struct {
+  const float* position;          /* [n,2] current_state["position"]                                              */
+  const float* heading;           /* [n,2] current_state["orientation"] = (cos, sin) of the yaw                   */
+  const float* linear_velocity;   /* [n,2] world frame                                                            */
+  const float* angular_velocity;  /* [n]                                                                          */
+  const float* actions;           /* [n,2] what Penalties sees (PENALTY only)                                     */
+  const float* target;            /* [n,2] _target_positions                                                      */
+  const uint8_t* just_reset;      /* [n] 1 = env in just_had_been_reset (distance reward zeroed) or NULL          */
+  float* prev_position_dist;      /* [n] in/out (REWARD)                                                          */
+  float* prev_angular_velocity;   /* [n] in/out (PENALTY): prev_state["angular_velocity"]                         */
+  float* prev_action_sum;         /* [n] in/out (PENALTY): sum(prev_actions, -1)                                  */
+  int32_t* goal_reached;          /* [n] in/out (REWARD updates, KILLS reads): _goal_reached                      */
+  float* obs;                     /* [n,13] out, clamped to +-clip_obs like VecEnvRLGames._process_data           */
+  float* reward;                  /* [n] out: compute_reward's return value (task reward, penalties NOT included) */
+  float* reward_terms;            /* [n,3] out or NULL: distance, alignment, speed reward                         */
+  float* penalty;                 /* [n] out: compute_penalty's return value                                      */
+  float* penalty_terms;           /* [n,5] out or NULL: linear vel, angular vel, its variation, energy, action variation */
+  int64_t* die;                   /* [n] out: update_kills                                                        */
+  float kill_dist;                /* curriculum-resolved kill distance of this step (update_kills(step))          */
+  uint32_t what;                  /* USV_CXY_* bits                                                               */
+  int32_t first_reward;           /* prev_position_dist is None: the progress term starts from the current distance */
+  int32_t first_penalty;          /* prev_state / prev_actions are None: both variations are zero                 */
+} UsvCaptureXYIO;
+int usv_capturexy_obs_reward_done_f32(const UsvCaptureXYIO* io, int64_t n, const UsvStepParams* p, void* stream);
+
 /* T control steps in ONE launch with the state held in registers between steps;
  * actions[T,n,2] are given up-front (open loop), outputs are [T,n,...]; obs/rew/done may be NULL
  * (then only the final state is written).  step_counter advances by 1 per step.           */

@@ -25,6 +25,7 @@ _CTYPES = {
     "float*": ctypes.c_void_p, "const float*": ctypes.c_void_p, "int64_t*": ctypes.c_void_p,
     "uint32_t*": ctypes.c_void_p, "int32_t*": ctypes.c_void_p, "double*": ctypes.c_void_p,
     "uint64_t*": ctypes.c_void_p, "const int32_t*": ctypes.c_void_p, "const uint64_t*": ctypes.c_void_p,
+    "const uint8_t*": ctypes.c_void_p, "uint8_t*": ctypes.c_void_p,
 }
 
 
@@ -99,6 +100,7 @@ UsvLiveBuffers = STRUCTS["UsvLiveBuffers"]
 PpoLossParams = STRUCTS["PpoLossParams"]
 PpoAdamParams = STRUCTS["PpoAdamParams"]
 PpoPeerComm = STRUCTS["PpoPeerComm"]
+UsvCaptureXYIO = STRUCTS["UsvCaptureXYIO"]
 
 _lib = None
 

@@ -57,6 +57,45 @@ def parse_penalty_lambda(src: str, c1: float = 0.0, c2: float = 0.0) -> PenaltyT
     raise NotImplementedError(f"penalty lambda not in the supported closed set: {src!r}")
 
 
+def task_section_kwargs(tp: dict) -> dict:
+    """UsvEnvConfig fields of a `task_parameters` YAML section (CaptureXYParameters [ref: OIGE/tasks/USV/USV_task_parameters.py:17-52])."""
+    return dict(
+        position_tolerance=tp.get("position_tolerance", 0.1),
+        kill_after_n_steps_in_tolerance=int(tp.get("kill_after_n_steps_in_tolerance", 1)),
+        kill_dist=tp.get("kill_dist", 20.0), boundary_cost=tp.get("boundary_cost", 25.0),
+        goal_reward=tp.get("goal_reward", 100.0), time_reward=tp.get("time_reward", -0.1),
+        goal_random_position=tp.get("goal_random_position", 0.0),
+        spawn_min_dist=tp.get("min_spawn_dist", 0.5), spawn_max_dist=tp.get("max_spawn_dist", 11.0),
+        spawn_curriculum=bool(tp.get("spawn_curriculum", False)), spawn_curriculum_min_dist=tp.get("spawn_curriculum_min_dist", 0.2),
+        spawn_curriculum_max_dist=tp.get("spawn_curriculum_max_dist", 3.0), spawn_curriculum_kill_dist=tp.get("spawn_curriculum_kill_dist", 30.0),
+        spawn_curriculum_warmup=int(tp.get("spawn_curriculum_warmup", 250)), spawn_curriculum_end=int(tp.get("spawn_curriculum_end", 1000)))
+
+
+def reward_section_kwargs(rp: dict) -> dict:
+    """UsvEnvConfig fields of a `reward_parameters` section (CaptureXYReward [ref: SNAP/USV_task_rewards.py:16-38])."""
+    return dict(
+        reward_mode=REWARD_MODES[str(rp.get("reward_mode", "exponential")).lower()],
+        position_scale=rp.get("position_scale", 1.0), exponential_reward_coeff=rp.get("exponential_reward_coeff", 0.25),
+        align_la1=rp.get("align_la1", 0.02), align_la2=rp.get("align_la2", -10.0), align_la3=rp.get("align_la3", -0.1))
+
+
+def penalty_section_kwargs(pp: dict) -> dict:
+    """UsvEnvConfig fields of a `penalties_parameters` section (Penalties [ref: SNAP/USV_task_rewards.py:381-420]); the lambda strings are
+    mapped onto the kernel's closed set (parse_penalty_lambda)."""
+    def pen(name, default_src, c1d, c2d=0.0):
+        if not pp.get(f"penalize_{name}", False):
+            return PenaltyTerm()
+        return parse_penalty_lambda(pp.get(f"penalize_{name}_fn", default_src), pp.get(f"penalize_{name}_c1", c1d),
+                                    pp.get(f"penalize_{name}_c2", c2d))
+
+    return dict(
+        pen_linear_vel=pen("linear_velocities", "lambda x,step : -torch.norm(x, dim=-1)*c1 + c2", 0.01),
+        pen_angular_vel=pen("angular_velocities", "lambda x,step : -torch.abs(x)*c1 + c2", 0.01),
+        pen_angular_vel_variation=pen("angular_velocities_variation", "lambda x,step: torch.exp(c1 * torch.abs(x)) - 1.0", -0.033),
+        pen_energy=pen("energy", "lambda x,step : -torch.sum(x**2)*c1 + c2", 0.01),
+        pen_action_variation=pen("action_variation", "lambda x,step: torch.exp(c1 * torch.abs(x)) - 1.0", -0.033))
+
+
 @dataclass
 class UsvEnvConfig:
     """Mirror of UsvStepParams with the classic snapshot's defaults
@@ -340,12 +379,6 @@ class UsvEnvConfig:
         L, Q = hd["linear_damping"], hd["quadratic_damping"]
         fw = hd["linear_damping_forward_speed"]
 
-        def pen(name, default_src, c1d, c2d=0.0):
-            if not pp.get(f"penalize_{name}", False):
-                return PenaltyTerm()
-            return parse_penalty_lambda(pp.get(f"penalize_{name}_fn", default_src), pp.get(f"penalize_{name}_c1", c1d),
-                                        pp.get(f"penalize_{name}_c2", c2d))
-
         num_envs = env["numEnvs"] if isinstance(env["numEnvs"], int) else 512
         clip_obs = env.get("clipObservations", {"state": 12.0})
         cfg = cls(
@@ -369,23 +402,7 @@ class UsvEnvConfig:
             use_const_force=bool(f["use_constant_force"]), use_sin_force=bool(f["use_sinusoidal_force"]),
             use_torque_disturbance=bool(t["use_torque_disturbance"]),
             use_const_torque=bool(t["use_constant_torque"]), use_sin_torque=bool(t["use_sinusoidal_torque"]),
-            position_tolerance=tp.get("position_tolerance", 0.1),
-            kill_after_n_steps_in_tolerance=int(tp.get("kill_after_n_steps_in_tolerance", 1)),
-            kill_dist=tp.get("kill_dist", 20.0), boundary_cost=tp.get("boundary_cost", 25.0),
-            goal_reward=tp.get("goal_reward", 100.0), time_reward=tp.get("time_reward", -0.1),
-            goal_random_position=tp.get("goal_random_position", 0.0),
-            spawn_min_dist=tp.get("min_spawn_dist", 0.5), spawn_max_dist=tp.get("max_spawn_dist", 11.0),
-            spawn_curriculum=bool(tp.get("spawn_curriculum", False)), spawn_curriculum_min_dist=tp.get("spawn_curriculum_min_dist", 0.2),
-            spawn_curriculum_max_dist=tp.get("spawn_curriculum_max_dist", 3.0), spawn_curriculum_kill_dist=tp.get("spawn_curriculum_kill_dist", 30.0),
-            spawn_curriculum_warmup=int(tp.get("spawn_curriculum_warmup", 250)), spawn_curriculum_end=int(tp.get("spawn_curriculum_end", 1000)),
-            reward_mode=REWARD_MODES[str(rp.get("reward_mode", "exponential")).lower()],
-            position_scale=rp.get("position_scale", 1.0), exponential_reward_coeff=rp.get("exponential_reward_coeff", 0.25),
-            align_la1=rp.get("align_la1", 0.02), align_la2=rp.get("align_la2", -10.0), align_la3=rp.get("align_la3", -0.1),
-            pen_linear_vel=pen("linear_velocities", "lambda x,step : -torch.norm(x, dim=-1)*c1 + c2", 0.01),
-            pen_angular_vel=pen("angular_velocities", "lambda x,step : -torch.abs(x)*c1 + c2", 0.01),
-            pen_angular_vel_variation=pen("angular_velocities_variation", "lambda x,step: torch.exp(c1 * torch.abs(x)) - 1.0", -0.033),
-            pen_energy=pen("energy", "lambda x,step : -torch.sum(x**2)*c1 + c2", 0.01),
-            pen_action_variation=pen("action_variation", "lambda x,step: torch.exp(c1 * torch.abs(x)) - 1.0", -0.033),
+            **task_section_kwargs(tp), **reward_section_kwargs(rp), **penalty_section_kwargs(pp),
             mass_rand=bool(m.get("add_mass_disturbances", False)), mass_min=float(m.get("min_mass", 0.0)),
             mass_max=float(m.get("max_mass", 0.0)), mass_base=float(m.get("base_mass", hs["mass"])),
             drag_rand=bool(dr["use_drag_randomization"]), lin_base=(L[0], L[1], L[5]), quad_base=(Q[0], Q[1], Q[5]),

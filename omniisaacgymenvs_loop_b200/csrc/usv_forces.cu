@@ -199,6 +199,7 @@ int64_t usv_b200_sizeof(const char* name) {
   USV_SZ(UsvPenaltyTerm);
   USV_SZ(UsvStepParams);
   USV_SZ(UsvEnvBuffers);
+  USV_SZ(UsvCaptureXYIO);
   USV_SZ(UsvLiveParams);
   USV_SZ(UsvLiveBuffers);
   USV_SZ(PpoLossParams);

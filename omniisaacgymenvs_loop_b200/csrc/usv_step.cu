@@ -15,8 +15,10 @@
 namespace usv {
 
 // Variant A (classic CaptureXY) task part of a control step: observation (13), reward + penalties, kills / done
+// `what` (USV_TASK_* bits) selects which of the reference's four calls advance their cross-step state: compute_reward owns the goal
+// counter and prev_position_dist, compute_penalty owns prev_state / prev_actions; the fused step passes the literal "all" (folded away)
 __device__ __forceinline__ void post_classic(EnvState& e, const EnvConst& k, const UsvStepParams& p, bool do_reset,
-                                             bool first_call, const DynOut& s, StepOut& o) {
+                                             bool first_call, const DynOut& s, StepOut& o, const int what = USV_CXY_ALL) {
   const float pxn = s.pxn, pyn = s.pyn, vxn = s.vxn, vyn = s.vyn, wn = s.wn, yawn = s.yawn, hs = s.hs, hc = s.hc;
   const float pa0 = s.pa0, pa1 = s.pa1;
   // get_state_observations  [ref SNAP/USV_capture_xy.py:80-97]
@@ -51,7 +53,7 @@ __device__ __forceinline__ void post_classic(EnvState& e, const EnvConst& k, con
   // compute_reward  [ref SNAP/USV_capture_xy.py:101-227 ; SNAP/USV_task_rewards.py:40-76]
   const float speed = sqrtf(vxn * vxn + vyn * vyn);
   const int goal = (d < p.position_tolerance) && (speed < p.goal_speed_gate);
-  e.goal_cnt = e.goal_cnt * goal + goal;
+  if (what & USV_CXY_REWARD) e.goal_cnt = e.goal_cnt * goal + goal;
   float dist_rew;
   if (p.reward_mode == USV_REWARD_LINEAR) {
     dist_rew = p.position_scale * (e.prev_d - d);
@@ -79,7 +81,7 @@ __device__ __forceinline__ void post_classic(EnvState& e, const EnvConst& k, con
   if (!(d == d)) speed_rew = 0.0f;  // NaN distance matches no mask in the reference -> zeros_like
   const float goal_rew = (float)e.goal_cnt * p.goal_reward;
   const float task_rew = dist_rew + align + speed_rew + goal_rew + p.time_reward;
-  e.prev_d = d;
+  if (what & USV_CXY_REWARD) e.prev_d = d;
   // Penalties.compute_penalty  [ref SNAP/USV_task_rewards.py:422-506]
   const float asum = pa0 + pa1;
   const float dw = first_call ? 0.0f : (wn - e.prev_w);
@@ -92,12 +94,17 @@ __device__ __forceinline__ void post_classic(EnvState& e, const EnvConst& k, con
   else if (p.pen_energy.form == USV_PEN_EXP_NEG_SUMSQ) pen_energy = (__expf(-(pa0 * pa0 + pa1 * pa1)) - 1.0f) * p.pen_energy.c1;
   if (p.pen_action_variation.form != USV_PEN_OFF) pen_actvar = penalty_scalar(p.pen_action_variation, dasum);
   const float penalties = pen_lin + pen_ang + pen_angvar + pen_energy + pen_actvar;
-  e.prev_w = wn;
-  e.prev_asum = asum;
+  if (what & USV_CXY_PENALTY) {
+    e.prev_w = wn;
+    e.prev_asum = asum;
+  }
+  o.task_rew = task_rew;
+  o.penalty = penalties;
   o.rew = task_rew + penalties;  // [ref SNAP/USV_Virtual.py:844]
   // update_kills + is_done  [ref SNAP/USV_capture_xy.py:231-275 ; SNAP/USV_Virtual.py:855-866]
   int die = (d > p.kill_dist) ? 1 : 0;
   if ((e.goal_cnt >= p.kill_after_n_steps_in_tolerance) && (speed < p.goal_speed_gate)) die = 1;
+  o.die = die;
   o.done = (e.progress >= p.max_episode_length - 1) ? 1 : die;
   // diagnostics
   o.dist_rew = dist_rew; o.align_rew = align; o.speed_rew = speed_rew; o.d = d; o.speed = speed;
@@ -317,11 +324,88 @@ static void ensure_smem(K kernel, size_t smem) {
   if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
+// CaptureXYTask.get_state_observations / compute_reward / update_kills and Penalties.compute_penalty on the caller's own state tensors:
+// the SAME device code as the task part of the fused step (post_classic), one env per thread, plain row-major inputs.
+__global__ void __launch_bounds__(256) capturexy_task_kernel(UsvCaptureXYIO io, int64_t n, UsvStepParams p) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float2 z2 = make_float2(0.f, 0.f);
+  const float2 pos = io.position ? reinterpret_cast<const float2*>(io.position)[i] : z2;
+  const float2 hd = io.heading ? reinterpret_cast<const float2*>(io.heading)[i] : make_float2(1.f, 0.f);
+  const float2 vel = io.linear_velocity ? reinterpret_cast<const float2*>(io.linear_velocity)[i] : z2;
+  const float2 act = io.actions ? reinterpret_cast<const float2*>(io.actions)[i] : z2;
+  const float2 tgt = io.target ? reinterpret_cast<const float2*>(io.target)[i] : z2;
+  DynOut s;
+  s.pxn = pos.x; s.pyn = pos.y; s.vxn = vel.x; s.vyn = vel.y;
+  s.wn = io.angular_velocity ? io.angular_velocity[i] : 0.f;
+  s.hc = hd.x; s.hs = hd.y;
+  s.yawn = fast_atan2(hd.y, hd.x);          // theta = atan2(orientation[:,1], orientation[:,0])  [ref SNAP/USV_capture_xy.py:88]
+  s.pa0 = act.x; s.pa1 = act.y;
+  s.raw0 = s.raw1 = s.t0 = s.t1 = s.c0 = s.c1 = 0.f;
+  EnvState e;
+  e.x = pos.x; e.y = pos.y; e.psi = s.yawn; e.vx = vel.x; e.vy = vel.y; e.r = s.wn; e.thrL = e.thrR = 0.f;
+  e.progress = 0;
+  e.goal_cnt = io.goal_reached ? io.goal_reached[i] : 0;
+  const bool jr = io.just_reset ? io.just_reset[i] != 0 : false;
+  EnvConst k;
+  k.tx = tgt.x; k.ty = tgt.y;
+  // prev_position_dist is None on the first compute_reward: it becomes the current distance (a zero progress term)
+  if (io.first_reward || !io.prev_position_dist) {
+    const float ex = tgt.x - pos.x, ey = tgt.y - pos.y;
+    e.prev_d = sqrtf(ex * ex + ey * ey);
+  } else {
+    e.prev_d = io.prev_position_dist[i];
+  }
+  e.prev_w = io.prev_angular_velocity ? io.prev_angular_velocity[i] : 0.f;
+  e.prev_asum = io.prev_action_sum ? io.prev_action_sum[i] : 0.f;
+  p.kill_dist = io.kill_dist;                // curriculum-resolved by the caller, like update_kills(step)
+  p.max_episode_length = 0x7fffffff;
+  StepOut o;
+  post_classic(e, k, p, jr, io.first_penalty != 0, s, o, io.what);
+  if ((io.what & USV_CXY_OBS) && io.obs) {
+#pragma unroll
+    for (int j = 0; j < kObs; ++j) io.obs[i * kObs + j] = o.obs[j];
+  }
+  if (io.what & USV_CXY_REWARD) {
+    if (io.reward) io.reward[i] = o.task_rew;
+    if (io.reward_terms) { io.reward_terms[i * 3] = o.dist_rew; io.reward_terms[i * 3 + 1] = o.align_rew; io.reward_terms[i * 3 + 2] = o.speed_rew; }
+    if (io.goal_reached) io.goal_reached[i] = e.goal_cnt;
+    if (io.prev_position_dist) io.prev_position_dist[i] = e.prev_d;
+  }
+  if (io.what & USV_CXY_PENALTY) {
+    if (io.penalty) io.penalty[i] = o.penalty;
+    if (io.penalty_terms) {
+      io.penalty_terms[i * 5] = o.pen_lin; io.penalty_terms[i * 5 + 1] = o.pen_ang; io.penalty_terms[i * 5 + 2] = o.pen_angvar;
+      io.penalty_terms[i * 5 + 3] = o.pen_energy; io.penalty_terms[i * 5 + 4] = o.pen_actvar;
+    }
+    if (io.prev_angular_velocity) io.prev_angular_velocity[i] = e.prev_w;
+    if (io.prev_action_sum) io.prev_action_sum[i] = e.prev_asum;
+  }
+  if ((io.what & USV_CXY_KILLS) && io.die) io.die[i] = o.die;
+}
+
 }  // namespace usv
 
 using namespace usv;
 
 extern "C" {
+
+int usv_capturexy_obs_reward_done_f32(const UsvCaptureXYIO* io, int64_t n, const UsvStepParams* p, void* stream) {
+  if (!io || !p) return USV_E_NULL;
+  if (n < 0) return USV_E_SIZE;
+  if (n == 0) return USV_OK;
+  if (!(io->what & USV_CXY_ALL) || (io->what & ~USV_CXY_ALL)) return USV_E_PARAM;
+  if (!io->position || !io->target || !io->linear_velocity) return USV_E_NULL;          // every call needs the distance and the speed
+  if ((io->what & USV_CXY_OBS) && (!io->obs || !io->heading || !io->angular_velocity)) return USV_E_NULL;
+  if ((io->what & USV_CXY_REWARD) && (!io->reward || !io->heading || !io->goal_reached)) return USV_E_NULL;
+  if ((io->what & USV_CXY_PENALTY) && (!io->penalty || !io->actions || !io->angular_velocity)) return USV_E_NULL;
+  if ((io->what & USV_CXY_KILLS) && (!io->die || !io->goal_reached)) return USV_E_NULL;
+  const uintptr_t al = (uintptr_t)io->position | (uintptr_t)io->target | (uintptr_t)io->linear_velocity | (uintptr_t)io->heading |
+                       (uintptr_t)io->actions;
+  if (al & 7) return USV_E_ALIGN;
+  capturexy_task_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(*io, n, *p);
+  return finish_launch();
+}
 
 int usv_step_fused_f32(const UsvEnvBuffers* b, const float* actions, float* obs, float* rew, int64_t n,
                        const UsvStepParams* p, void* stream) {

@@ -29,8 +29,8 @@ struct EnvConst {
 };
 struct StepOut {
   float obs[kObs];
-  float rew;
-  int done;
+  float rew, task_rew, penalty;
+  int done, die;
   bool finite;
   // diagnostics for stats
   float dist_rew, align_rew, speed_rew, d, speed, bpen, bdist;
