@@ -91,24 +91,27 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------
-def pick_threads(make_env, n_probe=4096):
-    """The CPU port may use every host thread; pick the thread count that is actually fastest on a short probe."""
+def pick_threads(make_env, n_probe=65536):
+    """The CPU port may use every host thread: time EVERY candidate thread count on a probe of the workload's own scale (65 536 envs per
+    step; the r01 probe of 4096 envs sat in launch overhead and picked 1 or 8 threads at random, a 4.5x swing of the reference arm) and
+    keep the fastest.  Returns (threads, {threads: env-steps/s})."""
     ncpu = os.cpu_count() or 1
-    best = (None, 0.0)
-    for nt in sorted({1, max(1, ncpu // 2), ncpu}):
+    cands = sorted({c for c in (1, 4, 8, 16, 32, 64, ncpu // 2, ncpu) if 1 <= c <= ncpu})
+    env = make_env(n_probe)
+    act = torch.zeros((n_probe, 2))
+    env.step(act)
+    rates = {}
+    for nt in cands:
         torch.set_num_threads(nt)
-        env = make_env(n_probe)
-        act = torch.zeros((n_probe, 2))
         env.step(act)
         t = time.perf_counter()
         for _ in range(3):
             env.step(act)
-        rate = 3 * n_probe / (time.perf_counter() - t)
-        log(f"  cpu probe: {nt} threads -> {rate:.3g} env-steps/s")
-        if rate > best[1]:
-            best = (nt, rate)
-    torch.set_num_threads(best[0])
-    return best[0]
+        rates[nt] = 3 * n_probe / (time.perf_counter() - t)
+        log(f"  cpu probe ({n_probe} envs): {nt} threads -> {rates[nt]:.3g} env-steps/s")
+    best = max(rates, key=rates.get)
+    torch.set_num_threads(best)
+    return best, rates
 
 
 def cpu_port(budget_s: float, steps: int | None = None, warmup: int = 1, envs: int | None = None):
@@ -117,7 +120,7 @@ def cpu_port(budget_s: float, steps: int | None = None, warmup: int = 1, envs: i
 
     cfg = O.EnvConfig().full_dr()
     mk = lambda n: O.ClassicEnvOracle(cfg, n)
-    threads = pick_threads(mk)
+    threads, probe_rates = pick_threads(mk)
     if envs is None or steps is None:
         # size the sample: n envs per step so that `steps` steps fit the budget
         probe = mk(16384)
@@ -143,7 +146,8 @@ def cpu_port(budget_s: float, steps: int | None = None, warmup: int = 1, envs: i
     dt = time.perf_counter() - t
     return {"value": envs * steps / dt, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"{envs} envs x {steps} control steps (oracle/usv_oracle.ClassicEnvOracle, torch CPU fp32, "
-                      f"{threads} of {os.cpu_count()} host threads), full DR, 5 sub-steps"}, dt / steps
+                      f"{threads} of {os.cpu_count()} host threads: the fastest of {sorted(probe_rates)} on a 65 536-env probe), full DR, 5 sub-steps",
+            "thread_probe": {str(k): round(v) for k, v in probe_rates.items()}}, dt / steps
 
 
 def run_reference(args, emit):
@@ -269,6 +273,73 @@ def time_e2e(env, steps, warmup, dist_on, device):
     return ms, h2d, d2h, float(h_rew[0].mean())
 
 
+def ppo_cpu_port(envs=2048, epochs=2, horizon=16, minibatch=8192, mini_epochs=8):
+    """The PPO half of the metric on the host cores: the oracle port of the whole rl_games epoch (rollout through the CPU env oracle +
+    policy inference, GAE, prepare_dataset, mini_epochs x minibatches of loss / autograd backward / clip / Adam / adaptive lr) on a
+    bounded sample (`envs` envs; the per-frame cost does not depend on the env count once a minibatch is 8192 rows)."""
+    from oracle import ppo_oracle as P
+    from oracle import usv_oracle as O
+
+    D = 13
+    threads = torch.get_num_threads()
+    env = O.ClassicEnvOracle(O.EnvConfig(), envs)
+    lay = P.param_layout(D)
+    g = torch.Generator().manual_seed(0)
+    params = torch.zeros(lay["P"])
+    for name in ("w1", "w2", "wv", "wmu"):
+        a, b = lay[name]
+        fan = D if name == "w1" else 128
+        params[a:b] = (torch.rand(b - a, generator=g) * 2 - 1) / fan ** 0.5
+    m, v, step, lr = torch.zeros_like(params), torch.zeros_like(params), 0, 1e-4
+    obs_rms, val_rms = P.RunningMeanStd((D,)), P.RunningMeanStd((1,))
+    obs, _, done = env.step(torch.zeros((envs, 2)))
+    times = []
+    for ep in range(epochs + 1):
+        t0 = time.perf_counter()
+        roll = {k: [] for k in ("obses", "actions", "neglogpacs", "values", "mus", "sigmas", "rewards", "dones")}
+        with torch.no_grad():
+            for t in range(horizon):
+                r = P.policy_inference(params, obs, D, obs_rms, val_rms, eps=torch.randn((envs, 2), generator=g))
+                roll["obses"].append(obs.clone()); roll["dones"].append(done.to(torch.uint8))
+                for k, src in (("actions", "actions"), ("neglogpacs", "neglogpacs"), ("values", "values"), ("mus", "mus"), ("sigmas", "sigmas")):
+                    roll[k].append(r[src])
+                obs, rew, done = env.step(torch.clamp(r["actions"], -1.0, 1.0))
+                roll["rewards"].append(rew * 0.01)
+            roll = {k: torch.stack(x) for k, x in roll.items()}
+            last_v = P.policy_inference(params, obs, D, obs_rms, val_rms)["values"][:, 0]
+            adv = P.discount_values(done.float(), last_v, roll["dones"].float(), roll["values"][..., 0], roll["rewards"])
+            ds = P.prepare_dataset(roll, (adv + roll["values"][..., 0]).unsqueeze(-1), val_rms)
+        params, m, v, step, lr = P.train_epoch(params, m, v, step, lr, ds, D, obs_rms, minibatch_size=min(minibatch, horizon * envs),
+                                               mini_epochs=mini_epochs)
+        if ep > 0:
+            times.append(time.perf_counter() - t0)
+    s_per_epoch = sum(times) / len(times)
+    return {"value": horizon * envs / s_per_epoch, "unit": "frames/s", "cores": threads, "kind": "port",
+            "sample": f"{envs} envs x horizon {horizon}, {mini_epochs} mini-epochs x {horizon * envs // min(minibatch, horizon * envs)} minibatches of "
+                      f"{min(minibatch, horizon * envs)} rows, {epochs} epochs (oracle/ppo_oracle + oracle/usv_oracle, torch CPU + autograd, {threads} threads)",
+            "s_per_epoch": s_per_epoch}
+
+
+def memcpy_probe(device, h2d_bytes, d2h_bytes, iters=30):
+    """Plain pinned cudaMemcpyAsync bandwidth of this rank with every rank copying at the same time: the ceiling of the e2e leg.
+    One H2D and one D2H stream, the e2e step's own byte counts per iteration; returns GB/s (both directions summed) of this rank."""
+    h_in, h_out = torch.empty(h2d_bytes, dtype=torch.uint8).pin_memory(), torch.empty(d2h_bytes, dtype=torch.uint8).pin_memory()
+    d_in, d_out = torch.empty(h2d_bytes, dtype=torch.uint8, device=device), torch.empty(d2h_bytes, dtype=torch.uint8, device=device)
+    s1, s2 = torch.cuda.Stream(device), torch.cuda.Stream(device)
+    def run(n):
+        for _ in range(n):
+            with torch.cuda.stream(s1):
+                d_in.copy_(h_in, non_blocking=True)
+            with torch.cuda.stream(s2):
+                h_out.copy_(d_out, non_blocking=True)
+        s1.synchronize(); s2.synchronize()
+    run(3)
+    t0 = time.perf_counter()
+    run(iters)
+    dt = time.perf_counter() - t0
+    return (h2d_bytes + d2h_bytes) * iters / dt / 1e9
+
+
 def bench_ppo(args, rank, world, device, dist_on):
     """BASELINE config[2]: CaptureXY + USV_PPOcontinuous_MLP, 16384 envs/GPU, env-sharded; gradient all-reduce = one kernel over NVLink
     peer memory per minibatch (rl/peer.py), update phase replayed as one CUDA graph per rank.
@@ -284,6 +355,13 @@ def bench_ppo(args, rank, world, device, dist_on):
     env = make_env(cfg.to_task_cfg(), str(device), seed=1234, env_id_offset=rank * n, collect_stats=False)
     env.env._task._nan_probe = False
     agent = A2CAgent(env, PPOConfig(seed=1234), device, rank, world)
+    ar_err = None
+    if dist_on and agent.peer is not None:          # warm-up: one result of the NVLink peer all-reduce against NCCL's
+        x = torch.randn(agent.policy.grads.numel(), device=device, generator=torch.Generator(device=device).manual_seed(77 + rank))
+        want = x.clone()
+        dist.all_reduce(want)
+        got = agent.peer(x.clone())
+        ar_err = float((got - want).abs().max())
     for _ in range(3):
         agent.train_epoch()
     torch.cuda.synchronize(device)
@@ -306,15 +384,19 @@ def bench_ppo(args, rank, world, device, dist_on):
         ms = float(t.item())
     frames = agent.batch_size * world * args.ppo_epochs
     st = agent.policy.stats()
-    if agent.peer is not None:
-        agent.peer.check()
-    return {"metric": "PPO frames/sec", "value": frames / (ms * 1e-3), "unit": "frames/s", "envs_per_gpu": n, "horizon": agent.T,
-            "minibatch": agent.minibatch_size, "mini_epochs": agent.cfg.mini_epochs, "epochs_timed": args.ppo_epochs,
-            "ms_per_epoch": ms / args.ppo_epochs, "host_play_s": play, "host_update_s": upd,
-            "our_kernel_launches_per_epoch": (_lib.launch_count() - l0) / args.ppo_epochs + sum(agent.graph_launches.values()),
-            "rollout_in_cuda_graph": agent._graph_play is not None,
-            "collective": agent.collective, "update_in_cuda_graph": agent._graph is not None,
-            "mlp": ("tcgen05 TF32 UMMA + TMEM (csrc/ppo_mlp_tc.cu)" if agent.policy.tensor_cores else "fp32 SIMT fused kernels (csrc/ppo_mlp.cu)"), "kl": st["kl"], "lr": st["lr"]}
+    agent.check_peers()
+    identical = agent.ranks_identical()             # all-gather of an exact checksum of parameters, Adam moments, lr and step count
+    launches = (_lib.launch_count() - l0) / args.ppo_epochs + sum(agent.graph_launches.values())
+    fused = agent.peer_step is not None and agent.fused_step
+    detail = {"horizon": agent.T, "minibatch": agent.minibatch_size, "mini_epochs": agent.cfg.mini_epochs, "epochs_timed": args.ppo_epochs,
+              "host_play_s": play, "host_update_s": upd, "rollout_in_cuda_graph": agent._graph_play is not None,
+              "update_in_cuda_graph": agent._graph is not None, "update_graph_launches": agent.graph_launches["update"],
+              "mlp": ("tcgen05 TF32 UMMA + TMEM (csrc/ppo_mlp_tc.cu)" if agent.policy.tensor_cores else "fp32 SIMT fused kernels (csrc/ppo_mlp.cu)"),
+              "kl": st["kl"], "lr": st["lr"]}
+    short = {"metric": "PPO frames/sec", "value": frames / (ms * 1e-3), "unit": "frames/s", "envs_per_gpu": n, "ms_per_epoch": ms / args.ppo_epochs,
+             "collective": ("none" if world == 1 else ("peer packets fused into the minibatch tail kernel (NVLink P2P)" if fused else agent.collective)),
+             "launches_per_epoch": launches, "ranks_identical": bool(identical), "allreduce_vs_nccl_max_abs_err": ar_err}
+    return short, detail
 
 
 def bench_gae_mlp(device):
@@ -573,13 +655,16 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "kernel": "usv::step_fused_kernel<2,false> (kDisturb = 2: all disturbance kinds on, stats off)", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": BYTES_PER_ENV_STEP * n}
-    tr = os.path.join(ROOT, "profiles", "traffic.json")      # dram bytes/launch from the committed ncu --set full capture
+    # dram bytes/launch come from the committed ncu --set full capture of this kernel at this env count (a profiler cannot run inside
+    # the timed run); `traffic_source` says so
+    tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):
         try:
             with open(tr) as f:
                 t = json.load(f)
             if int(t.get("envs", -1)) == n:
                 roofline["traffic"] = t["dram_bytes_per_launch"]
+                roofline["traffic_source"] = "profiles/traffic.json: ncu --set full capture of this kernel at this env count (" + str(t.get("source", "r01")) + "), not measured in this run"
         except Exception:
             pass
 
@@ -588,11 +673,29 @@ def main():
             "data": "synthetic", "config": workload_config(n), "roofline": roofline, "clocks": clocks,
             "gpu_launches": int(launches), "substeps_per_s": value * cfg.n_substeps}
 
+    if not args.no_extra and args.steps < 2000:
+        # the driver's K steps are ~1 ms of device time: the same measurement over 2000 steps beside it (one clock sample covers neither)
+        sampler2 = ClockSampler(local)
+        sampler2.start()
+        lms = time_steps(env, acts, 2000, 3, dist_on, device)
+        line["value_2000_steps"] = {"value": world * n * 2000 / (lms * 1e-3), "ms_per_step": lms / 2000, "steps": 2000,
+                                    "frac": BYTES_PER_ENV_STEP * n / (lms / 2000 * 1e-3) / 1e9 / peak, "clocks": sampler2.stop()}
     if not args.no_extra:
         e2e_steps = max(3, min(args.steps, 200))
         ems, h2d, d2h, _ = time_e2e(env, e2e_steps, 3, dist_on, device)
+        if dist_on:
+            dist.barrier()
+        link = memcpy_probe(device, h2d, d2h)           # every rank copies at once: the host side of the box is shared
+        if dist_on:
+            t = torch.tensor([link], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            link = float(t.item())
+        e2e_gbs = (h2d + d2h) * e2e_steps / (ems * 1e-3) / 1e9
         line["e2e"] = {"value": world * n * e2e_steps / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                        "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                       "roofline": {"bound": "pcie", "achieved": e2e_gbs, "peak": link, "unit": "GB/s per rank (H2D + D2H)", "frac": e2e_gbs / link,
+                                    "peak_source": f"plain pinned cudaMemcpyAsync of the same byte counts, both directions at once, all {world} ranks "
+                                                   "copying together (slowest rank), measured in this run"},
                        "path": "engine.HostStepper.submit -> usv_step_fused_f32 (C ABI): pinned host actions -> device, obs + reward + uint8 "
                                "done -> pinned host every step; copy-in / compute / copy-out on 3 streams, 2 staging slots"}
         # BASELINE config[1]: 4096 envs/GPU -- launch-latency bound (working set ~1 MB, L2 resident): reported, not the headline
@@ -629,22 +732,37 @@ def main():
                            "rollout_kernel_env_steps_per_s": world * 4096 * T * 4 / (rms * 1e-3),
                            "note": "one launch per control step vs one launch per 512 control steps (state in registers); "
                                    "latency-bound, working set L2-resident -> no HBM roofline claimed"}
+    ppo_short = None
     if not args.no_extra and not args.no_ppo:
-        line["ppo"] = bench_ppo(args, rank, world, device, dist_on)
-    if not args.no_extra and rank == 0:
+        ppo_short, line["ppo_detail"] = bench_ppo(args, rank, world, device, dist_on)
+    # single-GPU legs: on a multi-rank launch they would only hold the other ranks at a barrier (the N=1 run carries them)
+    if not args.no_extra and world == 1:
         line["secondary_kernels"] = bench_gae_mlp(device)
-    if not args.no_extra and not args.no_variant_b and rank == 0:
-        line["variant_b"] = bench_variant_b(device)
-    if not args.no_extra and not args.no_loopz and rank == 0:
-        line["loopz_ppo"] = bench_loopz(device)
+        if not args.no_variant_b:
+            line["variant_b"] = bench_variant_b(device)
+        if not args.no_loopz:
+            line["loopz_ppo"] = bench_loopz(device)
     if dist_on:
         dist.barrier()
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         cb, _ = cpu_port(20.0)
         line["cpu_baseline"] = cb
+        if ppo_short is not None:
+            ncpu = os.cpu_count() or 1
+            best = None
+            for nt in sorted({c for c in (8, 16, 32, 64, ncpu) if c <= ncpu}):      # every candidate, keep the fastest (as for the env step)
+                torch.set_num_threads(nt)
+                r = ppo_cpu_port(epochs=1)
+                log(f"  ppo cpu port: {nt} threads -> {r['value']:.3g} frames/s")
+                if best is None or r["value"] > best["value"]:
+                    best = r
+            torch.set_num_threads(best["cores"])
+            ppo_short["cpu_baseline"] = ppo_cpu_port(epochs=3)
     if dist_on:
         dist.barrier()
         dist.destroy_process_group()
+    if ppo_short is not None:
+        line["ppo"] = ppo_short         # LAST key: a truncated tail of the line (the driver keeps 1500 characters) still carries it
     if rank == 0:
         emit(line)
 
