@@ -86,7 +86,7 @@ for lg in (range(10, 21) if "A" in ONLY else []):
         dist.barrier()
     rows.append(r)
     if rank == 0:
-        print(json.dumps(r), flush=True)
+        sys.stdout.write(json.dumps(r) + "\n"); sys.stdout.flush()
     del env
 for lg in (range(10, 19) if "B" in ONLY else []):
     n = 1 << lg
@@ -100,7 +100,7 @@ for lg in (range(10, 19) if "B" in ONLY else []):
          "steady_state_us_per_step": full * 1e3, "steady_state_env_steps_per_s": world * n / (full * 1e-3)}
     rows.append(r)
     if rank == 0:
-        print(json.dumps(r), flush=True)
+        sys.stdout.write(json.dumps(r) + "\n"); sys.stdout.flush()
     del env
     torch.cuda.empty_cache()
 if world > 1:
