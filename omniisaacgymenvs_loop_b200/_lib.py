@@ -161,6 +161,10 @@ def ptr(t: torch.Tensor | None, dtype=None) -> ctypes.c_void_p:
         raise ValueError("libusv_b200 needs contiguous tensors")
     if dtype is not None and t.dtype != dtype:
         raise TypeError(f"expected {dtype}, got {t.dtype}")
+    if t.device.index != torch._C._cuda_getDevice():
+        # stream() hands the kernels the CURRENT device's stream: a tensor of another device would be launched on the wrong GPU
+        raise UsvLibraryError(f"tensor lives on {t.device} but the current CUDA device is {torch._C._cuda_getDevice()}: wrap the call in "
+                              "torch.cuda.device(...) or call torch.cuda.set_device() first (one process per GPU)")
     return ctypes.c_void_p(t.data_ptr())
 
 

@@ -167,7 +167,14 @@ class SquashedGaussianDiagonalCovariance:
     def load_state_dict(self, sd):
         self.std.copy_(torch.as_tensor(sd["std"], dtype=torch.float32).reshape(self.dim))
         if "action_scale" in sd:
-            self.action_scale = torch.as_tensor(sd["action_scale"], dtype=torch.float32).reshape(self.dim).clone()
+            # the kernels read the scale from the PpoLoopzNet struct the bound Actor was built with: a checkpoint with another (or a
+            # per-dimension) scale cannot be honoured by swapping this attribute, so it is refused instead of silently ignored
+            new = torch.as_tensor(sd["action_scale"], dtype=torch.float32).reshape(-1).cpu()
+            if new.numel() not in (1, self.dim) or not bool((new == new[0]).all()):
+                raise NotImplementedError("per-dimension action_scale in the checkpoint: the kernels take one scalar scale")
+            if abs(float(new[0]) - float(self.action_scale.reshape(-1)[0])) > 1e-6 * max(1.0, abs(float(new[0]))):
+                raise ValueError(f"checkpoint action_scale {float(new[0])} != {float(self.action_scale.reshape(-1)[0])} of this distribution "
+                                 "(construct SquashedGaussianDiagonalCovariance with the checkpoint's scale)")
 
     def enforce_minimum_std(self, min_std):
         if not self.std.is_cuda:

@@ -237,12 +237,68 @@ class PPO:
         self.lr.fill_(self.base_lr * (0.9998 ** self._sched_epoch))
 
     # ---- checkpoints (the reference's .pt dictionary, rlgames_train_loopz.py:1291-1297) ----------------------------
+    def _optimizer_tensors(self):
+        """(shape, offset) of every tensor of the flat vector in the reference optimiser's parameter order
+        [*actor.parameters(), *critic.parameters()] = actor architecture (12) | std | critic architecture (12)  [ref ppo.py:60]."""
+        import math
+        inner = lambda a: getattr(a, "architecture", a)          # MLPEncode_wrap -> MLPEncode
+        shapes = ([s for _, s in inner(self.actor.architecture)._shapes] + [(self.actor.distribution.dim,)] +
+                  [s for _, s in inner(self.critic.architecture)._shapes])
+        out, off = [], 0
+        for shp in shapes:
+            out.append((shp, off))
+            off += math.prod(shp)
+        if off != self.P:
+            raise RuntimeError(f"optimizer layout covers {off} of {self.P} parameters")
+        return out
+
+    def optimizer_state_dict(self):
+        """torch.optim.Adam.state_dict() layout (what the reference saves as 'optimizer_state_dict', rlgames_train_loopz.py:1295, and feeds
+        to ppo.optimizer.load_state_dict, :856): state[i] = {step, exp_avg, exp_avg_sq} per parameter tensor + one param group."""
+        import math
+        step = float(self.adam_step[self._parity].item())
+        state = {}
+        for i, (shp, off) in enumerate(self._optimizer_tensors()):
+            n = math.prod(shp)
+            state[i] = {"step": torch.tensor(step), "exp_avg": self.exp_avg[off:off + n].view(shp).clone(),
+                        "exp_avg_sq": self.exp_avg_sq[off:off + n].view(shp).clone()}
+        if step == 0:
+            state = {}                           # a fresh torch optimiser has no per-parameter state yet
+        group = {"lr": float(self.lr.item()), "betas": (0.9, 0.999), "eps": 1e-08, "weight_decay": 0, "amsgrad": False, "maximize": False,
+                 "foreach": None, "capturable": False, "differentiable": False, "fused": None, "decoupled_weight_decay": False,
+                 "initial_lr": self.base_lr, "params": list(range(len(self._optimizer_tensors())))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_optimizer_state_dict(self, sd) -> None:
+        import math
+        tens = self._optimizer_tensors()
+        state = sd.get("state", {})
+        if state and len(state) != len(tens):
+            raise ValueError(f"optimizer_state_dict holds {len(state)} parameter states, this learner has {len(tens)} tensors")
+        step = 0
+        for i, (shp, off) in enumerate(tens):
+            st = state.get(i, state.get(str(i)))
+            if st is None:
+                continue
+            n = math.prod(shp)
+            if tuple(st["exp_avg"].shape) != tuple(shp):
+                raise ValueError(f"optimizer state {i}: shape {tuple(st['exp_avg'].shape)} != {tuple(shp)}")
+            self.exp_avg[off:off + n].copy_(st["exp_avg"].reshape(-1))
+            self.exp_avg_sq[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+            step = int(float(st["step"]))
+        if not state:
+            self.exp_avg.zero_()
+            self.exp_avg_sq.zero_()
+        self.adam_step.fill_(step)
+        groups = sd.get("param_groups") or [{}]
+        if "lr" in groups[0]:
+            self.lr.fill_(float(groups[0]["lr"]))
+
     def state_dict(self, update: int = 0):
         return {"actor_architecture_state_dict": self.actor.architecture.state_dict(),
                 "actor_distribution_state_dict": self.actor.distribution.state_dict(),
                 "critic_architecture_state_dict": self.critic.architecture.state_dict(),
-                "optimizer_state": {"exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),
-                                    "step": int(self.adam_step[self._parity].item()), "lr": float(self.lr.item())},
+                "optimizer_state_dict": self.optimizer_state_dict(),
                 "update": int(update)}
 
     def load_state_dict(self, ckpt):
@@ -251,12 +307,17 @@ class PPO:
             self.actor.distribution.load_state_dict(ckpt["actor_distribution_state_dict"])
         if "critic_architecture_state_dict" in ckpt:
             self.critic.architecture.load_state_dict(ckpt["critic_architecture_state_dict"])
-        opt = ckpt.get("optimizer_state")
-        if opt is not None:
+        if "optimizer_state_dict" in ckpt:
+            self.load_optimizer_state_dict(ckpt["optimizer_state_dict"])
+        elif "optimizer_state" in ckpt:                     # round-1 files of this repo (flat blobs)
+            opt = ckpt["optimizer_state"]
             self.exp_avg.copy_(opt["exp_avg"])
             self.exp_avg_sq.copy_(opt["exp_avg_sq"])
             self.adam_step.fill_(int(opt["step"]))
             self.lr.fill_(float(opt["lr"]))
+        else:
+            import warnings
+            warnings.warn("checkpoint carries no optimizer state: Adam restarts from zero moments")
         return int(ckpt.get("update", -1)) + 1 if "update" in ckpt else 0
 
     def log(self, variables, width=80, pad=28):

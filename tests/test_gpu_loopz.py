@@ -396,3 +396,40 @@ def test_training_loop_on_the_live_task_learns():
     assert torch.isfinite(ppo.params).all() and float(ppo.actor.distribution.std.min()) >= 0.05
     rets = [h[1] for h in hist if h[1] == h[1]]
     assert len(rets) >= 6 and np.mean(rets[-3:]) > np.mean(rets[:3]), rets
+
+
+def test_checkpoint_optimizer_state_interchanges_with_torch_adam(golden):
+    """The .pt dictionary carries 'optimizer_state_dict' in torch.optim.Adam's own layout [ref: rlgames_train_loopz.py:855,1295]: what
+    this learner writes loads into a real torch Adam over tensors of the reference's shapes, and what torch Adam writes loads back."""
+    G = golden("loopz_ppo")
+    actor, critic, ppo = build()
+    ppo.params.copy_(T(G["params0"]))
+    fill_from_golden(ppo, G)
+    ppo.storage.compute_returns(critic.predict(T(G["roll_obs"]).to(DEV)[-1]), ppo.gamma, ppo.lam)
+    ppo._train_step()
+    ck = ppo.state_dict(update=3)
+    assert "optimizer_state_dict" in ck and "optimizer_state" not in ck
+    osd = ck["optimizer_state_dict"]
+    shapes = [shp for shp, _ in ppo._optimizer_tensors()]
+    assert len(osd["state"]) == len(shapes) == 25 and osd["param_groups"][0]["params"] == list(range(25))
+    prm = [torch.nn.Parameter(torch.zeros(s)) for s in shapes]           # [*actor.parameters(), *critic.parameters()] stand-ins
+    opt = torch.optim.Adam(prm, lr=5e-4)
+    opt.load_state_dict({"state": {k: {a: b.cpu() for a, b in v.items()} for k, v in osd["state"].items()}, "param_groups": osd["param_groups"]})
+    got = torch.cat([opt.state[p]["exp_avg"].reshape(-1) for p in prm])
+    assert torch.equal(got, ppo.exp_avg.cpu()) and float(opt.state[prm[0]]["step"]) == float(ppo.adam_step[ppo._parity])
+    # and back: a torch-written state dict restores moments, step count and lr
+    a2, c2, p2 = build(seed=5)
+    back = opt.state_dict()
+    back["param_groups"][0]["lr"] = 1.25e-4
+    assert p2.load_state_dict(dict(ck, optimizer_state_dict=back)) == 4
+    assert torch.equal(p2.exp_avg, ppo.exp_avg) and torch.equal(p2.exp_avg_sq, ppo.exp_avg_sq) and torch.equal(p2.params, ppo.params)
+    assert int(p2.adam_step[0]) == int(ppo.adam_step[ppo._parity]) and abs(float(p2.lr) - 1.25e-4) < 1e-10
+    # round-1 files of this repo (flat blobs) still load; a checkpoint with another action scale is refused, not ignored
+    legacy = {k: v for k, v in ck.items() if k != "optimizer_state_dict"}
+    legacy["optimizer_state"] = {"exp_avg": ppo.exp_avg.clone(), "exp_avg_sq": ppo.exp_avg_sq.clone(), "step": 16, "lr": 5e-4}
+    a3, c3, p3 = build(seed=6)
+    p3.load_state_dict(legacy)
+    assert torch.equal(p3.exp_avg, ppo.exp_avg) and int(p3.adam_step[0]) == 16
+    bad = dict(ck, actor_distribution_state_dict=dict(ck["actor_distribution_state_dict"], action_scale=torch.tensor([2.0, 2.0])))
+    with pytest.raises(ValueError):
+        p3.load_state_dict(bad)
