@@ -517,8 +517,8 @@ int ppo_adam_step_f32(float* params, float* grads /*[P+PPO_STAT_COUNT], scaled i
                       int32_t* step /*device int32[2]: [0] Adam step count (incremented), [1] scratch*/,
                       int64_t P, const PpoAdamParams* ap, void* stream);
 /* one whole minibatch step on a single rank: ppo_minibatch_grad_tc + ppo_adam_step_f32 + ppo_pack_weights_tc with the second-stage
- * reduction, clip, Adam, adaptive lr and the refresh of the packed operand tiles fused into ONE cooperative launch (+ a one-thread
- * lr / step roll: 4 launches per minibatch instead of 7) */
+ * reduction, clip, Adam, adaptive lr, the lr / step roll and the refresh of the packed operand tiles fused into ONE cooperative launch:
+ * T1 + T2 + tail = 3 launches per minibatch instead of 7 */
 int ppo_minibatch_step_tc(float* params, float* packed, const float* obs, int32_t obs_dim, const float* obs_mean, const float* obs_var,
                           const float* actions, const float* old_neglogp, const float* advantages, const float* old_values,
                           const float* returns, float* old_mu, float* old_sigma, const PpoLossParams* lp, float* grads, float* scratch,
@@ -548,7 +548,7 @@ int ppo_peer_allreduce_f32(const PpoPeerComm* c, const float* src, float* dst, i
 /* ppo_minibatch_step_tc on `world` ranks: the gradient all-reduce of trancate_gradients_and_step [ref: RLG/common/a2c_common.py:308-323]
  * runs INSIDE the cooperative tail kernel -- every 64-entry block of the span [gradient | loss statistics | KL] is pushed to the peers
  * as 8-byte {value, sequence} packets (P2P stores over NVLink, payload and flag in one word), summed in rank order as the packets
- * arrive, then clipped / Adam-stepped / re-packed by the same CTA: T1 + T2 + tail + roll = 4 launches per minibatch at any world size.
+ * arrive, then clipped / Adam-stepped / re-packed by the same CTA: T1 + T2 + tail = 3 launches per minibatch at any world size.
  * comm: windows from ppo_peer_window_alloc/open with cap >= world * ppo_minibatch_step_peer_entries(obs_dim) * 2 floats;
  * seq_dev as in ppo_peer_allreduce_f32 (its own counter); err_flag: set when a peer does not arrive within 10 s -- the parameters
  * are then left untouched by this and every later step until the host clears the flag.                                          */

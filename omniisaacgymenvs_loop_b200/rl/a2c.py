@@ -133,7 +133,7 @@ class A2CAgent:
             if self.collective == "peer":
                 from .peer import PeerAllReduce, PeerStepExchange
                 self.peer = PeerAllReduce(self.policy.grads.numel(), self.device, rank, world_size)
-                if self.policy.tensor_cores:      # the all-reduce fused into the cooperative minibatch tail (4 launches per minibatch)
+                if self.policy.tensor_cores:      # the all-reduce fused into the cooperative minibatch tail (3 launches per minibatch)
                     self.peer_step = PeerStepExchange(self.obs_dim, self.device, rank, world_size)
         N, T, D = self.num_actors, self.T, self.obs_dim
         f32 = dict(dtype=torch.float32, device=self.device)
@@ -230,7 +230,7 @@ class A2CAgent:
                 args = (ds["obs"][s], ds["actions"][s], ds["old_logp_actions"][s], ds["advantages"][s], ds["old_values"][s],
                         ds["returns"][s], ds["mu"][s], ds["sigma"][s])
                 if pol.tensor_cores and self.fused_step and (not self.multi_gpu or self.peer_step is not None):
-                    # gradient (+ all-reduce over NVLink inside the tail kernel) + clip + Adam + lr + operand-tile refresh: 4 launches
+                    # gradient (+ all-reduce over NVLink inside the tail kernel) + clip + Adam + lr + operand-tile refresh: 3 launches
                     pol.minibatch_step(*args, peer=self.peer_step)
                     continue
                 pol.minibatch_grad(*args)
