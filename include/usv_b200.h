@@ -377,6 +377,10 @@ typedef struct {
    * every env the BASE mass / CoM encodings and the encodings of priv_neutral[] (minmax: mid-range, else 1.0) instead of the
    * simulated values; the dynamics stay randomised                                                   */
   int32_t masscom_obs_base; float priv_neutral[4];
+  /* width of the privileged tail: 8 = [mass, CoM(3), k_drag, thr_L, thr_R, k_Iz] (obs 33 wide) or 4 = [mass, CoM(3)] (obs 29 wide:
+   * env.mass_dim / priv_dim = 4)  [ref: OIGE/tasks/USV_Virtual.py:484-488,854-856 ; OIGE/tasks/USV/USV_core.py:23-52,127-170].
+   * The obs tensor handed to usv_step_live_f32 is [n, 25 + priv_dim]; 0 reads as 8 (round-1 callers). */
+  int32_t priv_dim;
 } UsvLiveParams;
 
 typedef struct {

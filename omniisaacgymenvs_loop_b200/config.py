@@ -441,6 +441,7 @@ class UsvLiveConfig:
     map_size: float = 30.0
     fixed_horizon_eval: bool = False
     masscom_obs_base: bool = False           # mass.masscom_obs_source == "base": the tail shows base / neutral values (evaluation ablation)
+    priv_dim: int = 8                        # env.priv_dim / env.mass_dim: 8 = [mass, CoM, k_drag, thr_L, thr_R, k_Iz], 4 = [mass, CoM] (obs 29 wide)
     # Tier-3 tasks behind the same live step: 0 CaptureXY+obstacles, 1 GoToPose, 2 KeepXY, 3 TrackXYVelocity
     # [ref: OIGE/tasks/USV/USV_task_rewards.py:170-325 ; USV_task_parameters.py:95-177]
     task: int = 0
@@ -465,6 +466,9 @@ class UsvLiveConfig:
             lp.priv_a[j], lp.priv_b[j], lp.priv_active[j] = float(self.priv_a[j]), float(self.priv_b[j]), int(self.priv_active[j])
         lp.com_rand = int(self.com_rand)
         lp.masscom_obs_base = int(self.masscom_obs_base)
+        if int(self.priv_dim) not in (4, 8):
+            raise ValueError(f"Unsupported priv_dim/mass_dim={self.priv_dim}. Supported: 4 or 8.")      # [ref: USV_Virtual.py:485-488]
+        lp.priv_dim = int(self.priv_dim)
         for j in range(4):
             # minmax: `0.5 * (min + max)` in Python floats, then an fp32 tensor; raw / centered: ones  [ref: USV_Virtual.py:859-880]
             lp.priv_neutral[j] = float(np.float32(0.5 * (float(self.priv_a[j]) + (float(self.priv_a[j]) + float(self.priv_b[j]))))) \
@@ -512,7 +516,8 @@ class UsvLiveConfig:
                    com_rand=bool(m.get("add_mass_disturbances", False)) and disp is not None,
                    com_base=tuple(float(x) for x in m.get("base_com", [0.0, 0.0, 0.0])),
                    com_disp=tuple(float(x) for x in (disp or [0.0, 0.0, 0.0])),
-                   fixed_horizon_eval=bool(env.get("fixed_horizon_eval", False)), masscom_obs_base=source == "base")
+                   fixed_horizon_eval=bool(env.get("fixed_horizon_eval", False)), masscom_obs_base=source == "base",
+                   priv_dim=int(env.get("priv_dim", env.get("mass_dim", 4))))           # [ref: USV_Virtual.py:484]
 
 
 def live_env_config(task_cfg: dict, **overrides) -> "UsvEnvConfig":
@@ -564,7 +569,7 @@ def live_task_cfg(cfg: Optional["UsvEnvConfig"] = None, live: Optional["UsvLiveC
     live = live if live is not None else UsvLiveConfig()
     t = cfg.to_task_cfg()
     env, dist = t["env"], t["env"]["disturbances"]
-    env["mass_dim"] = 8
+    env["mass_dim"] = int(live.priv_dim)
     env["privileged_params"] = {"mode": ("raw", "centered", "minmax")[live.priv_mode], "nominal": 1.0}
     env["fixed_horizon_eval"] = live.fixed_horizon_eval
     env["action_processing"] = {"use_affine_thrust_mapping": cfg.action_affine, "initial_action_bias": cfg.action_bias,

@@ -277,16 +277,22 @@ __device__ __forceinline__ void post_live(EnvState& e, const EnvConst& k, LiveSt
 }
 
 // each warp stages its 32 x 33 observation tile (stride 33: conflict-free) and writes one contiguous 4224 B run
+// obs_w < 33 (the 4-wide privileged tail: 29): the staged rows keep their stride of 33, the global rows are obs_w wide
 __device__ __forceinline__ void write_obs_tile_b(float* s_obs, float* __restrict__ obs,
-                                                 int64_t block_start, int64_t n) {
+                                                 int64_t block_start, int64_t n, int obs_w = kObsB) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* sw = s_obs + warp * (32 * kObsB);
   __syncwarp();
   const int64_t warp_start = block_start + (int64_t)warp * 32;
   if (warp_start >= n) return;
   const int rows = (int)min((int64_t)32, n - warp_start);
-  float* g = obs + warp_start * kObsB;
-  if (rows == 32 && (((uintptr_t)g & 15) == 0)) {
+  float* g = obs + warp_start * obs_w;
+  if (obs_w != kObsB) {
+    for (int q = lane; q < rows * obs_w; q += 32) {
+      const int r = q / obs_w;
+      g[q] = sw[r * kObsB + (q - r * obs_w)];
+    }
+  } else if (rows == 32 && (((uintptr_t)g & 15) == 0)) {
     const float4* s4 = reinterpret_cast<const float4*>(sw);
     float4* g4 = reinterpret_cast<float4*>(g);
 #pragma unroll
@@ -353,7 +359,7 @@ __global__ void __launch_bounds__(kBlock, 3) step_live_kernel(UsvEnvBuffers b, U
       if (!isfinite(act.x) || !isfinite(act.y)) atomicOr(b.nonfinite_flag, 2u);
     }
   }
-  write_obs_tile_b(smem, obs, block_start, n);
+  write_obs_tile_b(smem, obs, block_start, n, lp.priv_dim == 4 ? kObsB - 4 : kObsB);
 }
 
 // ---- Tier-3 tasks behind the same 33-dim observation -------------------------------------------------
@@ -514,7 +520,7 @@ __global__ void __launch_bounds__(kBlock, 3) step_task_kernel(UsvEnvBuffers b, U
       if (!isfinite(act.x) || !isfinite(act.y)) atomicOr(b.nonfinite_flag, 2u);
     }
   }
-  write_obs_tile_b(smem, obs, block_start, n);
+  write_obs_tile_b(smem, obs, block_start, n, lp.priv_dim == 4 ? kObsB - 4 : kObsB);
 }
 
 }  // namespace usv
@@ -537,6 +543,7 @@ extern "C" int usv_step_live_f32(const UsvEnvBuffers* b, const UsvLiveBuffers* l
   if (p->n_substeps < 0 || p->n_substeps > 1024) return USV_E_PARAM;
   if (!(p->izz > 0.0f) || !(lp->map_size > 0.0f)) return USV_E_PARAM;
   if (lp->priv_mode < USV_PRIV_RAW || lp->priv_mode > USV_PRIV_MINMAX) return USV_E_PARAM;
+  if (lp->priv_dim != 0 && lp->priv_dim != 4 && lp->priv_dim != 8) return USV_E_PARAM;
   if (n == 0) return USV_OK;
   if (!actions || !obs || !rew) return USV_E_NULL;
   if ((uintptr_t)actions & 7) return USV_E_ALIGN;

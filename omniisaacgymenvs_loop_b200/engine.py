@@ -270,7 +270,8 @@ class FusedUsvLiveEnv(FusedUsvEnv):
         self.task = int(self.live.task)
         # task.global_potential_field (only the obstacle task has one)
         self.potential = torch.zeros((n, GRID, GRID), **f32) if self.task == 0 else torch.zeros((1, GRID, GRID), **f32)
-        self.obs = torch.zeros((n, LIVE_OBS_DIM), **f32)
+        self.obs_dim = LIVE_OBS_DIM - 8 + int(self.live.priv_dim)          # 33, or 29 with the 4-wide privileged tail
+        self.obs = torch.zeros((n, self.obs_dim), **f32)
         # BatchedMapGPU.__init__: cell-centre coordinates  [ref: d_multi_gemini.py:15-19]
         ms = self.live.map_size
         cell = ms / GRID
@@ -335,7 +336,7 @@ class FusedUsvLiveEnv(FusedUsvEnv):
     # ---- the hot path ------------------------------------------------------------------
     def step(self, actions: torch.Tensor, obs: Optional[torch.Tensor] = None, rew: Optional[torch.Tensor] = None,
              rebuild_scene: bool = True):
-        """One control step of every env (== VecEnvRLGames.step over the live task).  Returns (obs (N,33), rew, reset_buf)."""
+        """One control step of every env (== VecEnvRLGames.step over the live task).  Returns (obs (N, 25 + priv_dim), rew, reset_buf)."""
         obs = self.obs if obs is None else obs
         rew = self.rew if rew is None else rew
         p = self.params()

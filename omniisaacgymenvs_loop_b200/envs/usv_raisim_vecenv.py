@@ -11,39 +11,40 @@ import numpy as np
 import torch
 
 
+def _state_tensor(ret) -> torch.Tensor:
+    """The observation tensor inside what VecEnvRLGames.reset / step hand back: {"obs": {"state": tensor}} on this path; a bare
+    tensor or {"obs": tensor} from other rl_games-style envs is accepted too."""
+    seen = ret
+    for key in ("obs", "state"):
+        if isinstance(seen, dict):
+            if key not in seen:
+                if key == "state" and len(seen) == 1:            # a single observation group under another name
+                    seen = next(iter(seen.values()))
+                    continue
+                raise KeyError(f"observation dict has no '{key}' entry (keys: {sorted(seen)})")
+            seen = seen[key]
+    if not torch.is_tensor(seen):
+        raise TypeError(f"no observation tensor in a {type(ret).__name__} returned by the wrapped env")
+    return seen
+
+
 class USVRaisimVecEnv:
+    """observe() / step(action) -> (reward, dones) over a VecEnvRLGames.  The learner-facing sizes come from the task behind it."""
+
     def __init__(self, base_env: Any, *, reward_info_size: int = 16, device=None) -> None:
-        self._env = base_env
-        self._task = getattr(base_env, "_task", None)
-        if self._task is None:
-            raise ValueError("base_env must be a VecEnvRLGames-like env with attribute `_task`.")
-        self._device = torch.device(device) if device is not None else torch.device(getattr(self._task, "rl_device", self._task.device))
-        self.num_envs = int(getattr(self._env, "num_envs", self._task.num_envs))
-        self.num_obs = int(self._task.num_observations)
-        self.num_acts = int(self._task.num_actions)
+        task = getattr(base_env, "_task", None)
+        if task is None:
+            raise ValueError("USVRaisimVecEnv wraps a VecEnvRLGames whose task has been set (no `_task` on the given env)")
+        self._env, self._task = base_env, task
+        self._device = torch.device(device if device is not None else getattr(task, "rl_device", task.device))
+        self.num_envs, self.num_obs, self.num_acts = (int(getattr(base_env, "num_envs", task.num_envs)), int(task.num_observations),
+                                                      int(task.num_actions))
         self._reward_info_size = int(reward_info_size)
-        self._last_obs_torch: Optional[torch.Tensor] = None
-        self._last_reward_torch: Optional[torch.Tensor] = None
-        self._last_dones_torch: Optional[torch.Tensor] = None
+        # what the last reset / step left behind (device tensors; the numpy views are made on demand)
+        self._last_obs_torch = self._last_reward_torch = self._last_dones_torch = None
         self._last_extras: Dict[str, Any] = {}
 
-    @staticmethod
-    def _extract_obs_tensor(obs_dict) -> torch.Tensor:
-        if isinstance(obs_dict, dict):
-            obs = obs_dict.get("obs")
-            if obs is None:
-                raise KeyError("obs_dict does not contain key 'obs'.")
-            if isinstance(obs, dict):
-                if "state" in obs and torch.is_tensor(obs["state"]):
-                    return obs["state"]
-                vals = [v for v in obs.values() if torch.is_tensor(v)]
-                if len(vals) == 1:
-                    return vals[0]
-                raise TypeError("obs_dict['obs'] is a dict but no single tensor could be inferred")
-            return obs
-        if torch.is_tensor(obs_dict):
-            return obs_dict
-        raise TypeError("Unsupported observation type returned from base_env.reset/step")
+    _extract_obs_tensor = staticmethod(_state_tensor)
 
     def reset(self) -> None:
         self._last_obs_torch = self._extract_obs_tensor(self._env.reset())

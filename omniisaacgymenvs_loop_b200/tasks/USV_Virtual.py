@@ -67,8 +67,6 @@ class USVVirtual:
         if self._live:
             self.cfg = live_env_config(self._task_cfg, seed=seed)
             self.live_cfg = UsvLiveConfig.from_task_cfg(self._task_cfg)
-            if int(self._task_cfg["env"].get("mass_dim", 8)) != 8:
-                raise NotImplementedError("the fused live step builds the 8-wide privileged tail (env.mass_dim: 8)")
         else:
             self.cfg = UsvEnvConfig.from_task_cfg(self._task_cfg, seed=seed)
         envc = self._task_cfg["env"]
@@ -86,7 +84,8 @@ class USVVirtual:
         self.clip_actions = self.cfg.clip_actions
         self.randomize_actions = False
         self.randomize_observations = False
-        self._num_observations = self.num_observations = LIVE_OBS_DIM if self._live else OBS_DIM
+        # live: 3 + 20 + 2 + priv_dim (33, or 29 with env.mass_dim / priv_dim = 4)  [ref: OIGE/tasks/USV/USV_core.py:23-52]
+        self._num_observations = self.num_observations = (LIVE_OBS_DIM - 8 + int(self.live_cfg.priv_dim)) if self._live else OBS_DIM
         self._num_actions = self.num_actions = 2
         self._max_actions = 2
         self.num_states = 0

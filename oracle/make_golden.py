@@ -519,6 +519,49 @@ def variant_b():
     print("capture_xy_live.npz")
 
 
+def variant_b_pd4():
+    """The live CaptureXYTask with the 4-wide privileged tail (priv_dim = 4: obs = 3 + 20 + 2 + 4 = 29)
+    [OIGE/tasks/USV/USV_core.py:23-52,127-170 ; USV_capture_xy_static_obs.py:193-299].  Same seed and call order as variant_b(), so
+    obstacles / field / targets equal capture_xy_live.npz (asserted here) and only the states and the 29-wide observations are stored."""
+    live, dmap = ref_shim.load_live()
+    cfg = ref_shim.live_yaml()
+    NB, K = 12, 3
+    torch.manual_seed(21)
+    g = gen()
+    with ref_shim.quiet():
+        task = live.CaptureXYTask(cfg["env"]["task_parameters"], cfg["env"]["reward_parameters"], NB, "cpu", priv_dim=4)
+    task._env = types.SimpleNamespace(_env_pos=torch.zeros((NB, 3)))
+    ids = torch.arange(NB)
+    with ref_shim.quiet():
+        task.reset(ids)
+        task.get_goals(ids, torch.zeros((NB, 3)), torch.zeros((NB, 4)))
+        pos0, rot0 = task.get_spawns(ids, torch.zeros((NB, 3)), torch.zeros((NB, 4)))
+    G8 = np.load(os.path.join(OUT, "capture_xy_live.npz"))
+    assert np.array_equal(G8["obstacles0"], task.xunlian_pos[:, :, :2].numpy()) and np.array_equal(G8["target"], task._target_positions.numpy())
+    assert np.allclose(G8["field0"], task.global_potential_field.numpy(), rtol=0, atol=1e-6)
+    pos = pos0[:, :2].clone()
+    yaw = (torch.rand(NB, generator=g) * 2 - 1) * math.pi
+    vel = torch.rand((NB, 2), generator=g) * 2 - 1
+    w = torch.rand(NB, generator=g) * 1.2 - 0.6
+    S = {k: [] for k in ("pos", "yaw", "vel", "w", "prev_action", "priv", "obs")}
+    for k in range(K):
+        heading = torch.stack([torch.cos(yaw), torch.sin(yaw)], 1)
+        state = {"position": pos.clone(), "orientation": heading, "linear_velocity": vel.clone(), "angular_velocity": w.clone()}
+        prev_action = torch.rand((NB, 2), generator=g) * 2 - 1
+        priv = torch.rand((NB, 4), generator=g) * 2 - 1
+        with ref_shim.quiet():
+            obs = task.get_state_observations(state, "local", prev_action=prev_action, priv_tail=priv).clone()
+        assert obs.shape == (NB, 29)
+        for name, v in (("pos", pos), ("yaw", yaw), ("vel", vel), ("w", w), ("prev_action", prev_action), ("priv", priv), ("obs", obs)):
+            S[name].append(v.clone())
+        pos = pos + 0.15 * vel
+        yaw = yaw + 0.15 * w
+        vel = vel * 0.9 + 0.1 * (torch.rand((NB, 2), generator=g) * 2 - 1)
+        w = w * 0.8 + 0.2 * (torch.rand(NB, generator=g) * 1.2 - 0.6)
+    np.savez_compressed(os.path.join(OUT, "capture_xy_live_pd4.npz"), **t2n({k: torch.stack(v) for k, v in S.items()}))
+    print("capture_xy_live_pd4.npz")
+
+
 def live_virtual():
     """The live USVVirtual's own host-side chains that sit around the task (driven on a bare instance, no Isaac Sim):
     pre_physics_step action path (A12), get_observations privileged tail (B1), _apply_mass_driven_coupling (A11)
@@ -924,6 +967,7 @@ def main():
     ppo()
     ppo_epoch()
     variant_b()
+    variant_b_pd4()
     live_virtual()
     tier3()
     classic_curriculum()
