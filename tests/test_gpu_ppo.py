@@ -252,7 +252,9 @@ def test_fused_minibatch_step_equals_unfused():
             sa, sb = a.stats(), b.stats()
             assert all(abs(sa[k] - sb[k]) <= 1e-5 * abs(sa[k]) + 1e-7 for k in sa), (sa, sb)
             assert int(a.step) == int(b.step) == it + 1
-            assert_close(mu_b, mu_a, 1e-5, 1e-6, "mu write-back")     # the fused tail sums the five scalar gradients in another order
+            # the fused tail sums the partial gradients in another order; from the second step on the parameters differ in their last
+            # bits and TF32 rounding of the operands turns that into ~1e-5 of the mu scale
+            assert_close(mu_b, mu_a, 1e-5, 1e-6 if it == 0 else 2e-5, "mu write-back")
     # capturable (cooperative launch inside a graph)
     g = torch.cuda.CUDAGraph()
     before = b.params.clone()
@@ -305,10 +307,9 @@ def test_fused_peer_minibatch_step_packet_protocol(world):
             got_v = win[r][base:base + 2 * (P + 5):2].view(torch.float32)
             got_s = win[r][base + 1:base + 2 * (P + 5):2]
             assert bool((got_s == seq).all()), "sequence stamp"
-            if it == 0:       # same parameters as `ref`: the matrix entries (w1 .. value weights) are the same sums in the same order
-                assert torch.equal(got_v[2:P - 260], local[0][2:P - 260]), "matrix gradient entries travel bit-exact"
             gsc = float(local[0][:P].abs().max())
-            assert_close(got_v, local[0][:P + 5], 1e-5 if it == 0 else 2e-4, 1e-7 if it == 0 else 2e-4 * gsc, "packets of rank 0")
+            # same partial sums as minibatch_grad's second stage, added in another (fixed) order
+            assert_close(got_v, local[0][:P + 5], 1e-5 if it == 0 else 2e-4, 1e-6 * gsc if it == 0 else 2e-4 * gsc, "packets of rank 0")
             other = ((1 - par) * world + 0) * ecap * 2
             assert bool((win[r][other + 1:other + 2 * (P + 5):2] == (seq - 1 if seq > 1 else 0)).all()), "the other parity is untouched"
         ref.grads.copy_(torch.stack(local).sum(0))
@@ -320,7 +321,7 @@ def test_fused_peer_minibatch_step_packet_protocol(world):
         sa, sb = ref.stats(), pol.stats()
         assert all(abs(sa[k] - sb[k]) <= 1e-5 * abs(sa[k]) + 1e-7 for k in sa), (sa, sb)
         assert float(pol.lr) == float(ref.lr) and int(pol.step) == int(ref.step) == seq
-        assert_close(data[0]["mu"], data[0]["mu_ref"], 1e-5, 1e-6, "mu write-back")
+        assert_close(data[0]["mu"], data[0]["mu_ref"], 1e-5, 1e-6 if it == 0 else 2e-5, "mu write-back")
 
 
 def test_tensor_core_paths_at_live_obs_width():
