@@ -654,6 +654,33 @@ int ppo_loopz_adam_step_f32(float* params, float* grads, float* exp_avg, float* 
 /* SquashedGaussianDiagonalCovariance.enforce_minimum_std   [ref: module.py:649-659] */
 int ppo_loopz_enforce_min_std_f32(float* std, const float* min_std, int32_t dim, void* stream);
 
+/* ------------------------------------------------------------------------- */
+/* D  the USV SysID / DAgger student (second half): what OIGE/scripts/dagger_usv_sysid_loopz.py trains   */
+/*   StateHistoryEncoder: hist[M, tsteps*In] -> per-step Linear(In,32)+LeakyReLU -> RESHAPE (bs,32,T) (the reference's      */
+/*   reshape, not a transpose) -> Conv1d stack (tsteps 50: (8,4),(5,1),(5,1); 20: (6,2),(4,2); 10: (4,2),(2,1)) + LeakyReLU */
+/*   -> flatten 96 -> Linear(96,Out)+LeakyReLU.     [ref: OIGE/algo/ppo/module.py:392-448]                                   */
+/*   Flat fp32 parameters in StateHistoryEncoder.parameters() order: encoder.0.{weight,bias} | conv_layers.{0,2,(4)}.        */
+/*   {weight [32,32,k], bias} | linear_output.0.{weight [Out,96], bias}.  In <= 32, Out <= 8.                                */
+int64_t dagger_history_encoder_param_count(int32_t input_size, int32_t tsteps, int32_t output_size);   /* < 0: unsupported */
+int64_t dagger_train_scratch_floats(int32_t input_size, int32_t tsteps, int32_t output_size);
+/* id_encoder(history): latent[M, Out]; hist rows are hist_ld floats apart (sysid_obs = [history_flat | current] is read in place) */
+int dagger_history_encoder_forward_f32(const float* params, const float* hist /*[M, hist_ld]*/, int64_t hist_ld, int32_t input_size,
+                                       int32_t tsteps, int32_t output_size, float* latent /*[M, Out]*/, int64_t M, void* stream);
+/* one minibatch of USVSysIDTrainer._train_step: pred = id_encoder(hist); loss = MSELoss(pred, zstar); backward; Adam.step()    */
+/* (torch defaults: betas 0.9 / 0.999, eps 1e-8, no weight decay, no clipping).  grads[P + 1] = [gradient | the minibatch MSE];  */
+/* lr: device float (the host owns StepLR); step: device int32[2], current count in step[parity], new count to step[1 - parity]; */
+/* mse_accum: device float += MSE or NULL.  Deterministic (fixed summation order).   [ref: OIGE/algo/ppo/dagger.py:125-196]      */
+int dagger_sysid_minibatch_step_f32(float* params, const float* hist, int64_t hist_ld, const float* zstar /*[M, Out]*/, int32_t input_size,
+                                    int32_t tsteps, int32_t output_size, float* grads, float* scratch, float* exp_avg, float* exp_avg_sq,
+                                    const float* lr, int32_t* step, int32_t parity, float* mse_accum, int64_t M, void* stream);
+/* a small dense MLP (<= 3 nn.Linear layers, widths <= 128, LeakyReLU between them) out of a flat parameter vector: the frozen     */
+/* teacher mass encoder (priv tail -> z*) and the frozen action head ([current obs | z^] -> action) of USVSysIDAgent.              */
+/* last_activation: 0 LeakyReLU, 1 tanh, 2 none.   [ref: OIGE/algo/ppo/dagger.py:50-66]                                            */
+int dagger_mlp_forward_f32(const float* params, int32_t n_layers, const int32_t* dims /*host [n_layers + 1]*/,
+                           const int32_t* w_offsets /*host [n_layers]*/, const int32_t* b_offsets /*host [n_layers]*/,
+                           int32_t last_activation, const float* x /*[M, x_ld]*/, int64_t x_ld, float* y /*[M, dims[n_layers]]*/,
+                           int64_t M, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -130,6 +130,8 @@ def lib() -> ctypes.CDLL:
     L.usv_live_scene_workspace_bytes.restype = ctypes.c_int64
     L.ppo_peer_window_bytes.restype = ctypes.c_int64
     L.ppo_minibatch_step_peer_entries.restype = ctypes.c_int64
+    L.dagger_history_encoder_param_count.restype = ctypes.c_int64
+    L.dagger_train_scratch_floats.restype = ctypes.c_int64
     L.usv_live_scene_workspace_bytes.argtypes = [ctypes.c_int64]
     for name, st in STRUCTS.items():
         want = L.usv_b200_sizeof(name.encode())

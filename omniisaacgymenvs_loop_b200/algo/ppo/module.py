@@ -103,6 +103,26 @@ class MLPEncode:
     def parameters(self) -> List[torch.Tensor]:
         return list(self.views().values())
 
+    def _submodule(self, prefix: str, last_activation: int) -> "FlatMLP":
+        layers, off = [], 0
+        for name, shp in self._shapes:
+            n = math.prod(shp)
+            if name.startswith(prefix) and name.endswith(".weight"):
+                layers.append((off, off + n, int(shp[1]), int(shp[0])))           # weight offset, bias offset, in, out
+            off += n
+        return FlatMLP(lambda: self.flat, layers, last_activation)
+
+    @property
+    def mass_encoder(self) -> "FlatMLP":
+        """The privileged-tail encoder as a callable (priv [M, mass_dim] -> latent [M, 8]); reads this network's live parameters.
+        The SysID script takes it as the frozen teacher  [ref: dagger_usv_sysid_loopz.py ; module.py:250-270]."""
+        return self._submodule("mass_encoder.", 0)
+
+    @property
+    def action_mlp(self) -> "FlatMLP":
+        """The trunk on [speed | task | latent] as a callable ([M, obs_dim - mass_dim + 8] -> [M, out]); the SysID script's frozen action head."""
+        return self._submodule("action_mlp.", 1 if self.tanh_out else 2)
+
     def state_dict(self, prefix: str = "") -> Dict[str, torch.Tensor]:
         return {prefix + k: v.detach().clone() for k, v in self.views().items()}
 
@@ -113,6 +133,111 @@ class MLPEncode:
             raise KeyError(f"missing keys in state_dict: {missing}")
         for k, t in v.items():
             t.copy_(torch.as_tensor(sd[prefix + k], dtype=torch.float32).reshape(t.shape))
+
+
+class FlatMLP:
+    """<= 3 nn.Linear layers with LeakyReLU between them, evaluated by dagger_mlp_forward_f32 out of a flat CUDA parameter vector.
+    `flat` is a callable returning that vector (a view of its owner's storage, so a parameter update is seen without re-binding)."""
+
+    def __init__(self, flat, layers, last_activation: int):
+        self._flat, self.layers, self.last_activation = flat, list(layers), int(last_activation)
+        if not 1 <= len(self.layers) <= 3:
+            raise NotImplementedError("FlatMLP: 1..3 layers")
+        self.dims = [self.layers[0][2]] + [l[3] for l in self.layers]
+
+    def to(self, device):
+        return self
+
+    def parameters(self):
+        return []                                # frozen: nothing for an optimiser
+
+    def __call__(self, x) -> torch.Tensor:
+        flat = self._flat()
+        if not flat.is_cuda:
+            raise _lib.UsvLibraryError("FlatMLP needs its network bound to a CUDA Actor / Critic (no CPU fallback)")
+        x = _as_dev(x, flat.device)
+        if x.shape[1] < self.dims[0]:
+            raise ValueError(f"input width {x.shape[1]} < {self.dims[0]}")
+        M = x.shape[0]
+        y = torch.empty((M, self.dims[-1]), dtype=torch.float32, device=flat.device)
+        n = len(self.layers)
+        I32 = ctypes.c_int32
+        rc = _lib.lib().dagger_mlp_forward_f32(ctypes.c_void_p(flat.data_ptr()), I32(n), (I32 * (n + 1))(*self.dims),
+                                               (I32 * n)(*[l[0] for l in self.layers]), (I32 * n)(*[l[1] for l in self.layers]),
+                                               I32(self.last_activation), _lib.ptr(x), ctypes.c_int64(x.shape[1]), _lib.ptr(y),
+                                               ctypes.c_int64(M), _lib.stream())
+        _lib.check(rc, "dagger_mlp_forward_f32")
+        return y
+
+
+CONV_STACKS = {50: ((8, 4), (5, 1), (5, 1)), 20: ((6, 2), (4, 2)), 10: ((4, 2), (2, 1))}
+
+
+class StateHistoryEncoder:
+    """The SysID student [ref: OIGE/algo/ppo/module.py:392-448]: a history of `tsteps` non-privileged observations -> latent.
+    Same constructor and call as the reference's nn.Module; parameters are ONE flat fp32 CUDA vector in `parameters()` order
+    (encoder.0, conv_layers.{0,2,(4)}, linear_output.0), `state_dict()` uses the reference's keys.  forward runs
+    dagger_history_encoder_forward_f32 (one warp per sample, weights in shared memory); training is USVSysIDTrainer's kernel."""
+
+    def __init__(self, activation_fn, input_size, tsteps, output_size, device="cuda:0", seed: Optional[int] = None):
+        if not _is_leaky_relu(activation_fn):
+            raise NotImplementedError("StateHistoryEncoder kernels implement nn.LeakyReLU (dagger_usv_sysid_loopz.py passes it)")
+        if int(tsteps) not in CONV_STACKS:
+            raise NotImplementedError(f"tsteps {tsteps}: the reference defines 50, 20 and 10")
+        self.tsteps, self.input_size, self.output_size = int(tsteps), int(input_size), int(output_size)
+        self.input_shape, self.output_shape = self.input_size * self.tsteps, self.output_size
+        self.device = _cuda_device(device)
+        P = int(_lib.lib().dagger_history_encoder_param_count(ctypes.c_int32(self.input_size), ctypes.c_int32(self.tsteps),
+                                                              ctypes.c_int32(self.output_size)))
+        if P < 0:
+            raise NotImplementedError("StateHistoryEncoder kernels: input_size <= 32, output_size <= 8")
+        self._shapes = [("encoder.0.weight", (32, self.input_size)), ("encoder.0.bias", (32,))]
+        for i, (k, _) in enumerate(CONV_STACKS[self.tsteps]):
+            self._shapes += [(f"conv_layers.{2 * i}.weight", (32, 32, k)), (f"conv_layers.{2 * i}.bias", (32,))]
+        self._shapes += [("linear_output.0.weight", (self.output_size, 96)), ("linear_output.0.bias", (self.output_size,))]
+        assert sum(math.prod(s) for _, s in self._shapes) == P
+        self.flat = torch.zeros(P, dtype=torch.float32, device=self.device)
+        g = torch.Generator().manual_seed(int(seed)) if seed is not None else None
+        for name, t in self.views().items():     # nn.Linear / nn.Conv1d defaults: U(+-1/sqrt(fan_in)) for weight and bias
+            w = self.views()[name.replace(".bias", ".weight")]
+            bound = 1.0 / math.sqrt(math.prod(w.shape[1:]))
+            t.copy_(((torch.rand(t.shape, generator=g) * 2 - 1) * bound).to(self.device))
+
+    def views(self) -> Dict[str, torch.Tensor]:
+        out, off = {}, 0
+        for name, shp in self._shapes:
+            n = math.prod(shp)
+            out[name] = self.flat[off:off + n].view(shp)
+            off += n
+        return out
+
+    def parameters(self) -> List[torch.Tensor]:
+        return list(self.views().values())
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        return {k: v.detach().clone() for k, v in self.views().items()}
+
+    def load_state_dict(self, sd) -> None:
+        for k, t in self.views().items():
+            t.copy_(torch.as_tensor(sd[k], dtype=torch.float32).reshape(t.shape))
+
+    def to(self, device):
+        if torch.device(device) != self.device:
+            raise _lib.UsvLibraryError("StateHistoryEncoder lives on the CUDA device it was built on")
+        return self
+
+    def forward(self, obs: torch.Tensor, row_stride: Optional[int] = None) -> torch.Tensor:
+        """obs [bs, tsteps * input_size] (or wider rows: only the first tsteps * input_size columns are read) -> [bs, output_size]."""
+        obs = _as_dev(obs, self.device)
+        M = obs.shape[0]
+        out = torch.empty((M, self.output_size), dtype=torch.float32, device=self.device)
+        rc = _lib.lib().dagger_history_encoder_forward_f32(_lib.ptr(self.flat), _lib.ptr(obs), ctypes.c_int64(obs.shape[1]),
+                                                           ctypes.c_int32(self.input_size), ctypes.c_int32(self.tsteps),
+                                                           ctypes.c_int32(self.output_size), _lib.ptr(out), ctypes.c_int64(M), _lib.stream())
+        _lib.check(rc, "dagger_history_encoder_forward_f32")
+        return out
+
+    __call__ = forward
 
 
 class MLPEncode_wrap:

@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY (CPU restatement; not product code, nothing in the package imports it).
 
-The USV SysID distillation step of the fork's DAgger stack -- SURVEY 8(f) row 4, second half; the CUDA path for it is NOT built yet
-(DESIGN.md section 10 item 5), this oracle and its goldens are the parity gate it will be built against:
+The USV SysID distillation step of the fork's DAgger stack -- SURVEY 8(f) row 4, second half.  The CUDA path is csrc/dagger_sysid.cu behind
+algo/ppo/dagger.py and module.StateHistoryEncoder; this oracle and its goldens are the parity gate (tests/test_gpu_dagger.py):
 
   StateHistoryEncoder.forward           OIGE/algo/ppo/module.py:392-448   (student: history of T non-privileged observations -> latent)
   USVSysIDAgent.evaluate                OIGE/algo/ppo/dagger.py:50-66     (action head on [current obs | student latent])

@@ -1,5 +1,5 @@
 """The DAgger / SysID distillation oracle (oracle/dagger_oracle.py) against goldens produced by the reference's own StateHistoryEncoder,
-USVSysIDAgent and USVSysIDTrainer (oracle/make_golden_dagger.py).  The CUDA path for this row is not built yet: this is its parity gate."""
+USVSysIDAgent and USVSysIDTrainer (oracle/make_golden_dagger.py).  The parity gate of the CUDA path (csrc/dagger_sysid.cu, tests/test_gpu_dagger.py)."""
 import os
 
 import numpy as np
