@@ -99,6 +99,26 @@ class AverageMeter:
         return int(self.current_size)
 
 
+class ScalarLog:
+    """add_scalar(tag, value, step) into a JSON-lines file: the scalar stream the reference sends to tensorboardX's SummaryWriter
+    [ref: RLG/common/a2c_common.py:343-362], for an image without tensorboard.  Any object with that method can be passed instead."""
+
+    def __init__(self, path: str):
+        import json
+        import os
+        os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+        self._f, self._json = open(path, "a"), json
+
+    def add_scalar(self, tag: str, value, step) -> None:
+        self._f.write(self._json.dumps({"tag": tag, "value": float(value), "step": float(step)}) + "\n")
+
+    def flush(self) -> None:
+        self._f.flush()
+
+    def close(self) -> None:
+        self._f.close()
+
+
 class A2CAgent:
     def __init__(self, vec_env, cfg: PPOConfig, device="cuda:0", rank: int = 0, world_size: int = 1, use_cuda_graph: bool = True,
                  collective: str = "peer"):
@@ -343,24 +363,81 @@ class A2CAgent:
         self.ep_info_n.zero_()
         return out
 
-    def train(self, max_epochs: Optional[int] = None, log_every: int = 10, log=print):
+    def train(self, max_epochs: Optional[int] = None, log_every: int = 10, log=print, writer=None, nn_dir: Optional[str] = None,
+              name: str = "USV", save_freq: int = 0, save_best_after: int = 100, score_to_win: Optional[float] = None):
+        """The outer loop of ContinuousA2CBase.train [ref: RLG/common/a2c_common.py:1336-1486] with its scalar stream and checkpoint cadence.
+
+        `writer`: anything with add_scalar(tag, value, step) -- a tensorboard SummaryWriter, or `ScalarLog` below (JSON lines; the image has
+        no tensorboardX); tags are the reference's (write_stats :343-362 and the rewards / episode_lengths block :1399-1418).
+        `nn_dir`: checkpoints in the reference's .pth schema and naming: `last_<name>_ep_<epoch>_rew_<mean>.pth` every `save_freq` epochs when
+        the reward did not improve, `<name>.pth` whenever the mean reward of the last `games_to_track` episodes beats the best so far
+        (after `save_best_after` epochs), `last_<name>_ep_<epoch>_rew_<mean>.pth` at max_epochs.
+        Everything host-side happens at the log points only (every `log_every` epochs): one synchronize, a handful of scalar reads."""
+        import os
         max_epochs = max_epochs or self.cfg.max_epochs
+        if nn_dir:
+            os.makedirs(nn_dir, exist_ok=True)
+        self.last_mean_rewards = getattr(self, "last_mean_rewards", -1e9)
+        t_start, t_last, frames_last, play_acc, upd_acc = time.perf_counter(), time.perf_counter(), self.frame, 0.0, 0.0
         while self.epoch_num < max_epochs:
             play, update = self.train_epoch()
-            if self.epoch_num % log_every == 0:
+            play_acc += play
+            upd_acc += update
+            at_end = self.epoch_num >= max_epochs
+            if self.epoch_num % log_every == 0 or at_end:
                 torch.cuda.synchronize(self.device)
                 self.check_peers()
+                now = time.perf_counter()
                 rew, length, cnt = self.episode_stats()
                 if cnt:
                     self.mean_reward = rew
                 st = self.policy.stats()
+                frame, epoch, total_time = self.frame, self.epoch_num, now - t_start
+                have_games = len(self.game_rewards) > 0
+                mean_rewards, mean_lengths = self.game_rewards.get_mean(), self.game_lengths.get_mean()
+                if self.rank == 0 and writer is not None:
+                    dt, df = max(now - t_last, 1e-9), frame - frames_last
+                    writer.add_scalar("performance/step_inference_rl_update_fps", df / dt, frame)
+                    writer.add_scalar("performance/rl_update_time", upd_acc, frame)
+                    writer.add_scalar("performance/step_inference_time", play_acc, frame)
+                    writer.add_scalar("losses/a_loss", st["a_loss"], frame)
+                    writer.add_scalar("losses/c_loss", st["c_loss"], frame)
+                    writer.add_scalar("losses/entropy", st["entropy"], frame)
+                    writer.add_scalar("losses/bounds_loss", st["b_loss"], frame)
+                    writer.add_scalar("info/last_lr", st["lr"], frame)
+                    writer.add_scalar("info/lr_mul", 1.0, frame)
+                    writer.add_scalar("info/e_clip", self.cfg.e_clip, frame)
+                    writer.add_scalar("info/kl", st["kl"], frame)
+                    writer.add_scalar("info/epochs", epoch, frame)
+                    if have_games:
+                        for tag, val in (("rewards", mean_rewards), ("shaped_rewards", mean_rewards * self.cfg.reward_scale), ("episode_lengths", mean_lengths)):
+                            writer.add_scalar(tag + "/step", val, frame)
+                            writer.add_scalar(tag + "/iter", val, epoch)
+                            writer.add_scalar(tag + "/time", val, total_time)
+                t_last, frames_last, play_acc, upd_acc = now, frame, 0.0, 0.0
+                infos = self.episode_infos()
+                if self.rank == 0 and writer is not None:
+                    for k, v in infos.items():                 # RLGPUAlgoObserver.after_print_stats
+                        writer.add_scalar("Episode/" + k, v, frame)
                 if self.rank == 0 and log:
-                    log(f"epoch {self.epoch_num} frames {self.frame} reward {rew:.3f} len {length:.1f} ({cnt} eps) "
-                        f"meter[{len(self.game_rewards)}] {self.game_rewards.get_mean():.3f}/{self.game_lengths.get_mean():.1f} "
+                    log(f"epoch {epoch} frames {frame} reward {rew:.3f} len {length:.1f} ({cnt} eps) "
+                        f"meter[{len(self.game_rewards)}] {mean_rewards:.3f}/{mean_lengths:.1f} "
                         f"kl {st['kl']:.5f} lr {st['lr']:.2e} a_loss {st['a_loss']:.4f} c_loss {st['c_loss']:.4f}")
-                    infos = self.episode_infos()
                     if infos:
                         log("  Episode/ " + " ".join(f"{k}={v:.4g}" for k, v in infos.items()))
+                if self.rank == 0 and nn_dir and have_games:
+                    ck = f"{name}_ep_{epoch}_rew_{mean_rewards}"
+                    if save_freq > 0 and epoch % save_freq == 0 and mean_rewards <= self.last_mean_rewards:
+                        self.save(os.path.join(nn_dir, "last_" + ck + ".pth"))
+                    if mean_rewards > self.last_mean_rewards and epoch >= save_best_after:
+                        self.last_mean_rewards = mean_rewards
+                        self.save(os.path.join(nn_dir, name + ".pth"))
+                        if score_to_win is not None and mean_rewards > score_to_win:
+                            self.save(os.path.join(nn_dir, ck + ".pth"))
+                            max_epochs = self.epoch_num                 # "Network won": leave the loop like the reference
+                if self.rank == 0 and nn_dir and self.epoch_num >= max_epochs:
+                    tag = mean_rewards if have_games else float("-inf")
+                    self.save(os.path.join(nn_dir, f"last_{name}_ep_{epoch}_rew_{tag}.pth"))
         return self.mean_reward
 
     # ---- checkpoints: the reference's .pth schema  [ref: a2c_common.py:590-654] --------------------------

@@ -267,3 +267,28 @@ def test_reward_curves_tf32_vs_fp32_vs_recorded_oracle():
     assert abs(last["tf32"] - last["fp32"]) < 0.05, last             # seed-to-seed spread is ~0.1; the learners differ by < 0.01 in the record
     for name, v in last.items():
         assert 0.10 < v < 0.26, (name, v)                            # the oracle's recorded range, widened by the seed spread
+
+
+def test_train_loop_checkpoint_cadence_and_scalar_stream(tmp_path):
+    """A2CAgent.train with the reference's checkpoint cadence and scalar tags [ref: RLG/common/a2c_common.py:343-362,1399-1470]: the best
+    checkpoint `<name>.pth` appears once a mean reward beats the running best after `save_best_after`, `last_<name>_ep_<n>_rew_<r>.pth` at
+    max_epochs, every file loads back through the .pth schema, and the scalar stream carries the reference's tags."""
+    import json
+    from omniisaacgymenvs_loop_b200.rl.a2c import ScalarLog
+    cfg = UsvEnvConfig(num_envs=1024, max_episode_length=60)
+    env = make_env(cfg.to_task_cfg(), DEV, seed=5, collect_stats=False)
+    agent = A2CAgent(env, PPOConfig(seed=5, minibatch_size=8192), DEV)
+    nn_dir, log_path = os.path.join(tmp_path, "nn"), os.path.join(tmp_path, "scalars.jsonl")
+    w = ScalarLog(log_path)
+    agent.train(max_epochs=24, log_every=4, log=None, writer=w, nn_dir=nn_dir, name="USV", save_freq=8, save_best_after=8)
+    w.close()
+    files = sorted(os.listdir(nn_dir))
+    assert "USV.pth" in files and any(f.startswith("last_USV_ep_24_rew_") for f in files), files
+    ck = torch.load(os.path.join(nn_dir, "USV.pth"), weights_only=False)
+    assert set(ck) == {"model", "epoch", "optimizer", "frame", "last_mean_rewards", "env_state"} and 8 <= ck["epoch"] <= 24
+    tags = {json.loads(l)["tag"] for l in open(log_path)}
+    assert {"losses/a_loss", "losses/c_loss", "losses/entropy", "info/last_lr", "info/kl", "info/epochs", "rewards/step", "rewards/iter",
+            "rewards/time", "episode_lengths/step", "performance/step_inference_rl_update_fps"} <= tags, tags
+    fresh = A2CAgent(make_env(cfg.to_task_cfg(), DEV, seed=6, collect_stats=False), PPOConfig(seed=6, minibatch_size=8192), DEV)
+    fresh.restore(os.path.join(nn_dir, "USV.pth"))
+    assert fresh.epoch_num == ck["epoch"] and torch.equal(fresh.policy.views()["a2c_network.mu.weight"].cpu(), ck["model"]["a2c_network.mu.weight"].cpu())
