@@ -7,6 +7,7 @@
 //
 // HBM traffic per env-step (stats off, no disturbances): state 13+3 fields r/w (128 B), consts 13+35 fields (192 B), 4 field
 // taps (<= 4 x 32 B sectors), obs 132 B, action 8 B, reward 4 B, reset_buf 16 B  ->  ~610 B.
+#include <stdlib.h>
 #include "usv_step_core.cuh"
 
 namespace usv {
@@ -303,7 +304,7 @@ __device__ __forceinline__ void write_obs_tile_b(float* s_obs, float* __restrict
   __syncwarp();
 }
 
-template <int kDisturb, bool kStats>
+template <int kDisturb, bool kStats, bool kStage = true>
 __global__ void __launch_bounds__(kBlock, 3) step_live_kernel(UsvEnvBuffers b, UsvLiveBuffers lb, const float2* __restrict__ actions,
                                                               float* __restrict__ obs, float* __restrict__ rew, int64_t n,
                                                               const __grid_constant__ UsvStepParams p,
@@ -318,19 +319,37 @@ __global__ void __launch_bounds__(kBlock, 3) step_live_kernel(UsvEnvBuffers b, U
   o.sw = smem + (threadIdx.x >> 5) * (32 * kObsB) + (threadIdx.x & 31) * kObsB;
   o.chk = 0.0f;
   o.clip = p.clip_obs;
+  // The task part reads 35 per-episode constants per env (CoM + 16 obstacle centres) ~1500 instructions from here, one dependent
+  // load per obstacle (r02 ncu at 262 144 envs: 35 % of the stall samples sat on those loads, long-scoreboard 7.6 cycles per issue).
+  // A warp's tile of them is ONE contiguous 4480 B run in the AoSoA buffer: fetch it with cp.async now, wait right before the task part.
+  float* s_bc = smem + kBlock * kObsB + (threadIdx.x >> 5) * (USV_BC_COUNT * kTile);
+  if (kStage) {
+    const int64_t w0 = block_start + (int64_t)(threadIdx.x & ~31);
+    if (w0 < n) {
+      const float* src = lb.bconsts + (w0 >> 5) * (int64_t)(USV_BC_COUNT * kTile);
+      for (int q = threadIdx.x & 31; q < USV_BC_COUNT * kTile / 4; q += 32) {
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_bc + q * 4);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + q * 4) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  EnvState e;
+  EnvConst k;
+  LiveState ls;
+  DynOut s;
+  bool do_reset = false;
+  float2 act = make_float2(0.f, 0.f);
+  float* __restrict__ bs = lb.bstate + tile_base(active ? i : 0, USV_BS_COUNT);
+  float* __restrict__ bc = lb.bconsts + tile_base(active ? i : 0, USV_BC_COUNT);
   if (active) {
-    EnvState e;
-    EnvConst k;
-    LiveState ls;
     load_state(b.state, b.state_stride, i, e);
     load_consts<kDisturb>(b.consts, b.consts_stride, i, k);
-    float* __restrict__ bs = lb.bstate + tile_base(i, USV_BS_COUNT);
-    float* __restrict__ bc = lb.bconsts + tile_base(i, USV_BC_COUNT);
     ls.prev_h = bs[USV_BS_PREV_H * kTile];
     ls.prev_pot = bs[USV_BS_PREV_POT * kTile];
     ls.outcome = __float_as_int(bs[USV_BS_OUTCOME * kTile]);
-    const bool do_reset = b.reset_buf[i] != 0;
-    const float2 act = actions[i];
+    do_reset = b.reset_buf[i] != 0;
+    act = actions[i];
     const uint64_t gid = (uint64_t)(p.env_id_offset + i);
     if (do_reset && lp.com_rand) {  // MDD._randomize_com  [ref USV_disturbances.py:100-106]
       const Uniform4 rc = philox_uniform4(p.seed, gid, step, RS_RESET_COM);
@@ -338,9 +357,21 @@ __global__ void __launch_bounds__(kBlock, 3) step_live_kernel(UsvEnvBuffers b, U
       bc[USV_BC_COM_Y * kTile] = lp.com_base[1] + (rc.b * 2.0f - 1.0f) * lp.com_disp[1];
       bc[USV_BC_COM_Z * kTile] = lp.com_base[2] + (rc.c * 2.0f - 1.0f) * lp.com_disp[2];
     }
-    DynOut s;
     step_dynamics<kDisturb, true>(e, k, p, do_reset, act, gid, i, step, b.lut_left, b.lut_right, s);
-    post_live<kStats>(e, k, ls, bc, lb.field + i * (int64_t)(kGridB * kGridB), p, lp, do_reset, any_reset, p.first_call != 0, s, o);
+  }
+  // every lane of the warp (a ragged tail warp has inactive ones that issued copies too) waits for its own copies, then the warp
+  // meets: a __syncwarp inside the `active` branch would pair with the one in write_obs_tile_b that the inactive lanes reach first
+  if (kStage) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+  }
+  if (active) {
+    float* bcs = kStage ? s_bc + (threadIdx.x & 31) : bc;
+    if (kStage && do_reset && lp.com_rand) {   // the staged copy predates this step's CoM re-draw of a resetting env
+#pragma unroll
+      for (int j = 0; j < 3; ++j) bcs[(USV_BC_COM_X + j) * kTile] = bc[(USV_BC_COM_X + j) * kTile];
+    }
+    post_live<kStats>(e, k, ls, bcs, lb.field + i * (int64_t)(kGridB * kGridB), p, lp, do_reset, any_reset, p.first_call != 0, s, o);
     store_state(b.state, b.state_stride, i, e);
     if (do_reset) store_consts<kDisturb>(b.consts, b.consts_stride, i, k);
     bs[USV_BS_PREV_H * kTile] = ls.prev_h;
@@ -548,12 +579,31 @@ extern "C" int usv_step_live_f32(const UsvEnvBuffers* b, const UsvLiveBuffers* l
   if (!actions || !obs || !rew) return USV_E_NULL;
   if ((uintptr_t)actions & 7) return USV_E_ALIGN;
   const size_t smem = (size_t)kBlock * kObsB * sizeof(float);
+  const size_t smem_live = smem + (size_t)(kBlock / 32) * USV_BC_COUNT * kTile * sizeof(float);   // + the staged bconsts tiles
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(step_live_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_live);
+    cudaFuncSetAttribute(step_live_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_live);
+    cudaFuncSetAttribute(step_live_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_live);
+    cudaFuncSetAttribute(step_live_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_live);
+    attr = true;
+  }
   const int grid = grid_for(n, kBlock);
   const bool dis = p->use_force_disturbance || p->use_torque_disturbance || p->use_const_force || p->use_sin_force ||
                    p->use_const_torque || p->use_sin_torque;
   const bool st = lb->bstats != nullptr;
   cudaStream_t s = (cudaStream_t)stream;
-#define USV_LAUNCH_LIVE(D, S) step_live_kernel<D, S><<<grid, kBlock, smem, s>>>(*b, *lb, (const float2*)actions, obs, rew, n, *p, *lp)
+  // staged bconsts (cp.async into shared memory) vs direct loads, A/B on one B200 (r02, profiles/r02_live_kernels.md): 13.9 vs 14.9 us at
+  // 16 384 envs, 16.8 vs 18.4 at 65 536, 41.5 vs 44.7 at 131 072 -- but 83.5 vs 76.1 us at 262 144, where the 24 GB of per-env fields make
+  // every tap a DRAM access and the 36 KB of extra shared memory per CTA cost more L1 than the staging saves.  USV_LIVE_NO_STAGE / USV_LIVE_STAGE
+  // force one of them (profiling runs).
+  static const int force = getenv("USV_LIVE_NO_STAGE") ? 0 : (getenv("USV_LIVE_STAGE") ? 1 : -1);
+  const bool no_stage = force >= 0 ? force == 0 : n > 196608;
+#define USV_LAUNCH_LIVE(D, S)                                                                                                      \
+  do {                                                                                                                             \
+    if (no_stage) step_live_kernel<D, S, false><<<grid, kBlock, smem, s>>>(*b, *lb, (const float2*)actions, obs, rew, n, *p, *lp);  \
+    else step_live_kernel<D, S, true><<<grid, kBlock, smem_live, s>>>(*b, *lb, (const float2*)actions, obs, rew, n, *p, *lp);       \
+  } while (0)
 #define USV_LAUNCH_TASK(T, D) step_task_kernel<T, D><<<grid, kBlock, smem, s>>>(*b, *lb, (const float2*)actions, obs, rew, n, *p, *lp)
   if (lp->task == USV_TASK_GO_TO_POSE) { if (dis) USV_LAUNCH_TASK(USV_TASK_GO_TO_POSE, true); else USV_LAUNCH_TASK(USV_TASK_GO_TO_POSE, false); }
   else if (lp->task == USV_TASK_KEEP_XY) { if (dis) USV_LAUNCH_TASK(USV_TASK_KEEP_XY, true); else USV_LAUNCH_TASK(USV_TASK_KEEP_XY, false); }
