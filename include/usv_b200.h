@@ -262,6 +262,18 @@ int usv_step_fused_f32(const UsvEnvBuffers* b, const float* actions /*[n,2]*/,
                        float* obs /*[n,13]*/, float* rew /*[n]*/,
                        int64_t n, const UsvStepParams* p, void* stream);
 
+/* A7 stand-alone: the planar rigid body behind the simulator surface USVVirtual expects (HeronView.get_world_poses / get_velocities /
+ * set_*, <body>.apply_forces_and_torques_at_pos, world.step())  [ref: OIGE/tasks/USV_Virtual.py:772-774,1119-1133,1567-1572].
+ * wrench[n,3] accumulates (Fx, Fy, Tz) in the body frame over the apply_* calls of one physics step (forces / torques are the
+ * reference's [n,3] tensors, only their planar components enter; a force applied at the body-frame offset (offset_x, offset_y)
+ * -- a thruster mount -- adds r x F; is_global: rotate world-frame forces by R(psi)^T, pose[n,3] = (x, y, psi) then required);
+ * usv_planar_rigid_step_f32 integrates one sim dt with the fused step's semi-implicit Euler and clears the wrench.            */
+int usv_planar_wrench_accumulate_f32(float* wrench /*[n,3]*/, const float* forces /*[n,3] or NULL*/, const float* torques /*[n,3] or NULL*/,
+                                     const float* pose /*[n,3] or NULL*/, float offset_x, float offset_y, int32_t is_global, int64_t n,
+                                     void* stream);
+int usv_planar_rigid_step_f32(float* pose /*[n,3]*/, float* vel /*[n,3]: vx, vy (world), r*/, float* wrench /*[n,3]*/,
+                              const float* mass /*[n]*/, const float* izz /*[n]*/, float dt, int64_t n, void* stream);
+
 /* A9/A16-A18 stand-alone: the classic CaptureXYTask's get_state_observations / compute_reward / update_kills and
  * Penalties.compute_penalty on the CALLER's state tensors -- the same device code as the task part of usv_step_fused_f32, so the
  * reference's task classes can be fed identical state tensors and compared output by output.

@@ -185,6 +185,50 @@ __global__ void __launch_bounds__(256) randomize_rows_kernel(float* __restrict__
 
 using namespace usv;
 
+namespace usv {
+
+// ---- planar rigid body behind the simulator surface the task expects (row A7 as a stand-alone: HeronView / world.step()) ------------------
+// wrench[i] = (Fx, Fy, Tz) in the BODY frame, accumulated over the apply_forces_and_torques_at_pos calls of one physics step
+__global__ void planar_wrench_accumulate_kernel(float* __restrict__ wrench, const float* __restrict__ forces, const float* __restrict__ torques,
+                                                const float* __restrict__ pose, float off_x, float off_y, int is_global, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float fx = forces ? forces[i * 3] : 0.f, fy = forces ? forces[i * 3 + 1] : 0.f;
+  float tz = torques ? torques[i * 3 + 2] : 0.f;
+  if (is_global) {   // world -> body: R(psi)^T
+    float sn, cs;
+    sincosf(pose[i * 3 + 2], &sn, &cs);
+    const float bx = cs * fx + sn * fy, by = -sn * fx + cs * fy;
+    fx = bx; fy = by;
+  }
+  // a force applied at the body-frame offset (off_x, off_y) adds the moment r x F
+  tz += off_x * fy - off_y * fx;
+  wrench[i * 3] += fx;
+  wrench[i * 3 + 1] += fy;
+  wrench[i * 3 + 2] += tz;
+}
+
+// semi-implicit Euler of the planar body (the fused step's integrator, usv_step_core.cuh): pose (x, y, psi), vel (vx, vy world, r);
+// consumes and clears the accumulated wrench
+__global__ void planar_rigid_step_kernel(float* __restrict__ pose, float* __restrict__ vel, float* __restrict__ wrench,
+                                         const float* __restrict__ mass, const float* __restrict__ izz, float dt, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float sn, cs;
+  sincosf(pose[i * 3 + 2], &sn, &cs);
+  const float fx = wrench[i * 3], fy = wrench[i * 3 + 1], tz = wrench[i * 3 + 2];
+  const float inv_m = 1.0f / mass[i];
+  const float ax = (cs * fx - sn * fy) * inv_m, ay = (sn * fx + cs * fy) * inv_m;
+  float vx = vel[i * 3] + dt * ax, vy = vel[i * 3 + 1] + dt * ay, r = vel[i * 3 + 2] + dt * (tz / izz[i]);
+  vel[i * 3] = vx; vel[i * 3 + 1] = vy; vel[i * 3 + 2] = r;
+  pose[i * 3] += dt * vx;
+  pose[i * 3 + 1] += dt * vy;
+  pose[i * 3 + 2] += dt * r;
+  wrench[i * 3] = 0.f; wrench[i * 3 + 1] = 0.f; wrench[i * 3 + 2] = 0.f;
+}
+
+}  // namespace usv
+
 extern "C" {
 
 int usv_b200_abi_version(void) { return USV_B200_ABI_VERSION; }
@@ -309,6 +353,26 @@ int usv_randomize_rows_f32(float* dst, int64_t ld, const int64_t* env_ids, int64
                                                                                 lo, hi, log_space, seed, counter,
                                                                                 stream_id);
   return finish_launch();
+}
+
+
+int usv_planar_wrench_accumulate_f32(float* wrench, const float* forces, const float* torques, const float* pose, float offset_x,
+                                     float offset_y, int32_t is_global, int64_t n, void* stream) {
+  if (n < 0) return USV_E_SIZE;
+  if (n == 0) return USV_OK;
+  if (!wrench || (!forces && !torques) || (is_global && !pose)) return USV_E_NULL;
+  usv::planar_wrench_accumulate_kernel<<<usv::grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(wrench, forces, torques, pose, offset_x, offset_y,
+                                                                                               is_global, n);
+  return usv::finish_launch();
+}
+
+int usv_planar_rigid_step_f32(float* pose, float* vel, float* wrench, const float* mass, const float* izz, float dt, int64_t n, void* stream) {
+  if (n < 0) return USV_E_SIZE;
+  if (n == 0) return USV_OK;
+  if (!pose || !vel || !wrench || !mass || !izz) return USV_E_NULL;
+  if (!(dt > 0.0f)) return USV_E_PARAM;
+  usv::planar_rigid_step_kernel<<<usv::grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(pose, vel, wrench, mass, izz, dt, n);
+  return usv::finish_launch();
 }
 
 }  // extern "C"

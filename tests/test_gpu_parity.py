@@ -455,3 +455,59 @@ def test_captured_steps_equal_eager_steps():
     assert a.step_counter == b.step_counter and torch.equal(a.state, b.state)
     o1, o2 = a.step(warm)[0].clone(), b.step(warm)[0].clone()       # eager steps after replays stay in sequence
     assert torch.equal(o1, o2)
+
+
+def test_reference_style_apply_forces_on_the_planar_view_vs_float64_integration(golden):
+    """The simulator surface (robots.PlanarHeronView / PlanarWorld) driven the way the reference's USVVirtual.apply_forces drives Isaac Sim
+    [ref: OIGE/tasks/USV_Virtual.py:1103-1133 ; envs/vec_env_rlgames.py:154-171]: per physics sub-step the stand-alone force modules
+    (HydrodynamicsObject.ComputeHydrodynamicsEffects, DynamicsFirstOrder.update_forces) are evaluated on the view's poses / velocities,
+    pushed through base / thruster_left / thruster_right .apply_forces_and_torques_at_pos, and world.step() integrates -- against the float64
+    host integration of the same model (50 sub-steps)."""
+    from omniisaacgymenvs_loop_b200.robots import PlanarHeronView, PlanarWorld
+    n, dt = 512, 0.01
+    g = torch.Generator().manual_seed(6)
+    view = PlanarHeronView(n, DEV, mass=34.96, izz=10.0)
+    world = PlanarWorld(dt)
+    world.add(view)
+    pos = torch.zeros((n, 3)); pos[:, :2] = torch.rand((n, 2), generator=g) * 20 - 10
+    yaw = (torch.rand(n, generator=g) * 2 - 1) * math.pi
+    quat = torch.stack([torch.cos(yaw / 2), torch.zeros(n), torch.zeros(n), torch.sin(yaw / 2)], 1)
+    vel6 = torch.zeros((n, 6)); vel6[:, :2] = torch.rand((n, 2), generator=g) * 3 - 1.5; vel6[:, 5] = torch.rand(n, generator=g) * 2 - 1
+    view.set_world_poses(pos.to(DEV), quat.to(DEV))
+    view.set_velocities(vel6.to(DEV))
+    p, q = view.get_world_poses()
+    assert_close(p, pos, 0, 1e-6); assert_close(q, quat, 0, 1e-6); assert_close(view.get_velocities(), vel6, 0, 0)
+    D = _hydro(n)
+    GF = golden("force_modules")
+    Tm = DynamicsFirstOrder(dict(THR_CFG), n, DEV, 0.05, dt, 1000, GF["lut_classic_points_left"].tolist(), GF["lut_classic_points_right"].tolist(),
+                            [0.0] * 5, [0.0] * 5, -1.0, 1.0)
+    cmd = (torch.rand((n, 2), generator=g) * 2 - 1).to(DEV)
+    Tm.set_target_force(cmd)
+    target = Tm.thruster_forces_before_dynamics.double().cpu().numpy()
+    d = lambda t: t.double().cpu().numpy().copy()
+    lin, quad = torch.tensor(LIN)[[0, 1, 5]].double().numpy(), torch.tensor(QUAD)[[0, 1, 5]].double().numpy()
+    state = dict(x=d(pos[:, 0]), y=d(pos[:, 1]), psi=d(yaw), vx=d(vel6[:, 0]), vy=d(vel6[:, 1]), r=d(vel6[:, 5]), thrL=np.zeros(n), thrR=np.zeros(n))
+    const = dict(mass=np.full(n, 34.96), lin=np.tile(lin, (n, 1)), quad=np.tile(quad, (n, 1)), kdrag=np.ones(n), kiz=np.ones(n))
+    ref = integrator64.substeps(state, const, target, dt=dt, alpha=float(torch.exp(torch.tensor(-dt / 0.05))), n_substeps=50, izz=10.0,
+                                thr_y_left=0.377654, thr_y_right=-0.377654)
+    for _ in range(50):                                        # == USVVirtual.apply_forces() + world.step(), once per sub-step
+        _, quats = view.get_world_poses()
+        drag = D.ComputeHydrodynamicsEffects(dt, quats, view.get_velocities(), False, [0, 0, 0])
+        thr = Tm.update_forces()                               # [n,6]: left thrust in [:, :3], right in [:, 3:], along the thruster x axis
+        view.base.apply_forces_and_torques_at_pos(forces=drag[:, :3].contiguous(), torques=drag[:, 3:].contiguous(), is_global=False)
+        view.thruster_left.apply_forces_and_torques_at_pos(forces=thr[:, :3].contiguous(), is_global=False)
+        view.thruster_right.apply_forces_and_torques_at_pos(forces=thr[:, 3:].contiguous(), is_global=False)
+        world.step(render=False)
+    assert world.current_time_step_index == 50
+    for col, key in ((0, "x"), (1, "y")):
+        assert np.abs(view.pose[:, col].double().cpu().numpy() - ref[key]).max() < 3e-4, key
+    for col, key in ((0, "vx"), (1, "vy"), (2, "r")):
+        assert np.abs(view.vel[:, col].double().cpu().numpy() - ref[key]).max() < 3e-4, key
+    dpsi = view.pose[:, 2].double().cpu().numpy() - ref["psi"]
+    assert np.abs((dpsi + math.pi) % (2 * math.pi) - math.pi).max() < 3e-4
+    # a world-frame force is rotated into the body frame: pushing along +x_world accelerates vx only, whatever the heading
+    view.vel.zero_(); view.wrench.zero_()
+    f = torch.zeros((n, 3), device=DEV); f[:, 0] = 34.96
+    view.base.apply_forces_and_torques_at_pos(forces=f, is_global=True)
+    world.step()
+    assert_close(view.vel[:, 0], torch.full((n,), dt), 1e-5, 1e-7); assert float(view.vel[:, 1].abs().max()) < 1e-6 and float(view.wrench.abs().max()) == 0.0
