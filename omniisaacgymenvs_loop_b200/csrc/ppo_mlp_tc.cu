@@ -18,6 +18,7 @@
 // which remain the numerics reference.
 #include <cooperative_groups.h>
 #include <math_constants.h>
+#include <stdlib.h>
 #include <string.h>
 #include "philox.cuh"
 #include "usv_common.cuh"
