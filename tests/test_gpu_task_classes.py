@@ -141,3 +141,59 @@ def test_kill_curriculum_vs_reference_golden(golden):
     for k, step in enumerate(G["steps"].tolist()):
         assert torch.equal(task.update_kills(step).cpu(), torch.from_numpy(G["die"][k])), f"curriculum step {step}"
     assert int(G["die"].sum()) > 0 and int((1 - G["die"]).sum()) > 0
+
+
+def test_round2_entry_points_edge_sizes_and_error_codes():
+    """Empty / ragged inputs and the documented error codes of the entry points added in round 2 (stand-alone CaptureXY task calls, planar
+    rigid-body view, SysID student, fused multi-rank minibatch step): n = 0 is a no-op, NULL / size / parameter errors come back as codes,
+    CPU tensors and CPU devices are refused by the Python surfaces (no silent fallback)."""
+    import ctypes
+    from omniisaacgymenvs_loop_b200 import _lib
+    from omniisaacgymenvs_loop_b200.algo.ppo.module import StateHistoryEncoder
+    from omniisaacgymenvs_loop_b200.robots import PlanarHeronView
+    L, E = _lib.lib(), _lib.ENUMS
+    z, st = ctypes.c_void_p(0), _lib.stream()
+    p = UsvEnvConfig().to_params()
+    io = _lib.UsvCaptureXYIO()
+    io.what = E["USV_CXY_OBS"]
+    assert L.usv_capturexy_obs_reward_done_f32(ctypes.byref(io), ctypes.c_int64(0), ctypes.byref(p), st) == 0
+    assert L.usv_capturexy_obs_reward_done_f32(ctypes.byref(io), ctypes.c_int64(-1), ctypes.byref(p), st) == E["USV_E_SIZE"]
+    assert L.usv_capturexy_obs_reward_done_f32(ctypes.byref(io), ctypes.c_int64(4), ctypes.byref(p), st) == E["USV_E_NULL"]
+    assert L.usv_capturexy_obs_reward_done_f32(z, ctypes.c_int64(4), ctypes.byref(p), st) == E["USV_E_NULL"]
+    io.what = 0
+    assert L.usv_capturexy_obs_reward_done_f32(ctypes.byref(io), ctypes.c_int64(4), ctypes.byref(p), st) == E["USV_E_PARAM"]
+    # ragged sizes through the class surface: 1, 31, 257 envs against the golden's first rows repeated
+    for n in (1, 31, 257):
+        env = UsvEnvConfig().to_task_cfg()["env"]
+        task = task_factory.get(env["task_parameters"], env["reward_parameters"], n, DEV)
+        stt = {"position": torch.full((n, 2), 3.0, device=DEV), "orientation": torch.tensor([[1.0, 0.0]], device=DEV).repeat(n, 1),
+               "linear_velocity": torch.zeros((n, 2), device=DEV), "angular_velocity": torch.zeros(n, device=DEV)}
+        obs = task.get_state_observations(stt, "local")
+        assert obs.shape == (n, 13) and float((obs[:, 5] - 18.0 ** 0.5).abs().max()) < 1e-5
+        assert task.update_kills(0).sum() == 0
+    with pytest.raises(_lib.UsvLibraryError):
+        task_factory.get(env["task_parameters"], env["reward_parameters"], 4, "cpu")
+    # planar view
+    w = torch.zeros((4, 3), device=DEV)
+    assert L.usv_planar_wrench_accumulate_f32(_lib.ptr(w), z, z, z, ctypes.c_float(0), ctypes.c_float(0), ctypes.c_int32(0), ctypes.c_int64(4), st) == E["USV_E_NULL"]
+    assert L.usv_planar_wrench_accumulate_f32(_lib.ptr(w), _lib.ptr(w), z, z, ctypes.c_float(0), ctypes.c_float(0), ctypes.c_int32(1), ctypes.c_int64(4), st) == E["USV_E_NULL"]
+    assert L.usv_planar_rigid_step_f32(_lib.ptr(w), _lib.ptr(w), _lib.ptr(w), _lib.ptr(w), _lib.ptr(w), ctypes.c_float(0.0), ctypes.c_int64(4), st) == E["USV_E_PARAM"]
+    assert L.usv_planar_rigid_step_f32(z, z, z, z, z, ctypes.c_float(0.01), ctypes.c_int64(0), st) == 0
+    with pytest.raises(_lib.UsvLibraryError):
+        PlanarHeronView(4, "cpu")
+    # SysID student
+    assert L.dagger_history_encoder_param_count(ctypes.c_int32(25), ctypes.c_int32(50), ctypes.c_int32(8)) == 20136
+    assert L.dagger_history_encoder_param_count(ctypes.c_int32(25), ctypes.c_int32(30), ctypes.c_int32(8)) == -1
+    assert L.dagger_history_encoder_param_count(ctypes.c_int32(40), ctypes.c_int32(50), ctypes.c_int32(8)) == -1
+    assert L.dagger_history_encoder_forward_f32(z, z, ctypes.c_int64(1250), ctypes.c_int32(25), ctypes.c_int32(50), ctypes.c_int32(8), z, ctypes.c_int64(0), st) == 0
+    assert L.dagger_history_encoder_forward_f32(z, z, ctypes.c_int64(1250), ctypes.c_int32(25), ctypes.c_int32(50), ctypes.c_int32(8), z, ctypes.c_int64(3), st) == E["USV_E_NULL"]
+    assert L.dagger_history_encoder_forward_f32(z, z, ctypes.c_int64(100), ctypes.c_int32(25), ctypes.c_int32(50), ctypes.c_int32(8), z, ctypes.c_int64(3), st) == E["USV_E_SIZE"]
+    enc = StateHistoryEncoder("LeakyReLU", 25, 50, 8, DEV, seed=1)
+    assert enc(torch.zeros((1, 1250), device=DEV)).shape == (1, 8)                       # a single sample: one warp of one CTA
+    with pytest.raises(NotImplementedError):
+        StateHistoryEncoder("LeakyReLU", 25, 30, 8, DEV)
+    with pytest.raises(_lib.UsvLibraryError):
+        StateHistoryEncoder("LeakyReLU", 25, 50, 8, "cpu")
+    # fused multi-rank minibatch step: a window that is too small, a rank outside the world
+    assert L.ppo_minibatch_step_peer_entries(ctypes.c_int32(13)) == 293 * 64 and L.ppo_minibatch_step_peer_entries(ctypes.c_int32(60)) == -1
+    torch.cuda.synchronize()
