@@ -99,6 +99,36 @@ class AverageMeter:
         return int(self.current_size)
 
 
+def state_signature(tensors) -> torch.Tensor:
+    """Exact (bit-pattern) checksum of a list of fp32 / int32 tensors: [sum of words, position-weighted sum of words, word count] as int64.
+    Two ranks hold bit-identical state iff their signatures are equal (up to the collision odds of two 64-bit sums)."""
+    words = torch.cat([t.detach().reshape(-1).view(torch.int32) if t.dtype in (torch.float32, torch.int32) else t.detach().reshape(-1).to(torch.int32)
+                       for t in tensors]).to(torch.int64)
+    idx = torch.arange(1, words.numel() + 1, device=words.device, dtype=torch.int64)
+    return torch.stack([words.sum(), (words * idx).sum(), torch.tensor(words.numel(), device=words.device, dtype=torch.int64)])
+
+
+def ranks_hold_identical(tensors, world: int, group=None) -> bool:
+    """All-gather of state_signature(): True when every rank of the group holds bit-identical copies (any backend: nccl on the GPUs, gloo in
+    the CPU tests)."""
+    if world <= 1:
+        return True
+    sig = state_signature(tensors)
+    sigs = [torch.empty_like(sig) for _ in range(world)]
+    dist.all_gather(sigs, sig, group=group)
+    return all(torch.equal(s, sigs[0]) for s in sigs)
+
+
+def reduce_episode_stats(acc: torch.Tensor, world: int, group=None):
+    """(sum of returns, sum of lengths, count) of the finished episodes summed over ranks -> (mean return, mean length, count)
+    [ref: the per-print reward / length statistics of RLG/common/a2c_common.py:1399-1418 at N ranks]."""
+    acc = acc.clone()
+    if world > 1:
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
+    s, l, c = acc.tolist()
+    return (s / c, l / c, int(c)) if c > 0 else (float("nan"), float("nan"), 0)
+
+
 class ScalarLog:
     """add_scalar(tag, value, step) into a JSON-lines file: the scalar stream the reference sends to tensorboardX's SummaryWriter
     [ref: RLG/common/a2c_common.py:343-362], for an image without tensorboard.  Any object with that method can be passed instead."""
@@ -335,24 +365,14 @@ class A2CAgent:
 
     def ranks_identical(self) -> bool:
         """True when every rank holds bit-identical parameters, Adam moments and learning rate (all-gather of an exact checksum)."""
-        if not self.multi_gpu:
-            return True
         P = self.policy
-        words = torch.cat([P.params, P.exp_avg, P.exp_avg_sq, P.lr]).view(torch.int32).to(torch.int64)
-        idx = torch.arange(1, words.numel() + 1, device=self.device, dtype=torch.int64)
-        sig = torch.stack([words.sum(), (words * idx).sum(), P.step.to(torch.int64).sum()])
-        sigs = [torch.empty_like(sig) for _ in range(self.world)]
-        dist.all_gather(sigs, sig)
-        return all(torch.equal(s, sigs[0]) for s in sigs)
+        return ranks_hold_identical([P.params, P.exp_avg, P.exp_avg_sq, P.lr, P.step], self.world)
 
     def episode_stats(self):
         """Mean return / length of the episodes finished since the last call, reduced over ranks (one small all-reduce)."""
-        acc = self.episode_acc.clone()
-        if self.multi_gpu:
-            dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+        out = reduce_episode_stats(self.episode_acc, self.world)
         self.episode_acc.zero_()
-        s, l, c = acc.tolist()
-        return (s / c, l / c, int(c)) if c > 0 else (float("nan"), float("nan"), 0)
+        return out
 
     def episode_infos(self) -> dict:
         """Episode/<key>: the mean of extras['episode'][key] over the steps since the last call (RLGPUAlgoObserver.after_print_stats)."""

@@ -51,8 +51,24 @@ def _worker(rank, world, port, q):
         # --- episode statistics: (sum of returns, sum of lengths, count) reduced once per epoch
         acc = torch.tensor([10.0 * (rank + 1), 100.0 * (rank + 1), 2.0 * (rank + 1)], dtype=torch.float64)
         dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+        # --- PRODUCT host logic of the N > 1 path (rl/a2c.py), on CPU tensors over gloo: the cross-rank identity check that bench.py /
+        #     train() run after the fused gradient exchange, and the episode-statistics reduction
+        from omniisaacgymenvs_loop_b200.rl.a2c import ranks_hold_identical, reduce_episode_stats, state_signature
+        same = [torch.arange(100, dtype=torch.float32) * 0.37, torch.full((7,), 3, dtype=torch.int32)]
+        ident = ranks_hold_identical(same, world)
+        off_by_one_ulp = [same[0].clone(), same[1]]
+        if rank == 1:
+            off_by_one_ulp[0][41] = torch.nextafter(off_by_one_ulp[0][41], torch.tensor(1e9))
+        differ = ranks_hold_identical(off_by_one_ulp, world)
+        swapped = [same[0].clone(), same[1]]
+        if rank == 1:
+            swapped[0][[3, 4]] = swapped[0][[4, 3]]                 # same multiset of words, another order: the weighted sum catches it
+        differ2 = ranks_hold_identical(swapped, world)
+        stats = reduce_episode_stats(torch.tensor([10.0 * (rank + 1), 100.0 * (rank + 1), 2.0 * (rank + 1)], dtype=torch.float64), world)
+        empty = reduce_episode_stats(torch.zeros(3, dtype=torch.float64), world)
+        assert state_signature(same).dtype == torch.int64
         if rank == 0:
-            q.put((torch.cat(gathered, 1).numpy(), span.numpy(), params.numpy(), acc.numpy()))
+            q.put((torch.cat(gathered, 1).numpy(), span.numpy(), params.numpy(), acc.numpy(), (ident, differ, differ2, stats, empty)))
         dist.barrier()
     finally:
         dist.destroy_process_group()
@@ -66,7 +82,7 @@ def test_two_rank_sharding_matches_single_rank():
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    sharded, span, params, acc = q.get(timeout=180)
+    sharded, span, params, acc, product = q.get(timeout=180)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -84,6 +100,9 @@ def test_two_rank_sharding_matches_single_rank():
     assert np.allclose(span, np.arange(10) * 1.5)                # (1x + 2x)/2
     assert np.all(params == 7.0)
     assert np.allclose(acc, [30.0, 300.0, 6.0])
+    ident, differ, differ2, stats, empty = product
+    assert ident is True and differ is False and differ2 is False            # one ulp on one rank, or two swapped words, is a divergence
+    assert stats == (5.0, 50.0, 6) and empty[2] == 0 and np.isnan(empty[0])
 
 
 def test_averaged_gradient_step_equals_big_batch_step():
