@@ -236,6 +236,12 @@ typedef struct {
   int32_t kdrag_rand; float kdrag_min, kdrag_max; int32_t kdrag_log;
   int32_t thr_rand, thr_separate; float thr_rand_frac, thr_left_frac, thr_right_frac;
   int32_t mass_coupling; float couple_mass_max, couple_thr_a, couple_kiz_min, couple_kiz_max;
+  int32_t couple_targets;                  /* which scalars the mass-driven coupling overrides: bit 0 drag_scale, bit 1 thruster,
+                                              bit 2 yaw_inertia (7 = the shipped target list)  [ref: OIGE/tasks/USV_Virtual.py:393-411] */
+  int32_t kiz_rand, kiz_log;               /* independent episode-wise k_Iz ~ U / log-U [couple_kiz_min, couple_kiz_max] when yaw_inertia is
+                                              not a coupling target  [ref: OIGE/tasks/USV_Virtual.py:153-170,193-214,1532-1533] */
+  int32_t use_water_current; float flow_vel_xy[2];   /* env.water_current: drag acts on the velocity relative to a uniform world-frame
+                                              flow  [ref: OIGE/envs/USV/Hydrodynamics.py:224-237 ; OIGE/tasks/USV_Virtual.py:444-445,1111-1116] */
   float force_const_min, force_const_max, force_sin_min, force_sin_max;
   float force_min_freq, force_max_freq, force_min_shift, force_max_shift;
   float torque_const_min, torque_const_max, torque_sin_min, torque_sin_max;
@@ -374,7 +380,7 @@ typedef struct {
    * minmax -> active ? clamp(2*((x - a)/b) - 1, +-1) : 0 with a = min, b = max - min  (USV_Virtual.py:97-151,905-970) */
   float priv_a[4], priv_b[4]; int32_t priv_active[4];
   /* CoM re-draw at reset [ref: USV_disturbances.py:88-124] (observation only: the planar integrator has no CoM offset) */
-  int32_t com_rand; float com_base[3], com_disp[3];
+  int32_t com_rand; float com_base[3], com_disp[3];   /* com_rand: 0 off, 1 box +-com_disp per axis, 2 legacy XY disc of radius com_disp[0] */
   /* task */
   float collision_threshold;    /* 1.2  (:103)                                                       */
   float map_size;               /* 30.0                                                              */

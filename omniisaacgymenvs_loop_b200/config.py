@@ -203,8 +203,13 @@ class UsvEnvConfig:
     mass_coupling: bool = False
     couple_mass_max: float = 54.96
     couple_thr_a: float = 0.5
-    couple_kiz_min: float = 1.0
+    couple_kiz_min: float = 1.0              # inertia.k_Iz_min / k_Iz_max: the range of the coupled AND of the independent k_Iz
     couple_kiz_max: float = 1.5
+    couple_targets: int = 7                  # coupling.mass_driven.targets as bits: 1 drag_scale, 2 thruster, 4 yaw_inertia
+    kiz_rand: bool = False                   # inertia.use_yaw_inertia_randomization (independent draw; a yaw_inertia coupling target wins)
+    kiz_log: bool = False                    # inertia.k_Iz_sample_space == "log"
+    use_water_current: bool = False          # env.water_current  [ref: OIGE/tasks/USV_Virtual.py:444-445]
+    flow_vel_xy: Tuple[float, float] = (0.0, 0.0)
     force_const_min: float = 0.0
     force_const_max: float = 2.5
     force_sin_min: float = 0.0
@@ -302,7 +307,8 @@ class UsvEnvConfig:
             "env": {"numEnvs": self.num_envs, "envSpacing": self.env_spacing, "maxEpisodeLength": self.max_episode_length,
                     "action_mode": "Continuous", "horizon_length": self.horizon_length, "observation_frame": "local",
                     "controlFrequencyInv": self.n_substeps, "clipObservations": {"state": self.clip_obs}, "clipActions": self.clip_actions,
-                    "water_current": {"use_water_current": False, "flow_velocity": [0.0, 0.0, 0.0]},
+                    "water_current": {"use_water_current": self.use_water_current,
+                                      "flow_velocity": [self.flow_vel_xy[0], self.flow_vel_xy[1], 0.0]},
                     "disturbances": {
                         "forces": dict(use_force_disturbance=self.use_force_disturbance, use_constant_force=self.use_const_force,
                                        use_sinusoidal_force=self.use_sin_force, force_const_min=self.force_const_min,
@@ -378,6 +384,7 @@ class UsvEnvConfig:
         hd, hs, thr = dyn["hydrodynamics"], dyn["hydrostatics"], dyn["thrusters"]
         L, Q = hd["linear_damping"], hd["quadratic_damping"]
         fw = hd["linear_damping_forward_speed"]
+        wc = env.get("water_current", {}) or {}
 
         num_envs = env["numEnvs"] if isinstance(env["numEnvs"], int) else 512
         clip_obs = env.get("clipObservations", {"state": 12.0})
@@ -418,6 +425,8 @@ class UsvEnvConfig:
             torque_const_min=t["torque_const_min"], torque_const_max=t["torque_const_max"], torque_sin_min=t["torque_sin_min"],
             torque_sin_max=t["torque_sin_max"], torque_min_freq=t["torque_min_freq"], torque_max_freq=t["torque_max_freq"],
             torque_min_shift=t["torque_min_shift"], torque_max_shift=t["torque_max_shift"],
+            use_water_current=bool(wc.get("use_water_current", False)),
+            flow_vel_xy=tuple(float(x) for x in (list(wc.get("flow_velocity", [0.0, 0.0, 0.0])) + [0.0, 0.0])[:2]),
         )
         return dataclasses.replace(cfg, **overrides)
 
@@ -434,7 +443,7 @@ class UsvLiveConfig:
     priv_a: Tuple[float, float, float, float] = (1.0, 0.5, 0.5, 1.0)
     priv_b: Tuple[float, float, float, float] = (0.5, 0.5, 0.5, 0.5)
     priv_active: Tuple[bool, bool, bool, bool] = (True, True, True, True)
-    com_rand: bool = True
+    com_rand: int = 1                        # 0 off, 1 box (com_displacement_xyz), 2 legacy XY disc (CoM_max_displacement in com_disp[0])
     com_base: Tuple[float, float, float] = (0.0, 0.0, 0.0)
     com_disp: Tuple[float, float, float] = (0.15, 0.05, 0.02)
     collision_threshold: float = 1.2
@@ -507,17 +516,24 @@ class UsvLiveConfig:
         if source not in ("sim", "base"):
             raise ValueError(f"mass.masscom_obs_source must be 'sim' or 'base', got {source}")      # [ref: USV_Virtual.py:469-472]
         disp = m.get("com_displacement_xyz", None)
-        if disp is None and float(m.get("CoM_max_displacement", 0.0) or 0.0) > 0.0:
-            raise NotImplementedError("legacy disc-shaped CoM randomisation is not built into the fused live step")
+        legacy = float(m.get("CoM_max_displacement", 0.0) or 0.0)       # legacy XY disc, used when no box is given  [ref: USV_disturbances.py:108-124]
+        com_rand = 0
+        if bool(m.get("add_mass_disturbances", False)):
+            com_rand = 1 if disp is not None else (2 if legacy > 0.0 else 0)
+        if com_rand == 2:
+            disp = [legacy, 0.0, 0.0]
         scale = m.get("com_obs_scale", None) or [hs["box_length"], hs["box_width"], max(hs["heron_zero_height"], 1.0)]
         return cls(priv_mode=mode, mass_obs_relative=str(m.get("mass_obs_mode", "raw")) == "relative",
                    com_obs_scaled=str(m.get("com_obs_mode", "raw")) == "scaled", com_scale=tuple(float(x) for x in scale),
                    priv_a=tuple(pa), priv_b=tuple(pb), priv_active=tuple(active),
-                   com_rand=bool(m.get("add_mass_disturbances", False)) and disp is not None,
+                   com_rand=com_rand,
                    com_base=tuple(float(x) for x in m.get("base_com", [0.0, 0.0, 0.0])),
                    com_disp=tuple(float(x) for x in (disp or [0.0, 0.0, 0.0])),
                    fixed_horizon_eval=bool(env.get("fixed_horizon_eval", False)), masscom_obs_base=source == "base",
                    priv_dim=int(env.get("priv_dim", env.get("mass_dim", 4))))           # [ref: USV_Virtual.py:484]
+
+
+COUPLE_BITS = {"drag_scale": 1, "thruster": 2, "yaw_inertia": 4}
 
 
 def live_env_config(task_cfg: dict, **overrides) -> "UsvEnvConfig":
@@ -528,11 +544,13 @@ def live_env_config(task_cfg: dict, **overrides) -> "UsvEnvConfig":
     ap = env.get("action_processing", {}) or {}
     cp = (dist.get("coupling", {}) or {}).get("mass_driven", {}) or {}
     targets = set(cp.get("targets", []) or []) if cp.get("enabled", False) else set()
-    if targets and targets != {"drag_scale", "thruster", "yaw_inertia"}:
-        raise NotImplementedError("mass-driven coupling is built for the full target set [drag_scale, thruster, yaw_inertia]")
+    unknown = targets - set(COUPLE_BITS)
+    if unknown:
+        raise ValueError(f"coupling.mass_driven.targets: unknown target(s) {sorted(unknown)}")
     rp, m, dr, th, inr = env["reward_parameters"], dist["mass"], dist["drag"], dist["thruster"], dist.get("inertia", {}) or {}
-    if bool(inr.get("use_yaw_inertia_randomization", False)) and not targets:
-        raise NotImplementedError("independent k_Iz randomisation is not built into the fused step (coupled mode is)")
+    space = str(inr.get("k_Iz_sample_space", "linear"))
+    if space not in ("linear", "log"):
+        raise ValueError(f"k_Iz_sample_space must be 'linear' or 'log', got {space}")           # [ref: USV_Virtual.py:426-429]
     live = dict(
         action_affine=bool(ap.get("use_affine_thrust_mapping", True)), penalties_use_u=bool(ap.get("penalties_use_thrust_u", False)),
         action_bias=float(ap.get("initial_action_bias", 0.0)), action_bias_steps=int(ap.get("initial_action_bias_steps", 0)),
@@ -540,6 +558,8 @@ def live_env_config(task_cfg: dict, **overrides) -> "UsvEnvConfig":
         position_scale=rp.get("position_scale", 1.5), align_la1=rp.get("align_la1", 0.04),
         mass_coupling=bool(targets), couple_mass_max=float(m.get("max_mass", 0.0)), couple_thr_a=float(th.get("thruster_rand", 0.0)),
         couple_kiz_min=float(inr.get("k_Iz_min", 1.0)), couple_kiz_max=float(inr.get("k_Iz_max", 1.0)),
+        couple_targets=sum(COUPLE_BITS[t] for t in targets) if targets else 7,
+        kiz_rand=bool(inr.get("use_yaw_inertia_randomization", False)), kiz_log=space == "log",
         use_drag_scale=bool(dr.get("use_drag_scale_randomization", False)) or "drag_scale" in targets,
     )
     live.update(overrides)
@@ -574,15 +594,17 @@ def live_task_cfg(cfg: Optional["UsvEnvConfig"] = None, live: Optional["UsvLiveC
     env["fixed_horizon_eval"] = live.fixed_horizon_eval
     env["action_processing"] = {"use_affine_thrust_mapping": cfg.action_affine, "initial_action_bias": cfg.action_bias,
                                 "initial_action_bias_steps": cfg.action_bias_steps, "penalties_use_thrust_u": cfg.penalties_use_u}
-    dist["coupling"] = {"mass_driven": {"enabled": cfg.mass_coupling, "targets": ["drag_scale", "thruster", "yaw_inertia"]}}
-    dist["mass"].update(com_displacement_xyz=list(live.com_disp) if live.com_rand else None, base_com=list(live.com_base),
+    dist["coupling"] = {"mass_driven": {"enabled": cfg.mass_coupling,
+                                        "targets": [t for t, bit in COUPLE_BITS.items() if int(cfg.couple_targets) & bit]}}
+    dist["mass"].update(com_displacement_xyz=list(live.com_disp) if int(live.com_rand) == 1 else None,
+                        CoM_max_displacement=float(live.com_disp[0]) if int(live.com_rand) == 2 else 0.0, base_com=list(live.com_base),
                         apply_com_to_sim=True, mass_obs_mode="relative" if live.mass_obs_relative else "raw",
                         com_obs_mode="scaled" if live.com_obs_scaled else "raw",
                         masscom_obs_source="base" if live.masscom_obs_base else "sim")
     dist["drag"]["use_drag_scale_randomization"] = cfg.kdrag_rand
     dist["thruster"]["thruster_rand"] = cfg.couple_thr_a if cfg.mass_coupling else cfg.thr_rand_frac
-    dist["inertia"] = {"use_yaw_inertia_randomization": False, "k_Iz_min": cfg.couple_kiz_min, "k_Iz_max": cfg.couple_kiz_max,
-                       "k_Iz_sample_space": "linear"}
+    dist["inertia"] = {"use_yaw_inertia_randomization": bool(cfg.kiz_rand), "k_Iz_min": cfg.couple_kiz_min, "k_Iz_max": cfg.couple_kiz_max,
+                       "k_Iz_sample_space": "log" if cfg.kiz_log else "linear"}
     t["dynamics"]["hydrostatics"].update(box_length=live.com_scale[0], box_width=live.com_scale[1])
     return t
 

@@ -313,7 +313,7 @@ static int check_common(const UsvEnvBuffers* b, int64_t n, const UsvStepParams* 
 
 static bool wants_disturb(const UsvStepParams* p) {
   return p->use_force_disturbance || p->use_torque_disturbance || p->use_const_force || p->use_sin_force ||
-         p->use_const_torque || p->use_sin_torque;
+         p->use_const_torque || p->use_sin_torque || p->use_water_current;   // a water current rides in the generic variant
 }
 
 static size_t step_smem(const UsvStepParams* p) { return (size_t)(kBlock * kObs + 2 * p->n_lut) * sizeof(float); }
@@ -423,7 +423,7 @@ int usv_step_fused_f32(const UsvEnvBuffers* b, const float* actions, float* obs,
     ensure_smem(step_fused_kernel<D, S>, smem);                                                            \
     step_fused_kernel<D, S><<<grid, kBlock, smem, s>>>(*b, (const float2*)actions, obs, rew, n, *p);       \
   } while (0)
-  const bool all4 = p->use_const_force && p->use_sin_force && p->use_const_torque && p->use_sin_torque;
+  const bool all4 = p->use_const_force && p->use_sin_force && p->use_const_torque && p->use_sin_torque && !p->use_water_current;
   if (dis && all4 && !st) USV_LAUNCH_STEP(2, false);
   else if (dis && st) USV_LAUNCH_STEP(1, true);
   else if (dis) USV_LAUNCH_STEP(1, false);

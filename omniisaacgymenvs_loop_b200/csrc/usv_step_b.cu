@@ -304,6 +304,24 @@ __device__ __forceinline__ void write_obs_tile_b(float* s_obs, float* __restrict
   __syncwarp();
 }
 
+// MDD._randomize_com for one resetting env: com_rand 1 = per-axis box around base_com (com_displacement_xyz), 2 = the legacy disc in
+// the XY plane (radius U[0, CoM_max_displacement) kept in com_disp[0], angle U[0, 2 pi), z untouched)  [ref USV_disturbances.py:100-124]
+__device__ __forceinline__ void redraw_com(const UsvLiveParams& lp, const Uniform4& rc, float* __restrict__ bc) {
+  if (lp.com_rand == 2) {
+    const float r = rc.a * lp.com_disp[0];
+    const float th = rc.b * USV_PI_F * 2.0f;
+    float sn, cs;
+    fsincos(th, &sn, &cs);
+    bc[USV_BC_COM_X * kTile] = lp.com_base[0] + cs * r;
+    bc[USV_BC_COM_Y * kTile] = lp.com_base[1] + sn * r;
+    bc[USV_BC_COM_Z * kTile] = lp.com_base[2];
+  } else {
+    bc[USV_BC_COM_X * kTile] = lp.com_base[0] + (rc.a * 2.0f - 1.0f) * lp.com_disp[0];
+    bc[USV_BC_COM_Y * kTile] = lp.com_base[1] + (rc.b * 2.0f - 1.0f) * lp.com_disp[1];
+    bc[USV_BC_COM_Z * kTile] = lp.com_base[2] + (rc.c * 2.0f - 1.0f) * lp.com_disp[2];
+  }
+}
+
 template <int kDisturb, bool kStats, bool kStage = true>
 __global__ void __launch_bounds__(kBlock, 3) step_live_kernel(UsvEnvBuffers b, UsvLiveBuffers lb, const float2* __restrict__ actions,
                                                               float* __restrict__ obs, float* __restrict__ rew, int64_t n,
@@ -351,11 +369,9 @@ __global__ void __launch_bounds__(kBlock, 3) step_live_kernel(UsvEnvBuffers b, U
     do_reset = b.reset_buf[i] != 0;
     act = actions[i];
     const uint64_t gid = (uint64_t)(p.env_id_offset + i);
-    if (do_reset && lp.com_rand) {  // MDD._randomize_com  [ref USV_disturbances.py:100-106]
+    if (do_reset && lp.com_rand) {  // MDD._randomize_com  [ref USV_disturbances.py:100-124]
       const Uniform4 rc = philox_uniform4(p.seed, gid, step, RS_RESET_COM);
-      bc[USV_BC_COM_X * kTile] = lp.com_base[0] + (rc.a * 2.0f - 1.0f) * lp.com_disp[0];
-      bc[USV_BC_COM_Y * kTile] = lp.com_base[1] + (rc.b * 2.0f - 1.0f) * lp.com_disp[1];
-      bc[USV_BC_COM_Z * kTile] = lp.com_base[2] + (rc.c * 2.0f - 1.0f) * lp.com_disp[2];
+      redraw_com(lp, rc, bc);
     }
     step_dynamics<kDisturb, true>(e, k, p, do_reset, act, gid, i, step, b.lut_left, b.lut_right, s);
   }
@@ -524,11 +540,7 @@ __global__ void __launch_bounds__(kBlock, 3) step_task_kernel(UsvEnvBuffers b, U
     const uint64_t gid = (uint64_t)(p.env_id_offset + i);
     if (do_reset) {
       const Uniform4 rc = philox_uniform4(p.seed, gid, step, RS_RESET_COM);
-      if (lp.com_rand) {
-        bc[USV_BC_COM_X * kTile] = lp.com_base[0] + (rc.a * 2.0f - 1.0f) * lp.com_disp[0];
-        bc[USV_BC_COM_Y * kTile] = lp.com_base[1] + (rc.b * 2.0f - 1.0f) * lp.com_disp[1];
-        bc[USV_BC_COM_Z * kTile] = lp.com_base[2] + (rc.c * 2.0f - 1.0f) * lp.com_disp[2];
-      }
+      if (lp.com_rand) redraw_com(lp, rc, bc);
       if (!p.reset_pose_external) {
         // task.get_goals at the end of reset_idx  [ref USV_go_to_pose.py:244-246 ; USV_track_xy_velocity.py:141-146]
         if (kTask == USV_TASK_GO_TO_POSE) bc[USV_BC_TARGET_HEADING * kTile] = rc.d * USV_PI_F * 2.0f;
@@ -590,7 +602,7 @@ extern "C" int usv_step_live_f32(const UsvEnvBuffers* b, const UsvLiveBuffers* l
   }
   const int grid = grid_for(n, kBlock);
   const bool dis = p->use_force_disturbance || p->use_torque_disturbance || p->use_const_force || p->use_sin_force ||
-                   p->use_const_torque || p->use_sin_torque;
+                   p->use_const_torque || p->use_sin_torque || p->use_water_current;
   const bool st = lb->bstats != nullptr;
   cudaStream_t s = (cudaStream_t)stream;
   // staged bconsts (cp.async into shared memory) vs direct loads, A/B on one B200 (r02, profiles/r02_live_kernels.md): 13.9 vs 14.9 us at

@@ -298,6 +298,16 @@ __device__ __forceinline__ void reset_env(EnvState& e, EnvConst& k, const UsvSte
   }
   // MDD.randomize_masses  [ref USV_disturbances.py:127-151]
   k.mass = p.mass_rand ? urange(r1.d, p.mass_min, p.mass_max) : p.mass_base;
+  // _apply_yaw_inertia_randomization (skipped when yaw_inertia is a coupling target)  [ref OIGE/tasks/USV_Virtual.py:153-170,1532-1533]
+  if (p.kiz_rand && !(p.mass_coupling && (p.couple_targets & 4))) {
+    const Uniform4 r5 = philox_uniform4(p.seed, gid, step, RS_RESET_5);
+    if (p.kiz_log) {
+      const float l0 = logf(p.couple_kiz_min), l1 = logf(p.couple_kiz_max);
+      k.kiz = expf(l0 + r5.b * (l1 - l0));
+    } else {
+      k.kiz = p.couple_kiz_min + r5.b * (p.couple_kiz_max - p.couple_kiz_min);
+    }
+  }
   // hydrodynamics.reset_coefficients  [ref OIGE/envs/USV/Hydrodynamics.py:136-174]
   if (p.drag_rand) {
     const Uniform4 r3 = philox_uniform4(p.seed, gid, step, RS_RESET_3);
@@ -331,13 +341,15 @@ __device__ __forceinline__ void reset_env(EnvState& e, EnvConst& k, const UsvSte
     }
   }
   // _apply_mass_driven_coupling  [ref OIGE/tasks/USV_Virtual.py:988-1040]
-  if (p.mass_coupling) {
+  if (p.mass_coupling) {   // every target in p.couple_targets is overridden, the others keep their independent draw
     const float denom = fmaxf(p.couple_mass_max - p.mass_base, 1e-6f);
     const float rr = fminf(fmaxf((k.mass - p.mass_base) / denom, 0.0f), 1.0f);
-    k.kdrag = p.kdrag_min + rr * (p.kdrag_max - p.kdrag_min);
-    const float s = fminf(fmaxf(1.0f - rr * p.couple_thr_a, 1.0f - p.couple_thr_a), 1.0f);
-    k.mL = k.mR = s;
-    k.kiz = p.couple_kiz_min + rr * (p.couple_kiz_max - p.couple_kiz_min);
+    if (p.couple_targets & 1) k.kdrag = p.kdrag_min + rr * (p.kdrag_max - p.kdrag_min);
+    if (p.couple_targets & 2) {
+      const float s = fminf(fmaxf(1.0f - rr * p.couple_thr_a, 1.0f - p.couple_thr_a), 1.0f);
+      k.mL = k.mR = s;
+    }
+    if (p.couple_targets & 4) k.kiz = p.couple_kiz_min + rr * (p.couple_kiz_max - p.couple_kiz_min);
   }
   if (!p.reset_pose_external) {
     // goals [ref SNAP/USV_capture_xy.py:312-326]: the live reset_idx spawns around the OLD target and re-draws the target last
@@ -383,9 +395,15 @@ __device__ __forceinline__ void planar_wrench(const EnvState& e, const EnvConst&
                                               float& dr, float& Fx, float& Fy, float& Tz, float& ax, float& ay,
                                               float& rdot) {
   // R^T v (world -> body)  [ref Hydrodynamics.py:213-222, planar quaternion]
-  const float u = c * e.vx + s * e.vy;
-  const float v = -s * e.vx + c * e.vy;
+  float u = c * e.vx + s * e.vy;
+  float v = -s * e.vx + c * e.vy;
   const float w = e.r;
+  // water current: the damping acts on the velocity relative to the flow, both taken to the body frame first
+  // [ref Hydrodynamics.py:224-237].  Only the generic variant carries the test (the host routes a config with a current to it).
+  if (kDisturb == 1 && p.use_water_current) {
+    u -= c * p.flow_vel_xy[0] + s * p.flow_vel_xy[1];
+    v -= -s * p.flow_vel_xy[0] + c * p.flow_vel_xy[1];
+  }
   du = -fmaf(dm.bu, fabsf(u), dm.au) * u;
   dv = -fmaf(dm.bv, fabsf(v), dm.av) * v;
   dr = -fmaf(dm.br, fabsf(w), dm.ar) * w;

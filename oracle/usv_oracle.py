@@ -279,6 +279,11 @@ class EnvConfig:
     couple_thr_a: float = 0.5
     couple_kiz_min: float = 1.0
     couple_kiz_max: float = 1.5
+    couple_targets: int = 7            # bits: 1 drag_scale, 2 thruster, 4 yaw_inertia  [OIGE/tasks/USV_Virtual.py:393-411]
+    kiz_rand: bool = False             # independent k_Iz draw in [couple_kiz_min, couple_kiz_max]  [:153-170,1532-1533]
+    kiz_log: bool = False
+    use_water_current: bool = False    # [OIGE/tasks/USV_Virtual.py:444-445 ; Hydrodynamics.py:224-237]
+    flow_vel_xy: tuple = (0.0, 0.0)
     force_const_min: float = 0.0
     force_const_max: float = 2.5
     force_sin_min: float = 0.0
@@ -332,6 +337,25 @@ def curriculum(c: "EnvConfig", step: float):
     return (r * (c.spawn_min_dist - c.spawn_curriculum_min_dist) + c.spawn_curriculum_min_dist,
             r * (c.spawn_max_dist - c.spawn_curriculum_max_dist) + c.spawn_curriculum_max_dist,
             r * (c.kill_dist - c.spawn_curriculum_kill_dist) + c.spawn_curriculum_kill_dist)
+
+
+def sample_k_iz(u: torch.Tensor, kmin: float, kmax: float, log_space: bool) -> torch.Tensor:
+    """USVVirtual._sample_k_iz on given uniforms  [OIGE/tasks/USV_Virtual.py:153-170]."""
+    if log_space:
+        log_min = torch.log(torch.tensor(kmin, dtype=F32))
+        log_max = torch.log(torch.tensor(kmax, dtype=F32))
+        return torch.exp(log_min + u * (log_max - log_min))
+    return kmin + u * (kmax - kmin)
+
+
+def com_disc(base, u_r: torch.Tensor, u_theta: torch.Tensor, max_disp: float) -> torch.Tensor:
+    """MDD._randomize_com, legacy branch: a disc in the XY plane around base_com, z untouched  [OIGE/tasks/USV/USV_disturbances.py:108-124]."""
+    r = u_r * max_disp
+    theta = u_theta * math.pi * 2.0
+    com = torch.tensor(base, dtype=F32).unsqueeze(0).repeat(u_r.shape[0], 1)
+    com[:, 0] = com[:, 0] + torch.cos(theta) * r
+    com[:, 1] = com[:, 1] + torch.sin(theta) * r
+    return com
 
 
 def mass_coupling(c: "EnvConfig", mass: torch.Tensor):
@@ -426,6 +450,9 @@ class ClassicEnvOracle:
                 self.t_const[ids] = rr
         # MDD.randomize_masses  [USV_disturbances.py:127-151]
         self.mass[ids] = _u(r1[:, 3], c.mass_min, c.mass_max) if c.mass_rand else r1[:, 3] * 0 + c.mass_base
+        # _apply_yaw_inertia_randomization, unless the coupling owns k_Iz  [OIGE/tasks/USV_Virtual.py:1532-1533]
+        if c.kiz_rand and not (c.mass_coupling and (c.couple_targets & 4)):
+            self.k_iz[ids] = sample_k_iz(r5[:, 1], c.couple_kiz_min, c.couple_kiz_max, c.kiz_log)
         # hydrodynamics.reset_coefficients  [Hydrodynamics.py:136-174]
         if c.drag_rand:
             lr, qr = c.lin_rand, c.quad_rand
@@ -447,12 +474,15 @@ class ClassicEnvOracle:
                 m = r3[:, 3] * 2 * c.thr_rand_frac + (1 - c.thr_rand_frac)
                 self.thr_mult_left[ids] = m
                 self.thr_mult_right[ids] = m
-        if c.mass_coupling:
+        if c.mass_coupling:                                                 # _apply_mass_driven_coupling: only the listed targets
             kd, sthr, kiz = mass_coupling(c, self.mass[ids])
-            self.drag_scale[ids, 0] = kd
-            self.thr_mult_left[ids] = sthr
-            self.thr_mult_right[ids] = sthr
-            self.k_iz[ids] = kiz
+            if c.couple_targets & 1:
+                self.drag_scale[ids, 0] = kd
+            if c.couple_targets & 2:
+                self.thr_mult_left[ids] = sthr
+                self.thr_mult_right[ids] = sthr
+            if c.couple_targets & 4:
+                self.k_iz[ids] = kiz
         if not c.reset_pose_external:
             rmin, rmax, _ = curriculum(c, self.curriculum_step)
             # the kernel receives rmin / rmax as fp32 parameters and forms (rmax - rmin) in fp32
@@ -497,7 +527,8 @@ class ClassicEnvOracle:
                                 linear_damping_forward_speed=fwd6, offset_linear_damping=c.offset_linear_damping,
                                 offset_lin_forward_damping_speed=c.offset_lin_forward_damping_speed,
                                 offset_nonlin_damping=c.offset_nonlin_damping, scaling_damping=c.scaling_damping,
-                                use_drag_scale=c.use_drag_scale)
+                                use_drag_scale=c.use_drag_scale, use_water_current=c.use_water_current,
+                                flow_vel=(c.flow_vel_xy[0], c.flow_vel_xy[1], 0.0))
         # disturbances from WORLD position, applied in the body frame [USV_disturbances.py:386-410,510-530]
         wpos = self.pos + self.origin
         fd = torch.zeros((n, 2), dtype=F32)

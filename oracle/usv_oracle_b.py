@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import philox
-from .usv_oracle import ClassicEnvOracle, EnvConfig, penalties
+from .usv_oracle import ClassicEnvOracle, EnvConfig, com_disc, penalties
 
 GRID, MAP_SIZE, OBST_R = 150, 30.0, 0.5          # :30-32
 CELL = MAP_SIZE / GRID
@@ -363,7 +363,10 @@ class LiveEnvOracle(ClassicEnvOracle):
         self.S.reset(ids)
         if self.priv.com_rand:
             rc = torch.from_numpy(philox.uniform4(c.seed, gids, step, philox.RS_RESET_COM))
-            self.com[ids] = torch.tensor(self.priv.com_base, dtype=F32) + (rc[:, 0:3] * 2 - 1) * torch.tensor(self.priv.com_disp, dtype=F32)
+            if int(self.priv.com_rand) == 2:      # legacy XY disc, radius bound in com_disp[0]  [USV_disturbances.py:108-124]
+                self.com[ids] = com_disc(self.priv.com_base, rc[:, 0], rc[:, 1], float(self.priv.com_disp[0]))
+            else:
+                self.com[ids] = torch.tensor(self.priv.com_base, dtype=F32) + (rc[:, 0:3] * 2 - 1) * torch.tensor(self.priv.com_disp, dtype=F32)
         # scene: spawn point of this reset (same draw as ClassicEnvOracle.reset_idx) and the CURRENT target
         r0 = torch.from_numpy(philox.uniform4(c.seed, gids, step, philox.RS_RESET[0]))
         rmin32, rmax32 = torch.tensor(c.spawn_min_dist, dtype=F32), torch.tensor(c.spawn_max_dist, dtype=F32)

@@ -10,7 +10,7 @@ from dataclasses import dataclass
 import torch
 
 from . import philox
-from .usv_oracle import ClassicEnvOracle, EnvConfig, penalties
+from .usv_oracle import ClassicEnvOracle, EnvConfig, com_disc, penalties
 from .usv_oracle_b import LivePrivConfig, priv_encode
 
 F32 = torch.float32
@@ -125,7 +125,10 @@ class Tier3EnvOracle(ClassicEnvOracle):
         gids = self.env_ids[ids.numpy()]
         rc = torch.from_numpy(philox.uniform4(c.seed, gids, step, philox.RS_RESET_COM))
         if self.priv.com_rand:
-            self.com[ids] = torch.tensor(self.priv.com_base, dtype=F32) + (rc[:, 0:3] * 2 - 1) * torch.tensor(self.priv.com_disp, dtype=F32)
+            if int(self.priv.com_rand) == 2:      # legacy XY disc, radius bound in com_disp[0]  [USV_disturbances.py:108-124]
+                self.com[ids] = com_disc(self.priv.com_base, rc[:, 0], rc[:, 1], float(self.priv.com_disp[0]))
+            else:
+                self.com[ids] = torch.tensor(self.priv.com_base, dtype=F32) + (rc[:, 0:3] * 2 - 1) * torch.tensor(self.priv.com_disp, dtype=F32)
         if not c.reset_pose_external:
             if self.task.task == GO_TO_POSE:
                 self.target_heading[ids] = rc[:, 3] * math.pi * 2

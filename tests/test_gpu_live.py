@@ -193,6 +193,34 @@ def test_live_step_vs_oracle_lockstep():
     env.check_finite()
 
 
+def test_live_legacy_com_disc_vs_oracle():
+    """The configuration branches no shipped YAML takes, through the live step: legacy disc-shaped CoM re-draw (its oracle half is
+    pinned to MDD._randomize_com in tests/test_config_branches_cpu.py), a partial coupling target list with the independent log-space
+    k_Iz draw beside it, and a water current  [ref: OIGE/tasks/USV/USV_disturbances.py:108-124 ; OIGE/tasks/USV_Virtual.py:153-170,988-1040]."""
+    cfg = dataclasses.replace(LIVE_CFG, max_episode_length=6, kill_dist=12.5, couple_targets=3, kiz_rand=True, kiz_log=True,
+                              couple_kiz_min=0.8, couple_kiz_max=1.7, use_water_current=True, flow_vel_xy=(0.25, -0.15))
+    live = UsvLiveConfig(com_rand=2, com_base=(0.02, -0.01, 0.03), com_disp=(0.12, 0.0, 0.0))
+    n = 64 + 3
+    n_done = 0
+    for k, env, orc, (obs, rew, done), (o_obs, o_rew, o_done) in _lockstep(cfg, live, n, 14):
+        assert_close(obs, o_obs, 1e-5, 2e-5, f"obs step {k}")
+        assert_close(rew, o_rew, 1e-5, 2e-4, f"reward step {k}")
+        assert torch.equal(done, o_done), f"done mismatch at step {k}"
+        com = torch.stack([env.field(f"USV_BC_COM_{a}") for a in "XYZ"], 1).cpu()
+        assert_close(com, orc.com, 1e-6, 1e-7, f"CoM step {k}")
+        assert torch.equal(com[:, 2], torch.full((n,), 0.03))                       # the disc leaves z alone
+        es, os_ = engine_state(env), oracle_state(orc)
+        for name in ("USV_C_MASS", "USV_C_KDRAG", "USV_C_THR_ML", "USV_C_THR_MR", "USV_C_KIZ", "USV_S_VX", "USV_S_VY", "USV_S_R"):
+            assert_close(es[name], os_[name], 1e-5, 2e-5, f"{name} step {k}")
+        n_done += int(done.sum())
+    assert n_done > n
+    r = torch.linalg.vector_norm(com[:, :2] - torch.tensor([0.02, -0.01]), dim=1)
+    assert float(r.max()) <= 0.12 + 1e-6 and float(r.std()) > 0.01
+    kiz = env.field("USV_C_KIZ").cpu()
+    assert float(kiz.min()) >= 0.8 - 1e-6 and float(kiz.max()) <= 1.7 + 1e-6 and float(kiz.std()) > 0.05   # independent draw, not the coupled one
+    env.check_finite()
+
+
 def test_live_step_free_running_vs_oracle():
     """No re-sync: resets, obstacle re-draws and field rebuilds happen on the same steps for the same envs."""
     cfg = dataclasses.replace(LIVE_CFG, max_episode_length=9)

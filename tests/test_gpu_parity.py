@@ -148,12 +148,29 @@ def _lockstep(cfg, n, steps, seed=5, sync=True, collect_stats=False):
         yield k, env, orc, (obs.cpu(), rew.cpu(), done.cpu()), (o_obs, o_rew, o_done)
 
 
-@pytest.mark.parametrize("variant", ["classic", "full_dr", "curriculum"])
+# configuration branches no shipped YAML takes (their oracle halves are pinned to the reference in tests/test_config_branches_cpu.py)
+_BRANCHES = {
+    "water_current": dict(use_water_current=True, flow_vel_xy=(0.3, -0.2)),
+    "full_dr_water_current": dict(use_water_current=True, flow_vel_xy=(-0.45, 0.15)),
+    "couple_drag_only": dict(mass_rand=True, mass_min=30.0, mass_max=54.96, mass_base=34.96, mass_coupling=True, couple_targets=1,
+                             use_drag_scale=True, kdrag_min=1.0, kdrag_max=1.5, thr_rand=True, thr_separate=True, kiz_rand=True,
+                             couple_kiz_min=0.8, couple_kiz_max=1.7),
+    "couple_thruster_kiz": dict(mass_rand=True, mass_min=30.0, mass_max=54.96, mass_base=34.96, mass_coupling=True, couple_targets=6,
+                                use_drag_scale=True, kdrag_rand=True, kdrag_min=0.7, kdrag_max=1.6, kdrag_log=True, thr_rand=True,
+                                kiz_rand=True, couple_kiz_min=1.0, couple_kiz_max=1.5),
+    "kiz_linear": dict(kiz_rand=True, couple_kiz_min=0.8, couple_kiz_max=1.7),
+    "kiz_log": dict(kiz_rand=True, kiz_log=True, couple_kiz_min=0.8, couple_kiz_max=1.7, mass_rand=True),
+}
+
+
+@pytest.mark.parametrize("variant", ["classic", "full_dr", "curriculum"] + list(_BRANCHES))
 def test_fused_step_vs_oracle_lockstep(variant):
     """Every step starts from identical state (oracle state pushed to the GPU): obs/reward 1e-5, done bit-exact,
     reset index set bit-exact, next state 1e-5."""
     cfg = UsvEnvConfig(max_episode_length=12, kill_dist=12.5)
-    cfg = cfg.full_dr() if variant == "full_dr" else cfg
+    cfg = cfg.full_dr() if variant.startswith("full_dr") else cfg
+    if variant in _BRANCHES:
+        cfg = dataclasses.replace(cfg, **_BRANCHES[variant])
     if variant == "curriculum":      # spawn annulus and kill distance move every control step (knees at step 0.25 and 0.75)
         cfg = dataclasses.replace(cfg, spawn_curriculum=True, spawn_curriculum_min_dist=0.2, spawn_curriculum_max_dist=3.0,
                                   spawn_curriculum_kill_dist=4.0, spawn_curriculum_warmup=0.25, spawn_curriculum_end=0.75,
