@@ -20,6 +20,7 @@ namespace usv {
 
 constexpr int kG = USV_B_GRID;       // 150
 constexpr int kGP = kG + 2;          // padded row (halo of +inf)
+constexpr int kGPR = kGP + 2;        // rows of the padded buffer: the halo plus two spare +inf rows (a tile pass always reads 10 rows)
 constexpr int kCells = kG * kG;
 constexpr int kSceneThreads = 1024;  // 32 warps: warp w owns rows w, w+32, ...; lane l owns columns l, l+32, ...
 constexpr int kRowIters = (kG + 31) / 32;  // 5
@@ -170,7 +171,10 @@ __device__ __forceinline__ void place_obstacles(const UsvStepParams& p, uint64_t
 // (the env's own field slot) -- never seen with the task's obstacle placement, covered by a dense-batch test.
 constexpr int kCostThreads = 512, kCostWarps = kCostThreads / 32;
 constexpr int kAsyncSweepCap = 4 * kMaxSweeps;
-constexpr int kInner = 32;            // passes of a warp over its tile per outer sweep (one tile width)
+#ifndef USV_SCENE_INNER
+#define USV_SCENE_INNER 32
+#endif
+constexpr int kInner = USV_SCENE_INNER;            // passes of a warp over its tile per outer sweep (one tile width)
 constexpr float kJacobiSafeCost = 224.0f;
 
 __device__ __forceinline__ float block_reduce_max_cost(float v, float* s_red) {
@@ -227,7 +231,7 @@ __global__ void __launch_bounds__(kCostThreads, 2) scene_cost_kernel(SceneIO io,
   const uint64_t step = p.step_counter + (step_offset ? *step_offset : 0ull);   // device-side addend: CUDA-graph replays
   extern __shared__ __align__(16) float smem[];
   float* buf = smem;                  // padded 152 x 152, +inf halo
-  float* s_sc = buf + kGP * kGP;      // 34 floats
+  float* s_sc = buf + kGPR * kGP;     // 34 floats
   float* s_red = s_sc + 64;           // 32 floats
   int* s_act = reinterpret_cast<int*>(s_red + 32);        // [2][96] tile-active flags of the current / next sweep
   uint32_t* s_rowmask = reinterpret_cast<uint32_t*>(s_act + 2 * kActStride);  // [150] obstacles that can matter on a grid row
@@ -255,7 +259,7 @@ __global__ void __launch_bounds__(kCostThreads, 2) scene_cost_kernel(SceneIO io,
     } else {
       env = load_scene(io, j, s_sc);
     }
-    for (int q = threadIdx.x; q < kGP * kGP; q += kCostThreads) buf[q] = CUDART_INF_F;   // halo included
+    for (int q = threadIdx.x; q < kGPR * kGP; q += kCostThreads) buf[q] = CUDART_INF_F;   // halo and spare rows included
     if (threadIdx.x < 2 * kActStride) s_act[threadIdx.x] = 0;
     __syncthreads();
     if (threadIdx.x < kG) s_rowmask[threadIdx.x] = row_obstacle_mask(io.lin[threadIdx.x], s_sc + 16);
@@ -302,7 +306,6 @@ __global__ void __launch_bounds__(kCostThreads, 2) scene_cost_kernel(SceneIO io,
           const int chunk = t % kChunks, band = t / kChunks;
           const int x = chunk * 32 + lane, y0 = band * kBandRows;
           const int rows = min(kBandRows, kG - y0);
-          const bool xin = x < kG;
           const int xc = min(x, kG - 1);
           const uint32_t freemask = s_free[t * 32 + lane];
           // Temporal blocking: the warp relaxes ITS tile up to kInner times (until it stops changing) before the CTA-wide barrier, so a
@@ -310,29 +313,30 @@ __global__ void __launch_bounds__(kCostThreads, 2) scene_cost_kernel(SceneIO io,
           // fixed point).
           bool e_left = false, e_right = false, e_up = false, e_dn = false, changed = false, more = true;
           for (int inner = 0; inner < kInner && more; ++inner) {
-            // one block-Jacobi pass over the tile: all 10 x 3 window values are loaded first (independent loads), then the 8 cells of
-            // the lane's column are relaxed from those registers -- no loop-carried dependency, so the rows pipeline (a Gauss-Seidel
-            // walk that feeds each relaxed row into the next one serialises them: ~4x the latency per pass in the r01 capture)
+            // one block-Jacobi pass over the tile: all 10 x 3 window values are loaded first -- unconditionally, the buffer carries two
+            // spare +inf rows below the halo so that the last band (6 rows) reads in bounds -- and the 8 cells of the lane's column are
+            // then relaxed from those registers: no loop-carried dependency and no branch, so the rows pipeline.  (With guarded loads
+            // and a per-row `if (free)` the compiler sank every row's loads behind a divergent branch of the row before: ~1100 cycles
+            // per pass in the r02 instrumented run against ~200 instructions.)  A lane outside the grid or a row below it has no free
+            // bit, so the mask alone gates the store.
             const float* rp = buf + y0 * kGP + xc + 1;    // padded row y0 == grid row y0 - 1
-            float w[kBandRows + 2][3];
+            float wl[kBandRows + 2], wc[kBandRows + 2], wr[kBandRows + 2];
 #pragma unroll
             for (int r = 0; r < kBandRows + 2; ++r) {
-              if (r < rows + 2) { w[r][0] = rp[r * kGP - 1]; w[r][1] = rp[r * kGP]; w[r][2] = rp[r * kGP + 1]; }
-              else { w[r][0] = CUDART_INF_F; w[r][1] = CUDART_INF_F; w[r][2] = CUDART_INF_F; }
+              wl[r] = rp[r * kGP - 1];
+              wc[r] = rp[r * kGP];
+              wr[r] = rp[r * kGP + 1];
             }
             uint32_t chg = 0;
 #pragma unroll
             for (int i = 0; i < kBandRows; ++i) {
-              if (i < rows && ((freemask >> i) & 1u)) {
-                const float mc = w[i + 1][1];
-                const float a = fminf(fminf(w[i + 1][0], w[i + 1][2]), fminf(w[i][1], w[i + 2][1])) + 1.0f;
-                const float b = fminf(fminf(w[i][0], w[i][2]), fminf(w[i + 2][0], w[i + 2][2])) + 1.414f;
-                const float best = fminf(mc, fminf(a, b));
-                if (xin && best != mc) {
-                  buf[(y0 + i + 1) * kGP + xc + 1] = best;
-                  chg |= 1u << i;
-                }
-              }
+              const float mc = wc[i + 1];
+              const float a = fminf(fminf(wl[i + 1], wr[i + 1]), fminf(wc[i], wc[i + 2])) + 1.0f;
+              const float b = fminf(fminf(wl[i], wr[i]), fminf(wl[i + 2], wr[i + 2])) + 1.414f;
+              const float best = fminf(mc, fminf(a, b));
+              const bool upd = ((freemask >> i) & 1u) != 0u && best != mc;
+              if (upd) buf[(y0 + i + 1) * kGP + xc + 1] = best;
+              chg |= upd ? (1u << i) : 0u;
             }
             const uint32_t any_b = __ballot_sync(0xffffffffu, chg != 0u);
             more = any_b != 0u;
@@ -521,7 +525,7 @@ __global__ void compact_resets_kernel(const int64_t* __restrict__ reset_buf, int
   }
 }
 
-static size_t cost_smem_bytes() { return (size_t)(kGP * kGP + 64 + 32 + 2 * kActStride + 160) * sizeof(float) + (size_t)kTiles * 32; }
+static size_t cost_smem_bytes() { return (size_t)(kGPR * kGP + 64 + 32 + 2 * kActStride + 160) * sizeof(float) + (size_t)kTiles * 32; }
 
 static int scene_grid() {
   static int sms = 0;
