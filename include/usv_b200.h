@@ -425,12 +425,14 @@ int usv_step_live_f32(const UsvEnvBuffers* b, const UsvLiveBuffers* lb, const fl
  * step kernel will draw for the same (seed, env, step) and against the CURRENT target) and rebuild its potential field.
  * The batch-global maxima of the reference's builder (d_multi_gemini.py:204-210,257-260) are taken over the envs that reset
  * in this call.  Call before usv_step_live_f32 with the same p->step_counter.  cell_centres = torch.linspace(-14.9,14.9,150);
- * workspace: usv_live_scene_workspace_bytes(n) bytes, 16 B aligned.
+ * workspace: usv_live_scene_workspace_bytes(n) bytes, 16 B aligned (counters, the compacted reset list and 32 B of per-scene
+ * statistics that the cost kernel hands to the field kernel).
  *     [ref: USV_capture_xy_static_obs.py:936-1060 ; d_multi_gemini.py:66-271]                                               */
 int64_t usv_live_scene_workspace_bytes(int64_t n);
 int usv_live_reset_scene_f32(const UsvEnvBuffers* b, const UsvLiveBuffers* lb, const float* cell_centres /*[150]*/,
                              void* workspace, int64_t n, const UsvStepParams* p, void* stream);
-/* B6 alone on a dense batch (BatchedMapGPU.compute_occupancy_and_sdf -> compute_cost_field_wavefront -> compute_potential_field) */
+/* B6 alone on a dense batch (BatchedMapGPU.compute_occupancy_and_sdf -> compute_cost_field_wavefront -> compute_potential_field);
+ * workspace: usv_live_scene_workspace_bytes(m) bytes, 16 B aligned */
 int usv_live_build_fields_f32(const float* obstacles /*[m,16,2]*/, const float* targets /*[m,2]*/,
                               const float* cell_centres /*[150]*/, float* field /*[m,150,150]*/,
                               float* cost_out /*[m,150,150] raw cost-to-go or NULL*/, void* workspace, int64_t m, void* stream);

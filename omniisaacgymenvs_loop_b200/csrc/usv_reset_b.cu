@@ -5,12 +5,19 @@
 // The reference runs 225 Jacobi sweeps of an 8-neighbour min-plus relaxation as ~30 torch ops per sweep over the whole
 // (B,150,150) batch in HBM.  Here ONE CTA owns one env: the 150x150 cost buffer lives in shared memory (92 KB with an +inf halo,
 // two scenes per SM) and is relaxed in place until nothing changes -- the same fixed point, bit for bit, as the reference's Jacobi
-// sweeps (see the comment at scene_cost_kernel).  The reference's BATCH-GLOBAL maxima (max finite cost,
-// max repulsion: quirk 9 of SURVEY appendix C) need two grid-wide reductions, hence three kernels:
-//   scene_cost_kernel  : obstacles (warp 0) -> free mask -> wavefront -> raw cost into field[env], atomicMax(max cost)
-//   scene_jmax_kernel  : repulsion J per cell with the global max cost -> atomicMax(max J), any-inside flag
-//   scene_field_kernel : per-env min/max of G and J -> field[env] = norm(G) + 0.5 norm(J)
-// All three are persistent grids striding over the compacted list of resetting envs (or over a dense batch for the
+// sweeps (see the comment at scene_cost_kernel).  The reference's BATCH-GLOBAL maxima (max finite cost, max repulsion: quirk 9 of
+// SURVEY appendix C) and its per-scene min / max normalisation are reductions over cells whose inputs do not depend on those
+// maxima except through ONE scalar factor, so the cost kernel takes all of them in its write-out pass and the field itself is a
+// plain elementwise map:
+//   scene_cost_kernel  : obstacles (warp 0) -> free mask -> wavefront -> raw cost into field[env]; per-scene statistics (min / max
+//                        finite cost, min / max repulsion over finite-cost and over unreachable cells, flags) into the workspace,
+//                        batch maxima by atomicMax
+//   scene_field_kernel : field[env] = norm(G) + 0.5 norm(J) per cell, any number of CTAs per scene (no reduction left)
+// A cell the wavefront never reaches has G = 1.5 x (batch max cost) and a repulsion 20 q^2 * rep with rep = clamp(G * 0.2 / 3, 0, 1) the
+// same for every such cell: fl(a * rep) is monotone in a, so min / max over those cells are taken on 20 q^2 and scaled afterwards,
+// bit for bit what the reference's max over the products gives.  (r01 / early r02 ran a third kernel for the batch max of J and two
+// passes in the field kernel: 31 + 68 us of a 260 us control step at 16 384 envs.)
+// Both kernels are persistent grids striding over the compacted list of resetting envs (or over a dense batch for the
 // standalone builder entry), so their cost is ~0 when nothing resets.
 #include <math_constants.h>
 #include "philox.cuh"
@@ -22,8 +29,6 @@ constexpr int kG = USV_B_GRID;       // 150
 constexpr int kGP = kG + 2;          // padded row (halo of +inf)
 constexpr int kGPR = kGP + 2;        // rows of the padded buffer: the halo plus two spare +inf rows (a tile pass always reads 10 rows)
 constexpr int kCells = kG * kG;
-constexpr int kSceneThreads = 1024;  // 32 warps: warp w owns rows w, w+32, ...; lane l owns columns l, l+32, ...
-constexpr int kRowIters = (kG + 31) / 32;  // 5
 constexpr int kColIters = (kG + 31) / 32;  // 5
 constexpr int kMaxSweeps = (int)(kG * 1.5);  // 225  (d_multi_gemini.py:160)
 constexpr float kObstR = 0.5f;
@@ -32,7 +37,12 @@ constexpr int kActStride = 96;       // tile-active flags per sweep parity
 constexpr float kReach = 1.7f + 1e-3f;  // an obstacle matters to a cell only within 0.5 (radius) + 0.5 + 0.7 (influence) of its centre
 
 // counters (uint32[8]) in the workspace
-enum { CW_COUNT = 0, CW_MAXCOST = 1, CW_MAXJ = 2, CW_INSIDE = 3, CW_HAVE = 4, CW_WORDS = 8 };
+enum { CW_COUNT = 0, CW_MAXCOST = 1, CW_MAXJ = 2, CW_INSIDE = 3, CW_HAVE = 4, CW_MAXJ_INF = 5, CW_WORDS = 8 };
+// CW_MAXJ: batch max of the repulsion over finite-cost cells; CW_MAXJ_INF: batch max of 20 q^2 over unreachable cells (scaled by rep later)
+
+// per-scene statistics (floats) written by the cost kernel, read by the field kernel
+enum { SS_MIN_COST = 0, SS_MAX_COST = 1, SS_JFIN_MIN = 2, SS_JFIN_MAX = 3, SS_JINF_MIN = 4, SS_JINF_MAX = 5, SS_FLAGS = 6, SS_WORDS = 8 };
+enum { SSF_HAS_INF = 1, SSF_HAS_INSIDE = 2, SSF_HAS_JFIN = 4, SSF_HAS_JINF = 8 };
 
 struct SceneIO {
   // list mode (list != nullptr): env id = list[j]; obstacles in bconsts (AoSoA), target in consts, field[env]
@@ -47,36 +57,10 @@ struct SceneIO {
   float* field;            // [*,150,150]
   float* cost_out;         // dense mode only, or NULL
   const float* lin;        // [150] cell-centre coordinates (torch.linspace(-14.9, 14.9, 150))
+  float* stats;            // [scenes][SS_WORDS] per-scene statistics (workspace)
 };
 
 __device__ __forceinline__ int64_t scene_count(const SceneIO& io) { return io.list ? (int64_t)*io.count : io.m; }
-
-__device__ __forceinline__ float block_reduce_max(float v, float* s_red) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  __syncthreads();
-  if (lane == 0) s_red[warp] = v;
-  __syncthreads();
-  v = s_red[lane];  // kSceneThreads / 32 == 32 partials
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-__device__ __forceinline__ float block_reduce_min(float v, float* s_red) { return -block_reduce_max(-v, s_red); }
-
-// min over the 16 obstacles of the centre distance, minus the radius  (d_multi_gemini.py:84-92).  torch.norm over a
-// 2-vector evaluates sqrt(fma(y, y, x*x)) (ATen's sum-of-squares accumulation, CPU and CUDA): spelled out, because the
-// occupancy is the sign of this and the repulsion term amplifies 1 ulp of it by ~1e3 next to an obstacle
-__device__ __forceinline__ float cell_sdf(float cx, float cy, const float* s_ox, const float* s_oy) {
-  float best = CUDART_INF_F;
-#pragma unroll
-  for (int j = 0; j < USV_B_OBSTACLES; ++j) {
-    const float dx = __fsub_rn(cx, s_ox[j]), dy = __fsub_rn(cy, s_oy[j]);
-    best = fminf(best, sqrtf(__fmaf_rn(dy, dy, __fmul_rn(dx, dx))));
-  }
-  return __fsub_rn(best, kObstR);
-}
 
 // bit j set: obstacle j is within kReach of grid row cy (|dy| <= dist), i.e. it can make a cell of that row occupied / repelled
 __device__ __forceinline__ uint32_t row_obstacle_mask(float cy, const float* s_oy) {
@@ -85,8 +69,11 @@ __device__ __forceinline__ uint32_t row_obstacle_mask(float cy, const float* s_o
   for (int j = 0; j < USV_B_OBSTACLES; ++j) m |= (fabsf(cy - s_oy[j]) <= kReach) ? (1u << j) : 0u;
   return m;
 }
-// cell_sdf over the obstacles of `mask` only: exact wherever the result is below kReach - 0.5, +inf-ish (>= that) elsewhere --
-// every consumer only distinguishes values below 1.2 (occupancy: <= 0; repulsion: sdf - 0.5 < 0.7)
+// min over the obstacles of `mask` of the centre distance, minus the radius  (d_multi_gemini.py:84-92).  torch.norm over a 2-vector
+// evaluates sqrt(fma(y, y, x*x)) (ATen's sum-of-squares accumulation, CPU and CUDA): spelled out, because the occupancy is the sign
+// of this and the repulsion term amplifies 1 ulp of it by ~1e3 next to an obstacle.  Restricted to `mask` the result is exact
+// wherever it is below kReach - 0.5 and +inf-ish (>= that) elsewhere -- every consumer only distinguishes values below 1.2
+// (occupancy: <= 0; repulsion: sdf - 0.5 < 0.7)
 __device__ __forceinline__ float cell_sdf_masked(float cx, float cy, const float* s_ox, const float* s_oy, uint32_t mask) {
   float best = CUDART_INF_F;
   while (mask) {
@@ -190,6 +177,23 @@ __device__ __forceinline__ float block_reduce_max_cost(float v, float* s_red) {
   return v;
 }
 
+// cost-independent part of the repulsion of one cell: dist_to_edge = sdf - obstacle_radius (d_multi_gemini.py:220) and 20 q^2 with
+// q = 1/d - 1/0.7 inside the influence radius (0 outside)
+struct CellGeom { float edge, raw; };
+__device__ __forceinline__ CellGeom cell_geom(float sdf) {
+  CellGeom g;
+  g.edge = __fsub_rn(sdf, kObstR);
+  g.raw = 0.0f;
+  if (g.edge < 0.7f) {
+    const float dcl = fmaxf(g.edge, 1e-3f);
+    const float q = __fsub_rn(__fdiv_rn(1.0f, dcl), 1.42857146f);  // 1.0/d - fp32(1/0.7)
+    g.raw = __fmul_rn(20.0f, __fmul_rn(q, q));
+  }
+  return g;
+}
+// rep = clamp(G * 0.2 / 3, 0, 1): the factor that ties the repulsion to the cost-to-go
+__device__ __forceinline__ float cell_rep(float vis) { return fminf(fmaxf(__fdiv_rn(__fmul_rn(vis, 0.2f), 3.0f), 0.0f), 1.0f); }
+
 __device__ __forceinline__ bool cell_free(const unsigned char* s_free, int x, int y) {
   return (s_free[((y / kBandRows) * kChunks + (x >> 5)) * 32 + (x & 31)] >> (y % kBandRows)) & 1u;
 }
@@ -235,7 +239,8 @@ __global__ void __launch_bounds__(kCostThreads, 2) scene_cost_kernel(SceneIO io,
   float* s_red = s_sc + 64;           // 32 floats
   int* s_act = reinterpret_cast<int*>(s_red + 32);        // [2][96] tile-active flags of the current / next sweep
   uint32_t* s_rowmask = reinterpret_cast<uint32_t*>(s_act + 2 * kActStride);  // [150] obstacles that can matter on a grid row
-  unsigned char* s_free = reinterpret_cast<unsigned char*>(s_rowmask + 160);  // [95][32] free bits of a lane's 8 cells of a tile
+  uint32_t* s_colmask = s_rowmask + 160;                                      // [150] ... on a grid column
+  unsigned char* s_free = reinterpret_cast<unsigned char*>(s_colmask + 160);  // [95][32] free bits of a lane's 8 cells of a tile
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t total = scene_count(io);
   for (int64_t j = blockIdx.x; j < total; j += gridDim.x) {
@@ -262,7 +267,10 @@ __global__ void __launch_bounds__(kCostThreads, 2) scene_cost_kernel(SceneIO io,
     for (int q = threadIdx.x; q < kGPR * kGP; q += kCostThreads) buf[q] = CUDART_INF_F;   // halo and spare rows included
     if (threadIdx.x < 2 * kActStride) s_act[threadIdx.x] = 0;
     __syncthreads();
+    // an obstacle within kReach of a cell is within kReach of its row AND of its column: the AND of the two masks leaves the one
+    // or two obstacles a cell can feel (none for most cells)
     if (threadIdx.x < kG) s_rowmask[threadIdx.x] = row_obstacle_mask(io.lin[threadIdx.x], s_sc + 16);
+    else if (threadIdx.x >= 256 && threadIdx.x < 256 + kG) s_colmask[threadIdx.x - 256] = row_obstacle_mask(io.lin[threadIdx.x - 256], s_sc);
     // target cell: ((pos + map/2) / cell).long().clamp(0, 149)   (d_multi_gemini.py:148-155)
     const int txi = min(max((int)__fdiv_rn(s_sc[32] + 15.0f, 0.2f), 0), kG - 1);
     const int tyi = min(max((int)__fdiv_rn(s_sc[33] + 15.0f, 0.2f), 0), kG - 1);
@@ -281,11 +289,13 @@ __global__ void __launch_bounds__(kCostThreads, 2) scene_cost_kernel(SceneIO io,
       const int x = chunk * 32 + lane, y0 = band * kBandRows;
       uint32_t fm = 0;
       if (x < kG) {
+        const uint32_t cmask = s_colmask[x];
+        const float cx = io.lin[x];
 #pragma unroll 1
         for (int i = 0; i < kBandRows && y0 + i < kG; ++i) {
           const int y = y0 + i;
           const bool border = (y == 0) || (y == kG - 1) || (x == 0) || (x == kG - 1);
-          const float sdf = cell_sdf_masked(io.lin[x], io.lin[y], s_sc, s_sc + 16, s_rowmask[y]);
+          const float sdf = cell_sdf_masked(cx, io.lin[y], s_sc, s_sc + 16, s_rowmask[y] & cmask);
           if (!border && !(sdf <= 0.0f)) fm |= 1u << i;
         }
       }
@@ -388,28 +398,64 @@ __global__ void __launch_bounds__(kCostThreads, 2) scene_cost_kernel(SceneIO io,
       mx = block_reduce_max_cost(mx, s_red);
       if (pass == 1 || !exact || mx < kJacobiSafeCost) break;   // the fixed point is the 225th Jacobi iterate
     }
-    if (threadIdx.x == 0 && mx >= 0.0f) {  // non-negative floats order like their bit patterns
-      atomicMax(counters + CW_MAXCOST, __float_as_uint(mx));
-      atomicOr(counters + CW_HAVE, 1u);
+    // per-scene statistics for the field kernel + the batch maxima of the repulsion, from the converged costs still in shared memory
+    float mn = CUDART_INF_F, jfmn = CUDART_INF_F, jfmx = -1.0f, jimn = CUDART_INF_F, jimx = -1.0f, jall_fin = 0.0f, jall_inf = 0.0f;
+    int has_inf = 0, has_inside = 0;
+#pragma unroll 1
+    for (int y = warp; y < kG; y += kCostWarps) {
+      const uint32_t rmask = s_rowmask[y];
+      const float cy = io.lin[y];
+#pragma unroll
+      for (int ci = 0; ci < kColIters; ++ci) {
+        const int x = lane + 32 * ci;
+        if (x < kG) {
+          const float c = buf[(y + 1) * kGP + x + 1];
+          const CellGeom g = cell_geom(cell_sdf_masked(io.lin[x], cy, s_sc, s_sc + 16, rmask & s_colmask[x]));
+          const bool inside = g.edge <= 0.0f;
+          has_inside |= inside ? 1 : 0;
+          if (c < CUDART_INF_F) {
+            mn = fminf(mn, c);
+            const float J = (g.raw > 0.0f) ? __fmul_rn(g.raw, cell_rep(c)) : 0.0f;   // 0 * rep == 0: the division is skipped
+            jall_fin = fmaxf(jall_fin, J);
+            if (!inside) { jfmn = fminf(jfmn, J); jfmx = fmaxf(jfmx, J); }
+          } else {
+            has_inf = 1;
+            jall_inf = fmaxf(jall_inf, g.raw);
+            if (!inside) { jimn = fminf(jimn, g.raw); jimx = fmaxf(jimx, g.raw); }
+          }
+        }
+      }
+    }
+    mn = -block_reduce_max_cost(-mn, s_red);
+    jfmn = -block_reduce_max_cost(-jfmn, s_red);
+    jfmx = block_reduce_max_cost(jfmx, s_red);
+    jimn = -block_reduce_max_cost(-jimn, s_red);
+    jimx = block_reduce_max_cost(jimx, s_red);
+    jall_fin = block_reduce_max_cost(jall_fin, s_red);
+    jall_inf = block_reduce_max_cost(jall_inf, s_red);
+    has_inf = __syncthreads_or(has_inf);
+    has_inside = __syncthreads_or(has_inside);
+    if (threadIdx.x == 0) {
+      float* st = io.stats + j * SS_WORDS;
+      st[SS_MIN_COST] = mn;
+      st[SS_MAX_COST] = mx;       // -1 when no cell is reachable
+      st[SS_JFIN_MIN] = jfmn;
+      st[SS_JFIN_MAX] = jfmx;
+      st[SS_JINF_MIN] = jimn;
+      st[SS_JINF_MAX] = jimx;
+      st[SS_FLAGS] = __uint_as_float((has_inf ? SSF_HAS_INF : 0u) | (has_inside ? SSF_HAS_INSIDE : 0u) | (jfmx >= 0.0f ? SSF_HAS_JFIN : 0u) |
+                                     (jimx >= 0.0f ? SSF_HAS_JINF : 0u));
+      // non-negative floats order like their bit patterns
+      if (mx >= 0.0f) {
+        atomicMax(counters + CW_MAXCOST, __float_as_uint(mx));
+        atomicOr(counters + CW_HAVE, 1u);
+      }
+      atomicMax(counters + CW_MAXJ, __float_as_uint(jall_fin));
+      atomicMax(counters + CW_MAXJ_INF, __float_as_uint(jall_inf));
+      if (has_inside) atomicOr(counters + CW_INSIDE, 1u);
     }
     __syncthreads();
   }
-}
-
-struct CellTerms { float vis, J, edge; };
-
-__device__ __forceinline__ CellTerms cell_terms(float cost, float sdf, float vis_inf) {
-  CellTerms t;
-  t.vis = (cost == CUDART_INF_F) ? vis_inf : cost;  // torch.where(isinf(cost), max_val*1.5, cost)
-  t.edge = __fsub_rn(sdf, kObstR);                  // dist_to_edge = sdf - obstacle_radius  (:220)
-  const float rep = fminf(fmaxf(__fdiv_rn(__fmul_rn(t.vis, 0.2f), 3.0f), 0.0f), 1.0f);
-  t.J = 0.0f;
-  if (t.edge < 0.7f) {
-    const float dcl = fmaxf(t.edge, 1e-3f);
-    const float q = __fsub_rn(__fdiv_rn(1.0f, dcl), 1.42857146f);  // 1.0/d - fp32(1/0.7)
-    t.J = __fmul_rn(__fmul_rn(20.0f, __fmul_rn(q, q)), rep);
-  }
-  return t;
 }
 
 __device__ __forceinline__ float global_vis_inf(const uint32_t* counters, int have) {
@@ -418,102 +464,59 @@ __device__ __forceinline__ float global_vis_inf(const uint32_t* counters, int ha
   return __fmul_rn(max_val, 1.5f);
 }
 
-__global__ void __launch_bounds__(kSceneThreads, 1) scene_jmax_kernel(SceneIO io, uint32_t* __restrict__ counters) {
-  __shared__ float s_sc[64];
-  __shared__ float s_red[32];
-  __shared__ uint32_t s_rowmask[160];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t total = scene_count(io);
-  const float vis_inf = global_vis_inf(counters, counters[CW_HAVE] != 0u);
-  for (int64_t j = blockIdx.x; j < total; j += gridDim.x) {
-    const int64_t env = load_scene(io, j, s_sc);
-    __syncthreads();
-    if (threadIdx.x < kG) s_rowmask[threadIdx.x] = row_obstacle_mask(io.lin[threadIdx.x], s_sc + 16);
-    __syncthreads();
-    const float* f = io.field + env * (int64_t)kCells;
-    float mj = 0.0f;
-    int inside = 0;
-#pragma unroll 1
-    for (int ri = 0; ri < kRowIters; ++ri) {
-      const int y = warp + 32 * ri;
-      if (y < kG) {
-#pragma unroll
-        for (int ci = 0; ci < kColIters; ++ci) {
-          const int x = lane + 32 * ci;
-          if (x < kG) {
-            const CellTerms t = cell_terms(f[y * kG + x], cell_sdf_masked(io.lin[x], io.lin[y], s_sc, s_sc + 16, s_rowmask[y]), vis_inf);
-            mj = fmaxf(mj, t.J);
-            inside |= (t.edge <= 0.0f) ? 1 : 0;
-          }
-        }
-      }
-    }
-    mj = block_reduce_max(mj, s_red);
-    inside = __syncthreads_or(inside);
-    if (threadIdx.x == 0) {
-      atomicMax(counters + CW_MAXJ, __float_as_uint(mj));
-      if (inside) atomicOr(counters + CW_INSIDE, 1u);
-    }
-    __syncthreads();
-  }
-}
+// field[env] = (G - min G) / (max G - min G + 1e-6) + 0.5 (J - min J) / (max J - min J + 1e-6)  (d_multi_gemini.py:205-271), one cell per
+// thread-iteration; a scene is cut into kFieldChunks row blocks so that ~150 scenes spread over every SM instead of one CTA each
+constexpr int kFieldThreads = 256, kFieldChunks = 10, kFieldRows = kG / kFieldChunks;   // 15 rows = 2250 cells per item
+static_assert(kFieldRows * kFieldChunks == kG, "row blocks must tile the grid");
 
-__global__ void __launch_bounds__(kSceneThreads, 1) scene_field_kernel(SceneIO io, const uint32_t* __restrict__ counters) {
+__global__ void __launch_bounds__(kFieldThreads) scene_field_kernel(SceneIO io, const uint32_t* __restrict__ counters) {
   __shared__ float s_sc[64];
-  __shared__ float s_red[32];
-  __shared__ uint32_t s_rowmask[160];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ uint32_t s_rowmask[kFieldRows];
+  __shared__ uint32_t s_colmask[kG];
   const int64_t total = scene_count(io);
   const float vis_inf = global_vis_inf(counters, counters[CW_HAVE] != 0u);
+  const float rep_inf = cell_rep(vis_inf);
+  // batch max of J before the inside override (:236): finite-cost cells as they are, unreachable ones scaled by their common rep
+  const float cur_max = fmaxf(__uint_as_float(counters[CW_MAXJ]), __fmul_rn(__uint_as_float(counters[CW_MAXJ_INF]), rep_inf));
   const bool any_inside = counters[CW_INSIDE] != 0u;
-  const float cur_max = __uint_as_float(counters[CW_MAXJ]);
   const float high = (cur_max > 1e-6f) ? __fmul_rn(cur_max, 10.0f) : 100.0f;
-  for (int64_t j = blockIdx.x; j < total; j += gridDim.x) {
+  for (int64_t item = blockIdx.x; item < total * kFieldChunks; item += gridDim.x) {
+    const int64_t j = item / kFieldChunks;
+    const int y0 = (int)(item - j * kFieldChunks) * kFieldRows;
+    __syncthreads();                     // the previous item's readers of s_sc / s_rowmask are done
     const int64_t env = load_scene(io, j, s_sc);
     __syncthreads();
-    if (threadIdx.x < kG) s_rowmask[threadIdx.x] = row_obstacle_mask(io.lin[threadIdx.x], s_sc + 16);
-    __syncthreads();
-    float* f = io.field + env * (int64_t)kCells;
-    float gmn = CUDART_INF_F, gmx = -CUDART_INF_F, jmn = CUDART_INF_F, jmx = -CUDART_INF_F;
-#pragma unroll 1
-    for (int ri = 0; ri < kRowIters; ++ri) {
-      const int y = warp + 32 * ri;
-      if (y < kG) {
-#pragma unroll
-        for (int ci = 0; ci < kColIters; ++ci) {
-          const int x = lane + 32 * ci;
-          if (x < kG) {
-            CellTerms t = cell_terms(f[y * kG + x], cell_sdf_masked(io.lin[x], io.lin[y], s_sc, s_sc + 16, s_rowmask[y]), vis_inf);
-            if (any_inside && t.edge <= 0.0f) t.J = high;
-            gmn = fminf(gmn, t.vis); gmx = fmaxf(gmx, t.vis);
-            jmn = fminf(jmn, t.J); jmx = fmaxf(jmx, t.J);
-          }
-        }
-      }
-    }
-    gmn = block_reduce_min(gmn, s_red);
-    gmx = block_reduce_max(gmx, s_red);
-    jmn = block_reduce_min(jmn, s_red);
-    jmx = block_reduce_max(jmx, s_red);
+    if (threadIdx.x < kFieldRows) s_rowmask[threadIdx.x] = row_obstacle_mask(io.lin[y0 + threadIdx.x], s_sc + 16);
+    else if (threadIdx.x >= 64 && threadIdx.x < 64 + kG) s_colmask[threadIdx.x - 64] = row_obstacle_mask(io.lin[threadIdx.x - 64], s_sc);
+    // per-scene extrema from the cost kernel's statistics
+    const float* st = io.stats + j * SS_WORDS;
+    const uint32_t fl = __float_as_uint(st[SS_FLAGS]);
+    float gmn = st[SS_MIN_COST], gmx = (st[SS_MAX_COST] >= 0.0f) ? st[SS_MAX_COST] : -CUDART_INF_F;
+    if (fl & SSF_HAS_INF) { gmn = fminf(gmn, vis_inf); gmx = fmaxf(gmx, vis_inf); }
+    float jmn = CUDART_INF_F, jmx = -CUDART_INF_F;
+    if (fl & SSF_HAS_JFIN) { jmn = st[SS_JFIN_MIN]; jmx = st[SS_JFIN_MAX]; }
+    if (fl & SSF_HAS_JINF) { jmn = fminf(jmn, __fmul_rn(st[SS_JINF_MIN], rep_inf)); jmx = fmaxf(jmx, __fmul_rn(st[SS_JINF_MAX], rep_inf)); }
+    if (fl & SSF_HAS_INSIDE) { jmn = fminf(jmn, high); jmx = fmaxf(jmx, high); }   // a scene with an inside cell makes any_inside true
     const float gden = __fadd_rn(__fsub_rn(gmx, gmn), 1e-6f), jden = __fadd_rn(__fsub_rn(jmx, jmn), 1e-6f);
-#pragma unroll 1
-    for (int ri = 0; ri < kRowIters; ++ri) {
-      const int y = warp + 32 * ri;
-      if (y < kG) {
-#pragma unroll
-        for (int ci = 0; ci < kColIters; ++ci) {
-          const int x = lane + 32 * ci;
-          if (x < kG) {
-            CellTerms t = cell_terms(f[y * kG + x], cell_sdf_masked(io.lin[x], io.lin[y], s_sc, s_sc + 16, s_rowmask[y]), vis_inf);
-            if (any_inside && t.edge <= 0.0f) t.J = high;
-            const float gn = __fdiv_rn(__fsub_rn(t.vis, gmn), gden);
-            const float jn = __fdiv_rn(__fsub_rn(t.J, jmn), jden);
-            f[y * kG + x] = __fadd_rn(gn, __fmul_rn(0.5f, jn));
-          }
-        }
-      }
-    }
     __syncthreads();
+    float* f = io.field + env * (int64_t)kCells + y0 * kG;
+#pragma unroll 3
+    for (int q = threadIdx.x; q < kFieldRows * kG; q += kFieldThreads) {
+      const int r = q / kG, x = q - r * kG;
+      const float cost = f[q];
+      const float vis = (cost == CUDART_INF_F) ? vis_inf : cost;  // torch.where(isinf(cost), max_val*1.5, cost)
+      const uint32_t mask = s_rowmask[r] & s_colmask[x];
+      float J = 0.0f;
+      if (mask) {            // most cells feel no obstacle: no distance, no repulsion
+        const CellGeom g = cell_geom(cell_sdf_masked(io.lin[x], io.lin[y0 + r], s_sc, s_sc + 16, mask));
+        if (g.raw > 0.0f) J = __fmul_rn(g.raw, (cost == CUDART_INF_F) ? rep_inf : cell_rep(cost));
+        if (any_inside && g.edge <= 0.0f) J = high;
+      }
+      const float gn = __fdiv_rn(__fsub_rn(vis, gmn), gden);
+      const float jd = __fsub_rn(J, jmn);
+      const float jn = (jd == 0.0f) ? 0.0f : __fdiv_rn(jd, jden);   // +0 / jden == +0 (jden >= 1e-6): the division is skipped
+      f[q] = __fadd_rn(gn, __fmul_rn(0.5f, jn));
+    }
   }
 }
 
@@ -525,7 +528,7 @@ __global__ void compact_resets_kernel(const int64_t* __restrict__ reset_buf, int
   }
 }
 
-static size_t cost_smem_bytes() { return (size_t)(kGPR * kGP + 64 + 32 + 2 * kActStride + 160) * sizeof(float) + (size_t)kTiles * 32; }
+static size_t cost_smem_bytes() { return (size_t)(kGPR * kGP + 64 + 32 + 2 * kActStride + 160 + 160) * sizeof(float) + (size_t)kTiles * 32; }
 
 static int scene_grid() {
   static int sms = 0;
@@ -546,9 +549,8 @@ static int launch_scene(const SceneIO& io, uint32_t* counters, int place, const 
   }
   const int grid = scene_grid();
   scene_cost_kernel<<<2 * grid, kCostThreads, cost_smem_bytes(), s>>>(io, counters, place, *p, step_offset);   // two scenes per SM
-  scene_jmax_kernel<<<grid, kSceneThreads, 0, s>>>(io, counters);
-  scene_field_kernel<<<grid, kSceneThreads, 0, s>>>(io, counters);
-  return finish_launch(3);
+  scene_field_kernel<<<8 * grid, kFieldThreads, 0, s>>>(io, counters);
+  return finish_launch(2);
 }
 
 }  // namespace usv
@@ -557,7 +559,9 @@ using namespace usv;
 
 extern "C" {
 
-int64_t usv_live_scene_workspace_bytes(int64_t n) { return (int64_t)CW_WORDS * 4 + (n < 0 ? 0 : n) * 4; }
+// workspace: [CW_WORDS counters][n int32 reset list, padded to 16 B][n x SS_WORDS per-scene statistics]
+static int64_t stats_offset_bytes(int64_t n) { return (int64_t)CW_WORDS * 4 + (((n < 0 ? 0 : n) * 4 + 15) & ~(int64_t)15); }
+int64_t usv_live_scene_workspace_bytes(int64_t n) { return stats_offset_bytes(n) + (n < 0 ? 0 : n) * (int64_t)(SS_WORDS * 4); }
 
 int usv_live_reset_scene_f32(const UsvEnvBuffers* b, const UsvLiveBuffers* lb, const float* cell_centres, void* workspace,
                              int64_t n, const UsvStepParams* p, void* stream) {
@@ -581,6 +585,7 @@ int usv_live_reset_scene_f32(const UsvEnvBuffers* b, const UsvLiveBuffers* lb, c
   io.consts = b->consts;
   io.field = lb->field;
   io.lin = cell_centres;
+  io.stats = (float*)((char*)workspace + stats_offset_bytes(n));
   return launch_scene(io, counters, 1, p, b->step_offset, s);
 }
 
@@ -600,6 +605,7 @@ int usv_live_build_fields_f32(const float* obstacles, const float* targets, cons
   io.field = field;
   io.cost_out = cost_out;
   io.lin = cell_centres;
+  io.stats = (float*)((char*)workspace + stats_offset_bytes(m));
   UsvStepParams p{};
   return launch_scene(io, counters, 0, &p, nullptr, s);
 }

@@ -328,6 +328,9 @@ class FusedUsvLiveEnv(FusedUsvEnv):
         targets = targets.to(self.device, torch.float32).contiguous()
         field = torch.empty((m, GRID, GRID), dtype=torch.float32, device=self.device)
         cost = torch.empty_like(field) if want_cost else None
+        need = int(self.lib.usv_live_scene_workspace_bytes(m)) // 4 + 4
+        if self.workspace.numel() < need:       # a dense batch larger than the env count: the per-scene statistics need the room
+            self.workspace = torch.zeros(need, dtype=torch.int32, device=self.device)
         _lib.check(self.lib.usv_live_build_fields_f32(_lib.ptr(obstacles), _lib.ptr(targets), _lib.ptr(self.cell_centres),
                                                       _lib.ptr(field), _lib.ptr(cost), _lib.ptr(self.workspace),
                                                       ctypes.c_int64(m), _lib.stream()), "usv_live_build_fields_f32")
