@@ -26,13 +26,20 @@
 namespace usv {
 
 constexpr int kG = USV_B_GRID;       // 150
-constexpr int kGP = kG + 2;          // padded row (halo of +inf)
+constexpr int kGP = kG + 2;          // padded rows / columns (halo of +inf)
+constexpr int kGS = kGP + 1;         // row stride of the padded buffer, 153 words: the four 8-row groups of a tile pass (8 rows apart) fall on
+                                     // banks 0-7 / 8-15 / 16-23 / 24-31 (8 * 153 mod 32 == 8), one conflict-free wavefront per load
 constexpr int kGPR = kGP + 2;        // rows of the padded buffer: the halo plus two spare +inf rows (a tile pass always reads 10 rows)
 constexpr int kCells = kG * kG;
 constexpr int kColIters = (kG + 31) / 32;  // 5
 constexpr int kMaxSweeps = (int)(kG * 1.5);  // 225  (d_multi_gemini.py:160)
 constexpr float kObstR = 0.5f;
-constexpr int kChunks = 5, kBandRows = 8, kBands = (kG + kBandRows - 1) / kBandRows, kTiles = kChunks * kBands;  // wavefront tiles: 32 columns x 8 rows (95)
+// wavefront tiles: 8 columns x 32 rows, one warp per tile pass; lane = (column cx = lane & 7, row group g = lane >> 3), 8 rows per lane.
+// Inside a lane's column the pass is a Gauss-Seidel walk down and back up (a value crosses the lane's 8 rows in one pass), across
+// columns and row groups it is Jacobi: a value crosses a tile in <= 8 passes sideways and <= 4 vertically.  (r01 / early r02: 32
+// columns x 8 rows, pure Jacobi: up to 32 passes to cross sideways, ~20 passes per tile and scene in the instrumented run.)
+constexpr int kTileW = 8, kBandRows = 8, kGroups = 4, kTileH = kGroups * kBandRows;
+constexpr int kChunks = (kG + kTileW - 1) / kTileW, kBands = (kG + kTileH - 1) / kTileH, kTiles = kChunks * kBands;  // 19 x 5 = 95
 constexpr int kActStride = 96;       // tile-active flags per sweep parity
 constexpr float kReach = 1.7f + 1e-3f;  // an obstacle matters to a cell only within 0.5 (radius) + 0.5 + 0.7 (influence) of its centre
 
@@ -159,7 +166,7 @@ __device__ __forceinline__ void place_obstacles(const UsvStepParams& p, uint64_t
 constexpr int kCostThreads = 512, kCostWarps = kCostThreads / 32;
 constexpr int kAsyncSweepCap = 4 * kMaxSweeps;
 #ifndef USV_SCENE_INNER
-#define USV_SCENE_INNER 32
+#define USV_SCENE_INNER 16
 #endif
 constexpr int kInner = USV_SCENE_INNER;            // passes of a warp over its tile per outer sweep (one tile width)
 constexpr float kJacobiSafeCost = 224.0f;
@@ -195,25 +202,25 @@ __device__ __forceinline__ CellGeom cell_geom(float sdf) {
 __device__ __forceinline__ float cell_rep(float vis) { return fminf(fmaxf(__fdiv_rn(__fmul_rn(vis, 0.2f), 3.0f), 0.0f), 1.0f); }
 
 __device__ __forceinline__ bool cell_free(const unsigned char* s_free, int x, int y) {
-  return (s_free[((y / kBandRows) * kChunks + (x >> 5)) * 32 + (x & 31)] >> (y % kBandRows)) & 1u;
+  return (s_free[((y / kTileH) * kChunks + x / kTileW) * 32 + ((y % kTileH) / kBandRows) * kTileW + x % kTileW] >> (y % kBandRows)) & 1u;
 }
 
 // literal Jacobi sweeps (d_multi_gemini.py:160-190): cur = buf (shared), nxt = tmp (global), early exit at the first unchanged sweep
 __device__ void jacobi_exact(float* buf, float* __restrict__ tmp, const unsigned char* s_free, int txi, int tyi) {
-  for (int q = threadIdx.x; q < kGP * kGP; q += kCostThreads) buf[q] = CUDART_INF_F;
+  for (int q = threadIdx.x; q < kGPR * kGS; q += kCostThreads) buf[q] = CUDART_INF_F;
   __syncthreads();
-  if (threadIdx.x == 0) buf[(tyi + 1) * kGP + txi + 1] = 0.0f;
+  if (threadIdx.x == 0) buf[(tyi + 1) * kGS + txi + 1] = 0.0f;
   __syncthreads();
   for (int sweep = 0; sweep < kMaxSweeps; ++sweep) {
     int chg = 0;
     for (int cell = threadIdx.x; cell < kCells; cell += kCostThreads) {
       const int y = cell / kG, x = cell - y * kG;
-      const float* c = buf + (y + 1) * kGP + x + 1;
+      const float* c = buf + (y + 1) * kGS + x + 1;
       const float mc = c[0];
       float best = CUDART_INF_F;
       if (cell_free(s_free, x, y)) {
-        const float a = fminf(fminf(c[-1], c[1]), fminf(c[-kGP], c[kGP])) + 1.0f;
-        const float b = fminf(fminf(c[-kGP - 1], c[-kGP + 1]), fminf(c[kGP - 1], c[kGP + 1])) + 1.414f;
+        const float a = fminf(fminf(c[-1], c[1]), fminf(c[-kGS], c[kGS])) + 1.0f;
+        const float b = fminf(fminf(c[-kGS - 1], c[-kGS + 1]), fminf(c[kGS - 1], c[kGS + 1])) + 1.414f;
         best = fminf(mc, fminf(a, b));
       }
       tmp[cell] = best;
@@ -222,7 +229,7 @@ __device__ void jacobi_exact(float* buf, float* __restrict__ tmp, const unsigned
     const int any = __syncthreads_or(chg);
     for (int cell = threadIdx.x; cell < kCells; cell += kCostThreads) {
       const int y = cell / kG, x = cell - y * kG;
-      buf[(y + 1) * kGP + x + 1] = tmp[cell];
+      buf[(y + 1) * kGS + x + 1] = tmp[cell];
     }
     __syncthreads();
     if (!any) break;
@@ -235,7 +242,7 @@ __global__ void __launch_bounds__(kCostThreads, 2) scene_cost_kernel(SceneIO io,
   const uint64_t step = p.step_counter + (step_offset ? *step_offset : 0ull);   // device-side addend: CUDA-graph replays
   extern __shared__ __align__(16) float smem[];
   float* buf = smem;                  // padded 152 x 152, +inf halo
-  float* s_sc = buf + kGPR * kGP;     // 34 floats
+  float* s_sc = buf + kGPR * kGS;     // 34 floats
   float* s_red = s_sc + 64;           // 32 floats
   int* s_act = reinterpret_cast<int*>(s_red + 32);        // [2][96] tile-active flags of the current / next sweep
   uint32_t* s_rowmask = reinterpret_cast<uint32_t*>(s_act + 2 * kActStride);  // [150] obstacles that can matter on a grid row
@@ -264,7 +271,7 @@ __global__ void __launch_bounds__(kCostThreads, 2) scene_cost_kernel(SceneIO io,
     } else {
       env = load_scene(io, j, s_sc);
     }
-    for (int q = threadIdx.x; q < kGPR * kGP; q += kCostThreads) buf[q] = CUDART_INF_F;   // halo and spare rows included
+    for (int q = threadIdx.x; q < kGPR * kGS; q += kCostThreads) buf[q] = CUDART_INF_F;   // halo and spare rows included
     if (threadIdx.x < 2 * kActStride) s_act[threadIdx.x] = 0;
     __syncthreads();
     // an obstacle within kReach of a cell is within kReach of its row AND of its column: the AND of the two masks leaves the one
@@ -275,18 +282,18 @@ __global__ void __launch_bounds__(kCostThreads, 2) scene_cost_kernel(SceneIO io,
     const int txi = min(max((int)__fdiv_rn(s_sc[32] + 15.0f, 0.2f), 0), kG - 1);
     const int tyi = min(max((int)__fdiv_rn(s_sc[33] + 15.0f, 0.2f), 0), kG - 1);
     if (threadIdx.x == 0) {
-      buf[(tyi + 1) * kGP + txi + 1] = 0.0f;
-      const int tc = txi >> 5, tb = tyi / kBandRows;
+      buf[(tyi + 1) * kGS + txi + 1] = 0.0f;
+      const int tc = txi / kTileW, tb = tyi / kTileH;
       for (int db = -1; db <= 1; ++db)
         for (int dc = -1; dc <= 1; ++dc)
           if (tc + dc >= 0 && tc + dc < kChunks && tb + db >= 0 && tb + db < kBands) s_act[(tb + db) * kChunks + tc + dc] = 1;
     }
     __syncthreads();
-    // free bits of the 95 tiles of 32 columns x 8 rows (dealt round-robin to the warps, so that the ring of tiles the wavefront is
-    // crossing is spread over all of them)
+    // free bits of the 95 tiles (dealt round-robin to the warps, so that the ring of tiles the wavefront is crossing is spread over
+    // all of them): one byte per lane = its 8 rows
     for (int t = warp; t < kTiles; t += kCostWarps) {
       const int chunk = t % kChunks, band = t / kChunks;
-      const int x = chunk * 32 + lane, y0 = band * kBandRows;
+      const int x = chunk * kTileW + (lane & 7), y0 = band * kTileH + (lane >> 3) * kBandRows;
       uint32_t fm = 0;
       if (x < kG) {
         const uint32_t cmask = s_colmask[x];
@@ -314,48 +321,56 @@ __global__ void __launch_bounds__(kCostThreads, 2) scene_cost_kernel(SceneIO io,
           __syncwarp();
           if (lane == 0) act_cur[t] = 0;             // consumed; writers of this sweep only touch act_nxt
           const int chunk = t % kChunks, band = t / kChunks;
-          const int x = chunk * 32 + lane, y0 = band * kBandRows;
-          const int rows = min(kBandRows, kG - y0);
+          const int cxl = lane & 7, grp = lane >> 3;
+          const int x = chunk * kTileW + cxl;
+          const int y0 = min(band * kTileH + grp * kBandRows, kG - 6);   // a group wholly below the grid (no free bit) reads in bounds
           const int xc = min(x, kG - 1);
           const uint32_t freemask = s_free[t * 32 + lane];
+          const int bot = min(band * kTileH + kTileH, kG) - 1 - y0;      // bit of the tile's bottom row in this lane's byte, if 0..7
           // Temporal blocking: the warp relaxes ITS tile up to kInner times (until it stops changing) before the CTA-wide barrier, so a
-          // value crosses a whole 32 x 8 tile per outer sweep instead of one cell (legal: any fair asynchronous order reaches the same
-          // fixed point).
+          // value crosses a whole tile per outer sweep instead of one cell (legal: any fair asynchronous order reaches the same fixed
+          // point).
           bool e_left = false, e_right = false, e_up = false, e_dn = false, changed = false, more = true;
           for (int inner = 0; inner < kInner && more; ++inner) {
-            // one block-Jacobi pass over the tile: all 10 x 3 window values are loaded first -- unconditionally, the buffer carries two
-            // spare +inf rows below the halo so that the last band (6 rows) reads in bounds -- and the 8 cells of the lane's column are
-            // then relaxed from those registers: no loop-carried dependency and no branch, so the rows pipeline.  (With guarded loads
-            // and a per-row `if (free)` the compiler sank every row's loads behind a divergent branch of the row before: ~1100 cycles
-            // per pass in the r02 instrumented run against ~200 instructions.)  A lane outside the grid or a row below it has no free
-            // bit, so the mask alone gates the store.
-            const float* rp = buf + y0 * kGP + xc + 1;    // padded row y0 == grid row y0 - 1
-            float wl[kBandRows + 2], wc[kBandRows + 2], wr[kBandRows + 2];
+            // one pass over the tile: all 10 x 3 window values are loaded first -- unconditionally, the buffer carries two spare +inf
+            // rows below the halo so that the last rows read in bounds -- then the 8 cells of the lane's column are relaxed from
+            // registers, walking down and back up with each new value fed into the next row (the left / right columns stay as loaded).
+            // No branch: a lane outside the grid or a row below it has no free bit, so the mask alone gates the store.  (With guarded
+            // loads and a per-row `if (free)` the compiler sank every row's loads behind a divergent branch of the row before: ~1100
+            // cycles per pass in the r02 instrumented run against ~200 instructions.)
+            const float* rp = buf + y0 * kGS + xc + 1;    // padded row y0 == grid row y0 - 1
+            float wl[kBandRows + 2], wc[kBandRows + 2], wr[kBandRows + 2], was[kBandRows];
 #pragma unroll
             for (int r = 0; r < kBandRows + 2; ++r) {
-              wl[r] = rp[r * kGP - 1];
-              wc[r] = rp[r * kGP];
-              wr[r] = rp[r * kGP + 1];
+              wl[r] = rp[r * kGS - 1];
+              wc[r] = rp[r * kGS];
+              wr[r] = rp[r * kGS + 1];
+            }
+#pragma unroll
+            for (int i = 0; i < kBandRows; ++i) {         // down
+              was[i] = wc[i + 1];
+              const float a = fminf(fminf(wl[i + 1], wr[i + 1]), fminf(wc[i], wc[i + 2])) + 1.0f;
+              const float b = fminf(fminf(wl[i], wr[i]), fminf(wl[i + 2], wr[i + 2])) + 1.414f;
+              const float best = fminf(wc[i + 1], fminf(a, b));
+              wc[i + 1] = ((freemask >> i) & 1u) ? best : wc[i + 1];
             }
             uint32_t chg = 0;
 #pragma unroll
-            for (int i = 0; i < kBandRows; ++i) {
-              const float mc = wc[i + 1];
-              const float a = fminf(fminf(wl[i + 1], wr[i + 1]), fminf(wc[i], wc[i + 2])) + 1.0f;
-              const float b = fminf(fminf(wl[i], wr[i]), fminf(wl[i + 2], wr[i + 2])) + 1.414f;
-              const float best = fminf(mc, fminf(a, b));
-              const bool upd = ((freemask >> i) & 1u) != 0u && best != mc;
-              if (upd) buf[(y0 + i + 1) * kGP + xc + 1] = best;
+            for (int i = kBandRows - 1; i >= 0; --i) {    // and back up: only the row below can have moved since the walk down
+              const float best = fminf(wc[i + 1], wc[i + 2] + 1.0f);
+              if (i < kBandRows - 1) wc[i + 1] = ((freemask >> i) & 1u) ? best : wc[i + 1];
+              const bool upd = wc[i + 1] != was[i];
+              if (upd) buf[(y0 + i + 1) * kGS + xc + 1] = wc[i + 1];
               chg |= upd ? (1u << i) : 0u;
             }
             const uint32_t any_b = __ballot_sync(0xffffffffu, chg != 0u);
             more = any_b != 0u;
             if (more) {
               changed = true;
-              e_left |= (any_b & 1u) != 0u;
-              e_right |= ((any_b >> 31) & 1u) != 0u;
-              e_up |= __any_sync(0xffffffffu, chg & 1u) != 0;
-              e_dn |= __any_sync(0xffffffffu, (chg >> (rows - 1)) & 1u) != 0;
+              e_left |= (any_b & 0x01010101u) != 0u;      // column 0 of any row group
+              e_right |= (any_b & 0x80808080u) != 0u;     // column 7
+              e_up |= __any_sync(0xffffffffu, grp == 0 && (chg & 1u)) != 0;
+              e_dn |= __any_sync(0xffffffffu, bot >= 0 && bot < kBandRows && ((chg >> bot) & 1u)) != 0;
             }
             __syncwarp();
           }
@@ -388,7 +403,7 @@ __global__ void __launch_bounds__(kCostThreads, 2) scene_cost_kernel(SceneIO io,
         for (int ci = 0; ci < kColIters; ++ci) {
           const int x = lane + 32 * ci;
           if (x < kG) {
-            const float c = buf[(y + 1) * kGP + x + 1];
+            const float c = buf[(y + 1) * kGS + x + 1];
             out[y * kG + x] = c;
             if (io.cost_out) io.cost_out[j * (int64_t)kCells + y * kG + x] = c;
             if (c < CUDART_INF_F) mx = fmaxf(mx, c);
@@ -409,7 +424,7 @@ __global__ void __launch_bounds__(kCostThreads, 2) scene_cost_kernel(SceneIO io,
       for (int ci = 0; ci < kColIters; ++ci) {
         const int x = lane + 32 * ci;
         if (x < kG) {
-          const float c = buf[(y + 1) * kGP + x + 1];
+          const float c = buf[(y + 1) * kGS + x + 1];
           const CellGeom g = cell_geom(cell_sdf_masked(io.lin[x], cy, s_sc, s_sc + 16, rmask & s_colmask[x]));
           const bool inside = g.edge <= 0.0f;
           has_inside |= inside ? 1 : 0;
@@ -528,7 +543,7 @@ __global__ void compact_resets_kernel(const int64_t* __restrict__ reset_buf, int
   }
 }
 
-static size_t cost_smem_bytes() { return (size_t)(kGPR * kGP + 64 + 32 + 2 * kActStride + 160 + 160) * sizeof(float) + (size_t)kTiles * 32; }
+static size_t cost_smem_bytes() { return (size_t)(kGPR * kGS + 64 + 32 + 2 * kActStride + 160 + 160) * sizeof(float) + (size_t)kTiles * 32; }
 
 static int scene_grid() {
   static int sms = 0;
