@@ -515,22 +515,33 @@ __global__ void __launch_bounds__(kFieldThreads) scene_field_kernel(SceneIO io, 
     const float gden = __fadd_rn(__fsub_rn(gmx, gmn), 1e-6f), jden = __fadd_rn(__fsub_rn(jmx, jmn), 1e-6f);
     __syncthreads();
     float* f = io.field + env * (int64_t)kCells + y0 * kG;
-#pragma unroll 3
-    for (int q = threadIdx.x; q < kFieldRows * kG; q += kFieldThreads) {
-      const int r = q / kG, x = q - r * kG;
-      const float cost = f[q];
-      const float vis = (cost == CUDART_INF_F) ? vis_inf : cost;  // torch.where(isinf(cost), max_val*1.5, cost)
-      const uint32_t mask = s_rowmask[r] & s_colmask[x];
-      float J = 0.0f;
-      if (mask) {            // most cells feel no obstacle: no distance, no repulsion
-        const CellGeom g = cell_geom(cell_sdf_masked(io.lin[x], io.lin[y0 + r], s_sc, s_sc + 16, mask));
-        if (g.raw > 0.0f) J = __fmul_rn(g.raw, (cost == CUDART_INF_F) ? rep_inf : cell_rep(cost));
-        if (any_inside && g.edge <= 0.0f) J = high;
+    // all of the thread's costs are requested before the first one is used: one L2 round trip per item instead of three
+    constexpr int kPer = (kFieldRows * kG + kFieldThreads - 1) / kFieldThreads;   // 9
+    float cst[kPer];
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      const int q = threadIdx.x + k * kFieldThreads;
+      cst[k] = (q < kFieldRows * kG) ? f[q] : 0.0f;
+    }
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      const int q = threadIdx.x + k * kFieldThreads;
+      if (q < kFieldRows * kG) {
+        const int r = q / kG, x = q - r * kG;
+        const float cost = cst[k];
+        const float vis = (cost == CUDART_INF_F) ? vis_inf : cost;  // torch.where(isinf(cost), max_val*1.5, cost)
+        const uint32_t mask = s_rowmask[r] & s_colmask[x];
+        float J = 0.0f;
+        if (mask) {            // most cells feel no obstacle: no distance, no repulsion
+          const CellGeom g = cell_geom(cell_sdf_masked(io.lin[x], io.lin[y0 + r], s_sc, s_sc + 16, mask));
+          if (g.raw > 0.0f) J = __fmul_rn(g.raw, (cost == CUDART_INF_F) ? rep_inf : cell_rep(cost));
+          if (any_inside && g.edge <= 0.0f) J = high;
+        }
+        const float gn = __fdiv_rn(__fsub_rn(vis, gmn), gden);
+        const float jd = __fsub_rn(J, jmn);
+        const float jn = (jd == 0.0f) ? 0.0f : __fdiv_rn(jd, jden);   // +0 / jden == +0 (jden >= 1e-6): the division is skipped
+        f[q] = __fadd_rn(gn, __fmul_rn(0.5f, jn));
       }
-      const float gn = __fdiv_rn(__fsub_rn(vis, gmn), gden);
-      const float jd = __fsub_rn(J, jmn);
-      const float jn = (jd == 0.0f) ? 0.0f : __fdiv_rn(jd, jden);   // +0 / jden == +0 (jden >= 1e-6): the division is skipped
-      f[q] = __fadd_rn(gn, __fmul_rn(0.5f, jn));
     }
   }
 }
