@@ -322,13 +322,19 @@ __device__ __forceinline__ void redraw_com(const UsvLiveParams& lp, const Unifor
   }
 }
 
-template <int kDisturb, bool kStats, bool kStage = true>
-__global__ void __launch_bounds__(kBlock, 3) step_live_kernel(UsvEnvBuffers b, UsvLiveBuffers lb, const float2* __restrict__ actions,
+// kMinB = CTAs per SM the register allocation aims for: 3 (80 registers, a few spilled words) is the best trade at >= 131 072 envs, where
+// the kernel waits on DRAM; up to 2 x 148 CTAs -- one wave either way -- the 2-CTA build (112-128 registers, no spill) is 25-30 % faster
+// (14.5 vs 17.4 us at 65 536 envs, 14.8 vs 18.3 at 75 776, r02 A/B).  Above one wave the step time is (number of waves) x (latency of one
+// thread's ~2500-instruction chain with that many warps resident: 14.5 us at 16 warps per SM, ~20 us at 24), so 131 072 envs = 1.15 waves
+// cost two; a 224-thread x 4-CTA build (28 warps per SM, 72 registers, kB) turns that size into one wave (30 vs 41 us) but loses at
+// 262 144 (93 vs 77 us), and 64 registers lose everywhere: not kept, see profiles/r02_live_kernels.md.
+template <int kDisturb, bool kStats, bool kStage = true, int kMinB = 3, int kB = kBlock>
+__global__ void __launch_bounds__(kB, kMinB) step_live_kernel(UsvEnvBuffers b, UsvLiveBuffers lb, const float2* __restrict__ actions,
                                                               float* __restrict__ obs, float* __restrict__ rew, int64_t n,
                                                               const __grid_constant__ UsvStepParams p,
                                                               const __grid_constant__ UsvLiveParams lp) {
   extern __shared__ __align__(16) float smem[];
-  const int64_t block_start = (int64_t)blockIdx.x * kBlock;
+  const int64_t block_start = (int64_t)blockIdx.x * kB;
   const int64_t i = block_start + threadIdx.x;
   const bool active = i < n;
   const uint64_t step = p.step_counter + (b.step_offset ? *b.step_offset : 0ull);   // device-side addend: CUDA-graph replays
@@ -340,7 +346,7 @@ __global__ void __launch_bounds__(kBlock, 3) step_live_kernel(UsvEnvBuffers b, U
   // The task part reads 35 per-episode constants per env (CoM + 16 obstacle centres) ~1500 instructions from here, one dependent
   // load per obstacle (r02 ncu at 262 144 envs: 35 % of the stall samples sat on those loads, long-scoreboard 7.6 cycles per issue).
   // A warp's tile of them is ONE contiguous 4480 B run in the AoSoA buffer: fetch it with cp.async now, wait right before the task part.
-  float* s_bc = smem + kBlock * kObsB + (threadIdx.x >> 5) * (USV_BC_COUNT * kTile);
+  float* s_bc = smem + kB * kObsB + (threadIdx.x >> 5) * (USV_BC_COUNT * kTile);
   if (kStage) {
     const int64_t w0 = block_start + (int64_t)(threadIdx.x & ~31);
     if (w0 < n) {
@@ -598,6 +604,8 @@ extern "C" int usv_step_live_f32(const UsvEnvBuffers* b, const UsvLiveBuffers* l
     cudaFuncSetAttribute(step_live_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_live);
     cudaFuncSetAttribute(step_live_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_live);
     cudaFuncSetAttribute(step_live_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_live);
+    cudaFuncSetAttribute(step_live_kernel<true, false, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_live);
+    cudaFuncSetAttribute(step_live_kernel<false, false, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_live);
     attr = true;
   }
   const int grid = grid_for(n, kBlock);
@@ -611,9 +619,13 @@ extern "C" int usv_step_live_f32(const UsvEnvBuffers* b, const UsvLiveBuffers* l
   // force one of them (profiling runs).
   static const int force = getenv("USV_LIVE_NO_STAGE") ? 0 : (getenv("USV_LIVE_STAGE") ? 1 : -1);
   const bool no_stage = force >= 0 ? force == 0 : n > 196608;
+  // one wave at two CTAs per SM (and no statistics: the rarely used stats build stays on one register budget)
+  static const int sms = [] { int d = 0, v = 0; cudaGetDevice(&d); return (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d) == cudaSuccess && v > 0) ? v : 148; }();
+  const bool one_wave = !no_stage && grid <= 2 * sms && !getenv("USV_LIVE_MINB3");
 #define USV_LAUNCH_LIVE(D, S)                                                                                                      \
   do {                                                                                                                             \
     if (no_stage) step_live_kernel<D, S, false><<<grid, kBlock, smem, s>>>(*b, *lb, (const float2*)actions, obs, rew, n, *p, *lp);  \
+    else if (one_wave && !S) step_live_kernel<D, false, true, 2><<<grid, kBlock, smem_live, s>>>(*b, *lb, (const float2*)actions, obs, rew, n, *p, *lp); \
     else step_live_kernel<D, S, true><<<grid, kBlock, smem_live, s>>>(*b, *lb, (const float2*)actions, obs, rew, n, *p, *lp);       \
   } while (0)
 #define USV_LAUNCH_TASK(T, D) step_task_kernel<T, D><<<grid, kBlock, smem, s>>>(*b, *lb, (const float2*)actions, obs, rew, n, *p, *lp)
