@@ -10,6 +10,16 @@
 // RNG is Philox4x32-10 keyed (seed; env, step, stream): no RNG state in HBM.
 //
 // Roofline: HBM-bound by design -- algorithmic bytes per env-step are tabulated in DESIGN.md.
+// CTA shape of the classic kernels of this file: 128 threads, 7 CTAs per SM = 28 warps per SM at 72 registers (no spill).  The fused step is
+// issue-bound and ends in a partial wave: with 256 x 3 (24 warps per SM, 78 registers) 2^20 envs are 9.23 waves and the last 0.23 runs one
+// CTA per SM for a whole thread's latency; 28 warps per SM make it 7.9 waves.  Same-box A/B at 2^20 envs, 2000 steps (r02): 256 x 3 1.940e10
+// env-steps/s, 160 x 5 1.977, 224 x 4 2.014, 64 x 14 2.016, 128 x 7 2.02-2.05, 32 x 28 2.03; 64 registers (128 x 8, 96 x 10) 1.96-1.97.
+#ifndef USV_BLOCK
+#define USV_BLOCK 128
+#endif
+#ifndef USV_MINB
+#define USV_MINB 7
+#endif
 #include "usv_step_core.cuh"
 
 namespace usv {
