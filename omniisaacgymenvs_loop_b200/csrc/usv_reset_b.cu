@@ -33,6 +33,7 @@ constexpr int kGPR = kGP + 2;        // rows of the padded buffer: the halo plus
 constexpr int kCells = kG * kG;
 constexpr int kColIters = (kG + 31) / 32;  // 5
 constexpr int kMaxSweeps = (int)(kG * 1.5);  // 225  (d_multi_gemini.py:160)
+constexpr int kNearCap = USV_B_OBSTACLES * 18 * 18;   // cells with one obstacle within kReach on both axes: an interval of 2 x 1.701 holds <= 18 cell centres
 constexpr float kObstR = 0.5f;
 // wavefront tiles: 8 columns x 32 rows, one warp per tile pass; lane = (column cx = lane & 7, row group g = lane >> 3), 8 rows per lane.
 // Inside a lane's column the pass is a Gauss-Seidel walk down and back up (a value crosses the lane's 8 rows in one pass), across
@@ -248,6 +249,8 @@ __global__ void __launch_bounds__(kCostThreads, 2) scene_cost_kernel(SceneIO io,
   uint32_t* s_rowmask = reinterpret_cast<uint32_t*>(s_act + 2 * kActStride);  // [150] obstacles that can matter on a grid row
   uint32_t* s_colmask = s_rowmask + 160;                                      // [150] ... on a grid column
   unsigned char* s_free = reinterpret_cast<unsigned char*>(s_colmask + 160);  // [95][32] free bits of a lane's 8 cells of a tile
+  unsigned short* s_near = reinterpret_cast<unsigned short*>(s_free + kTiles * 32);   // [kNearCap] cells within reach of an obstacle
+  int* s_nnear = reinterpret_cast<int*>(s_red + 31);                          // their count (s_red holds 16 partials)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t total = scene_count(io);
   for (int64_t j = blockIdx.x; j < total; j += gridDim.x) {
@@ -273,6 +276,7 @@ __global__ void __launch_bounds__(kCostThreads, 2) scene_cost_kernel(SceneIO io,
     }
     for (int q = threadIdx.x; q < kGPR * kGS; q += kCostThreads) buf[q] = CUDART_INF_F;   // halo and spare rows included
     if (threadIdx.x < 2 * kActStride) s_act[threadIdx.x] = 0;
+    if (threadIdx.x == 0) *s_nnear = 0;
     __syncthreads();
     // an obstacle within kReach of a cell is within kReach of its row AND of its column: the AND of the two masks leaves the one
     // or two obstacles a cell can feel (none for most cells)
@@ -302,7 +306,12 @@ __global__ void __launch_bounds__(kCostThreads, 2) scene_cost_kernel(SceneIO io,
         for (int i = 0; i < kBandRows && y0 + i < kG; ++i) {
           const int y = y0 + i;
           const bool border = (y == 0) || (y == kG - 1) || (x == 0) || (x == kG - 1);
-          const float sdf = cell_sdf_masked(cx, io.lin[y], s_sc, s_sc + 16, s_rowmask[y] & cmask);
+          const uint32_t mask = s_rowmask[y] & cmask;
+          if (mask) {                                  // the statistics pass walks these densely
+            const int k = atomicAdd(s_nnear, 1);
+            if (k < kNearCap) s_near[k] = (unsigned short)(y * kG + x);
+          }
+          const float sdf = cell_sdf_masked(cx, io.lin[y], s_sc, s_sc + 16, mask);
           if (!border && !(sdf <= 0.0f)) fm |= 1u << i;
         }
       }
@@ -392,13 +401,18 @@ __global__ void __launch_bounds__(kCostThreads, 2) scene_cost_kernel(SceneIO io,
       exact = sweep < kAsyncSweepCap;
     }
     float* out = io.field + env * (int64_t)kCells;
-    float mx = -1.0f;
+    float mx = -1.0f, mn = CUDART_INF_F;
+    int far_fin = 0, far_inf = 0;
     for (int pass = 0; pass < 2; ++pass) {
       if (pass == 1 || !exact) jacobi_exact(buf, out, s_free, txi, tyi);
       // raw cost -> field[env] (and the optional dense cost output); max finite cost
       mx = -1.0f;
+      mn = CUDART_INF_F;
+      far_fin = 0;
+      far_inf = 0;
 #pragma unroll 1
       for (int y = warp; y < kG; y += kCostWarps) {
+        const uint32_t rmask = s_rowmask[y];
 #pragma unroll
         for (int ci = 0; ci < kColIters; ++ci) {
           const int x = lane + 32 * ci;
@@ -406,41 +420,43 @@ __global__ void __launch_bounds__(kCostThreads, 2) scene_cost_kernel(SceneIO io,
             const float c = buf[(y + 1) * kGS + x + 1];
             out[y * kG + x] = c;
             if (io.cost_out) io.cost_out[j * (int64_t)kCells + y * kG + x] = c;
-            if (c < CUDART_INF_F) mx = fmaxf(mx, c);
+            const bool fin = c < CUDART_INF_F, far = (rmask & s_colmask[x]) == 0u;
+            if (fin) { mx = fmaxf(mx, c); mn = fminf(mn, c); }
+            far_fin |= (far && fin) ? 1 : 0;      // cells no obstacle reaches: repulsion 0, not inside
+            far_inf |= (far && !fin) ? 1 : 0;
           }
         }
       }
       mx = block_reduce_max_cost(mx, s_red);
       if (pass == 1 || !exact || mx < kJacobiSafeCost) break;   // the fixed point is the 225th Jacobi iterate
     }
-    // per-scene statistics for the field kernel + the batch maxima of the repulsion, from the converged costs still in shared memory
-    float mn = CUDART_INF_F, jfmn = CUDART_INF_F, jfmx = -1.0f, jimn = CUDART_INF_F, jimx = -1.0f, jall_fin = 0.0f, jall_inf = 0.0f;
-    int has_inf = 0, has_inside = 0;
-#pragma unroll 1
-    for (int y = warp; y < kG; y += kCostWarps) {
-      const uint32_t rmask = s_rowmask[y];
-      const float cy = io.lin[y];
-#pragma unroll
-      for (int ci = 0; ci < kColIters; ++ci) {
-        const int x = lane + 32 * ci;
-        if (x < kG) {
-          const float c = buf[(y + 1) * kGS + x + 1];
-          const CellGeom g = cell_geom(cell_sdf_masked(io.lin[x], cy, s_sc, s_sc + 16, rmask & s_colmask[x]));
-          const bool inside = g.edge <= 0.0f;
-          has_inside |= inside ? 1 : 0;
-          if (c < CUDART_INF_F) {
-            mn = fminf(mn, c);
-            const float J = (g.raw > 0.0f) ? __fmul_rn(g.raw, cell_rep(c)) : 0.0f;   // 0 * rep == 0: the division is skipped
-            jall_fin = fmaxf(jall_fin, J);
-            if (!inside) { jfmn = fminf(jfmn, J); jfmx = fmaxf(jfmx, J); }
-          } else {
-            has_inf = 1;
-            jall_inf = fmaxf(jall_inf, g.raw);
-            if (!inside) { jimn = fminf(jimn, g.raw); jimx = fmaxf(jimx, g.raw); }
-          }
-        }
+    // per-scene statistics for the field kernel + the batch maxima of the repulsion, from the converged costs still in shared memory.
+    // Min / max cost and "is there a cell no obstacle reaches" came out of the write-out loop above; the distance / repulsion terms are
+    // evaluated only for the queued cells that an obstacle does reach (~20 % of the grid), every lane busy.
+    float jfmn = CUDART_INF_F, jfmx = -1.0f, jimn = CUDART_INF_F, jimx = -1.0f, jall_fin = 0.0f, jall_inf = 0.0f;
+    int has_inf = far_inf, has_inside = 0;
+    const int nnear = min(*s_nnear, kNearCap);
+    for (int k = threadIdx.x; k < nnear; k += kCostThreads) {
+      const int q = s_near[k];
+      const int y = q / kG, x = q - y * kG;
+      const float c = buf[(y + 1) * kGS + x + 1];
+      const CellGeom g = cell_geom(cell_sdf_masked(io.lin[x], io.lin[y], s_sc, s_sc + 16, s_rowmask[y] & s_colmask[x]));
+      const bool inside = g.edge <= 0.0f;
+      has_inside |= inside ? 1 : 0;
+      if (c < CUDART_INF_F) {
+        const float J = (g.raw > 0.0f) ? __fmul_rn(g.raw, cell_rep(c)) : 0.0f;   // 0 * rep == 0: the division is skipped
+        jall_fin = fmaxf(jall_fin, J);
+        if (!inside) { jfmn = fminf(jfmn, J); jfmx = fmaxf(jfmx, J); }
+      } else {
+        has_inf = 1;
+        jall_inf = fmaxf(jall_inf, g.raw);
+        if (!inside) { jimn = fminf(jimn, g.raw); jimx = fmaxf(jimx, g.raw); }
       }
     }
+    far_fin = __syncthreads_or(far_fin);
+    far_inf = __syncthreads_or(far_inf);
+    if (far_fin) { jfmn = fminf(jfmn, 0.0f); jfmx = fmaxf(jfmx, 0.0f); }   // the unreached-by-any-obstacle cells: J = 0 (20 q^2 = 0)
+    if (far_inf) { jimn = fminf(jimn, 0.0f); jimx = fmaxf(jimx, 0.0f); }
     mn = -block_reduce_max_cost(-mn, s_red);
     jfmn = -block_reduce_max_cost(-jfmn, s_red);
     jfmx = block_reduce_max_cost(jfmx, s_red);
@@ -554,7 +570,7 @@ __global__ void compact_resets_kernel(const int64_t* __restrict__ reset_buf, int
   }
 }
 
-static size_t cost_smem_bytes() { return (size_t)(kGPR * kGS + 64 + 32 + 2 * kActStride + 160 + 160) * sizeof(float) + (size_t)kTiles * 32; }
+static size_t cost_smem_bytes() { return (size_t)(kGPR * kGS + 64 + 32 + 2 * kActStride + 160 + 160) * sizeof(float) + (size_t)kTiles * 32 + (size_t)kNearCap * 2; }
 
 static int scene_grid() {
   static int sms = 0;
