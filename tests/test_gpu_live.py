@@ -4,6 +4,7 @@
 Bars: obs / reward terms 1e-5 relative (atol written at each assert), kills / outcome latches / obstacle placement and the
 cost-to-go field bit-exact."""
 import dataclasses
+import math
 
 import numpy as np
 import pytest
@@ -58,6 +59,40 @@ def test_potential_field_builder_vs_reference_golden(golden):
     assert torch.equal(c1.cpu()[0], T(G["cost0"][3]))
     want = B.potential_field(T(G["cost0"][3:4]), T(G["sdf0"][3:4]))
     assert_close(f1, want, 1e-6, 1e-6, "potential field (batch of one)")
+
+
+def test_field_builder_statistics_path_vs_oracle_on_walled_scenes():
+    """The cost kernel hands the field kernel per-scene extrema (finite-cost and unreachable cells apart, the latter scaled by their common
+    rep factor afterwards) and takes the batch maxima itself: scenes with a pocket the wavefront cannot enter (unreachable FREE cells next to
+    obstacles), scenes without any obstacle in reach (no inside cell, J = 0 everywhere) and ordinary ones in ONE batch, against the oracle's
+    BatchedMapGPU restatement (d_multi_gemini.py:194-271) -- and with more scenes than the env owns, so the workspace has to grow."""
+    env = FusedUsvLiveEnv(LIVE_CFG, UsvLiveConfig(), 8, DEV)
+    g = torch.Generator().manual_seed(11)
+    m = 24
+    obst = torch.full((m, 16, 2), 999.0)
+    tgt = torch.zeros((m, 2))
+    for k in range(m):
+        if k % 3 == 0:        # a ring of 16 overlapping discs of radius 0.5 at 1.9 m around (6, 6): the inside is free but unreachable
+            ang = torch.arange(16) * (2 * math.pi / 16)
+            obst[k, :, 0] = 6.0 + 1.9 * torch.cos(ang)
+            obst[k, :, 1] = 6.0 + 1.9 * torch.sin(ang)
+            tgt[k] = torch.tensor([-5.0, -4.0]) + torch.rand(2, generator=g)
+        elif k % 3 == 1:      # nothing on the map
+            tgt[k] = torch.rand(2, generator=g) * 20 - 10
+        else:                 # scattered
+            obst[k] = torch.rand((16, 2), generator=g) * 24 - 12
+            tgt[k] = torch.tensor([13.0, 13.0]) - torch.rand(2, generator=g)
+    field, cost = env.build_fields(obst, tgt, want_cost=True)
+    occ, sdf = B.occupancy_and_sdf(obst)
+    want_cost = B.cost_to_go(occ, tgt)
+    assert torch.equal(cost.cpu(), want_cost)
+    pocket = want_cost[0].isinf() & (occ[0] < 0.5)
+    assert int(pocket.sum()) > 20                                   # unreachable free cells exist
+    assert_close(field, B.potential_field(want_cost, sdf), 1e-6, 1e-6, "potential field, mixed batch")
+    # the same scenes one by one: other batch maxima, same machinery
+    for k in (0, 1, 2):
+        f1 = env.build_fields(obst[k:k + 1], tgt[k:k + 1])
+        assert_close(f1, B.potential_field(want_cost[k:k + 1], sdf[k:k + 1]), 1e-6, 1e-6, f"potential field, scene {k} alone")
 
 
 def test_cost_to_go_in_place_relaxation_equals_jacobi_on_odd_scenes():
