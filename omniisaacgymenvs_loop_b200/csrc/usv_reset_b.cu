@@ -274,7 +274,12 @@ __global__ void __launch_bounds__(kCostThreads, 2) scene_cost_kernel(SceneIO io,
     } else {
       env = load_scene(io, j, s_sc);
     }
-    for (int q = threadIdx.x; q < kGPR * kGS; q += kCostThreads) buf[q] = CUDART_INF_F;   // halo and spare rows included
+    {                                      // +inf everywhere, halo and spare rows included (16-byte stores; kGPR * kGS = 23 562 words)
+      const float4 inf4 = make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, CUDART_INF_F);
+      float4* b4 = reinterpret_cast<float4*>(buf);
+      for (int q = threadIdx.x; q < (kGPR * kGS) / 4; q += kCostThreads) b4[q] = inf4;
+      if (threadIdx.x < (kGPR * kGS) % 4) buf[((kGPR * kGS) / 4) * 4 + threadIdx.x] = CUDART_INF_F;
+    }
     if (threadIdx.x < 2 * kActStride) s_act[threadIdx.x] = 0;
     if (threadIdx.x == 0) *s_nnear = 0;
     __syncthreads();
@@ -302,9 +307,10 @@ __global__ void __launch_bounds__(kCostThreads, 2) scene_cost_kernel(SceneIO io,
       if (x < kG) {
         const uint32_t cmask = s_colmask[x];
         const float cx = io.lin[x];
-#pragma unroll 1
-        for (int i = 0; i < kBandRows && y0 + i < kG; ++i) {
+#pragma unroll
+        for (int i = 0; i < kBandRows; ++i) {
           const int y = y0 + i;
+          if (y >= kG) break;
           const bool border = (y == 0) || (y == kG - 1) || (x == 0) || (x == kG - 1);
           const uint32_t mask = s_rowmask[y] & cmask;
           if (mask) {                                  // the statistics pass walks these densely
