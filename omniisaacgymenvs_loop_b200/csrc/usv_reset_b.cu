@@ -169,7 +169,7 @@ constexpr int kAsyncSweepCap = 4 * kMaxSweeps;
 #ifndef USV_SCENE_INNER
 #define USV_SCENE_INNER 16
 #endif
-constexpr int kInner = USV_SCENE_INNER;            // passes of a warp over its tile per outer sweep (one tile width)
+constexpr int kInner = USV_SCENE_INNER;            // passes of a warp over its tile per outer sweep (a value crosses a tile in <= 8; 12..32 time alike)
 constexpr float kJacobiSafeCost = 224.0f;
 
 __device__ __forceinline__ float block_reduce_max_cost(float v, float* s_red) {

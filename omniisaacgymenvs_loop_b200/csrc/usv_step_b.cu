@@ -621,7 +621,8 @@ extern "C" int usv_step_live_f32(const UsvEnvBuffers* b, const UsvLiveBuffers* l
   const bool no_stage = force >= 0 ? force == 0 : n > 196608;
   // one wave at two CTAs per SM (and no statistics: the rarely used stats build stays on one register budget)
   static const int sms = [] { int d = 0, v = 0; cudaGetDevice(&d); return (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d) == cudaSuccess && v > 0) ? v : 148; }();
-  const bool one_wave = !no_stage && grid <= 2 * sms && !getenv("USV_LIVE_MINB3");
+  static const bool force3 = getenv("USV_LIVE_MINB3") != nullptr;      // profiling runs: always the 80-register build
+  const bool one_wave = !no_stage && grid <= 2 * sms && !force3;
 #define USV_LAUNCH_LIVE(D, S)                                                                                                      \
   do {                                                                                                                             \
     if (no_stage) step_live_kernel<D, S, false><<<grid, kBlock, smem, s>>>(*b, *lb, (const float2*)actions, obs, rew, n, *p, *lp);  \
