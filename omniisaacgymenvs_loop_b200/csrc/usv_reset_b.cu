@@ -503,7 +503,10 @@ __device__ __forceinline__ float global_vis_inf(const uint32_t* counters, int ha
 
 // field[env] = (G - min G) / (max G - min G + 1e-6) + 0.5 (J - min J) / (max J - min J + 1e-6)  (d_multi_gemini.py:205-271), one cell per
 // thread-iteration; a scene is cut into kFieldChunks row blocks so that ~150 scenes spread over every SM instead of one CTA each
-constexpr int kFieldThreads = 256, kFieldChunks = 10, kFieldRows = kG / kFieldChunks;   // 15 rows = 2250 cells per item
+#ifndef USV_FIELD_CHUNKS
+#define USV_FIELD_CHUNKS 10
+#endif
+constexpr int kFieldThreads = 256, kFieldChunks = USV_FIELD_CHUNKS, kFieldRows = kG / kFieldChunks;   // 15 rows = 2250 cells per item
 static_assert(kFieldRows * kFieldChunks == kG, "row blocks must tile the grid");
 
 __global__ void __launch_bounds__(kFieldThreads) scene_field_kernel(SceneIO io, const uint32_t* __restrict__ counters) {
