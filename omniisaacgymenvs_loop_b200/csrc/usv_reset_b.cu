@@ -3,7 +3,7 @@
 // [ref: OIGE/tasks/USV/d_multi_gemini.py:66-104 occupancy + SDF, :135-192 cost-to-go wavefront, :194-271 potential field].
 //
 // The reference runs 225 Jacobi sweeps of an 8-neighbour min-plus relaxation as ~30 torch ops per sweep over the whole
-// (B,150,150) batch in HBM.  Here ONE CTA owns one env: the 150x150 cost buffer lives in shared memory (92 KB with an +inf halo,
+// (B,150,150) batch in HBM.  Here ONE CTA owns one env: the 150x150 cost buffer lives in shared memory (94 KB with an +inf halo,
 // two scenes per SM) and is relaxed in place until nothing changes -- the same fixed point, bit for bit, as the reference's Jacobi
 // sweeps (see the comment at scene_cost_kernel).  The reference's BATCH-GLOBAL maxima (max finite cost, max repulsion: quirk 9 of
 // SURVEY appendix C) and its per-scene min / max normalisation are reductions over cells whose inputs do not depend on those
@@ -157,10 +157,11 @@ __device__ __forceinline__ void place_obstacles(const UsvStepParams& p, uint64_t
 // ---- cost-to-go -------------------------------------------------------------------------------------------------------------
 // The reference's 225 Jacobi sweeps converge to the greatest fixed point of  d(c) = min(d(c), min_nb fl(d(nb) + w))  with d = 0 at the
 // target; fl(d + w) is monotone in d, so ANY fair asynchronous (chaotic) iteration from +inf reaches the same fixed point bit for
-// bit.  That licenses an in-place relaxation: ONE 150x150 buffer per scene (92 KB instead of 185 KB: two scenes per SM, which removes
-// the second wave of the typical ~150 resets per control step on 148 SMs), values move a whole tile column per sweep (Gauss-Seidel
-// along the walking direction, which alternates down / up), tiles whose inputs did not change are skipped, and the scene ends at the
-// first sweep without a change.  The 225th Jacobi iterate IS the fixed point whenever every shortest path has <= 225 hops; a hop
+// bit.  That licenses an in-place relaxation: ONE 150x150 buffer per scene (94 KB instead of 185 KB: two scenes per SM, which removes
+// the second wave of the typical ~150 resets per control step on 148 SMs), relaxed tile by tile (8 columns x 32 rows; inside a lane's 8
+// rows a pass walks down and back up feeding each new value into the next row), a warp staying on its tile until it stops changing
+// before the CTA meets at the sweep barrier; tiles whose inputs did not change are skipped, and the scene ends at the first sweep
+// without a change.  The 225th Jacobi iterate IS the fixed point whenever every shortest path has <= 225 hops; a hop
 // costs >= 1, so "max finite cost < 224" proves it.  Otherwise (or when the target cell is not free: its 0 is overwritten after one
 // Jacobi sweep, which an asynchronous order does not reproduce) the scene is redone by literal Jacobi sweeps through a global scratch
 // (the env's own field slot) -- never seen with the task's obstacle placement, covered by a dense-batch test.
